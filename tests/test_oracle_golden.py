@@ -1,0 +1,130 @@
+"""Pin the CPU oracle (oracle/fusion_oracle.py) against golden vectors produced by the
+unmodified reference classes (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import detgen
+from oracle import fusion_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = [("v2_b8_t5_mask", "v2", "wce", True), ("v2_b4_t16_nomask", "v2", "focal_alpha", False),
+         ("v1_b8_t5_mask", "v1", "focal", False), ("v1_b32_t16_cfg1", "v1", "focal", False)]
+ALPHA = torch.tensor([1, 1, 1, 1, 1.2, 1.2], dtype=torch.float64)
+
+
+def summarize(t):
+    f = t.detach().double().flatten()
+    head = f[:16].numpy()
+    head = np.pad(head, (0, 16 - head.size))
+    return np.concatenate([[float(f.norm()), float(f.sum())], head])
+
+
+def load_case(name, variant):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    B, T = int(g["B"]), int(g["T"])
+    dims = dict(max_seq_len=T + 1)
+    if variant == "v2":
+        dims["hidden"] = 512
+    P = {k: torch.from_numpy(np.asarray(v)) for k, v in detgen.make_params(variant, **dims).items()}
+    v, a, m, y = detgen.make_batch(B, T, tag=name)
+    mask = torch.from_numpy(m) if int(g["use_mask"]) else None
+    return g, P, torch.from_numpy(v), torch.from_numpy(a), mask, torch.from_numpy(y)
+
+
+def to64(P):
+    return {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}
+
+
+@pytest.mark.parametrize("name,variant,loss,clip", CASES)
+def test_eval_forward_and_attention(name, variant, loss, clip):
+    g, P, video, audio, mask, labels = load_case(name, variant)
+    P = to64(P)
+    if variant == "v2":
+        probs, logits, fused, attn = O.model_forward_v2(P, video.double(), audio.double(), mask)
+    else:
+        probs, logits, fused, attn = O.model_forward_v1(P, video.double(), audio.double(), mask, training=False)
+    np.testing.assert_allclose(logits.numpy(), g["eval/logits"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(probs.numpy(), g["eval/probs"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(fused.numpy(), g["eval/fused"], rtol=2e-5, atol=2e-5)
+    assert (probs.argmax(1).numpy() == g["eval/probs"].argmax(1)).all()
+    last, audio_row = O.cross_modal_attention(attn)
+    np.testing.assert_allclose(last.numpy(), g["eval/attn_last_mean"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(attn[0][:, 0].numpy(), g["eval/attn_layer0_head0"], rtol=1e-4, atol=1e-6)
+    assert (audio_row.argmax(1).numpy() == g["eval/attn_last_mean"][:, -1, :].argmax(1)).all()
+    if mask is not None:  # masked keys get exactly zero weight
+        S = mask.shape[1] + 1
+        full = torch.cat([mask, torch.zeros(mask.shape[0], 1, dtype=torch.bool)], 1)
+        assert float(last.masked_select(full.view(-1, 1, S).expand_as(last)).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name,variant,loss,clip", CASES)
+def test_losses_and_dlogits(name, variant, loss, clip):
+    g, *_ = load_case(name, variant)
+    logits = torch.from_numpy(g["train/logits"]).double()
+    labels = torch.from_numpy(detgen.make_batch(int(g["B"]), int(g["T"]), tag=name)[3])
+    assert abs(float(O.focal_loss(logits, labels)) - float(g["loss/focal"])) < 2e-6
+    assert abs(float(O.focal_loss(logits, labels, alpha=ALPHA)) - float(g["loss/focal_alpha"])) < 2e-6
+    assert abs(float(O.focal_loss(logits, labels, reduction="sum")) - float(g["loss/focal_sum"])) < 2e-5
+    np.testing.assert_allclose(O.focal_loss(logits, labels, alpha=ALPHA, reduction="none").numpy(),
+                               g["loss/focal_none"], rtol=1e-5, atol=1e-6)
+    assert abs(float(O.weighted_ce(logits, labels, ALPHA)) - float(g["loss/wce"])) < 2e-6
+    np.testing.assert_allclose(O.focal_loss_grad(logits, labels, alpha=ALPHA).numpy(),
+                               g["dlogits/focal_alpha"], rtol=1e-4, atol=1e-7)
+    lg = logits.clone().requires_grad_(True)
+    O.weighted_ce(lg, labels, ALPHA).backward()
+    np.testing.assert_allclose(lg.grad.numpy(), g["dlogits/wce"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,variant,loss,clip", CASES)
+def test_train_step_grads_and_adam(name, variant, loss, clip):
+    g, P, video, audio, mask, labels = load_case(name, variant)
+    P64 = to64(P)
+    kw = dict(variant=variant, loss="wce" if loss == "wce" else "focal",
+              alpha=ALPHA if loss in ("wce", "focal_alpha") else None, clip=1.0 if clip else None)
+    vid = video.double().requires_grad_(True)
+    aud = audio.double().requires_grad_(True)
+    P1, S1, l1, logits, grads = O.train_step(P64, {}, 1, vid, aud, mask, labels, **kw)
+    np.testing.assert_allclose(logits.numpy(), g["train/logits"], rtol=2e-5, atol=2e-5)
+    for k, gr in grads.items():
+        ref = g["grad/" + k]
+        tol = 2e-4 * ref[0] + 1e-6  # pre-BatchNorm biases have an exactly-zero true gradient
+        assert abs(summarize(gr)[0] - ref[0]) <= tol, k
+        np.testing.assert_allclose(summarize(gr)[2:], ref[2:], rtol=0, atol=5e-4 * ref[0] + 1e-6, err_msg=k)
+    if clip:
+        total, _ = O.clip_coef(list(grads.values()), 1.0)
+        assert abs(total - float(g["clip/total_norm"])) < 1e-4 * total
+    for k in grads:
+        ref = g["delta1/" + k]
+        # Adam's first step moves every coordinate by ~lr; compare the update itself
+        np.testing.assert_allclose(summarize(P1[k] - P64[k])[2:], ref[2:], rtol=0, atol=2e-6, err_msg=k)
+        assert abs(summarize(P1[k] - P64[k])[0] - ref[0]) <= 2e-3 * ref[0] + 1e-9, k
+    # second step on the same batch: Adam state and bias correction
+    P2, S2, l2, logits2, _ = O.train_step(P1, S1, 2, vid, aud, mask, labels, **kw)
+    assert abs(l2 - float(g["step2/loss"])) < 5e-4
+    np.testing.assert_allclose(logits2.numpy(), g["step2/logits"], rtol=0, atol=3e-3)
+    if variant == "v1":
+        for k in P1:
+            if "running" in k:
+                np.testing.assert_allclose(P1[k].numpy(), g["bn_after_fwd/" + k], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,variant", [("v2_b8_t5_mask", "v2"), ("v1_b8_t5_mask", "v1")])
+def test_input_gradients(name, variant):
+    g, P, video, audio, mask, labels = load_case(name, variant)
+    P64 = to64(P)
+    vid = video.double().requires_grad_(True)
+    aud = audio.double().requires_grad_(True)
+    if variant == "v2":
+        _, logits, _, _ = O.model_forward_v2(P64, vid, aud, mask)
+        lval = O.weighted_ce(logits, labels, ALPHA)
+    else:
+        _, logits, _, _ = O.model_forward_v1(P64, vid, aud, mask, training=True)
+        lval = O.focal_loss(logits, labels)
+    lval.backward()
+    np.testing.assert_allclose(vid.grad[:4].numpy(), g["grad_in/video"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(aud.grad[:4].numpy(), g["grad_in/audio"], rtol=0, atol=1e-6)
+    if variant == "v2":  # padded video rows receive exactly zero gradient
+        assert float(vid.grad[mask].abs().max()) == 0.0
