@@ -1,0 +1,259 @@
+/* mmer.h -- C ABI of libmmer_sm100.so: the B200 (sm_100a) kernels behind the audio-visual
+ * fusion classifier step of EvanZJ/multi-modal-emotion-recognition.
+ *
+ * The reference has no native layer; its hot path is PyTorch module calls.  Each entry
+ * point below names the reference call site (file:line, relative to the reference repo)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ *
+ * Conventions:
+ *   - plain pointers and sizes; all pointers are DEVICE pointers unless stated otherwise
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocates, never synchronises, owns nothing
+ *   - returns 0 on success, a negative MMER_ERR_* code otherwise; the message is
+ *     available from mmer_last_error() (thread local)
+ *   - the device is the caller's current device
+ *   - `dtype` selects the storage type of activations: MMER_F32 or MMER_BF16.  All
+ *     statistics, reductions, losses, gradients of parameters and optimizer state are fp32.
+ *   - token matrices are batch-major: row = b * S + s, S = T + 1 (audio token last).
+ */
+#ifndef MMER_H_
+#define MMER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMER_VERSION 100
+
+#define MMER_OK 0
+#define MMER_ERR_ARG (-1)      /* bad argument / unsupported shape */
+#define MMER_ERR_CUDA (-2)     /* CUDA runtime or driver error */
+#define MMER_ERR_UNSUPPORTED (-3)
+
+#define MMER_F32 0
+#define MMER_BF16 1
+
+#define MMER_MAJOR_K 0   /* reduction dim contiguous: matrix stored [rows][K]  */
+#define MMER_MAJOR_MN 1  /* row dim contiguous:      matrix stored [K][rows]  */
+
+#define MMER_LOSS_FOCAL 0   /* FocalLoss, train.py:20-37 == train2.py:40-70          */
+#define MMER_LOSS_WCE 1     /* nn.CrossEntropyLoss(weight=w), train2.py:523          */
+#define MMER_REDUCE_MEAN 0
+#define MMER_REDUCE_SUM 1
+#define MMER_REDUCE_NONE 2
+
+int mmer_version(void);
+const char* mmer_last_error(void);
+/* debug knobs used by the GPU tests (descriptor variants, forcing the SIMT GEMM ...) */
+#define MMER_DEBUG_MN_SWAP 0     /* swap LBO/SBO in MN-major UMMA descriptors */
+#define MMER_DEBUG_FORCE_BN 1    /* force the tcgen05 GEMM N tile (128 or 256) */
+#define MMER_DEBUG_FORCE_SIMT 2  /* route bf16 GEMMs through the fp32 FMA kernel (debug only) */
+int mmer_debug_set(int key, int value);
+int mmer_debug_get(int key);
+
+/* ------------------------------------------------------------------------------------
+ * GEMM: D[M,N] = epilogue( A[M,K] . B[N,K]^T ).  Replaces every nn.Linear forward on the
+ * path (train2.py:150,153,217-228; the in_proj / out_proj / linear1 / linear2 of
+ * nn.TransformerEncoderLayer configured at train2.py:111-118, train.py:54-57) and their
+ * autograd dgrad / wgrad.  in_dtype MMER_BF16 runs on tcgen05 tensor cores (TMA-fed,
+ * accumulators in TMEM); in_dtype MMER_F32 runs an fp32 FMA kernel (parity mode).
+ *   forward : A = X [M,K] K-major,  B = W [N,K] K-major
+ *   dgrad   : A = dY [M,N'] K-major, B = W viewed as [K',N'] -> MMER_MAJOR_MN
+ *   wgrad   : A = dY viewed [N',M] MN-major, B = X viewed [K',M] MN-major, accumulate=1
+ * epilogue order: +bias, relu, *dropout, *gate, +residual.
+ * ---------------------------------------------------------------------------------- */
+typedef struct mmer_gemm_args {
+  const void* A;
+  const void* B;
+  void* D;
+  const float* bias;    /* [N] fp32 or NULL */
+  const void* residual; /* [M,N] out_dtype, leading dim ldd, or NULL */
+  const void* gate;     /* [M,N] out_dtype, leading dim ldd, or NULL: acc *= gate>0 ? gate_scale : 0 */
+  int64_t M, N, K;
+  int64_t lda, ldb, ldd; /* row stride, in elements, of each matrix as stored */
+  int32_t a_major, b_major;
+  int32_t in_dtype, out_dtype;
+  int32_t accumulate; /* D += result; requires out_dtype MMER_F32 (split-K, fp32 atomics) */
+  int32_t relu;
+  float drop_p;
+  float gate_scale;
+  uint64_t seed;
+  uint32_t drop_site;
+  uint32_t reserved;
+} mmer_gemm_args;
+int mmer_gemm(const mmer_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Token assembly: LayerNorm of both projections, concat, +pos_embed, dropout.
+ * train2.py:151,154,157-161.  pv [B*T,F], pa [B,F] are the projection outputs;
+ * x0 [B*S,F]; stats [B*S,2] fp32 (mean, rstd).  pos is fp32 [>=S,F].
+ * ---------------------------------------------------------------------------------- */
+int mmer_embed_fwd(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga,
+                   const float* ba, const float* pos, void* x0, float* stats, int64_t B, int64_t T,
+                   int64_t F, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* backward: dpv, dpa get the LayerNorm input gradients; dgv.. dpos are ACCUMULATED (+=) */
+int mmer_embed_bwd(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv,
+                   const float* ga, void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba,
+                   float* dpos, int64_t B, int64_t T, int64_t F, int dtype, float drop_p, uint64_t seed,
+                   uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Row kernel: z = x + dropout_a(a);  y = dropout_y(relu?(LayerNorm(z))).
+ * Encoder: x + dropout(sublayer) then norm1/norm2 (post-norm nn.TransformerEncoderLayer);
+ * head: Linear -> LayerNorm -> ReLU -> Dropout (train2.py:217-226).  x may be NULL (z = a).
+ * stats [M,2] fp32.  gamma NULL => no normalisation (identity).
+ * ---------------------------------------------------------------------------------- */
+int mmer_add_ln_fwd(const void* x, const void* a, const float* gamma, const float* beta, void* y,
+                    float* stats, int64_t M, int64_t F, int dtype, int relu, float drop_a_p,
+                    uint32_t site_a, float drop_y_p, uint32_t site_y, uint64_t seed, void* stream);
+/* backward.  dz = gradient w.r.t. z (goes to the residual stream x); da = dz * mask_a,
+ * written only when drop_a_p > 0 and da != NULL (otherwise da == dz).  dgamma/dbeta and
+ * dbias (column sum of da, i.e. the bias gradient of the Linear that produced `a`) are
+ * ACCUMULATED; each may be NULL.  Nothing of the forward output is re-read: the ReLU sign
+ * and both dropout masks are recomputed from x, a, stats, gamma, beta and the seed. */
+int mmer_add_ln_bwd(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
+                    const float* beta, void* dz, void* da, float* dgamma, float* dbeta, float* dbias,
+                    int64_t M, int64_t F, int dtype, int relu, float drop_a_p, uint32_t site_a,
+                    float drop_y_p, uint32_t site_y, uint64_t seed, void* stream);
+
+/* Masked mean pooling over the S tokens of each sample + out_norm (train2.py:184-191;
+ * train.py:100-104 without the norm: gamma == NULL).  mask [B,T] bytes, 1 = padded, or NULL. */
+int mmer_pool_ln_fwd(const void* x, const uint8_t* mask, const float* gamma, const float* beta,
+                     float* pooled, void* fused, float* stats, int64_t B, int64_t T, int64_t F, int dtype,
+                     void* stream);
+int mmer_pool_ln_bwd(const void* dfused, const float* pooled, const float* stats, const float* gamma,
+                     const uint8_t* mask, void* dx, float* dgamma, float* dbeta, int64_t B, int64_t T,
+                     int64_t F, int dtype, void* stream);
+
+/* out[n] += sum_m x[m,n]  (bias gradients) */
+int mmer_colsum(const void* x, float* out, int64_t M, int64_t N, int64_t ldx, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-head self-attention over [T video tokens ; 1 audio token] with key padding mask.
+ * Replaces nn.MultiheadAttention inside the encoder (called via train2.py:173-176).
+ * qkv [B*S, 3*H*d] packed as torch's in_proj output (q | k | v, heads contiguous);
+ * out [B*S, H*d].  probs (optional, fp32 [B,H,S,S]) receives the softmax weights: this is
+ * the defined attention-weight output for `return_attn=True`.
+ * ---------------------------------------------------------------------------------- */
+int mmer_mha_fwd(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T,
+                 int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+int mmer_mha_bwd(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int64_t B, int64_t T,
+                 int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+
+/* Final Linear(hidden -> C) + softmax (train2.py:228,290; train.py:128-129), C <= 16.
+ * logits/probs fp32 [B,C]. */
+int mmer_head_out_fwd(const void* h, const float* W, const float* b, float* logits, float* probs,
+                      int64_t B, int64_t K, int64_t C, int dtype, void* stream);
+/* dh [B,K] (dtype); dW [C,K], db [C] accumulated. */
+int mmer_head_out_bwd(const float* dlogits, const void* h, const float* W, void* dh, float* dW, float* db,
+                      int64_t B, int64_t K, int64_t C, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Loss forward + gradient in one kernel.  FocalLoss (train.py:27-37): alpha optional,
+ * plain mean over B.  Weighted CE (train2.py:523,572): sum(w_y ce)/sum(w_y).
+ * loss_out: 1 fp32 (zeroed by the call; for REDUCE_NONE unused), per_sample [B] optional,
+ * dlogits [B,C] optional (= grad_scale * dloss/dlogits).  scratch: >= 2 fp32.
+ * ---------------------------------------------------------------------------------- */
+int mmer_loss_fwd_bwd(const float* logits, const int64_t* labels, const float* alpha, int kind, float gamma,
+                      int reduction, float* loss_out, float* per_sample, float* dlogits, float* scratch,
+                      int64_t B, int64_t C, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * optim.Adam(lr, weight_decay) step over a flat fp32 buffer (train.py:252,297;
+ * train2.py:525,578) with optional fused clip_grad_norm_ (train2.py:576):
+ *   g' = g * grad_scale * min(1, max_norm / (sqrt(*sumsq * grad_scale^2) + 1e-6))
+ *   g' += wd * p;  m,v update;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+ * lr and step are runtime scalars (ReduceLROnPlateau, train2.py:526,614).  sumsq may be
+ * NULL (no clipping).  shadow (bf16 copy of p) may be NULL.
+ * ---------------------------------------------------------------------------------- */
+int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                   const float* sumsq, float max_norm, void* stream);
+int mmer_grad_sumsq(const float* g, int64_t n, float* out /* zeroed by the call */, void* stream);
+int mmer_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+int mmer_cast_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * BatchNorm1d of the train.py variant (train.py:51-52,66-74,116,125) over rows of [N,C].
+ * training: batch statistics (biased variance), running stats updated with momentum 0.1
+ * and unbiased variance; y = dropout(relu?(bn(x))).  stats_out is saved for backward.
+ * ---------------------------------------------------------------------------------- */
+int mmer_bn_fwd(const void* x, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, void* y, float* stats_out /* [2,C]: mean, rstd */, int64_t N, int64_t C,
+                int dtype, int training, int relu, float momentum, float drop_p, uint64_t seed, uint32_t site,
+                void* stream);
+/* dgamma/dbeta ACCUMULATED; scratch >= 2*C fp32.  ReLU sign and dropout mask are recomputed. */
+int mmer_bn_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
+                void* dx, float* dgamma, float* dbeta, float* scratch, int64_t N, int64_t C, int dtype,
+                int training, int relu, float drop_p, uint64_t seed, uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole-model entry points: MultimodalEmotionModel forward / backward / training step
+ * (train2.py:281-292,570-579; train.py:139-142,293-297), one call each, all kernels
+ * enqueued on `stream`.  See mmer_model in the engine section of DESIGN.md.
+ * ---------------------------------------------------------------------------------- */
+#define MMER_MAX_LAYERS 16
+enum {
+  MMER_G_POS = 0, MMER_G_WV, MMER_G_BV, MMER_G_WA, MMER_G_BA,
+  MMER_G_NV_W, MMER_G_NV_B, MMER_G_NA_W, MMER_G_NA_B,   /* norm_video/norm_audio or bn_video/bn_audio */
+  MMER_G_ON_W, MMER_G_ON_B,                             /* out_norm (v2 only) */
+  MMER_G_C0_W, MMER_G_C0_B, MMER_G_C1_W, MMER_G_C1_B,   /* net.0 + net.1   | fc1 + bn_fc1 */
+  MMER_G_C4_W, MMER_G_C4_B, MMER_G_C5_W, MMER_G_C5_B,   /* net.4 + net.5   | unused       */
+  MMER_G_C8_W, MMER_G_C8_B,                             /* net.8           | fc2          */
+  MMER_G_COUNT
+};
+enum {
+  MMER_L_IN_W = 0, MMER_L_IN_B, MMER_L_OUT_W, MMER_L_OUT_B, MMER_L_FF1_W, MMER_L_FF1_B,
+  MMER_L_FF2_W, MMER_L_FF2_B, MMER_L_N1_W, MMER_L_N1_B, MMER_L_N2_W, MMER_L_N2_B, MMER_L_COUNT
+};
+
+typedef struct mmer_model {
+  int32_t variant;   /* 2: LayerNorm model (train2.py / back-end), 1: BatchNorm model (train.py) */
+  int32_t dtype;     /* activation storage + GEMM input type */
+  int32_t B, T;      /* batch, padded video length; S = T + 1 */
+  int32_t video_dim, audio_dim, fused, heads, layers, ffn, hidden, classes;
+  int32_t training;  /* dropout on, BatchNorm batch statistics */
+  int32_t has_mask;
+  float p_fusion, p_classifier;
+  uint64_t seed;
+  int64_t n_params;                       /* elements of the flat parameter buffer */
+  int64_t off_g[MMER_G_COUNT];            /* element offsets into the flat buffers, -1 = absent */
+  int64_t off_l[MMER_MAX_LAYERS][MMER_L_COUNT];
+  /* buffers */
+  float* params;        /* fp32 master weights, flat */
+  void* shadow;         /* bf16 copy of params (dtype == MMER_BF16), flat, same offsets */
+  float* grads;         /* fp32 flat, same offsets; backward ACCUMULATES into it */
+  float* bn_state;      /* v1 only: running_mean/var for bn_video, bn_audio, bn_fc1: [2*F, 2*F, 2*H2] */
+  void* workspace;      /* >= mmer_workspace_bytes() */
+  int64_t workspace_bytes;
+  /* per-call tensors */
+  const void* video;    /* [B,T,video_dim] dtype */
+  const void* audio;    /* [B,audio_dim]   dtype */
+  const uint8_t* mask;  /* [B,T] 1 = padded, or NULL */
+  float* logits;        /* [B,classes] fp32 out */
+  float* probs;         /* [B,classes] fp32 out */
+  void* fused_out;      /* [B,fused] dtype out, optional */
+  float* attn_probs;    /* optional [layers,B,H,S,S] fp32 out (return_attn) */
+  /* backward */
+  const float* dlogits; /* [B,classes] fp32 */
+  void* dvideo;         /* optional [B,T,video_dim] dtype: input gradients (Captum IG path) */
+  void* daudio;         /* optional [B,audio_dim] dtype */
+  /* partial evaluation, for callers that use the sub-modules on their own */
+  int32_t stage;        /* 0 whole model; 1 CrossModalFusion only (train2.py:128-193); 2 EmotionClassifier only */
+  int32_t reserved;
+  const void* fused_in;  /* stage 2: classifier input [B,fused] dtype */
+  const void* dfused_in; /* stage 1 backward: gradient of the fused embedding [B,fused] dtype */
+  void* dfused_out;      /* stage 2 backward: optional gradient w.r.t. fused_in */
+} mmer_model;
+
+int64_t mmer_workspace_bytes(const mmer_model* m);
+int mmer_model_forward(const mmer_model* m, void* stream);
+int mmer_model_backward(const mmer_model* m, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMER_H_ */

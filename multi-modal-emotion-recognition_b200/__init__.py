@@ -1,0 +1,18 @@
+"""mmer_b200: B200-native (sm_100a) drop-in for the fusion classifier step of
+EvanZJ/multi-modal-emotion-recognition.  Import as ``mmer_b200`` (alias package at the repo
+root; this directory's name is not a valid Python identifier).
+
+Public surface (reference names):
+    FocalLoss, CrossModalFusion, EmotionClassifier, MultimodalEmotionModel   (train2.py variant)
+    v1.CrossModalFusion, v1.EmotionClassifier, v1.MultimodalEmotionModel     (train.py variant)
+plus FusedAdam, FusedTrainStep, WeightedCrossEntropyLoss and the raw ``ops``.
+"""
+from . import _lib, ops  # noqa: F401
+from ._lib import MmerError  # noqa: F401
+from .modules import (CrossModalFusion, EmotionClassifier, FocalLoss, MultimodalEmotionModel,  # noqa: F401
+                      WeightedCrossEntropyLoss)
+from . import modules_v1 as v1  # noqa: F401
+from .trainer import FusedAdam, FusedTrainStep  # noqa: F401
+
+__all__ = ["FocalLoss", "WeightedCrossEntropyLoss", "CrossModalFusion", "EmotionClassifier",
+           "MultimodalEmotionModel", "v1", "FusedAdam", "FusedTrainStep", "ops", "MmerError"]

@@ -1,0 +1,122 @@
+"""ctypes binding of libmmer_sm100.so (include/mmer.h).  No CPU fallback: if the library is
+missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch  # noqa: F401  (loads libcudart.so.12 before our library resolves it)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmmer_sm100.so")
+
+F32, BF16 = 0, 1
+MAJOR_K, MAJOR_MN = 0, 1
+LOSS_FOCAL, LOSS_WCE = 0, 1
+REDUCE_MEAN, REDUCE_SUM, REDUCE_NONE = 0, 1, 2
+DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT = 0, 1, 2
+MAX_LAYERS = 16
+G_NAMES = ["POS", "WV", "BV", "WA", "BA", "NV_W", "NV_B", "NA_W", "NA_B", "ON_W", "ON_B", "C0_W", "C0_B", "C1_W",
+           "C1_B", "C4_W", "C4_B", "C5_W", "C5_B", "C8_W", "C8_B"]
+L_NAMES = ["IN_W", "IN_B", "OUT_W", "OUT_B", "FF1_W", "FF1_B", "FF2_W", "FF2_B", "N1_W", "N1_B", "N2_W", "N2_B"]
+G_COUNT, L_COUNT = len(G_NAMES), len(L_NAMES)
+G = {n: i for i, n in enumerate(G_NAMES)}
+L = {n: i for i, n in enumerate(L_NAMES)}
+
+
+class MmerError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("D", C.c_void_p), ("bias", C.c_void_p),
+                ("residual", C.c_void_p), ("gate", C.c_void_p),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
+                ("a_major", C.c_int32), ("b_major", C.c_int32), ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+                ("accumulate", C.c_int32), ("relu", C.c_int32), ("drop_p", C.c_float), ("gate_scale", C.c_float),
+                ("seed", C.c_uint64), ("drop_site", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Model(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("dtype", C.c_int32), ("B", C.c_int32), ("T", C.c_int32),
+                ("video_dim", C.c_int32), ("audio_dim", C.c_int32), ("fused", C.c_int32), ("heads", C.c_int32),
+                ("layers", C.c_int32), ("ffn", C.c_int32), ("hidden", C.c_int32), ("classes", C.c_int32),
+                ("training", C.c_int32), ("has_mask", C.c_int32), ("p_fusion", C.c_float), ("p_classifier", C.c_float),
+                ("seed", C.c_uint64), ("n_params", C.c_int64),
+                ("off_g", C.c_int64 * G_COUNT), ("off_l", (C.c_int64 * L_COUNT) * MAX_LAYERS),
+                ("params", C.c_void_p), ("shadow", C.c_void_p), ("grads", C.c_void_p), ("bn_state", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("video", C.c_void_p), ("audio", C.c_void_p), ("mask", C.c_void_p),
+                ("logits", C.c_void_p), ("probs", C.c_void_p), ("fused_out", C.c_void_p), ("attn_probs", C.c_void_p),
+                ("dlogits", C.c_void_p), ("dvideo", C.c_void_p), ("daudio", C.c_void_p),
+                ("stage", C.c_int32), ("reserved", C.c_int32),
+                ("fused_in", C.c_void_p), ("dfused_in", C.c_void_p), ("dfused_out", C.c_void_p)]
+
+
+_P, _I64, _I, _F, _U64, _U32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_uint32
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/mmer.h one to one
+SIGNATURES = {
+    "mmer_version": [],
+    "mmer_last_error": [],
+    "mmer_debug_set": [_I, _I],
+    "mmer_debug_get": [_I],
+    "mmer_gemm": [C.POINTER(GemmArgs), _P],
+    "mmer_embed_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
+    "mmer_embed_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
+    "mmer_add_ln_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _U32, _F, _U32, _U64, _P],
+    "mmer_add_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _U32, _F, _U32, _U64, _P],
+    "mmer_pool_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
+    "mmer_pool_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
+    "mmer_colsum": [_P, _P, _I64, _I64, _I64, _I, _P],
+    "mmer_mha_fwd": [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
+    "mmer_mha_bwd": [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
+    "mmer_head_out_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
+    "mmer_head_out_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
+    "mmer_loss_fwd_bwd": [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _I64, _I64, _F, _P],
+    "mmer_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _F, _P, _F, _P],
+    "mmer_grad_sumsq": [_P, _I64, _P, _P],
+    "mmer_cast_bf16": [_P, _P, _I64, _P],
+    "mmer_cast_f32": [_P, _P, _I64, _P],
+    "mmer_bn_fwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _F, _F, _U64, _U32, _P],
+    "mmer_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _F, _U64, _U32, _P],
+    "mmer_workspace_bytes": [C.POINTER(Model)],
+    "mmer_model_forward": [C.POINTER(Model), _P],
+    "mmer_model_backward": [C.POINTER(Model), _P],
+}
+_RESTYPES = {"mmer_last_error": C.c_char_p, "mmer_workspace_bytes": C.c_int64}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is the job of __graft_entry__.build / build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MmerError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().mmer_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise MmerError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,50 @@
+// Library-level entry points: version, error reporting, debug knobs.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mmer {
+
+extern int g_debug[16];
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return MMER_ERR_CUDA;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace mmer
+
+extern "C" {
+
+int mmer_version(void) { return MMER_VERSION; }
+const char* mmer_last_error(void) { return mmer::g_err; }
+int mmer_debug_set(int key, int value) {
+  if (key < 0 || key >= 16) return MMER_ERR_ARG;
+  mmer::g_debug[key] = value;
+  return 0;
+}
+int mmer_debug_get(int key) { return (key < 0 || key >= 16) ? 0 : mmer::g_debug[key]; }
+
+}  // extern "C"

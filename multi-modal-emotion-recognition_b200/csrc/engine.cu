@@ -1,0 +1,410 @@
+// Whole-model orchestration: MultimodalEmotionModel forward and backward as one C call each.
+// Everything is enqueued asynchronously on the caller's stream; the workspace (activations
+// saved for backward + gradient scratch) is a single caller-owned allocation carved here.
+//
+// Reference data flow: train2.py:128-193,235-238,281-292 (LayerNorm variant, `variant == 2`)
+// and train.py:64-106,123-130,139-142 (BatchNorm variant, `variant == 1`).  The encoder layer is
+// the post-norm nn.TransformerEncoderLayer (ReLU, batch_first=False) configured at
+// train2.py:111-118 / train.py:54-57; tokens are kept batch-major here, which removes both
+// permutes of the reference (train2.py:172,181).
+#include "common.cuh"
+
+namespace mmer {
+
+int gemm_tc(const mmer_gemm_args& a, cudaStream_t st);
+int gemm_simt(const mmer_gemm_args& a, cudaStream_t st);
+extern int g_debug[16];
+
+int gemm_dispatch(const mmer_gemm_args& a, cudaStream_t st) {
+  if (a.in_dtype == MMER_BF16) return gemm_tc(a, st);
+  return gemm_simt(a, st);
+}
+
+struct Carver {
+  uint8_t* base;
+  size_t off;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)), off(0) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  }
+};
+
+struct LayerWs {
+  void *qkv, *att, *ao, *x1, *h, *f2, *x2;
+  float *st1, *st2;
+};
+struct Ws {
+  void *pv, *pa, *pvn, *pan, *x0;
+  float *st_e, *st_bnv, *st_bna, *st_fc;
+  LayerWs L[MMER_MAX_LAYERS];
+  float* pooled;
+  void* fused;
+  float* st_o;
+  void *h1p, *h1, *h2p, *h2;
+  float *st_h1, *st_h2;
+  // backward scratch
+  void *g_x, *g_z2, *g_f2, *g_h, *g_x1, *g_z1, *g_ao, *g_att, *g_qkv, *g_pv, *g_pa, *g_pvn, *g_pan;
+  void *g_fused, *g_h1, *g_h1p, *g_h2, *g_h2p;
+  float* bn_scratch;
+  size_t total;
+};
+
+static void carve(const mmer_model* m, void* base, Ws* w) {
+  Carver c(base);
+  const size_t e = m->dtype == MMER_BF16 ? 2 : 4;
+  const size_t B = m->B, T = m->T, S = T + 1, F = m->fused, Hd = m->hidden, FF = m->ffn;
+  const size_t M = B * S, Mv = B * T;
+  w->pv = c.take(Mv * F * e);
+  w->pa = c.take(B * F * e);
+  w->pvn = m->variant == 1 ? c.take(Mv * F * e) : nullptr;
+  w->pan = m->variant == 1 ? c.take(B * F * e) : nullptr;
+  w->x0 = c.take(M * F * e);
+  w->st_e = (float*)c.take(M * 2 * 4);
+  w->st_bnv = (float*)c.take(2 * F * 4);
+  w->st_bna = (float*)c.take(2 * F * 4);
+  w->st_fc = (float*)c.take(2 * Hd * 4);
+  for (int l = 0; l < m->layers; ++l) {
+    LayerWs& L = w->L[l];
+    L.qkv = c.take(M * 3 * F * e);
+    L.att = c.take(M * F * e);
+    L.ao = c.take(M * F * e);
+    L.x1 = c.take(M * F * e);
+    L.h = c.take(M * FF * e);
+    L.f2 = c.take(M * F * e);
+    L.x2 = c.take(M * F * e);
+    L.st1 = (float*)c.take(M * 2 * 4);
+    L.st2 = (float*)c.take(M * 2 * 4);
+  }
+  w->pooled = (float*)c.take(B * F * 4);
+  w->fused = c.take(B * F * e);
+  w->st_o = (float*)c.take(B * 2 * 4);
+  w->h1p = c.take(B * Hd * e);
+  w->h1 = c.take(B * Hd * e);
+  w->h2p = c.take(B * Hd * e);
+  w->h2 = c.take(B * Hd * e);
+  w->st_h1 = (float*)c.take(B * 2 * 4);
+  w->st_h2 = (float*)c.take(B * 2 * 4);
+  w->g_x = c.take(M * F * e);
+  w->g_z2 = c.take(M * F * e);
+  w->g_f2 = c.take(M * F * e);
+  w->g_h = c.take(M * FF * e);
+  w->g_x1 = c.take(M * F * e);
+  w->g_z1 = c.take(M * F * e);
+  w->g_ao = c.take(M * F * e);
+  w->g_att = c.take(M * F * e);
+  w->g_qkv = c.take(M * 3 * F * e);
+  w->g_pv = c.take(Mv * F * e);
+  w->g_pa = c.take(B * F * e);
+  w->g_pvn = m->variant == 1 ? c.take(Mv * F * e) : nullptr;
+  w->g_pan = m->variant == 1 ? c.take(B * F * e) : nullptr;
+  w->g_fused = c.take(B * F * e);
+  w->g_h1 = c.take(B * Hd * e);
+  w->g_h1p = c.take(B * Hd * e);
+  w->g_h2 = c.take(B * Hd * e);
+  w->g_h2p = c.take(B * Hd * e);
+  w->bn_scratch = (float*)c.take(2 * (F > Hd ? F : Hd) * 4);
+  w->total = c.off;
+}
+
+static int validate(const mmer_model* m, bool need_ws) {
+  MMER_CHECK_ARG(m != nullptr, "model: null");
+  MMER_CHECK_ARG(m->variant == 1 || m->variant == 2, "model: variant must be 1 (train.py) or 2 (train2.py)");
+  MMER_CHECK_ARG(m->dtype == MMER_F32 || m->dtype == MMER_BF16, "model: bad dtype");
+  MMER_CHECK_ARG(m->B > 0 && m->T > 0, "model: empty batch (B=%d T=%d)", m->B, m->T);
+  MMER_CHECK_ARG(m->layers >= 1 && m->layers <= MMER_MAX_LAYERS, "model: layers out of range");
+  MMER_CHECK_ARG(m->heads >= 1 && m->fused % m->heads == 0, "model: fused_dim not divisible by heads");
+  const int d = m->fused / m->heads;
+  MMER_CHECK_ARG(d == 32 || d == 64, "model: head dim %d unsupported (32 or 64)", d);
+  MMER_CHECK_ARG(m->fused % 8 == 0 && m->hidden % 8 == 0 && m->ffn % 8 == 0 && m->video_dim % 8 == 0 &&
+                     m->audio_dim % 8 == 0,
+                 "model: every feature dimension must be a multiple of 8");
+  MMER_CHECK_ARG(m->fused <= 2048 && m->hidden <= 2048, "model: fused/hidden width above 2048 unsupported");
+  MMER_CHECK_ARG(m->classes >= 1 && m->classes <= 16, "model: classes must be <= 16");
+  if (need_ws) {
+    MMER_CHECK_ARG(m->params != nullptr, "model: params is null");
+    MMER_CHECK_ARG(m->dtype != MMER_BF16 || m->shadow != nullptr, "model: bf16 mode needs the bf16 shadow weights");
+    MMER_CHECK_ARG(m->variant != 1 || m->bn_state != nullptr, "model: variant 1 needs bn_state");
+    Ws w;
+    carve(m, nullptr, &w);
+    MMER_CHECK_ARG(m->workspace != nullptr && (size_t)m->workspace_bytes >= w.total,
+                   "model: workspace too small (%lld < %lld)", (long long)m->workspace_bytes, (long long)w.total);
+  }
+  return 0;
+}
+
+static inline const float* P(const mmer_model* m, int64_t off) { return off < 0 ? nullptr : m->params + off; }
+static inline float* G(const mmer_model* m, int64_t off) { return off < 0 ? nullptr : m->grads + off; }
+static inline const void* Wt(const mmer_model* m, int64_t off) {
+  return m->dtype == MMER_BF16 ? (const void*)(reinterpret_cast<const bf16*>(m->shadow) + off)
+                               : (const void*)(m->params + off);
+}
+
+// y[M,N] = x[M,K] W[N,K]^T + b, optional relu / dropout
+static int lin_fwd(const mmer_model* m, const void* x, int64_t M, int64_t K, int64_t offW, int64_t offB, void* y,
+                   int64_t N, int relu, float drop_p, uint32_t site, cudaStream_t st) {
+  mmer_gemm_args a = {};
+  a.A = x; a.B = Wt(m, offW); a.D = y; a.bias = P(m, offB);
+  a.M = M; a.N = N; a.K = K; a.lda = K; a.ldb = K; a.ldd = N;
+  a.a_major = MMER_MAJOR_K; a.b_major = MMER_MAJOR_K;
+  a.in_dtype = m->dtype; a.out_dtype = m->dtype; a.relu = relu;
+  a.drop_p = drop_p; a.seed = m->seed; a.drop_site = site;
+  return gemm_dispatch(a, st);
+}
+// dx[M,K] = dy[M,N] W[N,K] (+ residual) (* gate)
+static int lin_dgrad(const mmer_model* m, const void* dy, int64_t M, int64_t N, int64_t offW, int64_t K, void* dx,
+                     const void* residual, const void* gate, float gate_scale, cudaStream_t st) {
+  mmer_gemm_args a = {};
+  a.A = dy; a.B = Wt(m, offW); a.D = dx; a.residual = residual; a.gate = gate; a.gate_scale = gate_scale;
+  a.M = M; a.N = K; a.K = N; a.lda = N; a.ldb = K; a.ldd = K;
+  a.a_major = MMER_MAJOR_K; a.b_major = MMER_MAJOR_MN;
+  a.in_dtype = m->dtype; a.out_dtype = m->dtype;
+  return gemm_dispatch(a, st);
+}
+// gW[N,K] += dy[M,N]^T x[M,K]
+static int lin_wgrad(const mmer_model* m, const void* dy, const void* x, int64_t M, int64_t N, int64_t K,
+                     int64_t offW, cudaStream_t st) {
+  mmer_gemm_args a = {};
+  a.A = dy; a.B = x; a.D = G(m, offW);
+  a.M = N; a.N = K; a.K = M; a.lda = N; a.ldb = K; a.ldd = K;
+  a.a_major = MMER_MAJOR_MN; a.b_major = MMER_MAJOR_MN;
+  a.in_dtype = m->dtype; a.out_dtype = MMER_F32; a.accumulate = 1;
+  return gemm_dispatch(a, st);
+}
+
+static inline uint32_t site_layer(int l, int k) { return 10u + 4u * (uint32_t)l + (uint32_t)k; }
+
+struct Dims {
+  int64_t B, T, S, F, Hd, FF, M, Mv;
+  int dt;
+  bool tr;
+  float pf, pc;
+  uint64_t seed;
+  const uint8_t* mask;
+  const int64_t* g;
+  explicit Dims(const mmer_model* m)
+      : B(m->B), T(m->T), S(m->T + 1), F(m->fused), Hd(m->hidden), FF(m->ffn), M((int64_t)m->B * (m->T + 1)),
+        Mv((int64_t)m->B * m->T), dt(m->dtype), tr(m->training != 0), pf(tr ? m->p_fusion : 0.f),
+        pc(tr ? m->p_classifier : 0.f), seed(m->seed), mask(m->has_mask ? m->mask : nullptr), g(m->off_g) {}
+};
+
+// CrossModalFusion.forward: projections -> token assembly -> encoder layers -> pooling (+ out_norm)
+static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
+  const Dims d(m);
+  const int64_t B = d.B, T = d.T, F = d.F, M = d.M, Mv = d.Mv, FF = d.FF;
+  const int64_t* g = d.g;
+  MMER_TRY(lin_fwd(m, m->video, Mv, m->video_dim, g[MMER_G_WV], g[MMER_G_BV], w.pv, F, 0, 0.f, 0, st));
+  MMER_TRY(lin_fwd(m, m->audio, B, m->audio_dim, g[MMER_G_WA], g[MMER_G_BA], w.pa, F, 0, 0.f, 0, st));
+  if (m->variant == 2) {
+    MMER_TRY(mmer_embed_fwd(w.pv, w.pa, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), P(m, g[MMER_G_NA_W]),
+                            P(m, g[MMER_G_NA_B]), P(m, g[MMER_G_POS]), w.x0, w.st_e, B, T, F, d.dt, d.pf, d.seed, 0, st));
+  } else {
+    float* bs = m->bn_state;
+    MMER_TRY(mmer_bn_fwd(w.pv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), bs, bs + F, w.pvn, w.st_bnv, Mv, F, d.dt, d.tr,
+                         0, 0.1f, 0.f, d.seed, 0, st));
+    MMER_TRY(mmer_bn_fwd(w.pa, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), bs + 2 * F, bs + 3 * F, w.pan, w.st_bna, B, F,
+                         d.dt, d.tr, 0, 0.1f, 0.f, d.seed, 0, st));
+    MMER_TRY(mmer_embed_fwd(w.pvn, w.pan, nullptr, nullptr, nullptr, nullptr, P(m, g[MMER_G_POS]), w.x0, w.st_e, B, T, F,
+                            d.dt, 0.f, d.seed, 0, st));
+  }
+  const void* x = w.x0;
+  const int64_t SS = d.S * d.S;
+  for (int l = 0; l < m->layers; ++l) {
+    const int64_t* o = m->off_l[l];
+    LayerWs& L = w.L[l];
+    MMER_TRY(lin_fwd(m, x, M, F, o[MMER_L_IN_W], o[MMER_L_IN_B], L.qkv, 3 * F, 0, 0.f, 0, st));
+    float* probs = m->attn_probs ? m->attn_probs + (int64_t)l * B * m->heads * SS : nullptr;
+    MMER_TRY(mmer_mha_fwd(L.qkv, d.mask, L.att, probs, B, T, m->heads, F / m->heads, d.dt, d.pf, d.seed,
+                          site_layer(l, 0), st));
+    MMER_TRY(lin_fwd(m, L.att, M, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], L.ao, F, 0, 0.f, 0, st));
+    MMER_TRY(mmer_add_ln_fwd(x, L.ao, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]), L.x1, L.st1, M, F, d.dt, 0, d.pf,
+                             site_layer(l, 1), 0.f, 0, d.seed, st));
+    MMER_TRY(lin_fwd(m, L.x1, M, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], L.h, FF, 1, d.pf, site_layer(l, 2), st));
+    MMER_TRY(lin_fwd(m, L.h, M, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], L.f2, F, 0, 0.f, 0, st));
+    MMER_TRY(mmer_add_ln_fwd(L.x1, L.f2, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]), L.x2, L.st2, M, F, d.dt, 0, d.pf,
+                             site_layer(l, 3), 0.f, 0, d.seed, st));
+    x = L.x2;
+  }
+  MMER_TRY(mmer_pool_ln_fwd(x, d.mask, m->variant == 2 ? P(m, g[MMER_G_ON_W]) : nullptr,
+                            m->variant == 2 ? P(m, g[MMER_G_ON_B]) : nullptr, w.pooled, w.fused, w.st_o, B, T, F, d.dt, st));
+  if (m->fused_out) {
+    cudaError_t e = cudaMemcpyAsync(m->fused_out, w.fused, (size_t)B * F * (d.dt == MMER_BF16 ? 2 : 4),
+                                    cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "copy fused");
+  }
+  return 0;
+}
+
+// EmotionClassifier.forward (+ the softmax of MultimodalEmotionModel.forward)
+static int head_forward(const mmer_model* m, Ws& w, const void* fused, cudaStream_t st) {
+  const Dims d(m);
+  const int64_t B = d.B, F = d.F, Hd = d.Hd;
+  const int64_t* g = d.g;
+  MMER_TRY(lin_fwd(m, fused, B, F, g[MMER_G_C0_W], g[MMER_G_C0_B], w.h1p, Hd, 0, 0.f, 0, st));
+  if (m->variant == 2) {
+    MMER_TRY(mmer_add_ln_fwd(nullptr, w.h1p, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.h1, w.st_h1, B, Hd, d.dt, 1,
+                             0.f, 0, d.pc, 200, d.seed, st));
+    MMER_TRY(lin_fwd(m, w.h1, B, Hd, g[MMER_G_C4_W], g[MMER_G_C4_B], w.h2p, Hd, 0, 0.f, 0, st));
+    MMER_TRY(mmer_add_ln_fwd(nullptr, w.h2p, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), w.h2, w.st_h2, B, Hd, d.dt, 1,
+                             0.f, 0, d.pc, 201, d.seed, st));
+    MMER_TRY(mmer_head_out_fwd(w.h2, P(m, g[MMER_G_C8_W]), P(m, g[MMER_G_C8_B]), m->logits, m->probs, B, Hd, m->classes,
+                               d.dt, st));
+  } else {
+    float* bs = m->bn_state + 4 * F;
+    MMER_TRY(mmer_bn_fwd(w.h1p, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), bs, bs + Hd, w.h1, w.st_fc, B, Hd, d.dt, d.tr,
+                         1, 0.1f, d.pc, d.seed, 200, st));
+    MMER_TRY(mmer_head_out_fwd(w.h1, P(m, g[MMER_G_C8_W]), P(m, g[MMER_G_C8_B]), m->logits, m->probs, B, Hd, m->classes,
+                               d.dt, st));
+  }
+  return 0;
+}
+
+int model_forward(const mmer_model* m, cudaStream_t st) {
+  MMER_TRY(validate(m, true));
+  MMER_CHECK_ARG(m->stage >= 0 && m->stage <= 2, "model_forward: bad stage");
+  MMER_CHECK_ARG(m->stage == 2 || (m->video && m->audio), "model_forward: video/audio must be set");
+  MMER_CHECK_ARG(m->stage == 1 || m->logits, "model_forward: logits must be set");
+  MMER_CHECK_ARG(m->stage != 2 || m->fused_in, "model_forward: stage 2 needs fused_in");
+  MMER_CHECK_ARG(m->stage != 1 || m->fused_out, "model_forward: stage 1 needs fused_out");
+  Ws w;
+  carve(m, m->workspace, &w);
+  if (m->stage != 2) MMER_TRY(fusion_forward(m, w, st));
+  if (m->stage != 1) MMER_TRY(head_forward(m, w, m->stage == 2 ? m->fused_in : w.fused, st));
+  return 0;
+}
+
+// gradient of the classifier head; leaves d(fused) in w.g_fused
+static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStream_t st) {
+  const Dims d(m);
+  const int64_t B = d.B, F = d.F, Hd = d.Hd;
+  const int64_t* g = d.g;
+  if (m->variant == 2) {
+    MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h2, P(m, g[MMER_G_C8_W]), w.g_h2, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
+                               B, Hd, m->classes, d.dt, st));
+    MMER_TRY(mmer_add_ln_bwd(w.g_h2, nullptr, w.h2p, w.st_h2, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), w.g_h2p, nullptr,
+                             G(m, g[MMER_G_C5_W]), G(m, g[MMER_G_C5_B]), G(m, g[MMER_G_C4_B]), B, Hd, d.dt, 1, 0.f, 0, d.pc,
+                             201, d.seed, st));
+    MMER_TRY(lin_wgrad(m, w.g_h2p, w.h1, B, Hd, Hd, g[MMER_G_C4_W], st));
+    MMER_TRY(lin_dgrad(m, w.g_h2p, B, Hd, g[MMER_G_C4_W], Hd, w.g_h1, nullptr, nullptr, 0.f, st));
+    MMER_TRY(mmer_add_ln_bwd(w.g_h1, nullptr, w.h1p, w.st_h1, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, nullptr,
+                             G(m, g[MMER_G_C1_W]), G(m, g[MMER_G_C1_B]), G(m, g[MMER_G_C0_B]), B, Hd, d.dt, 1, 0.f, 0, d.pc,
+                             200, d.seed, st));
+  } else {
+    MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h1, P(m, g[MMER_G_C8_W]), w.g_h1, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
+                               B, Hd, m->classes, d.dt, st));
+    MMER_TRY(mmer_bn_bwd(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
+                         G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st));
+    MMER_TRY(mmer_colsum(w.g_h1p, G(m, g[MMER_G_C0_B]), B, Hd, Hd, d.dt, st));
+  }
+  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], st));
+  MMER_TRY(lin_dgrad(m, w.g_h1p, B, Hd, g[MMER_G_C0_W], F, w.g_fused, nullptr, nullptr, 0.f, st));
+  return 0;
+}
+
+static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaStream_t st) {
+  const Dims d(m);
+  const int64_t B = d.B, T = d.T, F = d.F, M = d.M, Mv = d.Mv, FF = d.FF;
+  const int64_t* g = d.g;
+  const float pf = d.pf;
+  MMER_TRY(mmer_pool_ln_bwd(dfused, w.pooled, w.st_o, m->variant == 2 ? P(m, g[MMER_G_ON_W]) : nullptr, d.mask, w.g_x,
+                            m->variant == 2 ? G(m, g[MMER_G_ON_W]) : nullptr,
+                            m->variant == 2 ? G(m, g[MMER_G_ON_B]) : nullptr, B, T, F, d.dt, st));
+  const float relu_gate_scale = pf > 0.f ? make_drop(pf, d.seed, 0).scale : 1.f;
+  for (int l = m->layers - 1; l >= 0; --l) {
+    const int64_t* o = m->off_l[l];
+    LayerWs& L = w.L[l];
+    const void* xin = l == 0 ? w.x0 : w.L[l - 1].x2;
+    // norm2 <- linear2
+    void* d_f2 = pf > 0.f ? w.g_f2 : w.g_z2;
+    MMER_TRY(mmer_add_ln_bwd(w.g_x, L.x1, L.f2, L.st2, P(m, o[MMER_L_N2_W]), nullptr, w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
+                             G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, 0, pf,
+                             site_layer(l, 3), 0.f, 0, d.seed, st));
+    MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], st));
+    // through ReLU (+ its dropout): gate on the stored post-activation
+    MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, L.h, relu_gate_scale, st));
+    MMER_TRY(mmer_colsum(w.g_h, G(m, o[MMER_L_FF1_B]), M, FF, FF, d.dt, st));
+    MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], st));
+    MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
+    // norm1 <- attention
+    void* d_ao = pf > 0.f ? w.g_ao : w.g_z1;
+    MMER_TRY(mmer_add_ln_bwd(w.g_x1, xin, L.ao, L.st1, P(m, o[MMER_L_N1_W]), nullptr, w.g_z1, pf > 0.f ? w.g_ao : nullptr,
+                             G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, 0, pf,
+                             site_layer(l, 1), 0.f, 0, d.seed, st));
+    MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], st));
+    MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
+    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, B, T, m->heads, F / m->heads, d.dt, pf, d.seed,
+                          site_layer(l, 0), st));
+    MMER_TRY(mmer_colsum(w.g_qkv, G(m, o[MMER_L_IN_B]), M, 3 * F, 3 * F, d.dt, st));
+    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], st));
+    MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));
+  }
+  const void* dpv = w.g_pv;
+  const void* dpa = w.g_pa;
+  if (m->variant == 2) {
+    MMER_TRY(mmer_embed_bwd(w.g_x, w.pv, w.pa, w.st_e, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NA_W]), w.g_pv, w.g_pa,
+                            G(m, g[MMER_G_NV_W]), G(m, g[MMER_G_NV_B]), G(m, g[MMER_G_NA_W]), G(m, g[MMER_G_NA_B]),
+                            G(m, g[MMER_G_POS]), B, T, F, d.dt, pf, d.seed, 0, st));
+  } else {
+    MMER_TRY(mmer_embed_bwd(w.g_x, w.pvn, w.pan, w.st_e, nullptr, nullptr, w.g_pvn, w.g_pan, nullptr, nullptr, nullptr,
+                            nullptr, G(m, g[MMER_G_POS]), B, T, F, d.dt, 0.f, d.seed, 0, st));
+    MMER_TRY(mmer_bn_bwd(w.g_pvn, w.pv, w.st_bnv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), w.g_pv, G(m, g[MMER_G_NV_W]),
+                         G(m, g[MMER_G_NV_B]), w.bn_scratch, Mv, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
+    MMER_TRY(mmer_bn_bwd(w.g_pan, w.pa, w.st_bna, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), w.g_pa, G(m, g[MMER_G_NA_W]),
+                         G(m, g[MMER_G_NA_B]), w.bn_scratch, B, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
+  }
+  MMER_TRY(mmer_colsum(dpv, G(m, g[MMER_G_BV]), Mv, F, F, d.dt, st));
+  MMER_TRY(mmer_colsum(dpa, G(m, g[MMER_G_BA]), B, F, F, d.dt, st));
+  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], st));
+  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], st));
+  if (m->dvideo) MMER_TRY(lin_dgrad(m, dpv, Mv, F, g[MMER_G_WV], m->video_dim, m->dvideo, nullptr, nullptr, 0.f, st));
+  if (m->daudio) MMER_TRY(lin_dgrad(m, dpa, B, F, g[MMER_G_WA], m->audio_dim, m->daudio, nullptr, nullptr, 0.f, st));
+  return 0;
+}
+
+int model_backward(const mmer_model* m, cudaStream_t st) {
+  MMER_TRY(validate(m, true));
+  MMER_CHECK_ARG(m->stage >= 0 && m->stage <= 2, "model_backward: bad stage");
+  MMER_CHECK_ARG(m->grads != nullptr, "model_backward: grads must be set");
+  MMER_CHECK_ARG(m->stage == 1 || m->dlogits, "model_backward: dlogits must be set");
+  MMER_CHECK_ARG(m->stage == 2 || (m->video && m->audio), "model_backward: video/audio must be set");
+  MMER_CHECK_ARG(m->stage != 1 || m->dfused_in, "model_backward: stage 1 needs dfused_in");
+  MMER_CHECK_ARG(m->stage != 2 || m->fused_in, "model_backward: stage 2 needs fused_in");
+  Ws w;
+  carve(m, m->workspace, &w);
+  if (m->stage != 1) {
+    MMER_TRY(head_backward(m, w, m->stage == 2 ? m->fused_in : w.fused, st));
+    if (m->stage == 2) {
+      if (m->dfused_out) {
+        cudaError_t e = cudaMemcpyAsync(m->dfused_out, w.g_fused, (size_t)m->B * m->fused * (m->dtype == MMER_BF16 ? 2 : 4),
+                                        cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(e, "copy dfused");
+      }
+      return 0;
+    }
+  }
+  return fusion_backward(m, w, m->stage == 1 ? m->dfused_in : w.g_fused, st);
+}
+
+}  // namespace mmer
+
+using namespace mmer;
+
+extern "C" {
+
+int64_t mmer_workspace_bytes(const mmer_model* m) {
+  if (validate(m, false) != 0) return -1;
+  Ws w;
+  carve(m, nullptr, &w);
+  return (int64_t)w.total;
+}
+int mmer_model_forward(const mmer_model* m, void* stream) { return model_forward(m, (cudaStream_t)stream); }
+int mmer_model_backward(const mmer_model* m, void* stream) { return model_backward(m, (cudaStream_t)stream); }
+
+int mmer_gemm(const mmer_gemm_args* a, void* stream) {
+  MMER_CHECK_ARG(a != nullptr && a->A && a->B && a->D, "gemm: null pointer");
+  MMER_CHECK_ARG(a->in_dtype == MMER_F32 || a->in_dtype == MMER_BF16, "gemm: bad in_dtype");
+  return gemm_dispatch(*a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

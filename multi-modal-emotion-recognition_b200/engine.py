@@ -1,0 +1,298 @@
+"""Host-side engine: flat parameter storage + one-call forward/backward through the C ABI.
+
+The module classes (modules.py) keep stock ``nn.Linear`` / ``nn.LayerNorm`` /
+``nn.TransformerEncoder`` objects purely as parameter containers, so ``state_dict()`` has the
+reference's key names and shapes.  At run time the parameters are
+views into ONE flat fp32 buffer (plus a flat fp32 gradient buffer and, in bf16 mode, a flat
+bf16 shadow); the C engine addresses them by element offset.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from ._lib import BF16, F32, G, L, MmerError, Model
+
+PAD = 64  # every parameter starts on a 256-byte boundary of the fp32 buffer
+
+
+def _pad(n: int) -> int:
+    return (n + PAD - 1) // PAD * PAD
+
+
+class ParamContext:
+    """Flat master / gradient / shadow storage for the parameters of one module tree."""
+
+    def __init__(self, variant: int, g_slots: Dict[str, nn.Parameter], l_slots: List[Dict[str, nn.Parameter]],
+                 bn_buffers: Optional[List[Tuple[nn.Module, str]]] = None):
+        self.variant = variant
+        self.g_slots = g_slots
+        self.l_slots = l_slots
+        self.bn_buffers = bn_buffers or []   # [(module, 'running_mean'), (module, 'running_var'), ...] in engine order
+        self.params: List[nn.Parameter] = list(g_slots.values()) + [p for d in l_slots for p in d.values()]
+        self.flat: Optional[torch.Tensor] = None
+        self.grads: Optional[torch.Tensor] = None
+        self.shadow: Optional[torch.Tensor] = None
+        self.bn_state: Optional[torch.Tensor] = None
+        self.offsets: Dict[int, int] = {}
+        self._ptrs: List[int] = []
+        self.shadow_fresh = False
+
+    # ------------------------------------------------------------------ layout
+    def _build(self, device: torch.device) -> None:
+        off = 0
+        offsets = {}
+        for p in self.params:
+            if id(p) in offsets:
+                continue
+            if p.dtype != torch.float32:
+                raise MmerError("parameters must be float32 masters (bf16 compute uses an internal shadow copy)")
+            offsets[id(p)] = off
+            off += _pad(p.numel())
+        flat = torch.zeros(off, device=device, dtype=torch.float32)
+        grads = torch.zeros(off, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for p in self.params:
+                o = offsets[id(p)]
+                view = flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                gview = grads[o:o + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    gview.copy_(p.grad)
+                    p.grad = gview
+            if self.bn_buffers:
+                n = sum(getattr(m, name).numel() for m, name in self.bn_buffers)
+                self.bn_state = torch.zeros(n, device=device, dtype=torch.float32)
+                o = 0
+                for m, name in self.bn_buffers:
+                    buf = getattr(m, name)
+                    v = self.bn_state[o:o + buf.numel()]
+                    v.copy_(buf)
+                    m._buffers[name] = v
+                    o += buf.numel()
+        self.flat, self.grads, self.offsets, self.shadow = flat, grads, offsets, None
+        self.shadow_fresh = False
+        self._ptrs = [p.data_ptr() for p in self.params] + [getattr(m, n).data_ptr() for m, n in self.bn_buffers]
+
+    def ensure(self) -> None:
+        """(Re)build the flat storage if parameters were moved or replaced (``.to()``, ``.cuda()``...)."""
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise MmerError("mmer_b200 modules run on CUDA only (no CPU fallback): call model.cuda() first")
+        ptrs = [p.data_ptr() for p in self.params] + [getattr(m, n).data_ptr() for m, n in self.bn_buffers]
+        if self.flat is None or ptrs != self._ptrs or self.flat.device != dev:
+            self._build(dev)
+
+    def grad_view(self, p: nn.Parameter) -> torch.Tensor:
+        o = self.offsets[id(p)]
+        return self.grads[o:o + p.numel()].view(p.shape)
+
+    def bind_grads(self) -> bool:
+        """Make every ``param.grad`` a view of the flat gradient buffer.  Returns True when the
+        buffer must be zeroed first (all grads were None: the usual ``zero_grad()`` state)."""
+        none = [p.grad is None for p in self.params]
+        if all(none):
+            return True
+        for p in self.params:
+            gv = self.grad_view(p)
+            if p.grad is None:
+                gv.zero_()
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)
+        return False
+
+    def attach_grads(self) -> None:
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * self.offsets[id(p)]:
+                p.grad = self.grad_view(p)
+
+    def refresh_shadow(self) -> None:
+        if self.shadow is None:
+            self.shadow = torch.empty(self.flat.numel(), device=self.flat.device, dtype=torch.bfloat16)
+            self.shadow_fresh = False
+        if not self.shadow_fresh:
+            ops.cast_bf16(self.flat, self.shadow)
+
+    # ------------------------------------------------------------------ C struct
+    def fill_offsets(self, m: Model) -> None:
+        for i in range(_lib.G_COUNT):
+            m.off_g[i] = -1
+        for name, p in self.g_slots.items():
+            m.off_g[G[name]] = self.offsets[id(p)]
+        for l, d in enumerate(self.l_slots):
+            for name, p in d.items():
+                m.off_l[l][L[name]] = self.offsets[id(p)]
+        m.n_params = self.flat.numel()
+
+
+class Engine:
+    """Builds the ``mmer_model`` struct for one call and runs the C forward / backward."""
+
+    def __init__(self, ctx: ParamContext, *, variant: int, video_dim: int, audio_dim: int, fused: int, heads: int,
+                 layers: int, ffn: int, hidden: int, classes: int):
+        self.ctx = ctx
+        self.cfg = dict(variant=variant, video_dim=video_dim, audio_dim=audio_dim, fused=fused, heads=heads,
+                        layers=layers, ffn=ffn, hidden=hidden, classes=classes)
+        if layers > _lib.MAX_LAYERS:
+            raise MmerError(f"at most {_lib.MAX_LAYERS} encoder layers are supported")
+
+    def make(self, B: int, T: int, dtype: torch.dtype, training: bool, p_fusion: float, p_classifier: float, seed: int,
+             stage: int = 0) -> Model:
+        self.ctx.ensure()
+        m = Model()
+        for k, v in self.cfg.items():
+            setattr(m, k, v)
+        m.dtype = BF16 if dtype == torch.bfloat16 else F32
+        m.B, m.T = B, T
+        m.training = int(training)
+        m.p_fusion, m.p_classifier = float(p_fusion), float(p_classifier)
+        m.seed = seed & 0xFFFFFFFFFFFFFFFF
+        m.stage = stage
+        self.ctx.fill_offsets(m)
+        m.params = self.ctx.flat.data_ptr()
+        m.grads = self.ctx.grads.data_ptr()
+        if self.ctx.bn_state is not None:
+            m.bn_state = self.ctx.bn_state.data_ptr()
+        return m
+
+    @staticmethod
+    def workspace_bytes(m: Model) -> int:
+        n = _lib.load().mmer_workspace_bytes(C.byref(m))
+        if n < 0:
+            raise MmerError("mmer_workspace_bytes: " + _lib.last_error())
+        return int(n)
+
+    def attach_shadow(self, m: Model) -> None:
+        if m.dtype == BF16:
+            self.ctx.refresh_shadow()
+            m.shadow = self.ctx.shadow.data_ptr()
+
+    @staticmethod
+    def forward(m: Model) -> None:
+        _lib.check(_lib.load().mmer_model_forward(C.byref(m), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "mmer_model_forward")
+
+    @staticmethod
+    def backward(m: Model) -> None:
+        _lib.check(_lib.load().mmer_model_backward(C.byref(m), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "mmer_model_backward")
+
+
+def _compute_dtype(video: torch.Tensor, requested: Optional[torch.dtype]) -> torch.dtype:
+    if requested is not None:
+        return requested
+    return torch.bfloat16 if video.dtype == torch.bfloat16 else torch.float32
+
+
+class ModelFn(torch.autograd.Function):
+    """Autograd node for a whole forward pass of the engine (stage 0, 1 or 2).
+
+    Parameter gradients are accumulated straight into the flat gradient buffer that
+    ``param.grad`` views alias (the Megatron ``main_grad`` convention); the node returns
+    gradients only for the data inputs (needed by Captum-style attribution, train2.py:808-836).
+    """
+
+    @staticmethod
+    def forward(ctx, anchor, video, audio, fused_in, owner, mask, stage, return_attn):
+        eng: Engine = owner._engine
+        dev = anchor.device
+        training = owner.training
+        if stage == 2:
+            B, T = fused_in.shape[0], 1
+            cdt = _compute_dtype(fused_in, owner.compute_dtype)
+        else:
+            B, T = video.shape[0], video.shape[1]
+            cdt = _compute_dtype(video, owner.compute_dtype)
+        seed = owner._next_seed() if training else 0
+        m = eng.make(B, T, cdt, training, owner._p_fusion, owner._p_classifier, seed, stage)
+        eng.attach_shadow(m)
+        ws = torch.empty(eng.workspace_bytes(m), device=dev, dtype=torch.uint8)
+        m.workspace, m.workspace_bytes = ws.data_ptr(), ws.numel()
+        keep = [ws]
+        if stage != 2:
+            v = video.detach().to(cdt).contiguous()
+            a = audio.detach().to(cdt).contiguous()
+            m.video, m.audio = v.data_ptr(), a.data_ptr()
+            keep += [v, a]
+            if mask is not None:
+                mk = mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
+                m.mask, m.has_mask = mk.data_ptr(), 1
+                keep.append(mk)
+        else:
+            f = fused_in.detach().to(cdt).contiguous()
+            m.fused_in = f.data_ptr()
+            keep.append(f)
+        F_, Cn = eng.cfg["fused"], eng.cfg["classes"]
+        outs = []
+        logits = probs = fused = attn = None
+        if stage != 1:
+            logits = torch.empty((B, Cn), device=dev, dtype=torch.float32)
+            probs = torch.empty((B, Cn), device=dev, dtype=torch.float32)
+            m.logits, m.probs = logits.data_ptr(), probs.data_ptr()
+        if stage == 1:
+            fused = torch.empty((B, F_), device=dev, dtype=cdt)
+            m.fused_out = fused.data_ptr()
+        if return_attn and stage != 2:
+            S = T + 1
+            attn = torch.empty((eng.cfg["layers"], B, eng.cfg["heads"], S, S), device=dev, dtype=torch.float32)
+            m.attn_probs = attn.data_ptr()
+        Engine.forward(m)
+        m.attn_probs = None
+        m.fused_out = None
+        ctx.m, ctx.keep, ctx.owner, ctx.stage, ctx.cdt = m, keep, owner, stage, cdt
+        ctx.in_dtypes = (video.dtype if video is not None else None, audio.dtype if audio is not None else None,
+                         fused_in.dtype if fused_in is not None else None)
+        ctx.mark_non_differentiable(*[t for t in (probs, attn) if t is not None])
+        if stage == 1:
+            out_main = fused if fused.dtype == video.dtype else fused.to(video.dtype)
+        else:
+            out_main = logits
+        empty = torch.empty(0, device=dev)
+        return out_main, (probs if probs is not None else empty), (attn if attn is not None else empty)
+
+    @staticmethod
+    def backward(ctx, d_main, _dp, _da):
+        m, owner, stage, cdt = ctx.m, ctx.owner, ctx.stage, ctx.cdt
+        eng: Engine = owner._engine
+        pc = eng.ctx
+        if pc.flat is None or m.params != pc.flat.data_ptr():
+            raise MmerError("parameters were re-allocated between forward and backward")
+        need_v, need_a, need_f = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        if pc.bind_grads():
+            pc.grads.zero_()
+        keep = list(ctx.keep)
+        B, T = m.B, m.T
+        dvideo = daudio = dfused_out = None
+        if stage == 1:
+            df = d_main.detach().to(cdt).contiguous()
+            m.dfused_in = df.data_ptr()
+            keep.append(df)
+        else:
+            dl = d_main.detach().to(torch.float32).contiguous()
+            m.dlogits = dl.data_ptr()
+            keep.append(dl)
+        dev = d_main.device
+        if stage != 2:
+            if need_v:
+                dvideo = torch.empty((B, T, eng.cfg["video_dim"]), device=dev, dtype=cdt)
+                m.dvideo = dvideo.data_ptr()
+            if need_a:
+                daudio = torch.empty((B, eng.cfg["audio_dim"]), device=dev, dtype=cdt)
+                m.daudio = daudio.data_ptr()
+        elif need_f:
+            dfused_out = torch.empty((B, eng.cfg["fused"]), device=dev, dtype=cdt)
+            m.dfused_out = dfused_out.data_ptr()
+        Engine.backward(m)
+        pc.attach_grads()
+        ctx.keep = None
+        vd, ad, fd = ctx.in_dtypes
+        return (None,
+                dvideo.to(vd) if dvideo is not None else None,
+                daudio.to(ad) if daudio is not None else None,
+                dfused_out.to(fd) if dfused_out is not None else None,
+                None, None, None, None)

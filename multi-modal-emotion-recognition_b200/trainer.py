@@ -1,0 +1,160 @@
+"""Fused optimizer and the one-call training step.
+
+``FusedAdam`` mirrors ``torch.optim.Adam(params, lr, weight_decay)`` as used by the reference
+(train.py:252, train2.py:525): coupled L2, bias correction, lr read from ``param_groups`` each
+step so ``ReduceLROnPlateau`` works unchanged.  ``FusedTrainStep`` is the reference's hot loop
+body (train2.py:570-579 / train.py:293-297): zero_grad -> forward -> loss -> backward ->
+[clip_grad_norm_] -> Adam, plus the data-parallel gradient all-reduce, with no host sync.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import BF16, MmerError
+from .engine import Engine, ParamContext
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Adam over the flat parameter buffer of an mmer_b200 model: one kernel per step."""
+
+    def __init__(self, model_or_params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_grad_norm: Optional[float] = None):
+        if isinstance(model_or_params, torch.nn.Module):
+            model = model_or_params
+            params = list(model.parameters())
+            self._owner = model
+        else:
+            params = list(model_or_params)
+            self._owner = None
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.max_grad_norm = max_grad_norm
+        self._step = 0
+        self._m = self._v = None
+        self._sumsq = None
+        self._ctx: Optional[ParamContext] = None
+
+    def _context(self) -> ParamContext:
+        if self._owner is not None and hasattr(self._owner, "_engine"):
+            ctx = self._owner._engine.ctx
+        else:
+            raise MmerError("FusedAdam needs the mmer_b200 module (pass the model, not model.parameters())")
+        ctx.ensure()
+        mine = {id(p) for g in self.param_groups for p in g["params"]}
+        if mine != {id(p) for p in ctx.params}:
+            raise MmerError("FusedAdam must own exactly the parameters of the model")
+        return ctx
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = closure() if closure is not None else None
+        ctx = self._context()
+        if self._m is None or getattr(self, "_ctx_flat_ptr", 0) != ctx.flat.data_ptr():
+            self._m = torch.zeros_like(ctx.flat)
+            self._v = torch.zeros_like(ctx.flat)
+            self._sumsq = torch.zeros(1, device=ctx.flat.device, dtype=torch.float32)
+            self._ctx_flat_ptr = ctx.flat.data_ptr()
+        g = self.param_groups[0]
+        self._step += 1
+        sumsq = None
+        if self.max_grad_norm is not None:
+            sumsq = ops.grad_sumsq(ctx.grads, self._sumsq)
+        ops.adam_step(ctx.flat, ctx.grads, self._m, self._v, ctx.shadow, self._step, g["lr"], g["betas"][0],
+                      g["betas"][1], g["eps"], g["weight_decay"], grad_scale, sumsq, self.max_grad_norm or 0.0)
+        ctx.shadow_fresh = ctx.shadow is not None
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        # gradients live in one flat buffer: a single memset instead of one per tensor
+        ctx = self._context()
+        ctx.grads.zero_()
+        ctx.attach_grads()
+
+
+class FusedTrainStep:
+    """zero_grad + forward + loss + backward + [all-reduce] + [clip] + Adam as one host call."""
+
+    def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 loss: str = "focal", gamma: float = 2.0, alpha: Optional[torch.Tensor] = None,
+                 clip_grad_norm: Optional[float] = None, compute_dtype: torch.dtype = torch.bfloat16,
+                 process_group=None):
+        self.model = model
+        self.engine: Engine = model._engine
+        self.ctx: ParamContext = self.engine.ctx
+        self.opt = FusedAdam(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                             max_grad_norm=clip_grad_norm)
+        self.loss_kind = {"focal": _lib.LOSS_FOCAL, "wce": _lib.LOSS_WCE}[loss]
+        self.gamma = gamma
+        self.alpha = alpha
+        self.compute_dtype = compute_dtype
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._key = None
+        self._ws = None
+        self.launch_count = 0
+
+    @property
+    def lr(self):
+        return self.opt.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, v):
+        self.opt.param_groups[0]["lr"] = v
+
+    def _prepare(self, B: int, T: int, dev):
+        key = (B, T, self.compute_dtype, self.ctx.flat.data_ptr() if self.ctx.flat is not None else 0)
+        if key == self._key:
+            return
+        m = self.engine.make(B, T, self.compute_dtype, True, self.model._p_fusion, self.model._p_classifier, 0, 0)
+        self._ws = torch.empty(Engine.workspace_bytes(m), device=dev, dtype=torch.uint8)
+        Cn = self.engine.cfg["classes"]
+        self._logits = torch.empty((B, Cn), device=dev, dtype=torch.float32)
+        self._probs = torch.empty((B, Cn), device=dev, dtype=torch.float32)
+        self._dlogits = torch.empty((B, Cn), device=dev, dtype=torch.float32)
+        self._loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._scratch = torch.zeros(2, device=dev, dtype=torch.float32)
+        if self.alpha is not None:
+            self.alpha = self.alpha.to(device=dev, dtype=torch.float32).contiguous()
+        self._key = (B, T, self.compute_dtype, self.ctx.flat.data_ptr())
+
+    @torch.no_grad()
+    def step(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor], labels: torch.Tensor):
+        """Runs one optimisation step; returns (loss [1] fp32 device tensor, probs (B,C))."""
+        if not video.is_cuda:
+            raise MmerError("FusedTrainStep needs CUDA tensors (no CPU fallback)")
+        B, T = video.shape[0], video.shape[1]
+        self.ctx.ensure()
+        self._prepare(B, T, video.device)
+        eng, ctx = self.engine, self.ctx
+        m = eng.make(B, T, self.compute_dtype, True, self.model._p_fusion, self.model._p_classifier,
+                     self.model._next_seed(), 0)
+        eng.attach_shadow(m)
+        v = video if video.dtype == self.compute_dtype else video.to(self.compute_dtype)
+        a = audio if audio.dtype == self.compute_dtype else audio.to(self.compute_dtype)
+        v, a = v.contiguous(), a.contiguous()
+        m.video, m.audio = v.data_ptr(), a.data_ptr()
+        if mask is not None:
+            mk = mask.contiguous().view(torch.uint8)
+            m.mask, m.has_mask = mk.data_ptr(), 1
+        m.workspace, m.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        m.logits, m.probs, m.dlogits = self._logits.data_ptr(), self._probs.data_ptr(), self._dlogits.data_ptr()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib = _lib.load()
+        ctx.grads.zero_()
+        _lib.check(lib.mmer_model_forward(C.byref(m), stream), "mmer_model_forward")
+        _lib.check(lib.mmer_loss_fwd_bwd(self._logits.data_ptr(), labels.data_ptr(),
+                                         self.alpha.data_ptr() if self.alpha is not None else None, self.loss_kind,
+                                         float(self.gamma), _lib.REDUCE_MEAN, self._loss.data_ptr(), None,
+                                         self._dlogits.data_ptr(), self._scratch.data_ptr(), B,
+                                         self.engine.cfg["classes"], 1.0, stream), "mmer_loss_fwd_bwd")
+        _lib.check(lib.mmer_model_backward(C.byref(m), stream), "mmer_model_backward")
+        scale = 1.0
+        if self.world > 1:
+            dist.all_reduce(ctx.grads, op=dist.ReduceOp.SUM, group=self.group)
+            scale = 1.0 / self.world
+        self.opt.step(grad_scale=scale)
+        return self._loss, self._probs
