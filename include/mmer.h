@@ -53,6 +53,8 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_FORCE_SIMT 2  /* route bf16 GEMMs through the fp32 FMA kernel (debug only) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);
+/* number of kernels this library has launched in the current process (bench accounting) */
+int64_t mmer_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * GEMM: D[M,N] = epilogue( A[M,K] . B[N,K]^T ).  Replaces every nn.Linear forward on the

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mmer_last_error": [],
     "mmer_debug_set": [_I, _I],
     "mmer_debug_get": [_I],
+    "mmer_launch_count": [],
     "mmer_gemm": [C.POINTER(GemmArgs), _P],
     "mmer_embed_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
     "mmer_embed_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
@@ -86,7 +87,7 @@ SIGNATURES = {
     "mmer_model_forward": [C.POINTER(Model), _P],
     "mmer_model_backward": [C.POINTER(Model), _P],
 }
-_RESTYPES = {"mmer_last_error": C.c_char_p, "mmer_workspace_bytes": C.c_int64}
+_RESTYPES = {"mmer_last_error": C.c_char_p, "mmer_workspace_bytes": C.c_int64, "mmer_launch_count": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

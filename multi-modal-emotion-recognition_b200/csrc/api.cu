@@ -20,6 +20,10 @@ int cuda_fail(cudaError_t e, const char* what) {
   return MMER_ERR_CUDA;
 }
 
+static long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static thread_local int cached_dev = -1;
   static thread_local int cached = 0;
@@ -45,6 +49,7 @@ int mmer_debug_set(int key, int value) {
   mmer::g_debug[key] = value;
   return 0;
 }
+int64_t mmer_launch_count(void) { return (int64_t)mmer::launch_count(); }
 int mmer_debug_get(int key) { return (key < 0 || key >= 16) ? 0 : mmer::g_debug[key]; }
 
 }  // extern "C"

@@ -189,6 +189,7 @@ static int bn_fwd_t(const void* x, const float* gamma, const float* beta, float*
   }
   bn_apply_kernel<T><<<ew_grid(N, C), 256, 0, st>>>((const T*)x, stats, gamma, beta, (T*)y, N, (int)C, relu, dc);
   MMER_LAUNCH_CHECK("bn_fwd");
+  count_launch(training ? 4 : 1);
   return 0;
 }
 
@@ -202,6 +203,7 @@ static int bn_bwd_t(const void* dy, const void* x, const float* stats, const flo
   bn_bwd_apply_kernel<T><<<ew_grid(N, C), 256, 0, st>>>((const T*)dy, (const T*)x, stats, gamma, beta, scratch, (T*)dx, N, (int)C, relu, training, dc);
   bn_param_grad_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(scratch, dgamma, dbeta, (int)C);
   MMER_LAUNCH_CHECK("bn_bwd");
+  count_launch(2);
   return 0;
 }
 

@@ -18,6 +18,7 @@ typedef __nv_bfloat16 bf16;
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
+void count_launch(int n = 1);
 
 #define MMER_CHECK_ARG(cond, ...)                 \
   do {                                            \
@@ -31,6 +32,7 @@ int sm_count();
   do {                                                            \
     cudaError_t _e = cudaGetLastError();                          \
     if (_e != cudaSuccess) return mmer::cuda_fail(_e, what);      \
+    mmer::count_launch();                                         \
   } while (0)
 
 #define MMER_TRY(expr)            \

@@ -19,6 +19,19 @@ from ._lib import BF16, MmerError
 from .engine import Engine, ParamContext
 
 
+def allreduce_flat_gradients(flat: torch.Tensor, group=None) -> float:
+    """Sum the flat gradient buffer over the data-parallel ranks (NCCL on GPUs, gloo in the CPU
+    tests) and return the factor that turns the sum of per-rank mean-loss gradients into the
+    global-batch gradient (1 / world size; equal shards)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
 class FusedAdam(torch.optim.Optimizer):
     """Adam over the flat parameter buffer of an mmer_b200 model: one kernel per step."""
 
@@ -152,9 +165,6 @@ class FusedTrainStep:
                                          self._dlogits.data_ptr(), self._scratch.data_ptr(), B,
                                          self.engine.cfg["classes"], 1.0, stream), "mmer_loss_fwd_bwd")
         _lib.check(lib.mmer_model_backward(C.byref(m), stream), "mmer_model_backward")
-        scale = 1.0
-        if self.world > 1:
-            dist.all_reduce(ctx.grads, op=dist.ReduceOp.SUM, group=self.group)
-            scale = 1.0 / self.world
+        scale = allreduce_flat_gradients(ctx.grads, self.group) if self.world > 1 else 1.0
         self.opt.step(grad_scale=scale)
         return self._loss, self._probs

@@ -1,0 +1,374 @@
+"""GPU parity tests of every C-ABI kernel against the CPU oracle / closed-form torch fp32-fp64 math.
+All calls go through the C ABI (mmer_b200.ops -> libmmer_sm100.so)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mmer_b200 as mm  # noqa: E402
+from mmer_b200 import _lib, ops  # noqa: E402
+from oracle import fusion_oracle as O  # noqa: E402
+
+DEV = "cuda"
+DT = [torch.float32, torch.bfloat16]
+
+
+def tol(dt):
+    return 2e-5 if dt == torch.float32 else 2e-2
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rnd(*shape, dt=torch.float32, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dt).to(DEV)
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("majors", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (384, 512, 512), (304, 200, 136), (128, 8, 64), (1000, 1536, 512),
+                                   (17, 6 * 8, 2048)])
+def test_gemm_all_majors(dt, majors, shape):
+    M, N, K = shape
+    A, B = rnd(M, K, dt=dt, seed=1), rnd(N, K, dt=dt, seed=2)
+    ref = A.double() @ B.double().t()
+    As = A if majors[0] == 0 else A.t().contiguous()
+    Bs = B if majors[1] == 0 else B.t().contiguous()
+    out = ops.gemm(As, Bs, M=M, N=N, K=K, a_major=majors[0], b_major=majors[1])
+    assert rel(out, ref) < (1e-5 if dt == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gemm_epilogues(dt):
+    M, N, K = 520, 384, 256
+    A, B = rnd(M, K, dt=dt, seed=3), rnd(N, K, dt=dt, seed=4)
+    bias = rnd(N, seed=5)
+    res = rnd(M, N, dt=dt, seed=6)
+    gate = rnd(M, N, dt=dt, seed=7)
+    acc = A.double() @ B.double().t()
+    out = ops.gemm(A, B, M=M, N=N, K=K, bias=bias, relu=True)
+    assert rel(out, torch.relu(acc + bias.double())) < (1e-5 if dt == torch.float32 else 6e-3)
+    out = ops.gemm(A, B, M=M, N=N, K=K, residual=res, gate=gate, gate_scale=1.25)
+    ref = acc * (gate.double() > 0) * 1.25 + res.double()
+    assert rel(out, ref) < (1e-5 if dt == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gemm_wgrad_accumulate_split_k(dt):
+    Mtok, N, K = 4096 + 40, 512, 768      # dW[N,K] += dY[Mtok,N]^T X[Mtok,K]; ragged reduction length
+    dy, x = rnd(Mtok, N, dt=dt, seed=8, scale=0.1), rnd(Mtok, K, dt=dt, seed=9)
+    out = torch.full((N, K), 0.5, device=DEV)
+    ops.linear_wgrad(dy, x, out)
+    ref = dy.double().t() @ x.double() + 0.5
+    assert rel(out, ref) < (1e-5 if dt == torch.float32 else 4e-3)
+
+
+def test_gemm_relu_dropout_statistics():
+    M, N, K = 1024, 512, 64
+    A, B = rnd(M, K, dt=torch.bfloat16, seed=10), rnd(N, K, dt=torch.bfloat16, seed=11)
+    base = ops.gemm(A, B, M=M, N=N, K=K).float()
+    dropped = ops.gemm(A, B, M=M, N=N, K=K, drop_p=0.25, seed=1234, site=3).float()
+    kept = dropped != 0
+    frac = float(kept.float().mean())
+    assert abs(frac - 0.75) < 0.01
+    sel = kept & (base.abs() > 1.0)   # away from bf16 rounding noise
+    ratio = dropped[sel] / base[sel]
+    assert float((ratio - 1 / 0.75).abs().max()) < 0.02
+    again = ops.gemm(A, B, M=M, N=N, K=K, drop_p=0.25, seed=1234, site=3).float()
+    assert torch.equal(again, dropped)               # same seed -> same mask
+    other = ops.gemm(A, B, M=M, N=N, K=K, drop_p=0.25, seed=1235, site=3).float()
+    assert not torch.equal(other != 0, kept)
+
+
+def test_gemm_rejects_bad_arguments():
+    A = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)   # ld 12 is not a multiple of 8
+    with pytest.raises(mm.MmerError):
+        ops.gemm(A, A, M=8, N=8, K=12)
+    with pytest.raises(mm.MmerError):
+        ops.gemm(torch.zeros(8, 16), torch.zeros(8, 16), M=8, N=8, K=16)   # CPU tensors: no fallback
+
+
+# ----------------------------------------------------------------------------- LayerNorm rows
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("F", [512, 256, 72, 1024])
+@pytest.mark.parametrize("relu,with_x", [(False, True), (True, False)])
+def test_add_ln_fwd_bwd(dt, F, relu, with_x):
+    M = 203
+    x = rnd(M, F, dt=dt, seed=1) if with_x else None
+    a = rnd(M, F, dt=dt, seed=2)
+    gamma, beta = rnd(F, seed=3) * 0.2 + 1, rnd(F, seed=4) * 0.2
+    dy = rnd(M, F, dt=dt, seed=5)
+    y, stats = ops.add_ln_fwd(x, a, gamma, beta, relu=relu)
+    xr = x.double().requires_grad_(True) if with_x else None
+    ar = a.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    z = ar + xr if with_x else ar
+    yr = O.layer_norm(z, gr, br)
+    if relu:
+        yr = torch.relu(yr)
+    assert rel(y, yr) < tol(dt)
+    yr.backward(dy.double())
+    dg, db, dbias = (torch.zeros(F, device=DEV) for _ in range(3))
+    dz, da = ops.add_ln_bwd(dy, x, a, stats, gamma, beta, dg, db, dbias, relu=relu)
+    assert da is None
+    assert rel(dz, ar.grad) < tol(dt)
+    assert rel(dg, gr.grad) < tol(dt) and rel(db, br.grad) < tol(dt)
+    assert rel(dbias, ar.grad.sum(0)) < max(tol(dt), 1e-4)
+
+
+def test_add_ln_dropout_consistency():
+    M, F = 512, 512
+    x, a = rnd(M, F, seed=1), rnd(M, F, seed=2)
+    gamma, beta = torch.ones(F, device=DEV), torch.zeros(F, device=DEV)
+    y0, _ = ops.add_ln_fwd(None, a, None if False else gamma, beta)
+    # dropout on the branch input: recover the mask from z = x + f*a by solving with a second seedless run
+    p = 0.2
+    y, stats = ops.add_ln_fwd(x, a, gamma, beta, drop_a_p=p, site_a=7, seed=99)
+    dy = rnd(M, F, seed=3)
+    dg, db, dbias = (torch.zeros(F, device=DEV) for _ in range(3))
+    dz, da = ops.add_ln_bwd(dy, x, a, stats, gamma, beta, dg, db, dbias, drop_a_p=p, site_a=7, seed=99)
+    mask = (da != 0)
+    assert abs(float(mask.float().mean()) - (1 - p)) < 0.01
+    scale = 1 / (1 - round(p * 65536) / 65536)
+    assert torch.allclose(da[mask], dz[mask] * scale, rtol=1e-5, atol=1e-7)
+    # forward used the same mask: rebuild z with it and compare
+    z = x.double() + a.double() * mask.double() * scale
+    assert rel(y, O.layer_norm(z, gamma.double(), beta.double())) < 2e-5
+    # dropout on the output
+    y2, st2 = ops.add_ln_fwd(None, a, gamma, beta, relu=True, drop_y_p=0.3, site_y=8, seed=5)
+    base = torch.relu(O.layer_norm(a.double(), gamma.double(), beta.double()))
+    keep = (y2 != 0) | (base.to(DEV) == 0)
+    frac = float(((y2 != 0).float().sum() / (base.to(DEV) > 0).float().sum()))
+    assert abs(frac - 0.7) < 0.01 and bool(keep.any())
+
+
+# ----------------------------------------------------------------------------- token assembly / pooling
+@pytest.mark.parametrize("dt", DT)
+def test_embed_fwd_bwd(dt):
+    B, T, F = 9, 5, 512
+    pv, pa = rnd(B * T, F, dt=dt, seed=1), rnd(B, F, dt=dt, seed=2)
+    gv, bv, ga, ba = rnd(F, seed=3) * .2 + 1, rnd(F, seed=4) * .2, rnd(F, seed=5) * .2 + 1, rnd(F, seed=6) * .2
+    pos = rnd(T + 3, F, seed=7)
+    x0, stats = ops.embed_fwd(pv, pa, gv, bv, ga, ba, pos, B, T)
+    leaves = [t.double().requires_grad_(True) for t in (pv, pa, gv, bv, ga, ba, pos)]
+    pvr, par, gvr, bvr, gar, bar, posr = leaves
+    v = O.layer_norm(pvr.view(B, T, F), gvr, bvr)
+    a = O.layer_norm(par, gar, bar).unsqueeze(1)
+    ref = torch.cat([v, a], 1) + posr[: T + 1]
+    assert rel(x0.view(B, T + 1, F), ref) < tol(dt)
+    dx0 = rnd(B * (T + 1), F, dt=dt, seed=8)
+    ref.backward(dx0.double().view(B, T + 1, F))
+    dgv, dbv, dga, dba = (torch.zeros(F, device=DEV) for _ in range(4))
+    dpos = torch.zeros(T + 3, F, device=DEV)
+    dpv, dpa = ops.embed_bwd(dx0, pv, pa, stats, gv, ga, B, T, dgv, dbv, dga, dba, dpos)
+    for got, want in ((dpv, pvr.grad), (dpa, par.grad), (dgv, gvr.grad), (dbv, bvr.grad), (dga, gar.grad),
+                      (dba, bar.grad), (dpos, posr.grad)):
+        assert rel(got, want) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("use_mask,use_ln", [(True, True), (False, True), (True, False)])
+def test_pool_ln_fwd_bwd(dt, use_mask, use_ln):
+    B, T, F = 11, 6, 512
+    S = T + 1
+    x = rnd(B * S, F, dt=dt, seed=1)
+    lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(3))
+    mask = (torch.arange(T)[None] >= lens[:, None])
+    gamma, beta = rnd(F, seed=2) * .2 + 1, rnd(F, seed=3) * .2
+    mk = mask.to(DEV).view(torch.uint8) if use_mask else None
+    fused, pooled, stats = ops.pool_ln_fwd(x, mk, gamma if use_ln else None, beta if use_ln else None, B, T)
+    xr = x.double().view(B, S, F).requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    full = torch.cat([mask, torch.zeros(B, 1, dtype=torch.bool)], 1).to(DEV) if use_mask else None
+    pr = O._pool(xr, full.cpu() if full is not None else None) if False else None
+    keep = (~full).double().unsqueeze(-1) if use_mask else torch.ones(B, S, 1, device=DEV, dtype=torch.double)
+    pr = (xr * keep).sum(1) / keep.sum(1).clamp(min=1e-6)
+    ref = O.layer_norm(pr, gr, br) if use_ln else pr
+    assert rel(fused, ref) < tol(dt)
+    d = rnd(B, F, dt=dt, seed=9)
+    ref.backward(d.double())
+    dg, db = torch.zeros(F, device=DEV), torch.zeros(F, device=DEV)
+    dx = ops.pool_ln_bwd(d, pooled, stats, gamma if use_ln else None, mk, B, T, dg, db)
+    assert rel(dx.view(B, S, F), xr.grad) < tol(dt)
+    if use_ln:
+        assert rel(dg, gr.grad) < tol(dt) and rel(db, br.grad) < tol(dt)
+    if use_mask:   # padded rows get exactly zero gradient
+        assert float(dx.view(B, S, F)[full].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_colsum(dt):
+    x = rnd(1000, 1536, dt=dt, seed=1)
+    out = torch.ones(1536, device=DEV)
+    ops.colsum(x, out)
+    assert rel(out, x.double().sum(0) + 1) < 1e-5
+
+
+# ----------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("T,H,d", [(16, 8, 64), (5, 8, 64), (1, 4, 32), (31, 2, 64)])
+@pytest.mark.parametrize("use_mask", [True, False])
+def test_mha_fwd_bwd(dt, T, H, d, use_mask):
+    B, S, F = 7, T + 1, H * d
+    qkv = rnd(B * S, 3 * F, dt=dt, seed=1)
+    lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(5))
+    mask = (torch.arange(T)[None] >= lens[:, None])
+    mk = mask.to(DEV).view(torch.uint8) if use_mask else None
+    out, probs = ops.mha_fwd(qkv, mk, B, T, H, d, want_probs=True)
+    qr = qkv.double().view(B, S, 3 * F).requires_grad_(True)
+    q, k, v = qr.split(F, dim=-1)
+    sp = lambda t: t.reshape(B, S, H, d).permute(0, 2, 1, 3)
+    scores = sp(q) @ sp(k).transpose(-1, -2) / math.sqrt(d)
+    if use_mask:
+        full = torch.cat([mask, torch.zeros(B, 1, dtype=torch.bool)], 1).to(DEV)
+        scores = scores.masked_fill(full.view(B, 1, 1, S), float("-inf"))
+    p = torch.softmax(scores, -1)
+    ref = (p @ sp(v)).permute(0, 2, 1, 3).reshape(B, S, F)
+    assert rel(out.view(B, S, F), ref) < tol(dt)
+    assert rel(probs, p) < (1e-5 if dt == torch.float32 else 1e-2)
+    if use_mask:
+        assert float(probs.masked_select(full.view(B, 1, 1, S).expand_as(probs)).abs().max()) == 0.0
+    do = rnd(B * S, F, dt=dt, seed=2)
+    ref.backward(do.double().view(B, S, F))
+    dqkv = ops.mha_bwd(qkv, mk, do, B, T, H, d)
+    assert rel(dqkv.view(B, S, 3 * F), qr.grad) < tol(dt)
+
+
+def test_mha_dropout_fwd_bwd_consistent():
+    B, T, H, d = 64, 16, 8, 64
+    S, F = T + 1, H * d
+    qkv = rnd(B * S, 3 * F, seed=3)
+    out0, _ = ops.mha_fwd(qkv, None, B, T, H, d)
+    out1, _ = ops.mha_fwd(qkv, None, B, T, H, d, drop_p=0.1, seed=7, site=2)
+    out2, _ = ops.mha_fwd(qkv, None, B, T, H, d, drop_p=0.1, seed=7, site=2)
+    assert torch.equal(out1, out2) and not torch.equal(out0, out1)
+    # directional derivative check of the stochastic function with its mask frozen by the seed
+    do = rnd(B * S, F, seed=4)
+    dqkv = ops.mha_bwd(qkv, None, do, B, T, H, d, drop_p=0.1, seed=7, site=2)
+    u = rnd(B * S, 3 * F, seed=5)
+    eps = 1e-2
+    fp, _ = ops.mha_fwd(qkv + eps * u, None, B, T, H, d, drop_p=0.1, seed=7, site=2)
+    fm, _ = ops.mha_fwd(qkv - eps * u, None, B, T, H, d, drop_p=0.1, seed=7, site=2)
+    num = float(((fp - fm).double() * do.double()).sum() / (2 * eps))
+    ana = float((dqkv.double() * u.double()).sum())
+    assert abs(num - ana) < 2e-3 * max(abs(num), 1.0)
+
+
+# ----------------------------------------------------------------------------- head + loss
+@pytest.mark.parametrize("dt", DT)
+def test_head_out_fwd_bwd(dt):
+    B, K, Cn = 77, 512, 6
+    h = rnd(B, K, dt=dt, seed=1)
+    W, b = rnd(Cn, K, seed=2) * 0.05, rnd(Cn, seed=3) * 0.1
+    logits, probs = ops.head_out_fwd(h, W, b)
+    hr, Wr, br = h.double().requires_grad_(True), W.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = hr @ Wr.t() + br
+    assert rel(logits, ref) < 1e-5 and rel(probs, torch.softmax(ref, -1)) < 1e-5
+    dl = rnd(B, Cn, seed=4)
+    ref.backward(dl.double())
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    dh = ops.head_out_bwd(dl, h, W, dW, db)
+    assert rel(dh, hr.grad) < tol(dt) and rel(dW, Wr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["focal", "focal_alpha", "wce"])
+@pytest.mark.parametrize("reduction", ["mean", "sum", "none"])
+def test_loss_matches_oracle(kind, reduction):
+    B, Cn = 300, 6
+    logits = rnd(B, Cn, seed=1) * 2
+    labels = torch.randint(0, Cn, (B,), generator=torch.Generator().manual_seed(2)).to(DEV)
+    alpha = torch.tensor([1, 1, 1, 1, 1.2, 1.2], device=DEV)
+    lr = logits.double().requires_grad_(True)
+    if kind == "wce":
+        if reduction != "mean":
+            pytest.skip("the reference only uses the weighted mean")
+        crit, ref = mm.WeightedCrossEntropyLoss(alpha), O.weighted_ce(lr, labels, alpha.double())
+    else:
+        a = alpha if kind == "focal_alpha" else None
+        crit = mm.FocalLoss(2.0, a, reduction)
+        ref = O.focal_loss(lr, labels, 2.0, a.double() if a is not None else None, reduction)
+    lg = logits.clone().requires_grad_(True)
+    out = crit(lg, labels)
+    assert rel(out, ref) < 1e-5
+    w = rnd(*out.shape, seed=5) if reduction == "none" else None
+    (out * w).sum().backward() if w is not None else out.backward()
+    (ref * w.double()).sum().backward() if w is not None else ref.backward()
+    assert rel(lg.grad, lr.grad) < 2e-5
+
+
+def test_focal_gradient_closed_form():
+    B, Cn = 64, 6
+    logits = rnd(B, Cn, seed=3) * 3
+    labels = torch.randint(0, Cn, (B,), generator=torch.Generator().manual_seed(4)).to(DEV)
+    _, d = ops.loss_fwd_bwd(logits, labels, None, _lib.LOSS_FOCAL, 2.0)
+    assert rel(d, O.focal_loss_grad(logits.double(), labels, 2.0)) < 2e-5
+
+
+# ----------------------------------------------------------------------------- optimizer
+def test_adam_matches_oracle_over_three_steps():
+    n = 10_007
+    p = rnd(n, seed=1)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    pr, mr, vr = p.double(), m.double(), v.double()
+    for step in (1, 2, 3):
+        g = rnd(n, seed=10 + step) * 0.1
+        ops.adam_step(p, g, m, v, shadow, step, 3e-4, weight_decay=1e-4)
+        pr, mr, vr = O.adam_step(pr, g.double(), mr, vr, step, 3e-4, weight_decay=1e-4)
+        assert rel(p, pr) < 1e-6 and rel(m, mr) < 1e-5 and rel(v, vr) < 1e-5
+    assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+def test_adam_fused_clip_and_grad_scale():
+    n = 4096
+    p, g = rnd(n, seed=1), rnd(n, seed=2)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sumsq = ops.grad_sumsq(g)
+    assert rel(sumsq, (g.double() ** 2).sum().reshape(1)) < 1e-5
+    total, coef = O.clip_coef([g * 0.5], 1.0)
+    pr, _, _ = O.adam_step(p.double(), g.double() * 0.5 * coef, m.double(), v.double(), 1, 1e-3, weight_decay=0.0)
+    ops.adam_step(p, g, m, v, None, 1, 1e-3, weight_decay=0.0, grad_scale=0.5, sumsq=sumsq, max_norm=1.0)
+    assert rel(p, pr) < 1e-6
+
+
+def test_cast_roundtrip():
+    x = rnd(1001, seed=1)
+    b = ops.cast_bf16(x)
+    assert torch.equal(b, x.to(torch.bfloat16))
+    assert torch.equal(ops.cast_f32(b), b.float())
+
+
+# ----------------------------------------------------------------------------- BatchNorm (train.py variant)
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("relu", [False, True])
+def test_bn_fwd_bwd(dt, relu):
+    N, Cn = 333, 256
+    x = rnd(N, Cn, dt=dt, seed=1) * 1.5 + 0.3
+    gamma, beta = rnd(Cn, seed=2) * .2 + 1, rnd(Cn, seed=3) * .2
+    rm, rv = rnd(Cn, seed=4) * .1, rnd(Cn, seed=5).abs() + .5
+    rm0, rv0 = rm.clone(), rv.clone()
+    y, stats = ops.bn_fwd(x, gamma, beta, rm, rv, training=True, relu=relu)
+    xr, gr, br = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    upd = {}
+    ref = O.batch_norm(xr, gr, br, rm0.double(), rv0.double(), True, update=upd)
+    if relu:
+        ref = torch.relu(ref)
+    assert rel(y, ref) < tol(dt)
+    assert rel(rm, upd["running_mean"]) < 1e-5 and rel(rv, upd["running_var"]) < 1e-4
+    dy = rnd(N, Cn, dt=dt, seed=6)
+    ref.backward(dy.double())
+    dg, db = torch.zeros(Cn, device=DEV), torch.zeros(Cn, device=DEV)
+    dx = ops.bn_bwd(dy, x, stats, gamma, beta, dg, db, training=True, relu=relu)
+    assert rel(dx, xr.grad) < max(tol(dt), 1e-4)
+    assert rel(dg, gr.grad) < tol(dt) and rel(db, br.grad) < tol(dt)
+    # eval mode uses the running statistics
+    y2, _ = ops.bn_fwd(x, gamma, beta, rm, rv, training=False, relu=relu)
+    ref2 = O.batch_norm(x.double(), gamma.double(), beta.double(), rm.double(), rv.double(), False)
+    assert rel(y2, torch.relu(ref2) if relu else ref2) < tol(dt)
