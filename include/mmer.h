@@ -51,6 +51,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_MN_SWAP 0     /* swap LBO/SBO in MN-major UMMA descriptors */
 #define MMER_DEBUG_FORCE_BN 1    /* force the tcgen05 GEMM N tile (128 or 256) */
 #define MMER_DEBUG_FORCE_SIMT 2  /* route bf16 GEMMs through the fp32 FMA kernel (debug only) */
+#define MMER_DEBUG_DIRECT_STORE 3 /* tcgen05 GEMM: bypass the smem + TMA-store epilogue */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);
 /* number of kernels this library has launched in the current process (bench accounting) */

@@ -120,8 +120,7 @@ __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
 }
 // keep-mask bits for the element pair (2*pair, 2*pair+1): bit0, bit1
 __device__ __forceinline__ uint32_t drop_pair(const DropCfg& d, uint64_t pair) {
-  uint32_t h = mix32((uint32_t)pair * 0x9E3779B1u + d.key) ^ (uint32_t)(pair >> 32) * 0x85EBCA77u;
-  h = mix32(h + d.key);
+  const uint32_t h = mix32(((uint32_t)pair ^ d.key) + (uint32_t)(pair >> 32) * 0x85EBCA77u);
   return ((h & 0xFFFFu) >= d.thr ? 1u : 0u) | ((h >> 16) >= d.thr ? 2u : 0u);
 }
 // multiplicative factors for 8 consecutive elements starting at idx (idx % 8 == 0)

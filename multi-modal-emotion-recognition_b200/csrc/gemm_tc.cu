@@ -66,6 +66,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols));
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -124,7 +129,8 @@ struct GemmParams {
   const void* gate;
   float gate_scale;
   int out_f32, accumulate, relu;
-  int mn_swap;  // debug: swap LBO/SBO of MN-major descriptors
+  int mn_swap;    // debug: swap LBO/SBO of MN-major descriptors
+  int tma_store;  // bf16 output leaves through swizzled smem staging + TMA store (coalesced)
   DropCfg drop;
 };
 
@@ -135,16 +141,19 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * 4096;  // 32 rows x 128 B each
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   using C = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base slot
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
@@ -260,6 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     const bool vec_ok = (p.ldd % 8 == 0);
+    uint8_t* stg = epi_smem + (warp - 2) * 8192;
+    int sbuf = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int n_blk = item % p.num_n;
       const int m_blk = (item / p.num_n) % p.num_m;
@@ -267,6 +278,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const long long row = (long long)m_blk * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      if (p.tma_store) {
+        // ---- bf16 output: registers -> 128B-swizzled smem tile (32 rows x 64 cols) -> TMA store
+#pragma unroll 1
+        for (int j = 0; j < BN / 64; ++j) {
+          const int col0 = n_blk * BN + j * 64;
+          if (col0 >= p.N) break;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          uint8_t* sb = stg + sbuf * 4096;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + j * 64 + h * 32), r);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + h * 32 + g * 8;
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              const bool full8 = col + 8 <= p.N;
+              if (p.bias) {
+                if (full8) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              const long long off = row * p.ldd + col;
+              if (p.drop.thr) {
+                float f[8];
+                drop8(p.drop, (uint64_t)off, f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= f[i];
+              }
+              if (row_ok && full8) {
+                if (p.gate) {
+                  float gv[8];
+                  load8(reinterpret_cast<const bf16*>(p.gate) + off, gv);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] *= (gv[i] > 0.f) ? p.gate_scale : 0.f;
+                }
+                if (p.residual) {
+                  float rv[8];
+                  load8(reinterpret_cast<const bf16*>(p.residual) + off, rv);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += rv[i];
+                }
+              } else if (row_ok && (p.gate || p.residual)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (col + i < p.N) {
+                    if (p.gate) v[i] *= (to_f(reinterpret_cast<const bf16*>(p.gate)[off + i]) > 0.f) ? p.gate_scale : 0.f;
+                    if (p.residual) v[i] += to_f(reinterpret_cast<const bf16*>(p.residual)[off + i]);
+                  }
+                }
+              }
+              uint4 pk;
+              __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              const int chunk = (h * 4 + g) ^ (lane & 7);
+              *reinterpret_cast<uint4*>(sb + lane * 128 + chunk * 16) = pk;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmD, smem_u32(sb), col0, m_blk * BM + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          sbuf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        tphase[buf] ^= 1;
+        buf ^= 1;
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
@@ -357,6 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -428,7 +528,8 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int grid,
+                  cudaStream_t st) {
   using C = TileCfg<BN>;
   static bool attr_done = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
@@ -437,7 +538,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
     attr_done = true;
   }
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, td, p);
   MMER_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -485,7 +586,12 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
     MMER_TRY(make_map(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, BK));
   }
 
+  CUtensorMap td = ta;  // placeholder when the staged store is not used
+  const bool tma_store = a.out_dtype == MMER_BF16 && !a.accumulate && a.ldd % 8 == 0 && !g_debug[MMER_DEBUG_DIRECT_STORE];
+  if (tma_store) MMER_TRY(make_map(&td, a.D, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
+
   GemmParams p;
+  p.tma_store = tma_store ? 1 : 0;
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
   p.num_m = num_m; p.num_n = num_n; p.splits = splits; p.kb_total = kb_total; p.kb_per_split = kb_per;
   p.D = a.D; p.ldd = a.ldd; p.bias = a.bias; p.residual = a.residual; p.gate = a.gate; p.gate_scale = a.gate_scale;
@@ -497,13 +603,13 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
 
   const bool amn = a.a_major == MMER_MAJOR_MN, bmn = a.b_major == MMER_MAJOR_MN;
   if (bn == 256) {
-    if (!amn && !bmn) return launch<256, false, false>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<256, false, true>(ta, tb, p, grid, st);
-    return launch<256, true, true>(ta, tb, p, grid, st);
+    if (!amn && !bmn) return launch<256, false, false>(ta, tb, td, p, grid, st);
+    if (!amn && bmn) return launch<256, false, true>(ta, tb, td, p, grid, st);
+    return launch<256, true, true>(ta, tb, td, p, grid, st);
   } else {
-    if (!amn && !bmn) return launch<128, false, false>(ta, tb, p, grid, st);
-    if (!amn && bmn) return launch<128, false, true>(ta, tb, p, grid, st);
-    return launch<128, true, true>(ta, tb, p, grid, st);
+    if (!amn && !bmn) return launch<128, false, false>(ta, tb, td, p, grid, st);
+    if (!amn && bmn) return launch<128, false, true>(ta, tb, td, p, grid, st);
+    return launch<128, true, true>(ta, tb, td, p, grid, st);
   }
 }
 

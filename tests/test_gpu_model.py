@@ -98,8 +98,10 @@ def test_fp32_training_step_matches_reference_golden(name, variant, loss, clip):
     lval.backward()
     np.testing.assert_allclose(video.grad[:4].cpu().numpy(), g["grad_in/video"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(audio.grad[:4].cpu().numpy(), g["grad_in/audio"], rtol=0, atol=2e-6)
-    if mask is not None:
-        assert float(video.grad[mask].abs().max()) == 0.0       # padded rows: exactly zero
+    if mask is not None and variant == "v2":
+        assert float(video.grad[mask].abs().max()) == 0.0       # padded rows: exactly zero (LayerNorm model)
+    # (train.py's BatchNorm statistics include the padded rows, so the reference itself gives them a small
+    #  non-zero gradient; the golden comparison above covers those rows for v1.)
     for k, p in model.named_parameters():
         ref = g["grad/" + k]
         got = summarize(p.grad)
