@@ -1,13 +1,16 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] . B[N,K]^T), bf16 in, fp32 accumulate.
 //
-// One persistent CTA per SM, 6 warps:
+// One persistent CTA per SM, 10 warps:
 //   warp 0   : TMA producer (one elected lane) -- cp.async.bulk.tensor into a 4-stage smem ring,
 //              128B-swizzled tiles, completion on "full" mbarriers
 //   warp 1   : MMA issuer (one elected lane) -- tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16,
 //              accumulators in TMEM (2 x BN columns, double buffered); tcgen05.commit releases smem
 //              stages and publishes finished accumulators.  Also owns tcgen05.alloc / dealloc.
-//   warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / dropout / gate /
-//              residual, then bf16 or fp32 stores, or fp32 vector atomics for split-K weight gradients.
+//   warps 2-9: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp; two warps per TMEM lane quarter, each
+//              taking half of the BN columns), bias / ReLU / dropout in registers; the gate or residual tile
+//              arrives by TMA (L2-prefetched while the tile's MMAs run); bf16 results leave through a
+//              128B-swizzled smem tile and a TMA store.  fp32 outputs and split-K weight gradients
+//              (fp32 vector atomics) use direct stores.
 // Either operand may be K-major (nn.Linear forward, dgrad's dY) or MN-major (dgrad's W, wgrad's dY and X),
 // which is what lets dgrad and wgrad run without any transposed copies in HBM.
 #include <cuda.h>
@@ -22,7 +25,6 @@ namespace mmer {
 static constexpr int BM = 128;
 static constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int GEMM_THREADS = 192;
 
 int g_debug[16] = {0};
 
@@ -131,8 +133,12 @@ struct GemmParams {
   int out_f32, accumulate, relu;
   int mn_swap;    // debug: swap LBO/SBO of MN-major descriptors
   int tma_store;  // bf16 output leaves through swizzled smem staging + TMA store (coalesced)
+  int aux_mode;   // staged path only: 0 none, 1 residual add, 2 ReLU gate; the aux tile arrives by TMA
   DropCfg drop;
 };
+
+static constexpr int EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
 template <int BN>
 struct TileCfg {
@@ -141,25 +147,54 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * 4096;  // 32 rows x 128 B each
+  static constexpr int EPI_BYTES = EPI_WARPS * 4096;  // per warp: one 32-row x 64-column bf16 tile (128 B rows)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 8 <= 256, "barrier area");
 };
+
+// element-wise part of the epilogue on 8 consecutive accumulator columns of one row
+__device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], int col, long long off, bool full8) {
+  if (p.bias) {
+    if (full8) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.drop.thr) {
+    float f[8];
+    drop8(p.drop, (uint64_t)off, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= f[i];
+  }
+}
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   using C = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem base slot
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4..2S+12) aux, then tmem slot
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * C::STAGES);
   const uint32_t bar_tempty = smem_u32(bars + 2 * C::STAGES + 2);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * C::STAGES + 4);
+  const uint32_t bar_aux = smem_u32(bars + 2 * C::STAGES + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * C::STAGES + 4 + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,11 +206,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4);
+      mbar_init(bar_tempty + 8 * b, EPI_WARPS);
     }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(bar_aux + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (p.aux_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), C::TMEM_COLS);
   tc_fence_before();
@@ -264,64 +302,155 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================================================== epilogue (warps 2..9)
+    // A warp may only touch the TMEM lane quarter (warp % 4); two warps share each quarter and split the
+    // BN accumulator columns in halves.
+    constexpr int HALF = BN / 2;
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int hsel = ew >> 2;
+    uint8_t* stg = epi_smem + ew * 4096;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const uint32_t auxbar = bar_aux + 8 * ew;
+    uint32_t aux_phase = 0;
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     const bool vec_ok = (p.ldd % 8 == 0);
-    uint8_t* stg = epi_smem + (warp - 2) * 8192;
-    int sbuf = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int n_blk = item % p.num_n;
       const int m_blk = (item / p.num_n) % p.num_m;
+      const int row0 = m_blk * BM + q * 32;
+      const long long row = (long long)row0 + lane;
+      const bool row_ok = row < p.M;
+      if (p.aux_mode && lane < HALF / 64) {
+        // warm L2 with this tile's gate / residual sub-tiles while the MMAs of the tile are still running
+        const int pc = n_blk * BN + hsel * HALF + lane * 64;
+        if (pc < p.N && row0 < p.M)
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmX), "r"(pc), "r"(row0)
+                       : "memory");
+      }
       mbar_wait(bar_tfull + 8 * buf, tphase[buf]);
       tc_fence_after();
-      const long long row = (long long)m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hsel * HALF);
       if (p.tma_store) {
-        // ---- bf16 output: registers -> 128B-swizzled smem tile (32 rows x 64 cols) -> TMA store
+        // ---- bf16 output: registers -> 128B-swizzled smem tile (32 rows x 64 columns) -> TMA store
 #pragma unroll 1
-        for (int j = 0; j < BN / 64; ++j) {
-          const int col0 = n_blk * BN + j * 64;
+        for (int j = 0; j < HALF / 64; ++j) {
+          const int col0 = n_blk * BN + hsel * HALF + j * 64;
           if (col0 >= p.N) break;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has drained the tile
+            if (p.aux_mode) {
+              mbar_expect_tx(auxbar, 4096);
+              tma_load_2d(stg_u32, &tmX, auxbar, col0, row0);
+            }
+          }
           __syncwarp();
-          uint8_t* sb = stg + sbuf * 4096;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + j * 64 + h * 32), r);
+            tmem_ld32(trow + (uint32_t)(j * 64 + h * 32), r);
+            if (p.aux_mode && h == 0) {
+              mbar_wait(auxbar, aux_phase);
+              aux_phase ^= 1;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int col = col0 + h * 32 + g * 8;
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              const bool full8 = col + 8 <= p.N;
-              if (p.bias) {
-                if (full8) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                } else {
+              epi_math8(p, v, col, row * p.ldd + col, col + 8 <= p.N);
+              uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4));
+              if (p.aux_mode) {
+                const uint4 xr = *slot;
+                const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
+                for (int i = 0; i < 4; ++i) {
+                  const float2 xf = __bfloat1622float2(xh[i]);
+                  if (p.aux_mode == 1) {
+                    v[2 * i] += xf.x;
+                    v[2 * i + 1] += xf.y;
+                  } else {
+                    v[2 * i] *= (xf.x > 0.f) ? p.gate_scale : 0.f;
+                    v[2 * i + 1] *= (xf.y > 0.f) ? p.gate_scale : 0.f;
+                  }
                 }
               }
-              if (p.relu) {
+              uint4 pk;
+              __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-              }
-              const long long off = row * p.ldd + col;
-              if (p.drop.thr) {
-                float f[8];
-                drop8(p.drop, (uint64_t)off, f);
+              for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              *slot = pk;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmD, stg_u32, col0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
+        // ---- direct path: fp32 outputs, split-K accumulation (fp32 vector atomics), unaligned leading dims
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + (uint32_t)c, r);
+          const int col0 = n_blk * BN + hsel * HALF + c;
+          if (!row_ok || col0 >= p.N) continue;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= f[i];
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= p.N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+            const bool full8 = vec_ok && (col + 8 <= p.N);
+            const int nvalid = min(8, p.N - col);
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < nvalid) v[i] += __ldg(p.bias + col + i);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            const long long off = row * p.ldd + col;
+            if (p.drop.thr && full8) {
+              float f[8];
+              drop8(p.drop, (uint64_t)off, f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= f[i];
+            } else if (p.drop.thr) {
+              for (int i = 0; i < nvalid; ++i) v[i] *= drop1(p.drop, (uint64_t)(off + i));
+            }
+            if (p.out_f32) {
+              float* D = reinterpret_cast<float*>(p.D) + off;
+              if (p.gate) {
+                const float* G = reinterpret_cast<const float*>(p.gate) + off;
+                for (int i = 0; i < nvalid; ++i) v[i] *= (G[i] > 0.f) ? p.gate_scale : 0.f;
               }
-              if (row_ok && full8) {
+              if (p.residual) {
+                const float* R = reinterpret_cast<const float*>(p.residual) + off;
+                for (int i = 0; i < nvalid; ++i) v[i] += R[i];
+              }
+              if (p.accumulate) {
+                if (full8) {
+                  atomicAdd(reinterpret_cast<float4*>(D), make_float4(v[0], v[1], v[2], v[3]));
+                  atomicAdd(reinterpret_cast<float4*>(D + 4), make_float4(v[4], v[5], v[6], v[7]));
+                } else {
+                  for (int i = 0; i < nvalid; ++i) atomicAdd(D + i, v[i]);
+                }
+              } else if (full8) {
+                store8(D, v);
+              } else {
+                for (int i = 0; i < nvalid; ++i) D[i] = v[i];
+              }
+            } else {
+              bf16* D = reinterpret_cast<bf16*>(p.D) + off;
+              if (full8) {
                 if (p.gate) {
                   float gv[8];
                   load8(reinterpret_cast<const bf16*>(p.gate) + off, gv);
@@ -334,115 +463,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] += rv[i];
                 }
-              } else if (row_ok && (p.gate || p.residual)) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if (col + i < p.N) {
-                    if (p.gate) v[i] *= (to_f(reinterpret_cast<const bf16*>(p.gate)[off + i]) > 0.f) ? p.gate_scale : 0.f;
-                    if (p.residual) v[i] += to_f(reinterpret_cast<const bf16*>(p.residual)[off + i]);
-                  }
-                }
-              }
-              uint4 pk;
-              __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              const int chunk = (h * 4 + g) ^ (lane & 7);
-              *reinterpret_cast<uint4*>(sb + lane * 128 + chunk * 16) = pk;
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmD, smem_u32(sb), col0, m_blk * BM + q * 32);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          sbuf ^= 1;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        tphase[buf] ^= 1;
-        buf ^= 1;
-        continue;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c), r);
-        const int col0 = n_blk * BN + c;
-        if (!row_ok || col0 >= p.N) continue;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = col0 + g * 8;
-          if (col >= p.N) break;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-          const bool full8 = vec_ok && (col + 8 <= p.N);
-          const int nvalid = min(8, p.N - col);
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < nvalid) v[i] += __ldg(p.bias + col + i);
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          const long long off = row * p.ldd + col;
-          if (p.drop.thr && full8) {
-            float f[8];
-            drop8(p.drop, (uint64_t)off, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= f[i];
-          } else if (p.drop.thr) {
-            for (int i = 0; i < nvalid; ++i) v[i] *= drop1(p.drop, (uint64_t)(off + i));
-          }
-          if (p.out_f32) {
-            float* D = reinterpret_cast<float*>(p.D) + off;
-            if (p.gate) {
-              const float* G = reinterpret_cast<const float*>(p.gate) + off;
-              for (int i = 0; i < nvalid; ++i) v[i] *= (G[i] > 0.f) ? p.gate_scale : 0.f;
-            }
-            if (p.residual) {
-              const float* R = reinterpret_cast<const float*>(p.residual) + off;
-              for (int i = 0; i < nvalid; ++i) v[i] += R[i];
-            }
-            if (p.accumulate) {
-              if (full8) {
-                atomicAdd(reinterpret_cast<float4*>(D), make_float4(v[0], v[1], v[2], v[3]));
-                atomicAdd(reinterpret_cast<float4*>(D + 4), make_float4(v[4], v[5], v[6], v[7]));
+                store8(D, v);
               } else {
-                for (int i = 0; i < nvalid; ++i) atomicAdd(D + i, v[i]);
-              }
-            } else if (full8) {
-              store8(D, v);
-            } else {
-              for (int i = 0; i < nvalid; ++i) D[i] = v[i];
-            }
-          } else {
-            bf16* D = reinterpret_cast<bf16*>(p.D) + off;
-            if (full8) {
-              if (p.gate) {
-                float gv[8];
-                load8(reinterpret_cast<const bf16*>(p.gate) + off, gv);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= (gv[i] > 0.f) ? p.gate_scale : 0.f;
-              }
-              if (p.residual) {
-                float rv[8];
-                load8(reinterpret_cast<const bf16*>(p.residual) + off, rv);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += rv[i];
-              }
-              store8(D, v);
-            } else {
-              for (int i = 0; i < nvalid; ++i) {
-                float x = v[i];
-                if (p.gate) x *= (to_f(reinterpret_cast<const bf16*>(p.gate)[off + i]) > 0.f) ? p.gate_scale : 0.f;
-                if (p.residual) x += to_f(reinterpret_cast<const bf16*>(p.residual)[off + i]);
-                D[i] = __float2bfloat16_rn(x);
+                for (int i = 0; i < nvalid; ++i) {
+                  float x = v[i];
+                  if (p.gate) x *= (to_f(reinterpret_cast<const bf16*>(p.gate)[off + i]) > 0.f) ? p.gate_scale : 0.f;
+                  if (p.residual) x += to_f(reinterpret_cast<const bf16*>(p.residual)[off + i]);
+                  D[i] = __float2bfloat16_rn(x);
+                }
               }
             }
           }
@@ -454,9 +482,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tphase[buf] ^= 1;
       buf ^= 1;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
-  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -528,8 +556,8 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int grid,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
+                  const GemmParams& p, int grid, cudaStream_t st) {
   using C = TileCfg<BN>;
   static bool attr_done = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
@@ -538,7 +566,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
     attr_done = true;
   }
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, td, p);
+  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, td, tx, p);
   MMER_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -586,12 +614,20 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
     MMER_TRY(make_map(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, BK));
   }
 
-  CUtensorMap td = ta;  // placeholder when the staged store is not used
-  const bool tma_store = a.out_dtype == MMER_BF16 && !a.accumulate && a.ldd % 8 == 0 && !g_debug[MMER_DEBUG_DIRECT_STORE];
-  if (tma_store) MMER_TRY(make_map(&td, a.D, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
+  CUtensorMap td = ta, tx = ta;  // placeholders when the staged store / aux tile are not used
+  const bool tma_store = a.out_dtype == MMER_BF16 && !a.accumulate && a.ldd % 8 == 0 && !(a.gate && a.residual) &&
+                         !g_debug[MMER_DEBUG_DIRECT_STORE];
+  const void* aux = a.gate ? a.gate : a.residual;
+  if (tma_store) {
+    MMER_CHECK_ARG(aux == nullptr || (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
+                   "gemm_tc: gate/residual must be 16-byte aligned");
+    MMER_TRY(make_map(&td, a.D, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
+    if (aux) MMER_TRY(make_map(&tx, aux, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
+  }
 
   GemmParams p;
   p.tma_store = tma_store ? 1 : 0;
+  p.aux_mode = !tma_store ? 0 : (a.gate ? 2 : (a.residual ? 1 : 0));
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
   p.num_m = num_m; p.num_n = num_n; p.splits = splits; p.kb_total = kb_total; p.kb_per_split = kb_per;
   p.D = a.D; p.ldd = a.ldd; p.bias = a.bias; p.residual = a.residual; p.gate = a.gate; p.gate_scale = a.gate_scale;
@@ -603,13 +639,13 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
 
   const bool amn = a.a_major == MMER_MAJOR_MN, bmn = a.b_major == MMER_MAJOR_MN;
   if (bn == 256) {
-    if (!amn && !bmn) return launch<256, false, false>(ta, tb, td, p, grid, st);
-    if (!amn && bmn) return launch<256, false, true>(ta, tb, td, p, grid, st);
-    return launch<256, true, true>(ta, tb, td, p, grid, st);
+    if (!amn && !bmn) return launch<256, false, false>(ta, tb, td, tx, p, grid, st);
+    if (!amn && bmn) return launch<256, false, true>(ta, tb, td, tx, p, grid, st);
+    return launch<256, true, true>(ta, tb, td, tx, p, grid, st);
   } else {
-    if (!amn && !bmn) return launch<128, false, false>(ta, tb, td, p, grid, st);
-    if (!amn && bmn) return launch<128, false, true>(ta, tb, td, p, grid, st);
-    return launch<128, true, true>(ta, tb, td, p, grid, st);
+    if (!amn && !bmn) return launch<128, false, false>(ta, tb, td, tx, p, grid, st);
+    if (!amn && bmn) return launch<128, false, true>(ta, tb, td, tx, p, grid, st);
+    return launch<128, true, true>(ta, tb, td, tx, p, grid, st);
   }
 }
 
