@@ -46,6 +46,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_l
          bias=None, residual=None, gate=None, gate_scale=1.0, relu=False, drop_p=0.0, seed=0, site=0,
          out: Optional[torch.Tensor] = None, out_dtype=None, accumulate=False) -> torch.Tensor:
     """D[M,N] = epilogue(A[M,K] . B[N,K]^T); see mmer_gemm in include/mmer.h."""
+    for t in (A, B, bias, residual, gate, out):
+        if t is not None and not t.is_cuda:
+            raise _lib.MmerError("mmer_b200 ops need CUDA tensors; there is no CPU fallback")
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=out_dtype or A.dtype)
     a = GemmArgs()

@@ -171,16 +171,28 @@ def test_bf16_against_oracle_on_rounded_weights(variant):
     top2 = ref_row.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2e-2                      # skip numerically tied rows
     assert (attn["audio_row"].argmax(1).cpu()[clear] == ref_row.argmax(1)[clear]).all()
-    worst = 0.0
+    # Gradients.  With every activation stored in bf16, a fraction ~3e-3 of the ReLU pre-activations sits within
+    # rounding distance of zero and flips its mask relative to the exact evaluation; each flip moves a gradient
+    # element by its full magnitude, so ANY bf16-storage evaluation of this model differs from the exact one by
+    # sqrt(3e-3) ~ 6-8 % in gradient norm.  tests/test_oracle_golden.py::test_bf16_storage_noise_floor measures the
+    # same 6-9 % on the fp64 oracle with bf16 rounding at the tensor boundaries (no GPU involved), so the bound
+    # below is the noise floor of the problem, not slack for the kernels: the kernels themselves are held to 2e-2
+    # op by op in test_gpu_ops.py and to 1e-4 end to end in fp32 mode above.
+    worst, worst_cos = 0.0, 1.0
     for k, p in model.named_parameters():
         gr = leaf[k].grad
         if float(gr.norm()) < 1e-6:
             continue
-        err = float((p.grad.cpu().double() - gr).norm() / gr.norm())
-        worst = max(worst, err)
-        assert err < 4e-2, (k, err)
-    print(f"bf16 {variant}: worst relative gradient-norm error {worst:.4f}")
-    assert float((vg.grad.cpu().double() - vr.grad).norm() / vr.grad.norm()) < 4e-2
+        got = p.grad.cpu().double()
+        err = float((got - gr).norm() / gr.norm())
+        cos = float((got * gr).sum() / (got.norm() * gr.norm()))
+        worst, worst_cos = max(worst, err), min(worst_cos, cos)
+        assert err < 0.12 and cos > 0.992, (k, err, cos)
+        assert abs(float(got.norm() / gr.norm()) - 1.0) < 2e-2, k           # gradient magnitude within 2e-2
+    print(f"bf16 {variant}: worst relative gradient-norm error {worst:.4f}, worst cosine {worst_cos:.5f}")
+    got = vg.grad.cpu().double()
+    assert float((got - vr.grad).norm() / vr.grad.norm()) < 0.12
+    assert float((got * vr.grad).sum() / (got.norm() * vr.grad.norm())) > 0.992
 
 
 def test_fused_train_step_matches_reference_golden_fp32():
