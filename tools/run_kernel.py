@@ -1,0 +1,61 @@
+"""Launch one family of kernels at the cfg2 shapes a few times (target for `ncu --set full -k regex:...`).
+
+  python tools/run_kernel.py mha|add_ln|gemm|colsum|embed|adam [reps]
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mmer_b200 import _lib, ops  # noqa: E402
+
+dev = torch.device("cuda")
+B, T, H, D, F = 4096, 16, 8, 64, 512
+S = T + 1
+M = B * S
+bf = torch.bfloat16
+
+
+def main():
+    what = sys.argv[1]
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g).to(bf)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    if what == "mha":
+        qkv, do = rnd(M, 3 * F), rnd(M, F)
+        fn = lambda: (ops.mha_fwd(qkv, None, B, T, H, D, drop_p=0.1, seed=1, site=1),
+                      ops.mha_bwd(qkv, None, do, B, T, H, D, drop_p=0.1, seed=1, site=1))
+    elif what == "add_ln":
+        x, a, dy = rnd(M, F), rnd(M, F), rnd(M, F)
+        gam, bet = torch.ones(F, device=dev), torch.zeros(F, device=dev)
+        dg, db, dbias = torch.zeros(F, device=dev), torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+
+        def fn():
+            y, st = ops.add_ln_fwd(x, a, gam, bet, drop_a_p=0.1, site_a=1, seed=1)
+            ops.add_ln_bwd(dy, x, a, st, gam, bet, dg, db, dbias, drop_a_p=0.1, site_a=1, seed=1)
+    elif what == "colsum":
+        x = rnd(M, 2048)
+        out = torch.zeros(2048, device=dev)
+        fn = lambda: ops.colsum(x, out)
+    elif what == "gemm":
+        x, w, bias = rnd(M, 512), rnd(2048, 512), torch.zeros(2048, device=dev)
+        out = torch.empty(M, 2048, device=dev, dtype=bf)
+        fn = lambda: ops.gemm(x, w, M=M, N=2048, K=512, bias=bias, relu=True, drop_p=0.1, seed=1, site=1, out=out)
+    else:
+        raise SystemExit("unknown kernel family")
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    print(f"{what}: {ev[0].elapsed_time(ev[1]) / reps * 1e3:.1f} us per iteration")
+
+
+if __name__ == "__main__":
+    main()
