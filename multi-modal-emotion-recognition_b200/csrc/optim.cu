@@ -1,13 +1,15 @@
 // Flat fused Adam (coupled L2 weight decay, bias correction) with optional global-norm
 // gradient clipping and a bf16 shadow copy of the updated weights for the tensor-core
 // GEMMs.  28 B/param of fp32 traffic (+2 B for the shadow): a pure HBM-bandwidth kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mmer {
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            bf16* __restrict__ shadow, long long n, float lr_over_bc1, float beta1, float beta2, float eps,
+            bf16* __restrict__ shadow, long long n, float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps,
             float wd, float inv_sqrt_bc2, float grad_scale, const float* __restrict__ sumsq, float max_norm) {
   float gs = grad_scale;
   if (sumsq != nullptr) {
@@ -25,8 +27,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float gr = fmaf(wd, pp[k], gg[k] * gs);
-      mm[k] = fmaf(beta1, mm[k], (1.f - beta1) * gr);
-      vq[k] = fmaf(beta2, vq[k], (1.f - beta2) * gr * gr);
+      mm[k] = fmaf(beta1, mm[k], omb1 * gr);
+      vq[k] = fmaf(beta2, vq[k], omb2 * gr * gr);
       pp[k] -= lr_over_bc1 * mm[k] / (sqrtf(vq[k]) * inv_sqrt_bc2 + eps);
     }
     *reinterpret_cast<float4*>(p + i) = pv;
@@ -42,8 +44,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   } else {
     for (long long k = i; k < n; ++k) {
       const float gr = fmaf(wd, p[k], g[k] * gs);
-      const float mk = fmaf(beta1, m[k], (1.f - beta1) * gr);
-      const float vk = fmaf(beta2, v[k], (1.f - beta2) * gr * gr);
+      const float mk = fmaf(beta1, m[k], omb1 * gr);
+      const float vk = fmaf(beta2, v[k], omb2 * gr * gr);
       m[k] = mk; v[k] = vk;
       p[k] -= lr_over_bc1 * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
       if (shadow != nullptr) shadow[k] = __float2bfloat16_rn(p[k]);
@@ -89,11 +91,19 @@ int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
                      (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
                  "adam: buffers must be 16-byte aligned");
   if (n <= 0) return 0;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  // The reference's optimizer holds the betas as Python doubles (0.9, 0.999) and derives 1-beta and the bias
+  // corrections in double; recover the decimal the caller meant from the float that crossed the C ABI.
+  char buf[32];
+  snprintf(buf, sizeof(buf), "%.7g", (double)beta1);
+  const double b1 = strtod(buf, nullptr);
+  snprintf(buf, sizeof(buf), "%.7g", (double)beta2);
+  const double b2 = strtod(buf, nullptr);
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
   const long long nt = (n + 3) / 4;
   adam_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, (bf16*)shadow_bf16, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay,
+      p, g, m, v, (bf16*)shadow_bf16, n, (float)(lr / bc1), beta1, beta2, (float)(1.0 - b1),
+      (float)(1.0 - b2), eps, weight_decay,
       (float)(1.0 / sqrt(bc2)), grad_scale, sumsq, max_norm);
   MMER_LAUNCH_CHECK("adam_kernel");
   return 0;
