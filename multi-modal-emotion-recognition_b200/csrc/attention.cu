@@ -1,5 +1,6 @@
 // Multi-head self-attention entry points: dispatch on sequence length, head size and dtype.
-// Short sequences (S = T+1 <= 32): attention_small.cuh (one warp per (sample, head), register tiled).
+// Short sequences (S = T+1 <= 32): bf16 -> attention_mma.cu (one CTA per sample, bulk-copied rows, warp-level
+// tensor-core MMAs); fp32 parity mode -> attention_small.cuh (one warp per (sample, head), register tiled FMA).
 // Longer sequences: attention_generic.cu (one CTA per (sample, head), K/V resident in shared memory).
 #include "common.cuh"
 
@@ -13,6 +14,11 @@ int mha_bwd_small_bf16(int d, int SP, const void* qkv, const uint8_t* mask, cons
                        int H, DropCfg dc, cudaStream_t st);
 int mha_bwd_small_f32(int d, int SP, const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn,
                       int H, DropCfg dc, cudaStream_t st);
+int mha_fwd_mma(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, int d, DropCfg dc,
+                cudaStream_t st);
+int mha_bwd_mma(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn, int H, int d,
+                DropCfg dc, cudaStream_t st);
+extern int g_debug[16];
 int mha_fwd_generic(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T, int64_t H,
                     int64_t d, int dtype, DropCfg dc, cudaStream_t st);
 int mha_bwd_generic(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int64_t B, int64_t T,
@@ -34,6 +40,8 @@ int mmer_mha_fwd(const void* qkv, const uint8_t* mask, void* out, float* probs, 
   cudaStream_t st = (cudaStream_t)stream;
   if (T + 1 > 32) return mha_fwd_generic(qkv, mask, out, probs, B, T, H, d, dtype, dc, st);
   const int SP = (int)((T + 1 + 3) & ~3LL);
+  if (dtype == MMER_BF16 && !g_debug[MMER_DEBUG_ATT_SIMT])
+    return mha_fwd_mma(qkv, mask, out, probs, (int)B, (int)T, (int)H, (int)d, dc, st);
   if (dtype == MMER_BF16) return mha_fwd_small_bf16((int)d, SP, qkv, mask, out, probs, (int)B, (int)T, (int)H, dc, st);
   return mha_fwd_small_f32((int)d, SP, qkv, mask, out, probs, (int)B, (int)T, (int)H, dc, st);
 }
@@ -48,6 +56,8 @@ int mmer_mha_bwd(const void* qkv, const uint8_t* mask, const void* dout, void* d
   cudaStream_t st = (cudaStream_t)stream;
   if (T + 1 > 32) return mha_bwd_generic(qkv, mask, dout, dqkv, B, T, H, d, dtype, dc, st);
   const int SP = (int)((T + 1 + 3) & ~3LL);
+  if (dtype == MMER_BF16 && !g_debug[MMER_DEBUG_ATT_SIMT])
+    return mha_bwd_mma(qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, (int)d, dc, st);
   if (dtype == MMER_BF16) return mha_bwd_small_bf16((int)d, SP, qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, dc, st);
   return mha_bwd_small_f32((int)d, SP, qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, dc, st);
 }

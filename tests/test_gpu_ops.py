@@ -297,6 +297,56 @@ def test_mha_dropout_fwd_bwd_consistent(B, T):
     assert abs(num - ana) < 2e-3 * max(abs(num), 1.0)
 
 
+@pytest.mark.parametrize("T,H,d", [(16, 8, 64), (5, 8, 64), (31, 4, 32), (9, 16, 64), (23, 2, 64)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_mha_mma_kernels_match_fma_kernels_bf16(T, H, d, p):
+    """bf16: the tensor-core (mma.sync) kernels and the FMA kernels regenerate the same dropout decisions from the
+    same (seed, site, index) hash, so forward outputs and gradients must agree to bf16 rounding, mask included."""
+    B, S, F = 37, T + 1, H * d
+    qkv = rnd(B * S, 3 * F, dt=torch.bfloat16, seed=11)
+    do = rnd(B * S, F, dt=torch.bfloat16, seed=12)
+    lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(6))
+    mk = (torch.arange(T)[None] >= lens[:, None]).to(DEV).view(torch.uint8)
+    lib = _lib.load()
+    res = []
+    try:
+        for simt in (0, 1):
+            lib.mmer_debug_set(_lib.DEBUG_ATT_SIMT, simt)
+            out, probs = ops.mha_fwd(qkv, mk, B, T, H, d, want_probs=True, drop_p=p, seed=5, site=3)
+            dq = ops.mha_bwd(qkv, mk, do, B, T, H, d, drop_p=p, seed=5, site=3)
+            res.append((out, probs, dq))
+    finally:
+        lib.mmer_debug_set(_lib.DEBUG_ATT_SIMT, 0)
+    assert rel(res[0][0], res[1][0]) < 1e-2
+    assert rel(res[0][1], res[1][1]) < 1e-2
+    assert rel(res[0][2], res[1][2]) < 2e-2
+    if p > 0:   # same elements dropped: zeros of the dropped-out outputs cannot be compared directly, but a different
+        # mask would show up as O(1) differences in out, which the bound above excludes
+        out_nodrop, _ = ops.mha_fwd(qkv, mk, B, T, H, d)
+        assert rel(res[0][0], out_nodrop) > 5e-2
+
+
+def test_mha_mma_large_batch_linearity_in_v_and_dout():
+    """cfg2 size (B=4096, T=16): O is linear in V and dV is linear in dO for fixed Q, K -- a size-independent
+    property checked at the full benchmark shape."""
+    B, T, H, d = 4096, 16, 8, 64
+    S, F = T + 1, H * d
+    qkv = rnd(B * S, 3 * F, dt=torch.bfloat16, seed=21)
+    o1, _ = ops.mha_fwd(qkv, None, B, T, H, d)
+    q2 = qkv.clone()
+    q2.view(B * S, 3, F)[:, 2] *= 2                      # exact in bf16
+    o2, _ = ops.mha_fwd(q2, None, B, T, H, d)
+    assert torch.equal(o2.float(), 2 * o1.float())
+    do = rnd(B * S, F, dt=torch.bfloat16, seed=22)
+    g1 = ops.mha_bwd(qkv, None, do, B, T, H, d)
+    g2 = ops.mha_bwd(qkv, None, do * 2, B, T, H, d)
+    assert torch.equal(g2.float(), 2 * g1.float())
+    # every sample is independent: a permutation of the batch permutes the outputs
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(DEV)
+    op, _ = ops.mha_fwd(qkv.view(B, S, 3 * F)[perm].reshape(B * S, 3 * F).contiguous(), None, B, T, H, d)
+    assert torch.equal(op.view(B, S, F), o1.view(B, S, F)[perm])
+
+
 # ----------------------------------------------------------------------------- head + loss
 @pytest.mark.parametrize("dt", DT)
 def test_head_out_fwd_bwd(dt):

@@ -1,0 +1,106 @@
+"""Per-kernel timing at the cfg2 shapes (B=4096, T=16, F=512): CUDA events on the launching stream, rotating
+buffers larger than L2, algorithmic bytes / time against the measured HBM peak.
+
+  python tools/kernel_bench.py [mha] [add_ln] [colsum] [embed] [pool] [adam] [head]     (default: all)
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mmer_b200 import _lib, ops  # noqa: E402
+
+dev = torch.device("cuda")
+B, T, H, D, F, FF = 4096, 16, 8, 64, 512, 2048
+S = T + 1
+M = B * S
+bf = torch.bfloat16
+NBUF = 3   # rotating sets: every kernel below touches >= 140 MB per launch, 3 sets > 126 MB L2 by a wide margin
+
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def rnd(*s, dt=bf):
+    return torch.randn(*s, device=dev, generator=g).to(dt)
+
+
+def timeit(name, fns, bytes_per_launch, reps=20):
+    """fns: list of NBUF closures, each launching the kernel once on its own buffer set"""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fns[i % len(fns)]()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    gbs = bytes_per_launch / us * 1e-3
+    print(f"{name:34s} {us:8.1f} us   {bytes_per_launch / 1e6:8.1f} MB   {gbs:7.0f} GB/s   {gbs / PEAK:5.2f} of measured HBM peak")
+    return us
+
+
+def bench_mha():
+    lib = _lib.load()
+    sets = [(rnd(M, 3 * F), rnd(M, F)) for _ in range(NBUF)]
+    fb = M * 3 * F * 2 + M * F * 2
+    bb = 2 * M * 3 * F * 2 + M * F * 2
+    for simt in (0, 1):
+        lib.mmer_debug_set(_lib.DEBUG_ATT_SIMT, simt)
+        tag = "simt" if simt else "mma"
+        for p in (0.0, 0.1):
+            timeit(f"mha_fwd[{tag}] p={p}", [lambda q=q: ops.mha_fwd(q, None, B, T, H, D, drop_p=p, seed=1, site=1)
+                                             for q, _ in sets], fb)
+            timeit(f"mha_bwd[{tag}] p={p}", [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=p, seed=1, site=1)
+                                             for q, d in sets], bb)
+    lib.mmer_debug_set(_lib.DEBUG_ATT_SIMT, 0)
+
+
+def bench_add_ln():
+    gam, bet = torch.ones(F, device=dev), torch.zeros(F, device=dev)
+    dg, db, dbias = (torch.zeros(F, device=dev) for _ in range(3))
+    sets = [(rnd(M, F), rnd(M, F), rnd(M, F)) for _ in range(NBUF)]
+    stats = ops.add_ln_fwd(sets[0][0], sets[0][1], gam, bet)[1]
+    e = 2
+    for p in (0.0, 0.1):
+        timeit(f"add_ln_fwd p={p}", [lambda x=x, a=a: ops.add_ln_fwd(x, a, gam, bet, drop_a_p=p, site_a=1, seed=1)
+                                     for x, a, _ in sets], 3 * M * F * e)
+        nb = (5 if p > 0 else 4) * M * F * e
+        timeit(f"add_ln_bwd p={p}",
+               [lambda x=x, a=a, dy=dy: ops.add_ln_bwd(dy, x, a, stats, gam, bet, dg, db, dbias, drop_a_p=p, site_a=1, seed=1)
+                for x, a, dy in sets], nb)
+
+
+def bench_colsum():
+    for N in (512, 1536, 2048):
+        sets = [rnd(M, N) for _ in range(NBUF)]
+        out = torch.zeros(N, device=dev)
+        timeit(f"colsum N={N}", [lambda x=x: ops.colsum(x, out) for x in sets], M * N * 2)
+
+
+def bench_adam():
+    n = 7_765_510
+    p, gr, m, v = (torch.randn(n, device=dev) for _ in range(4))
+    v.abs_()
+    sh = torch.empty(n, device=dev, dtype=bf)
+    timeit("adam (7.77M params, 30 B each)", [lambda: ops.adam_step(p, gr, m, v, sh, 3, 1e-4, weight_decay=1e-4)], n * 30, reps=50)
+
+
+def main():
+    which = sys.argv[1:] or ["mha", "add_ln", "colsum", "adam"]
+    print(torch.cuda.get_device_name(0), f"HBM peak {PEAK:.0f} GB/s (measured)")
+    for w in which:
+        {"mha": bench_mha, "add_ln": bench_add_ln, "colsum": bench_colsum, "adam": bench_adam}[w]()
+
+
+if __name__ == "__main__":
+    main()
