@@ -140,7 +140,7 @@ mha_fwd_generic_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ ma
           float p = s[t] * inv;
           if (j < S) {
             if (probs) probs[bh * S * S + (long long)i * S + j] = p;
-            if (dc.thr) p *= drop1(dc, (uint64_t)(bh * S * S + (long long)i * S + j));
+            if (dc.thr) p *= drop1(dc, att_drop_index(bh * S + i, j, att_drop_stride(S)));
           } else {
             p = 0.f;
           }
@@ -212,7 +212,7 @@ mha_bwd_generic_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ ma
         dp[t] = 0.f;
         if (j < S) {
           dp[t] = ga_dot<D>(vec, M2 + (size_t)j * RP);
-          if (dc.thr) dp[t] *= drop1(dc, (uint64_t)(bh * S * S + (long long)i * S + j));
+          if (dc.thr) dp[t] *= drop1(dc, att_drop_index(bh * S + i, j, att_drop_stride(S)));
         }
       }
       sum = warp_sum(sum);
@@ -269,7 +269,7 @@ mha_bwd_generic_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ ma
           float ds = 0.f, pd = 0.f;
           if (i < S) {
             float f = 1.f;
-            if (dc.thr) f = drop1(dc, (uint64_t)(bh * S * S + (long long)i * S + j));
+            if (dc.thr) f = drop1(dc, att_drop_index(bh * S + i, j, att_drop_stride(S)));
             const float dpv = ga_dot<D>(vec, M2 + (size_t)i * RP) * f;
             ds = p[t] * (dpv - st_dot[i]) * scale;
             pd = p[t] * f;

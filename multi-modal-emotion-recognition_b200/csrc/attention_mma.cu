@@ -199,17 +199,22 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int i = mt * 16 + g + 8 * r;
+          if (i < S) {
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = nt * 8 + t * 2 + e;
-              if (i < S && j < S) {
-                const long long idx = bh * S * S + (long long)i * S + j;
-                if (probs != nullptr) probs[idx] = p[mt][nt][r * 2 + e];
-                if (dc.thr) p[mt][nt][r * 2 + e] *= drop1(dc, (uint64_t)idx);
+            for (int nt = 0; nt < NT; ++nt) {
+              const int j = nt * 8 + t * 2;
+              if (probs != nullptr) {
+                if (j < S) probs[(bh * S + i) * S + j] = p[mt][nt][r * 2];
+                if (j + 1 < S) probs[(bh * S + i) * S + j + 1] = p[mt][nt][r * 2 + 1];
+              }
+              if (dc.thr) {
+                float f0, f1;
+                drop2(dc, att_drop_index(bh * S + i, j, NT * 8), f0, f1);
+                p[mt][nt][r * 2] *= f0;
+                p[mt][nt][r * 2 + 1] *= f1;
               }
             }
+          }
         }
     }
     uint32_t pa[MT][(NT + 1) / 2][4];
@@ -315,17 +320,17 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
         float f[NT][2];
         float dot = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
+        for (int nt = 0; nt < NT; ++nt) {
+          f[nt][0] = 1.f;
+          f[nt][1] = 1.f;
+          if (dc.thr && row_ok) drop2(dc, att_drop_index(bh * S + i, nt * 8 + t * 2, NT * 8), f[nt][0], f[nt][1]);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int j = nt * 8 + t * 2 + e;
-            float fe = 1.f;
-            if (dc.thr && row_ok && j < S) fe = drop1(dc, (uint64_t)(bh * S * S + (long long)i * S + j));
-            f[nt][e] = fe;
-            const float dpm = dp[mt][nt][r * 2 + e] * fe;
+            const float dpm = dp[mt][nt][r * 2 + e] * f[nt][e];
             dp[mt][nt][r * 2 + e] = dpm;
             dot = fmaf(dpm, p[mt][nt][r * 2 + e], dot);
           }
+        }
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         dot += __shfl_xor_sync(0xffffffffu, dot, 2);
 #pragma unroll

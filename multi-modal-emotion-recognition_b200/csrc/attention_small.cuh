@@ -168,7 +168,7 @@ mha_fwd_small_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ mask
       for (int j = 0; j < S; ++j) {
         float p = row[j] * inv;
         if (pg) pg[j] = p;
-        if (dc.thr) p *= drop1(dc, (uint64_t)(bh * S * S + lane * S + j));
+        if (dc.thr) p *= drop1(dc, att_drop_index(bh * S + lane, j, att_drop_stride(S)));
         row[j] = p;
       }
       for (int j = S; j < SP; ++j) row[j] = 0.f;
@@ -229,7 +229,7 @@ mha_bwd_small_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ mask
         for (int j = 0; j < S; ++j) {
           const float p = prow[j] * inv;
           float f = 1.f;
-          if (dc.thr) f = drop1(dc, (uint64_t)(bh * S * S + lane * S + j));
+          if (dc.thr) f = drop1(dc, att_drop_index(bh * S + lane, j, att_drop_stride(S)));
           const float dp = drow[j] * f;
           dot = fmaf(dp, p, dot);
           drow[j] = dp;

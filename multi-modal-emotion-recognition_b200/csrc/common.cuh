@@ -93,16 +93,20 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------
-// counter-based dropout.  One 32-bit hash of (seed, site, index/2) yields two
-// 16-bit uniforms; an element is KEPT when its uniform >= thr, thr = p * 65536.
-// Forward and backward regenerate the same decision from the element index, so
-// no mask is ever stored.  (torch's Philox stream cannot be matched bit for bit;
-// parity tests run with p = 0 and dropout is tested statistically.)
+// counter-based dropout.  Elements are grouped in octets (8 consecutive indices, the
+// width of one 16-byte bf16 access).  One 32-bit mix of (seed, site, octet index) is
+// expanded into four words, i.e. eight 16-bit uniforms; an element is KEPT when its
+// uniform >= thr, thr = p * 65536.  Forward and backward regenerate the same decision
+// from the element index, so no mask is ever stored.  About 4 integer instructions per
+// element, which keeps the GEMM epilogues and the row kernels off the issue limit.
+// (torch's Philox stream cannot be matched bit for bit; parity tests run with p = 0 and
+// dropout is tested statistically.)  Tensors of up to 2^35 elements per site.
 // ---------------------------------------------------------------------------
 struct DropCfg {
   uint32_t thr;     // 0 => disabled
   float scale;      // 1 / (1 - thr/65536)
   uint32_t key;     // seed mixed with the site id
+  uint32_t thr_hi;  // thr << 16
 };
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
@@ -110,31 +114,56 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 }
 __host__ inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
   DropCfg d;
-  if (!(p > 0.f)) { d.thr = 0; d.scale = 1.f; d.key = 0; return d; }
+  if (!(p > 0.f)) { d.thr = 0; d.scale = 1.f; d.key = 0; d.thr_hi = 0; return d; }
   uint32_t thr = (uint32_t)(p * 65536.f + 0.5f);
   if (thr > 65535u) thr = 65535u;
   d.thr = thr;
+  d.thr_hi = thr << 16;
   d.scale = 65536.f / (float)(65536u - thr);
   d.key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u * (site + 1u)));
   return d;
 }
-// keep-mask bits for the element pair (2*pair, 2*pair+1): bit0, bit1
-__device__ __forceinline__ uint32_t drop_pair(const DropCfg& d, uint64_t pair) {
-  const uint32_t h = mix32(((uint32_t)pair ^ d.key) + (uint32_t)(pair >> 32) * 0x85EBCA77u);
-  return ((h & 0xFFFFu) >= d.thr ? 1u : 0u) | ((h >> 16) >= d.thr ? 2u : 0u);
+// well-mixed 32-bit value of one octet
+__device__ __forceinline__ uint32_t drop_base(const DropCfg& d, uint32_t octet) {
+  uint32_t a = (octet ^ d.key) * 0x9E3779B1u;
+  a ^= a >> 16; a *= 0x7feb352dU; a ^= a >> 15;
+  return a;
 }
+// word k (0..3) of an octet: uniforms of elements 2k (low half) and 2k+1 (high half)
+__device__ __forceinline__ uint32_t drop_mult(int k) {
+  return k == 0 ? 0x846ca68bU : k == 1 ? 0xc2b2ae35U : k == 2 ? 0x85ebca6bU : 0x27d4eb2fU;
+}
+__device__ __forceinline__ uint32_t drop_word(uint32_t base, uint32_t mult) {
+  uint32_t w = base * mult;
+  return w ^ (w >> 16);
+}
+__device__ __forceinline__ float drop_lo(const DropCfg& d, uint32_t w) { return (w << 16) >= d.thr_hi ? d.scale : 0.f; }
+__device__ __forceinline__ float drop_hi(const DropCfg& d, uint32_t w) { return w >= d.thr_hi ? d.scale : 0.f; }
 // multiplicative factors for 8 consecutive elements starting at idx (idx % 8 == 0)
 __device__ __forceinline__ void drop8(const DropCfg& d, uint64_t idx, float (&f)[8]) {
+  const uint32_t a = drop_base(d, (uint32_t)(idx >> 3));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t m = drop_pair(d, (idx >> 1) + i);
-    f[2 * i] = (m & 1u) ? d.scale : 0.f;
-    f[2 * i + 1] = (m & 2u) ? d.scale : 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t w = drop_word(a, drop_mult(k));
+    f[2 * k] = drop_lo(d, w);
+    f[2 * k + 1] = drop_hi(d, w);
   }
 }
+// factors of the aligned element pair (idx, idx + 1), idx even
+__device__ __forceinline__ void drop2(const DropCfg& d, uint64_t idx, float& f0, float& f1) {
+  const uint32_t w = drop_word(drop_base(d, (uint32_t)(idx >> 3)), drop_mult((int)((idx >> 1) & 3)));
+  f0 = drop_lo(d, w);
+  f1 = drop_hi(d, w);
+}
 __device__ __forceinline__ float drop1(const DropCfg& d, uint64_t idx) {
-  uint32_t m = drop_pair(d, idx >> 1);
-  return ((m >> (idx & 1)) & 1u) ? d.scale : 0.f;
+  const uint32_t w = drop_word(drop_base(d, (uint32_t)(idx >> 3)), drop_mult((int)((idx >> 1) & 3)));
+  return (idx & 1) ? drop_hi(d, w) : drop_lo(d, w);
+}
+// element index of attention probability (head-row `bhi` = (b*H + h)*S + i, key j): rows are padded to a multiple
+// of 8 keys so that an octet never straddles two rows (every attention kernel must use this)
+__host__ __device__ __forceinline__ int att_drop_stride(int S) { return (S + 7) & ~7; }
+__device__ __forceinline__ uint64_t att_drop_index(long long bhi, int j, int stride) {
+  return (uint64_t)(bhi * stride + j);
 }
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

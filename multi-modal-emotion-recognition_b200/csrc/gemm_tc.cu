@@ -36,33 +36,101 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-CTA pair: the copy lands in this CTA's shared memory, its bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1)
                : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): TMEM reads are ordered by
+  // tcgen05.fence::before_thread_sync, no cluster-scope memory fence is needed (and it is expensive)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
+// arrive on the mbarrier at this shared-memory offset once all previously issued MMAs have completed; with a CTA
+// pair the arrival is multicast to the same barrier in both CTAs
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -105,35 +173,53 @@ struct GemmParams {
   DropCfg drop;
 };
 
+// MMER_GEMM_PROFILE: per-role cycle accounting printed by CTA 0 (tools/ builds only, never the shipped library)
+#ifdef MMER_GEMM_PROFILE
+#define PROF_DECL(n) long long prof_t[n] = {0}; long long prof_c = clock64(); (void)prof_c
+#define PROF_TICK(i) do { long long _n = clock64(); prof_t[i] += _n - prof_c; prof_c = _n; } while (0)
+#else
+#define PROF_DECL(n)
+#define PROF_TICK(i)
+#endif
 static constexpr int EPI_WARPS = 8;
+#ifndef MMER_EPI_BUFS
+#define MMER_EPI_BUFS 2
+#endif
 static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
-template <int BN>
+// BN is the N extent of the accumulator tile.  CG = 1: one CTA computes 128 x BN.  CG = 2: a CTA pair computes
+// 256 x BN with cta_group::2 MMAs; each CTA loads its own 128 rows of A and HALF of the B tile (BN/2 rows), so the
+// L2 -> shared-memory traffic per MMA drops from 48 KB to 32 KB per CTA and k-block at BN = 256.
+template <int BN, int CG, bool STAGED>
 struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int EPI_BYTES = EPI_WARPS * 4096;  // per warp: one 32-row x 64-column bf16 tile (128 B rows)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // staged epilogue: per warp EPI_BUFS 32-row x 64-column bf16 tiles (128 B rows; two of them double-buffer the
+  // TMA store that drains them); per column half and tile parity one fp32 bias slice of BN/2 columns
+  static constexpr int EPI_TILE = 4096;
+  static constexpr int EPI_BUFS = MMER_EPI_BUFS;
+  static constexpr int BIAS_BYTES = STAGED ? 2 * 2 * (BN / 2) * 4 : 0;
+  static constexpr int EPI_BYTES = STAGED ? EPI_WARPS * EPI_BUFS * EPI_TILE : 0;
+  static constexpr int FIXED_BYTES = EPI_BYTES + BIAS_BYTES + 256 /*barriers*/;
+  static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 8 <= 256, "barrier area");
 };
 
-// element-wise part of the epilogue on 8 consecutive accumulator columns of one row
-__device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], int col, long long off, bool full8) {
-  if (p.bias) {
-    if (full8) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
-    }
+// element-wise part of the staged epilogue on 8 consecutive accumulator columns of one row; `bias8` points at the
+// 8 bias values in shared memory (zero-filled beyond N), or is null
+__device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], const float* bias8, long long off) {
+  if (bias8 != nullptr) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
   if (p.relu) {
 #pragma unroll
@@ -147,15 +233,20 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], in
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
-  using C = TileCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using C = TileCfg<BN, CG, STAGED>;
+  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment: the dynamic shared window is declared (and checked) so
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("mmer gemm_tc: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
+  float* bias_smem = reinterpret_cast<float*>(epi_smem + C::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES + C::BIAS_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4..2S+12) aux, then tmem slot
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
@@ -166,6 +257,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // CTA of the pair; rank 0 leads (issues the MMAs)
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent work unit (CTA or CTA pair)
+  const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -174,62 +268,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, EPI_WARPS);
+      mbar_init(bar_tempty + 8 * b, EPI_WARPS * CG);   // the epilogue warps of both CTAs release the leader's MMA issuer
     }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(bar_aux + 8 * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (STAGED) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
     if (p.aux_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), C::TMEM_COLS);
+  if (warp == 1) tmem_alloc<CG>(smem_u32((const void*)tmem_slot), C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_items = p.num_m * p.num_n * p.splits;
+  const int total_items = p.num_m * p.num_n * p.splits;   // num_m counts (CG*128)-row blocks
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      PROF_DECL(2);
+      for (int item = unit; item < total_items; item += num_units) {
         const int n_blk = item % p.num_n;
         const int t = item / p.num_n;
         const int m_blk = t % p.num_m;
         const int split = t / p.num_m;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = (m_blk * CG + (int)rank) * BM;            // this CTA's rows of A
+        const int n0 = n_blk * BN + (int)rank * C::B_ROWS;       // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
+          PROF_TICK(1);
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, C::STAGE_BYTES);
+          PROF_TICK(0);
+          uint32_t full = bar_full + 8 * stage;
+          if (rank == 0) mbar_expect_tx(full, C::STAGE_BYTES * CG);   // the leader's barrier counts both CTAs' bytes
+          if (CG == 2) full = mapa_u32(full, 0);
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+            if (CG == 2) tma_load_2d_cg2(dst, map, full, c0, c1); else tma_load_2d(dst, map, full, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tmA, full, kb * BK, m_blk * BM);
+            load(sa, &tmA, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, full, m_blk * BM + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) load(sa + c * (BK * 128), &tmA, m0 + c * 64, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, full, kb * BK, n_blk * BN);
+            load(sb, &tmB, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, full, n_blk * BN + c * 64, kb * BK);
+            for (int c = 0; c < C::B_ROWS / 64; ++c) load(sb + c * (BK * 128), &tmB, n0 + c * 64, kb * BK);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+#ifdef MMER_GEMM_PROFILE
+      if (blockIdx.x == 0) printf("producer: wait_empty %lld issue %lld\n", prof_t[0], prof_t[1]);
+#endif
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major SW128: 64-element column
       // blocks BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO).
       const uint32_t mn_lbo = p.mn_swap ? 1024u : (uint32_t)(BK * 128);
@@ -242,15 +348,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int buf = 0;
       uint32_t tphase[2] = {0, 0};
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      PROF_DECL(3);
+      for (int item = unit; item < total_items; item += num_units) {
         const int split = (item / p.num_n) / p.num_m;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        PROF_TICK(2);
         mbar_wait(bar_tempty + 8 * buf, tphase[buf] ^ 1);
+        PROF_TICK(0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
+          PROF_TICK(2);
           mbar_wait(bar_full + 8 * stage, phase);
+          PROF_TICK(1);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
@@ -258,16 +369,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          umma_commit<CG>(bar_empty + 8 * stage);  // frees the smem stage (in both CTAs) when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * buf);  // accumulator complete
+        umma_commit<CG>(bar_tfull + 8 * buf);  // accumulator complete (published to both CTAs' epilogues)
         tphase[buf] ^= 1;
         buf ^= 1;
       }
+#ifdef MMER_GEMM_PROFILE
+      if (blockIdx.x == 0) printf("mma: wait_tmem_empty %lld wait_smem_full %lld issue %lld\n", prof_t[0], prof_t[1], prof_t[2]);
+#endif
     }
   } else {
     // ===================================================== epilogue (warps 2..9)
@@ -277,62 +391,125 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 2;
     const int q = warp & 3;
     const int hsel = ew >> 2;
-    uint8_t* stg = epi_smem + ew * 4096;
+    // staging tiles are 1024-byte aligned, as the 128B swizzle pattern assumes
+    uint8_t* stg = epi_smem + ew * (C::EPI_BUFS * C::EPI_TILE);
     const uint32_t stg_u32 = smem_u32(stg);
     const uint32_t auxbar = bar_aux + 8 * ew;
     uint32_t aux_phase = 0;
+    uint32_t it = 0;   // staging-tile parity
+    bool aux_prefetched = false;
+    const float* bias_rd = nullptr;
+    float* bias_s = nullptr;
+    float4 bias_reg = make_float4(0.f, 0.f, 0.f, 0.f);
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     const bool vec_ok = (p.ldd % 8 == 0);
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const uint32_t tempty_leader = CG == 2 ? mapa_u32(bar_tempty, 0) : bar_tempty;
+    PROF_DECL(6);
+    for (int item = unit; item < total_items; item += num_units) {
       const int n_blk = item % p.num_n;
       const int m_blk = (item / p.num_n) % p.num_m;
-      const int row0 = m_blk * BM + q * 32;
+      const int row0 = (m_blk * CG + (int)rank) * BM + q * 32;
       const long long row = (long long)row0 + lane;
       const bool row_ok = row < p.M;
-      if (p.aux_mode && lane < HALF / 64) {
-        // warm L2 with this tile's gate / residual sub-tiles while the MMAs of the tile are still running
-        const int pc = n_blk * BN + hsel * HALF + lane * 64;
-        if (pc < p.N && row0 < p.M)
-          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmX), "r"(pc), "r"(row0)
-                       : "memory");
+      if (STAGED) {
+        if (p.aux_mode && lane < HALF / 64) {
+          // warm L2 with this tile's gate / residual sub-tiles while the MMAs of the tile are still running
+          const int pc = n_blk * BN + hsel * HALF + lane * 64;
+          if (pc < p.N && row0 < p.M)
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmX), "r"(pc), "r"(row0)
+                         : "memory");
+        }
+        if (p.bias) {
+          // the bias slice of this warp's column half (HALF <= 128 values: one float4 per lane) is fetched before
+          // the wait for the accumulator and parked in shared memory after it (read back as broadcasts; zero beyond
+          // N).  The four warps of a column half write identical values into the same slot; slots alternate with
+          // the accumulator buffer.
+          bias_s = bias_smem + (buf * 2 + hsel) * HALF;
+          const int c = lane * 4;
+          if (c < HALF) {
+            const int col = n_blk * BN + hsel * HALF + c;
+            if (col + 4 <= p.N) {
+              bias_reg = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            } else {
+              bias_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col < p.N) bias_reg.x = __ldg(p.bias + col);
+              if (col + 1 < p.N) bias_reg.y = __ldg(p.bias + col + 1);
+              if (col + 2 < p.N) bias_reg.z = __ldg(p.bias + col + 2);
+            }
+          }
+        }
       }
+      PROF_TICK(5);
       mbar_wait(bar_tfull + 8 * buf, tphase[buf]);
+      PROF_TICK(0);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hsel * HALF);
-      if (p.tma_store) {
+      if (STAGED && p.bias) {
+        // the accumulator of this buffer is ready => every warp has left the tile that last used this bias slot
+        if (lane * 4 < HALF) *reinterpret_cast<float4*>(bias_s + lane * 4) = bias_reg;
+        bias_rd = bias_s;
+        __syncwarp();
+      }
+      if (STAGED) {
         // ---- bf16 output: registers -> 128B-swizzled smem tile (32 rows x 64 columns) -> TMA store
 #pragma unroll 1
         for (int j = 0; j < HALF / 64; ++j) {
           const int col0 = n_blk * BN + hsel * HALF + j * 64;
           if (col0 >= p.N) break;
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has drained the tile
+          const uint32_t tsel = C::EPI_BUFS == 2 ? (it & 1u) : 0u;
+          uint8_t* tile = stg + tsel * C::EPI_TILE;
+          const uint32_t tile_u32 = stg_u32 + tsel * C::EPI_TILE;
+          ++it;
+          if (lane == 0 && !aux_prefetched) {
+            // the last store that read this staging tile has drained it
+            if (C::EPI_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (p.aux_mode) {
               mbar_expect_tx(auxbar, 4096);
-              tma_load_2d(stg_u32, &tmX, auxbar, col0, row0);
+              tma_load_2d(tile_u32, &tmX, auxbar, col0, row0);
             }
           }
+          aux_prefetched = false;
           __syncwarp();
+          PROF_TICK(1);
+          uint32_t r[2][32];
+          tmem_ld32_nowait(trow + (uint32_t)(j * 64), r[0]);
+          tmem_ld32_nowait(trow + (uint32_t)(j * 64 + 32), r[1]);
+          tmem_ld_wait();
+          PROF_TICK(2);
+          if (p.aux_mode) {
+            mbar_wait(auxbar, aux_phase);
+            aux_phase ^= 1;
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t r[32];
-            tmem_ld32(trow + (uint32_t)(j * 64 + h * 32), r);
-            if (p.aux_mode && h == 0) {
-              mbar_wait(auxbar, aux_phase);
-              aux_phase ^= 1;
+            // bias values of the 32 columns first (broadcast reads), so that no shared-memory load has to be ordered
+            // behind the staging-tile stores below
+            float4 bv[8];
+            if (bias_rd != nullptr) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) bv[g] = *reinterpret_cast<const float4*>(bias_rd + j * 64 + h * 32 + g * 4);
+            }
+            uint4 xr[4];
+            if (p.aux_mode) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                xr[g] = *reinterpret_cast<const uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4));
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int col = col0 + h * 32 + g * 8;
               float v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              epi_math8(p, v, col, row * p.ldd + col, col + 8 <= p.N);
-              uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4));
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h][g * 8 + i]);
+              if (bias_rd != nullptr) {
+                v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
+                v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
+              }
+              epi_math8(p, v, nullptr, row * p.ldd + col);
               if (p.aux_mode) {
-                const uint4 xr = *slot;
-                const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
+                const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr[g]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 xf = __bfloat1622float2(xh[i]);
@@ -349,15 +526,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
               for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              *slot = pk;
+              *reinterpret_cast<uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4)) = pk;
             }
           }
+          PROF_TICK(3);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmD, stg_u32, col0, row0);
+            tma_store_2d(&tmD, tile_u32, col0, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (C::EPI_BUFS == 2 && p.aux_mode) {
+            // fetch the gate / residual tile of the NEXT sub-tile into the other staging tile now, so that its
+            // latency is covered by this sub-tile's store and the next accumulator wait
+            int ncol = col0 + 64, nrow = row0;
+            bool have = (j + 1 < HALF / 64) && ncol < p.N;
+            if (!have) {
+              const int nitem = item + num_units;
+              if (nitem < total_items) {
+                ncol = (nitem % p.num_n) * BN + hsel * HALF;
+                nrow = (((nitem / p.num_n) % p.num_m) * CG + (int)rank) * BM + q * 32;
+                have = ncol < p.N;
+              }
+            }
+            if (have) {
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store before this one has drained
+                mbar_expect_tx(auxbar, 4096);
+                tma_load_2d(stg_u32 + (it & 1u) * C::EPI_TILE, &tmX, auxbar, ncol, nrow);
+              }
+              aux_prefetched = true;
+            }
+          }
+          PROF_TICK(4);
         }
       } else {
         // ---- direct path: fp32 outputs, split-K accumulation (fp32 vector atomics), unaligned leading dims
@@ -446,16 +647,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * buf); else mbar_arrive(bar_tempty + 8 * buf);
+      }
       tphase[buf] ^= 1;
       buf ^= 1;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef MMER_GEMM_PROFILE
+    if (blockIdx.x == 0 && lane == 0)
+      printf("epi warp %d: wait_tmem_full %lld wait_store_drain %lld tmem_ld %lld math %lld fence+store %lld other %lld\n", ew,
+             prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5]);
+#endif
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // no CTA of a pair leaves while its peer may still signal it
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -523,18 +731,35 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                   const GemmParams& p, int grid, cudaStream_t st) {
-  using C = TileCfg<BN>;
+  using C = TileCfg<BN, CG, STAGED>;
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, STAGED>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
     attr_done = true;
   }
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, td, tx, p);
+  if (CG == 1) {
+    kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, td, tx, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, p);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc, CTA pair)");
+  }
   MMER_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -551,17 +776,31 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   MMER_CHECK_ARG(!(a.a_major == MMER_MAJOR_MN && a.b_major == MMER_MAJOR_K), "gemm_tc: (MN,K) operand majors unused");
 
   const int nsm = sm_count();
-  const int num_m = ceil_div(a.M, BM);
+  // CTA pairs (cta_group::2, 256 x 256 tiles) whenever the problem offers enough of them to fill the machine;
+  // otherwise single CTAs with 128 x 256 or 128 x 128 tiles.
+  const int pairs = nsm / 2;
+  int cg = 1;
   int bn = 256;
-  if ((long long)num_m * ceil_div(a.N, 256) < nsm && a.N > 128 && !a.accumulate) bn = 128;
-  if (a.N <= 128) bn = 128;
-  if (g_debug[MMER_DEBUG_FORCE_BN] == 128 || g_debug[MMER_DEBUG_FORCE_BN] == 256) bn = g_debug[MMER_DEBUG_FORCE_BN];
+  {
+    const long long pair_tiles = (long long)ceil_div(a.M, 2 * BM) * ceil_div(a.N, 256);
+    const long long kb = ceil_div(a.K, BK);
+    const bool enough = a.accumulate ? (pair_tiles * (kb / 8 > 0 ? kb / 8 : 1) >= pairs / 2) : (pair_tiles >= pairs);
+    if (a.M >= 2 * BM && a.N > 128 && enough && g_debug[MMER_DEBUG_NO_PAIR] == 0) cg = 2;
+  }
+  const int bm_eff = BM * cg;
+  const int num_m = ceil_div(a.M, bm_eff);
+  if (cg == 1) {
+    if ((long long)num_m * ceil_div(a.N, 256) < nsm && a.N > 128 && !a.accumulate) bn = 128;
+    if (a.N <= 128) bn = 128;
+    if (g_debug[MMER_DEBUG_FORCE_BN] == 128 || g_debug[MMER_DEBUG_FORCE_BN] == 256) bn = g_debug[MMER_DEBUG_FORCE_BN];
+  }
+  const int units = cg == 2 ? pairs : nsm;
   const int num_n = ceil_div(a.N, bn);
   const int kb_total = ceil_div(a.K, BK);
   int splits = 1;
   if (a.accumulate) {
     const int tiles = num_m * num_n;
-    int want = nsm / tiles;
+    int want = units / tiles;
     if (want < 1) want = 1;
     const int max_by_k = kb_total / 8 > 0 ? kb_total / 8 : 1;  // at least 8 k-blocks per split
     if (want > max_by_k) want = max_by_k;
@@ -577,7 +816,7 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
     MMER_TRY(make_map(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, BK));
   }
   if (a.b_major == MMER_MAJOR_K) {
-    MMER_TRY(make_map(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)bn));
+    MMER_TRY(make_map(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(bn / cg)));
   } else {
     MMER_TRY(make_map(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, BK));
   }
@@ -603,18 +842,24 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   p.mn_swap = g_debug[MMER_DEBUG_MN_SWAP];
   p.drop = make_drop(a.drop_p, a.seed, a.drop_site);
   long long items = (long long)num_m * num_n * splits;
-  int grid = (int)(items < nsm ? items : nsm);
+  int grid = (int)(items < units ? items : units) * cg;
 
   const bool amn = a.a_major == MMER_MAJOR_MN, bmn = a.b_major == MMER_MAJOR_MN;
-  if (bn == 256) {
-    if (!amn && !bmn) return launch<256, false, false>(ta, tb, td, tx, p, grid, st);
-    if (!amn && bmn) return launch<256, false, true>(ta, tb, td, tx, p, grid, st);
-    return launch<256, true, true>(ta, tb, td, tx, p, grid, st);
-  } else {
-    if (!amn && !bmn) return launch<128, false, false>(ta, tb, td, tx, p, grid, st);
-    if (!amn && bmn) return launch<128, false, true>(ta, tb, td, tx, p, grid, st);
-    return launch<128, true, true>(ta, tb, td, tx, p, grid, st);
-  }
+#define MMER_GEMM_LAUNCH(BN_, CG_)                                                                             \
+  do {                                                                                                         \
+    if (tma_store) {                                                                                           \
+      if (!amn && !bmn) return launch<BN_, false, false, CG_, true>(ta, tb, td, tx, p, grid, st);              \
+      if (!amn && bmn) return launch<BN_, false, true, CG_, true>(ta, tb, td, tx, p, grid, st);                \
+      return launch<BN_, true, true, CG_, true>(ta, tb, td, tx, p, grid, st);                                  \
+    }                                                                                                          \
+    if (!amn && !bmn) return launch<BN_, false, false, CG_, false>(ta, tb, td, tx, p, grid, st);               \
+    if (!amn && bmn) return launch<BN_, false, true, CG_, false>(ta, tb, td, tx, p, grid, st);                 \
+    return launch<BN_, true, true, CG_, false>(ta, tb, td, tx, p, grid, st);                                   \
+  } while (0)
+  if (cg == 2) MMER_GEMM_LAUNCH(256, 2);
+  if (bn == 256) MMER_GEMM_LAUNCH(256, 1);
+  MMER_GEMM_LAUNCH(128, 1);
+#undef MMER_GEMM_LAUNCH
 }
 
 }  // namespace mmer

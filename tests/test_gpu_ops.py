@@ -94,6 +94,49 @@ def test_gemm_staged_epilogue_many_tiles(shape):
             _lib.load().mmer_debug_set(_lib.DEBUG_FORCE_BN, 0)
 
 
+@pytest.mark.parametrize("shape", [(4096 + 140, 2560 + 72, 200), (20000, 1536, 512), (69632, 512, 128)])
+@pytest.mark.parametrize("majors", [(0, 0), (0, 1)])
+def test_gemm_cta_pair_matches_single_cta_and_reference(shape, majors):
+    """Large problems run as CTA pairs (cta_group::2, 256 x 256 tiles, B tile split between the two CTAs).  Same
+    operands through the single-CTA kernel (debug knob) and through fp64: ragged M (the second CTA of the last pair
+    is partly or wholly out of range), ragged N and K, every epilogue variant."""
+    M, N, K = shape
+    A, B = rnd(M, K, dt=torch.bfloat16, seed=41), rnd(N, K, dt=torch.bfloat16, seed=42)
+    Bs = B if majors[1] == 0 else B.t().contiguous()
+    res = rnd(M, N, dt=torch.bfloat16, seed=43)
+    bias = rnd(N, seed=44)
+    acc = (A.float() @ B.float().t()).double()
+    lib = _lib.load()
+    outs = {}
+    try:
+        for nopair in (0, 1):
+            lib.mmer_debug_set(_lib.DEBUG_NO_PAIR, nopair)
+            kw = dict(M=M, N=N, K=K, b_major=majors[1])
+            outs[nopair] = [
+                ops.gemm(A, Bs, bias=bias, **kw),
+                ops.gemm(A, Bs, bias=bias, relu=True, drop_p=0.1, seed=3, site=2, **kw),
+                ops.gemm(A, Bs, residual=res, **kw),
+                ops.gemm(A, Bs, gate=res, gate_scale=1.5, **kw),
+                ops.gemm(A, Bs, out_dtype=torch.float32, **kw),
+            ]
+    finally:
+        lib.mmer_debug_set(_lib.DEBUG_NO_PAIR, 0)
+    refs = [acc + bias.double(), None, acc + res.double(), acc * (res.double() > 0) * 1.5, acc]
+    for i, (a, b) in enumerate(zip(outs[0], outs[1])):
+        assert torch.equal(a, b), f"variant {i}: CTA-pair result differs from the single-CTA result"
+        if refs[i] is not None:
+            assert rel(a, refs[i]) < 6e-3
+
+
+def test_gemm_cta_pair_wgrad_split_k():
+    Mtok, N, K = 69632 + 24, 1536, 512     # dW[N,K] += dY^T X at the cfg2 in_proj shape, ragged reduction length
+    dy, x = rnd(Mtok, N, dt=torch.bfloat16, seed=8, scale=0.05), rnd(Mtok, K, dt=torch.bfloat16, seed=9)
+    out = torch.full((N, K), 0.5, device=DEV)
+    ops.linear_wgrad(dy, x, out)
+    ref = (dy.float().t() @ x.float()).double() + 0.5
+    assert rel(out, ref) < 4e-3
+
+
 @pytest.mark.parametrize("dt", DT)
 def test_gemm_wgrad_accumulate_split_k(dt):
     Mtok, N, K = 4096 + 40, 512, 768      # dW[N,K] += dY[Mtok,N]^T X[Mtok,K]; ragged reduction length

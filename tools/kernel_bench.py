@@ -37,10 +37,16 @@ def timeit(name, fns, bytes_per_launch, reps=20):
     for f in fns:
         f()
     torch.cuda.synchronize()
+    # replay from a CUDA graph so that short kernels are not timed by the Python launch overhead
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(reps):
+            fns[i % len(fns)]()
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(reps):
-        fns[i % len(fns)]()
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3

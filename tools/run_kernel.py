@@ -44,6 +44,18 @@ def main():
         x, w, bias = rnd(M, 512), rnd(2048, 512), torch.zeros(2048, device=dev)
         out = torch.empty(M, 2048, device=dev, dtype=bf)
         fn = lambda: ops.gemm(x, w, M=M, N=2048, K=512, bias=bias, relu=True, drop_p=0.1, seed=1, site=1, out=out)
+    elif what == "gemm_gate":
+        dy, w, h = rnd(M, 512), rnd(512, 2048), rnd(M, 2048)
+        out = torch.empty(M, 2048, device=dev, dtype=bf)
+        fn = lambda: ops.gemm(dy, w, M=M, N=2048, K=512, b_major=_lib.MAJOR_MN, gate=h, gate_scale=1.1, out=out)
+    elif what == "gemm_res":
+        dy, w, r = rnd(M, 2048), rnd(2048, 512), rnd(M, 512)
+        out = torch.empty(M, 512, device=dev, dtype=bf)
+        fn = lambda: ops.gemm(dy, w, M=M, N=512, K=2048, b_major=_lib.MAJOR_MN, residual=r, out=out)
+    elif what == "gemm_plain":
+        x, w, bias = rnd(M, 512), rnd(1536, 512), torch.zeros(1536, device=dev)
+        out = torch.empty(M, 1536, device=dev, dtype=bf)
+        fn = lambda: ops.gemm(x, w, M=M, N=1536, K=512, bias=bias, out=out)
     else:
         raise SystemExit("unknown kernel family")
     for _ in range(2):
