@@ -9,6 +9,13 @@
 
 namespace mmer {
 
+// ln_pipe.cu
+int add_ln_fwd_pipe(const void* x, const void* a, const float* gamma, const float* beta, void* y, float* stats,
+                    long long M, long long F, int dtype, int relu, DropCfg da, DropCfg dy, cudaStream_t st);
+int add_ln_bwd_pipe(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
+                    const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias, long long M,
+                    long long F, int dtype, int relu, DropCfg da, DropCfg ddy, cudaStream_t st);
+
 static constexpr float LN_EPS = 1e-5f;
 static constexpr int ROW_WARPS = 8;  // warps per CTA for the row kernels
 
@@ -642,8 +649,7 @@ int mmer_add_ln_fwd(const void* x, const void* a, const float* gamma, const floa
   if (M <= 0) return 0;
   DropCfg da = make_drop(drop_a_p, seed, site_a), dy = make_drop(drop_y_p, seed, site_y);
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == MMER_BF16 ? add_ln_fwd_t<bf16>(x, a, gamma, beta, y, stats, M, F, relu, da, dy, st)
-                            : add_ln_fwd_t<float>(x, a, gamma, beta, y, stats, M, F, relu, da, dy, st);
+  return add_ln_fwd_pipe(x, a, gamma, beta, y, stats, M, F, dtype, relu, da, dy, st);
 }
 
 int mmer_add_ln_bwd(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
@@ -656,9 +662,7 @@ int mmer_add_ln_bwd(const void* dy, const void* x, const void* a, const float* s
   if (M <= 0) return 0;
   DropCfg dca = make_drop(drop_a_p, seed, site_a), dcy = make_drop(drop_y_p, seed, site_y);
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == MMER_BF16
-             ? add_ln_bwd_t<bf16>(dy, x, a, stats, gamma, beta, dz, da, dgamma, dbeta, dbias, M, F, relu, dca, dcy, st)
-             : add_ln_bwd_t<float>(dy, x, a, stats, gamma, beta, dz, da, dgamma, dbeta, dbias, M, F, relu, dca, dcy, st);
+  return add_ln_bwd_pipe(dy, x, a, stats, gamma, beta, dz, da, dgamma, dbeta, dbias, M, F, dtype, relu, dca, dcy, st);
 }
 
 int mmer_embed_fwd(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga, const float* ba,

@@ -34,7 +34,7 @@ def timeit(fn, reps):
 
 
 def main():
-    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    reps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20
     print(torch.cuda.get_device_name(0))
     NS = 3
     total_ms = 0.0
@@ -68,6 +68,14 @@ def main():
             ("wgrad", lambda i: ops.gemm(dys[i % NS], xs[i % NS], M=n, N=k, K=m, a_major=_lib.MAJOR_MN,
                                          b_major=_lib.MAJOR_MN, out=gw, accumulate=True)),
         ]
+        if "--cublas" in sys.argv:
+            # library reference on the same operands (torch.matmul -> cuBLASLt): not part of the product path
+            wt = w.t().contiguous()
+            cases += [
+                ("cuBLAS fwd (x@W^T)", lambda i: torch.matmul(xs[i % NS], w.t(), out=ys[i % NS])),
+                ("cuBLAS dgrad (dy@W)", lambda i: torch.matmul(dys[i % NS], w, out=dxs[i % NS])),
+                ("cuBLAS wgrad (dy^T@x)", lambda i: torch.matmul(dys[i % NS].t(), xs[i % NS])),
+            ]
         for cname, fn in cases:
             ms = timeit(fn, reps)
             print(f"{name:11s} {cname:22s} M={m:6d} K={k:5d} N={n:5d}  {ms * 1e3:8.1f} us  {flop / ms / 1e9:8.1f} TFLOP/s",
