@@ -48,47 +48,93 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons DURING the timed region: NVML polled every few milliseconds from a
+    thread (nvidia-smi's own loop is too slow to see a region of ~100 ms), nvidia-smi as the fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons = index, [], None, set()
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+        self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        self._ready.set()
+        while not self._stop.is_set():
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(get_reasons(h))
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.004)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            c = [x.strip() for x in r.split(",")]
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        proc = subprocess.Popen(["nvidia-smi", "-i", str(self._visible_index()), f"--query-gpu={q}",
+                                 "--format=csv,noheader,nounits", "-lms", "20"],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.source = "nvidia-smi"
+        for line in proc.stdout:
+            self._ready.set()
+            if self._stop.is_set():
+                break
+            c = [x.strip() for x in line.split(",")]
             if len(c) < 6:
                 continue
             try:
-                sm.append(float(c[0])); mx = float(c[1])
+                self.sm.append(float(c[0])); self.mx = float(c[1])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+            for (name, _), v in zip(self.REASONS, c[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        # the busiest half of the samples approximates "under load" for a short run
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    self.reasons.add(name)
+        proc.terminate()
+
+    def _run(self):
+        try:
+            self._poll_nvml()
+        except Exception:
+            try:
+                self._poll_smi()
+            except Exception:
+                self.source = None
+                self._ready.set()
+
+    def start(self):
+        """Returns once the first sample can be taken, so that the timed region that follows is covered."""
+        self._ready = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        self._ready.wait(timeout=10.0)
+        self.sm.clear()
+        self.reasons.clear()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no clock samples: NVML and nvidia-smi unavailable"],
+                    "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------- CPU arms
@@ -303,7 +349,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -88,6 +88,8 @@ typedef struct mmer_gemm_args {
   uint64_t seed;
   uint32_t drop_site;
   uint32_t reserved;
+  float* a_rowsum; /* optional fp32 [M]: += sum_k A[m][k].  Needs accumulate != 0 and an MN-major A: in a weight-gradient
+                    * GEMM (A = dY^T) this is the bias gradient of the same Linear, produced by the same kernel */
 } mmer_gemm_args;
 int mmer_gemm(const mmer_gemm_args* args, void* stream);
 
@@ -145,8 +147,9 @@ int mmer_colsum(const void* x, float* out, int64_t M, int64_t N, int64_t ldx, in
  * ---------------------------------------------------------------------------------- */
 int mmer_mha_fwd(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T,
                  int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
-int mmer_mha_bwd(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int64_t B, int64_t T,
-                 int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* dbias_qkv (optional, fp32 [3*H*d]): += column sums of dqkv = gradient of in_proj_bias (fused into the kernel). */
+int mmer_mha_bwd(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias_qkv, int64_t B,
+                 int64_t T, int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
 
 /* Final Linear(hidden -> C) + softmax (train2.py:228,290; train.py:128-129), C <= 16.
  * logits/probs fp32 [B,C]. */

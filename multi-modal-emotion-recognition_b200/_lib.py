@@ -37,7 +37,8 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
                 ("a_major", C.c_int32), ("b_major", C.c_int32), ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
                 ("accumulate", C.c_int32), ("relu", C.c_int32), ("drop_p", C.c_float), ("gate_scale", C.c_float),
-                ("seed", C.c_uint64), ("drop_site", C.c_uint32), ("reserved", C.c_uint32)]
+                ("seed", C.c_uint64), ("drop_site", C.c_uint32), ("reserved", C.c_uint32),
+                ("a_rowsum", C.c_void_p)]
 
 
 class Model(C.Structure):
@@ -74,7 +75,7 @@ SIGNATURES = {
     "mmer_pool_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
     "mmer_colsum": [_P, _P, _I64, _I64, _I64, _I, _P],
     "mmer_mha_fwd": [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
-    "mmer_mha_bwd": [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
+    "mmer_mha_bwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
     "mmer_head_out_fwd": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
     "mmer_head_out_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
     "mmer_loss_fwd_bwd": [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _I64, _I64, _F, _P],

@@ -243,36 +243,44 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 template <int D, int MT, int NT>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 2)
 mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mask, const bf16* __restrict__ dout,
-                   bf16* __restrict__ dqkv, MmaGeom gm, DropCfg dc) {
+                   bf16* __restrict__ dqkv, float* __restrict__ dbias, int B, MmaGeom gm, DropCfg dc) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int KS = D / 16;
   constexpr int MTK = (NT + 1) / 2;   // 16-row tiles over keys
   const int S = gm.S, F = gm.F, H = gm.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
   const size_t in_bytes = ((size_t)S * gm.in_stride + 15) & ~size_t(15);
   const size_t do_bytes = ((size_t)S * gm.do_stride + 15) & ~size_t(15);
   uint8_t* do_s = smem + in_bytes;
   uint8_t* scr = do_s + do_bytes + warp * SCR_BYTES;
   uint64_t* bar = reinterpret_cast<uint64_t*>(do_s + do_bytes + MMA_WARPS * SCR_BYTES);
+  float* colacc = reinterpret_cast<float*>(bar + 2);   // [3F] running column sums of dqkv (in_proj bias gradient)
   const uint32_t bar_a = smem_u32(bar), in_a = smem_u32(smem), do_a = smem_u32(do_s), scr_a = smem_u32(scr);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
   }
+  if (dbias != nullptr)
+    for (int c = threadIdx.x; c < 3 * F; c += blockDim.x) colacc[c] = 0.f;
   __syncthreads();
-  if (warp == 0) {
+  // persistent over samples: the loads of a sample are issued as soon as the previous sample's stores have drained
+  // the shared-memory rows (a second CTA on the SM covers the gap)
+  auto issue_loads = [&](int b) {
     if (lane == 0) mbar_expect_tx(bar_a, (uint32_t)S * (gm.in_row + gm.do_row));
     __syncwarp();
     for (int r = lane; r < S; r += 32) {
       bulk_g2s(in_a + r * gm.in_stride, qkv + ((long long)b * S + r) * 3 * F, gm.in_row, bar_a);
       bulk_g2s(do_a + r * gm.do_stride, dout + ((long long)b * S + r) * F, gm.do_row, bar_a);
     }
-  }
+  };
+  if (warp == 0 && (int)blockIdx.x < B) issue_loads(blockIdx.x);
   const int g = lane >> 2, t = lane & 3;
-  const uint32_t kvalid = key_valid_bits<NT>(mask, b, gm.Tn, S, t);
   const float scale = rsqrtf((float)D);
-  mbar_wait(bar_a, 0);
+  uint32_t phase = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  const uint32_t kvalid = key_valid_bits<NT>(mask, b, gm.Tn, S, t);
+  mbar_wait(bar_a, phase);
+  phase ^= 1;
 
   for (int h = warp; h < H; h += MMA_WARPS) {
     const uint32_t qbase = in_a + h * D * 2, kbase = qbase + F * 2, vbase = kbase + F * 2, dobase = do_a + h * D * 2;
@@ -426,7 +434,30 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
       bulk_s2g(drow + F, in_a + r * gm.in_stride + gm.do_row, 2 * gm.do_row);        // dK, dV
     }
     bulk_commit();
-    bulk_wait_read0();
+  }
+  if (dbias != nullptr) {
+    // column sums of this sample's dQ | dK | dV rows (what is stored), two columns per thread
+    for (int p2 = threadIdx.x; p2 < 3 * F / 2; p2 += blockDim.x) {
+      const int c = p2 * 2;
+      const uint8_t* src = c < F ? do_s + c * 2 : smem + gm.do_row + (c - F) * 2;
+      const uint32_t stride = c < F ? gm.do_stride : gm.in_stride;
+      float a0 = 0.f, a1 = 0.f;
+      for (int r = 0; r < S; ++r) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + (size_t)r * stride));
+        a0 += v.x;
+        a1 += v.y;
+      }
+      colacc[c] += a0;
+      colacc[c + 1] += a1;
+    }
+  }
+  if (warp == 0) bulk_wait_read0();
+  __syncthreads();   // rows drained by the stores and read by the column sums: the next sample may land
+  if (warp == 0 && b + (int)gridDim.x < B) issue_loads(b + gridDim.x);
+  }  // sample loop
+  if (dbias != nullptr) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < 3 * F; c += blockDim.x) atomicAdd(dbias + c, colacc[c]);
   }
 }
 
@@ -440,7 +471,7 @@ static MmaGeom make_geom(int Tn, int H, int D) {
 static size_t fwd_smem(const MmaGeom& g) { return (((size_t)g.S * g.in_stride + 15) & ~size_t(15)) + 16; }
 static size_t bwd_smem(const MmaGeom& g) {
   return (((size_t)g.S * g.in_stride + 15) & ~size_t(15)) + (((size_t)g.S * g.do_stride + 15) & ~size_t(15)) +
-         (size_t)MMA_WARPS * SCR_BYTES + 16;
+         (size_t)MMA_WARPS * SCR_BYTES + 16 + (size_t)3 * g.F * sizeof(float);
 }
 
 template <typename K>
@@ -466,13 +497,22 @@ static int fwd_launch(const void* qkv, const uint8_t* mask, void* out, float* pr
   return 0;
 }
 template <int D, int MT, int NT>
-static int bwd_launch(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, const MmaGeom& g,
-                      DropCfg dc, cudaStream_t st) {
+static int bwd_launch(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias, int B,
+                      const MmaGeom& g, DropCfg dc, cudaStream_t st) {
   static size_t configured = 0;
+  static int bps = 0;
   auto kern = mha_bwd_mma_kernel<D, MT, NT>;
   const size_t smem = bwd_smem(g);
+  if (smem > configured) bps = 0;
   MMER_TRY(set_smem(kern, smem, &configured));
-  kern<<<B, MMA_WARPS * 32, smem, st>>>((const bf16*)qkv, mask, (const bf16*)dout, (bf16*)dqkv, g, dc);
+  if (bps == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, MMA_WARPS * 32, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy(mha_bwd_mma)");
+    if (bps < 1) bps = 1;
+  }
+  const long long cap = (long long)sm_count() * bps;
+  const int grid = (int)(B < cap ? B : cap);
+  kern<<<grid, MMA_WARPS * 32, smem, st>>>((const bf16*)qkv, mask, (const bf16*)dout, (bf16*)dqkv, dbias, B, g, dc);
   MMER_LAUNCH_CHECK("mha_bwd_mma_kernel");
   return 0;
 }
@@ -486,12 +526,12 @@ static int fwd_d(const void* qkv, const uint8_t* mask, void* out, float* probs, 
   return fwd_launch<D, 2, 4>(qkv, mask, out, probs, B, g, dc, st);
 }
 template <int D>
-static int bwd_d(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, const MmaGeom& g, DropCfg dc,
-                 cudaStream_t st) {
-  if (g.S <= 8) return bwd_launch<D, 1, 1>(qkv, mask, dout, dqkv, B, g, dc, st);
-  if (g.S <= 16) return bwd_launch<D, 1, 2>(qkv, mask, dout, dqkv, B, g, dc, st);
-  if (g.S <= 24) return bwd_launch<D, 2, 3>(qkv, mask, dout, dqkv, B, g, dc, st);
-  return bwd_launch<D, 2, 4>(qkv, mask, dout, dqkv, B, g, dc, st);
+static int bwd_d(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias, int B,
+                 const MmaGeom& g, DropCfg dc, cudaStream_t st) {
+  if (g.S <= 8) return bwd_launch<D, 1, 1>(qkv, mask, dout, dqkv, dbias, B, g, dc, st);
+  if (g.S <= 16) return bwd_launch<D, 1, 2>(qkv, mask, dout, dqkv, dbias, B, g, dc, st);
+  if (g.S <= 24) return bwd_launch<D, 2, 3>(qkv, mask, dout, dqkv, dbias, B, g, dc, st);
+  return bwd_launch<D, 2, 4>(qkv, mask, dout, dqkv, dbias, B, g, dc, st);
 }
 
 // bf16, S = Tn + 1 <= 32, d in {32, 64}
@@ -502,13 +542,15 @@ int mha_fwd_mma(const void* qkv, const uint8_t* mask, void* out, float* probs, i
                  "mha_fwd: qkv/out must be 16-byte aligned");
   return d == 64 ? fwd_d<64>(qkv, mask, out, probs, B, g, dc, st) : fwd_d<32>(qkv, mask, out, probs, B, g, dc, st);
 }
-int mha_bwd_mma(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn, int H, int d,
-                DropCfg dc, cudaStream_t st) {
+// dbias (optional): += column sums of dqkv, i.e. the gradient of in_proj_bias
+int mha_bwd_mma(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias, int B, int Tn, int H,
+                int d, DropCfg dc, cudaStream_t st) {
   const MmaGeom g = make_geom(Tn, H, d);
   MMER_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0,
                  "mha_bwd: qkv/dout/dqkv must be 16-byte aligned");
-  return d == 64 ? bwd_d<64>(qkv, mask, dout, dqkv, B, g, dc, st) : bwd_d<32>(qkv, mask, dout, dqkv, B, g, dc, st);
+  return d == 64 ? bwd_d<64>(qkv, mask, dout, dqkv, dbias, B, g, dc, st)
+                 : bwd_d<32>(qkv, mask, dout, dqkv, dbias, B, g, dc, st);
 }
 
 }  // namespace mmer

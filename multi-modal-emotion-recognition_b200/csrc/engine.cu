@@ -17,7 +17,13 @@ extern int g_debug[16];
 
 int gemm_dispatch(const mmer_gemm_args& a, cudaStream_t st) {
   if (a.in_dtype == MMER_BF16) return gemm_tc(a, st);
-  return gemm_simt(a, st);
+  MMER_TRY(gemm_simt(a, st));
+  if (a.a_rowsum != nullptr) {
+    // fp32 parity mode: the row sums of an MN-major A are the column sums of A as stored ([K][M])
+    MMER_CHECK_ARG(a.a_major == MMER_MAJOR_MN, "gemm: a_rowsum needs an MN-major A");
+    return mmer_colsum(a.A, a.a_rowsum, a.K, a.M, a.lda, a.in_dtype, st);
+  }
+  return 0;
 }
 
 struct Carver {
@@ -162,11 +168,11 @@ static int lin_dgrad(const mmer_model* m, const void* dy, int64_t M, int64_t N, 
   a.in_dtype = m->dtype; a.out_dtype = m->dtype;
   return gemm_dispatch(a, st);
 }
-// gW[N,K] += dy[M,N]^T x[M,K]
+// gW[N,K] += dy[M,N]^T x[M,K];  gb[N] += column sums of dy (offB < 0: no bias gradient wanted)
 static int lin_wgrad(const mmer_model* m, const void* dy, const void* x, int64_t M, int64_t N, int64_t K,
-                     int64_t offW, cudaStream_t st) {
+                     int64_t offW, int64_t offB, cudaStream_t st) {
   mmer_gemm_args a = {};
-  a.A = dy; a.B = x; a.D = G(m, offW);
+  a.A = dy; a.B = x; a.D = G(m, offW); a.a_rowsum = G(m, offB);
   a.M = N; a.N = K; a.K = M; a.lda = N; a.ldb = K; a.ldd = K;
   a.a_major = MMER_MAJOR_MN; a.b_major = MMER_MAJOR_MN;
   a.in_dtype = m->dtype; a.out_dtype = MMER_F32; a.accumulate = 1;
@@ -283,21 +289,20 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
     MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h2, P(m, g[MMER_G_C8_W]), w.g_h2, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
                                B, Hd, m->classes, d.dt, st));
     MMER_TRY(mmer_add_ln_bwd(w.g_h2, nullptr, w.h2p, w.st_h2, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), w.g_h2p, nullptr,
-                             G(m, g[MMER_G_C5_W]), G(m, g[MMER_G_C5_B]), G(m, g[MMER_G_C4_B]), B, Hd, d.dt, 1, 0.f, 0, d.pc,
+                             G(m, g[MMER_G_C5_W]), G(m, g[MMER_G_C5_B]), nullptr, B, Hd, d.dt, 1, 0.f, 0, d.pc,
                              201, d.seed, st));
-    MMER_TRY(lin_wgrad(m, w.g_h2p, w.h1, B, Hd, Hd, g[MMER_G_C4_W], st));
+    MMER_TRY(lin_wgrad(m, w.g_h2p, w.h1, B, Hd, Hd, g[MMER_G_C4_W], g[MMER_G_C4_B], st));
     MMER_TRY(lin_dgrad(m, w.g_h2p, B, Hd, g[MMER_G_C4_W], Hd, w.g_h1, nullptr, nullptr, 0.f, st));
     MMER_TRY(mmer_add_ln_bwd(w.g_h1, nullptr, w.h1p, w.st_h1, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, nullptr,
-                             G(m, g[MMER_G_C1_W]), G(m, g[MMER_G_C1_B]), G(m, g[MMER_G_C0_B]), B, Hd, d.dt, 1, 0.f, 0, d.pc,
+                             G(m, g[MMER_G_C1_W]), G(m, g[MMER_G_C1_B]), nullptr, B, Hd, d.dt, 1, 0.f, 0, d.pc,
                              200, d.seed, st));
   } else {
     MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h1, P(m, g[MMER_G_C8_W]), w.g_h1, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
                                B, Hd, m->classes, d.dt, st));
     MMER_TRY(mmer_bn_bwd(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
                          G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st));
-    MMER_TRY(mmer_colsum(w.g_h1p, G(m, g[MMER_G_C0_B]), B, Hd, Hd, d.dt, st));
   }
-  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], st));
+  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], g[MMER_G_C0_B], st));
   MMER_TRY(lin_dgrad(m, w.g_h1p, B, Hd, g[MMER_G_C0_W], F, w.g_fused, nullptr, nullptr, 0.f, st));
   return 0;
 }
@@ -318,25 +323,24 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     // norm2 <- linear2
     void* d_f2 = pf > 0.f ? w.g_f2 : w.g_z2;
     MMER_TRY(mmer_add_ln_bwd(w.g_x, L.x1, L.f2, L.st2, P(m, o[MMER_L_N2_W]), nullptr, w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
-                             G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, 0, pf,
+                             G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), nullptr, M, F, d.dt, 0, pf,
                              site_layer(l, 3), 0.f, 0, d.seed, st));
-    MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], st));
-    // through ReLU (+ its dropout): gate on the stored post-activation
+    MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], st));
+    // through ReLU (+ its dropout): gate on the stored post-activation.  Every bias gradient is the row sum of the
+    // matching weight-gradient GEMM's A operand (a_rowsum): no separate column-sum pass over the gradients
     MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, L.h, relu_gate_scale, st));
-    MMER_TRY(mmer_colsum(w.g_h, G(m, o[MMER_L_FF1_B]), M, FF, FF, d.dt, st));
-    MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], st));
+    MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], st));
     MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
     // norm1 <- attention
     void* d_ao = pf > 0.f ? w.g_ao : w.g_z1;
     MMER_TRY(mmer_add_ln_bwd(w.g_x1, xin, L.ao, L.st1, P(m, o[MMER_L_N1_W]), nullptr, w.g_z1, pf > 0.f ? w.g_ao : nullptr,
-                             G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, 0, pf,
+                             G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), nullptr, M, F, d.dt, 0, pf,
                              site_layer(l, 1), 0.f, 0, d.seed, st));
-    MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], st));
+    MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], st));
     MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
-    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, B, T, m->heads, F / m->heads, d.dt, pf, d.seed,
-                          site_layer(l, 0), st));
-    MMER_TRY(mmer_colsum(w.g_qkv, G(m, o[MMER_L_IN_B]), M, 3 * F, 3 * F, d.dt, st));
-    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], st));
+    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, nullptr, B, T, m->heads, F / m->heads, d.dt, pf,
+                          d.seed, site_layer(l, 0), st));
+    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], o[MMER_L_IN_B], st));
     MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));
   }
   const void* dpv = w.g_pv;
@@ -353,10 +357,8 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     MMER_TRY(mmer_bn_bwd(w.g_pan, w.pa, w.st_bna, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), w.g_pa, G(m, g[MMER_G_NA_W]),
                          G(m, g[MMER_G_NA_B]), w.bn_scratch, B, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
   }
-  MMER_TRY(mmer_colsum(dpv, G(m, g[MMER_G_BV]), Mv, F, F, d.dt, st));
-  MMER_TRY(mmer_colsum(dpa, G(m, g[MMER_G_BA]), B, F, F, d.dt, st));
-  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], st));
-  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], st));
+  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], g[MMER_G_BV], st));
+  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], g[MMER_G_BA], st));
   if (m->dvideo) MMER_TRY(lin_dgrad(m, dpv, Mv, F, g[MMER_G_WV], m->video_dim, m->dvideo, nullptr, nullptr, 0.f, st));
   if (m->daudio) MMER_TRY(lin_dgrad(m, dpa, B, F, g[MMER_G_WA], m->audio_dim, m->daudio, nullptr, nullptr, 0.f, st));
   return 0;

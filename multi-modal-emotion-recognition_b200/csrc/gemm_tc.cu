@@ -168,6 +168,7 @@ struct GemmParams {
   float gate_scale;
   int out_f32, accumulate, relu;
   int mn_swap;    // debug: swap LBO/SBO of MN-major descriptors
+  float* rowsum;  // direct (accumulate) path: += sum_k A[m][k] per output row m
   int tma_store;  // bf16 output leaves through swizzled smem staging + TMA store (coalesced)
   int aux_mode;   // staged path only: 0 none, 1 residual add, 2 ReLU gate; the aux tile arrives by TMA
   DropCfg drop;
@@ -196,14 +197,15 @@ struct TileCfg {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = STAGED ? 2 * BN : 512;   // direct kernels keep 16 columns at 256 for the row sums of A
   // staged epilogue: per warp EPI_BUFS 32-row x 64-column bf16 tiles (128 B rows; two of them double-buffer the
   // TMA store that drains them); per column half and tile parity one fp32 bias slice of BN/2 columns
   static constexpr int EPI_TILE = 4096;
   static constexpr int EPI_BUFS = MMER_EPI_BUFS;
   static constexpr int BIAS_BYTES = STAGED ? 2 * 2 * (BN / 2) * 4 : 0;
   static constexpr int EPI_BYTES = STAGED ? EPI_WARPS * EPI_BUFS * EPI_TILE : 0;
-  static constexpr int FIXED_BYTES = EPI_BYTES + BIAS_BYTES + 256 /*barriers*/;
+  static constexpr int ONES_BYTES = STAGED ? 0 : 2048;   // a 16 x 64 bf16 tile of ones: B operand of the row-sum MMAs
+  static constexpr int FIXED_BYTES = EPI_BYTES + BIAS_BYTES + ONES_BYTES + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
@@ -246,7 +248,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
   float* bias_smem = reinterpret_cast<float*>(epi_smem + C::EPI_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES + C::BIAS_BYTES);
+  uint8_t* ones_smem = epi_smem;   // direct kernels only (EPI_BYTES == 0 there): 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES + C::BIAS_BYTES + C::ONES_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4..2S+12) aux, then tmem slot
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + C::STAGES);
@@ -276,6 +279,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (STAGED) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
     if (p.aux_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+  }
+  const bool want_rowsum = !STAGED && p.rowsum != nullptr;
+  if (want_rowsum) {
+    // bf16 ones: with them as the B operand an extra N = 16 MMA per k-step accumulates sum_k A[m][k] -- for a
+    // weight-gradient GEMM (A = dY^T) that is the bias gradient of the same Linear, at 1/16 of the tile's MMA time
+    for (int i = threadIdx.x; i < C::ONES_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<CG>(smem_u32((const void*)tmem_slot), C::TMEM_COLS);
   tc_fence_before();
@@ -344,6 +354,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t b_lbo = B_MN ? mn_lbo : 16u, b_sbo = B_MN ? mn_sbo : 1024u;
       const uint32_t a_adv = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;  // descriptor units of 16 B
       const uint32_t b_adv = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t idesc_rs = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((uint32_t)(16 >> 3) << 17) |
+                                ((uint32_t)((BM * CG) >> 4) << 24);
+      const uint64_t ones_desc = make_smem_desc(smem_u32(ones_smem), 16u, 1024u);
+      const int nbuf = (want_rowsum && BN == 256) ? 1 : 2;   // the row sums live where the second accumulator would
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
@@ -351,6 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       PROF_DECL(3);
       for (int item = unit; item < total_items; item += num_units) {
         const int split = (item / p.num_n) / p.num_m;
+        const bool do_rowsum = want_rowsum && (item % p.num_n) == 0;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         PROF_TICK(2);
@@ -372,12 +387,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16<CG>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
                           (kb > kb0 || k > 0) ? 1u : 0u);
           }
+          if (do_rowsum) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16<CG>(tmem_base + 256u, adesc + (uint64_t)(k * a_adv), ones_desc + (uint64_t)(k * 2), idesc_rs,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           umma_commit<CG>(bar_empty + 8 * stage);  // frees the smem stage (in both CTAs) when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit<CG>(bar_tfull + 8 * buf);  // accumulator complete (published to both CTAs' epilogues)
         tphase[buf] ^= 1;
-        buf ^= 1;
+        if (nbuf == 2) buf ^= 1;
       }
 #ifdef MMER_GEMM_PROFILE
       if (blockIdx.x == 0) printf("mma: wait_tmem_empty %lld wait_smem_full %lld issue %lld\n", prof_t[0], prof_t[1], prof_t[2]);
@@ -405,6 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tphase[2] = {0, 0};
     const bool vec_ok = (p.ldd % 8 == 0);
     const uint32_t tempty_leader = CG == 2 ? mapa_u32(bar_tempty, 0) : bar_tempty;
+    const int nbuf = (want_rowsum && BN == 256) ? 1 : 2;
     PROF_DECL(6);
     for (int item = unit; item < total_items; item += num_units) {
       const int n_blk = item % p.num_n;
@@ -645,13 +667,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if (want_rowsum && n_blk == 0 && hsel == 0) {
+        uint32_t rs;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rs) : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + 256u));
+        tmem_ld_wait();
+        if (row_ok) atomicAdd(p.rowsum + row, __uint_as_float(rs));
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * buf); else mbar_arrive(bar_tempty + 8 * buf);
       }
       tphase[buf] ^= 1;
-      buf ^= 1;
+      if (nbuf == 2) buf ^= 1;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef MMER_GEMM_PROFILE
@@ -773,6 +801,8 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
                      (reinterpret_cast<uintptr_t>(a.D) & 15) == 0,
                  "gemm_tc: pointers must be 16-byte aligned");
   MMER_CHECK_ARG(!a.accumulate || a.out_dtype == MMER_F32, "gemm_tc: accumulate needs fp32 output");
+  MMER_CHECK_ARG(a.a_rowsum == nullptr || (a.accumulate && a.a_major == MMER_MAJOR_MN),
+                 "gemm_tc: a_rowsum needs accumulate mode and an MN-major A (weight-gradient GEMM)");
   MMER_CHECK_ARG(!(a.a_major == MMER_MAJOR_MN && a.b_major == MMER_MAJOR_K), "gemm_tc: (MN,K) operand majors unused");
 
   const int nsm = sm_count();
@@ -837,6 +867,7 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   p.aux_mode = !tma_store ? 0 : (a.gate ? 2 : (a.residual ? 1 : 0));
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
   p.num_m = num_m; p.num_n = num_n; p.splits = splits; p.kb_total = kb_total; p.kb_per_split = kb_per;
+  p.rowsum = a.a_rowsum;
   p.D = a.D; p.ldd = a.ldd; p.bias = a.bias; p.residual = a.residual; p.gate = a.gate; p.gate_scale = a.gate_scale;
   p.out_f32 = a.out_dtype == MMER_F32; p.accumulate = a.accumulate; p.relu = a.relu;
   p.mn_swap = g_debug[MMER_DEBUG_MN_SWAP];

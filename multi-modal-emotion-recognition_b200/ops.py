@@ -44,7 +44,8 @@ def _f32(t: Optional[torch.Tensor]):
 
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_lib.MAJOR_K, b_major=_lib.MAJOR_K,
          bias=None, residual=None, gate=None, gate_scale=1.0, relu=False, drop_p=0.0, seed=0, site=0,
-         out: Optional[torch.Tensor] = None, out_dtype=None, accumulate=False) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, out_dtype=None, accumulate=False,
+         a_rowsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M,N] = epilogue(A[M,K] . B[N,K]^T); see mmer_gemm in include/mmer.h."""
     for t in (A, B, bias, residual, gate, out):
         if t is not None and not t.is_cuda:
@@ -63,6 +64,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_l
     a.a_major, a.b_major = a_major, b_major
     a.in_dtype, a.out_dtype = _dt(A), _dt(out)
     a.accumulate, a.relu = int(accumulate), int(relu)
+    if a_rowsum is not None:
+        if a_rowsum.dtype != torch.float32 or not a_rowsum.is_cuda:
+            raise TypeError("a_rowsum must be a CUDA float32 tensor")
+        a.a_rowsum = a_rowsum.data_ptr()
     a.drop_p, a.gate_scale, a.seed, a.drop_site = float(drop_p), float(gate_scale), int(seed), int(site)
     call("mmer_gemm", C.byref(a), _stream())
     return out
@@ -79,10 +84,11 @@ def linear_dgrad(dy, w, residual=None, gate=None, gate_scale=1.0):
                 gate_scale=gate_scale)
 
 
-def linear_wgrad(dy, x, out: torch.Tensor):
-    """out[N,K] (fp32) += dy[M,N]^T x[M,K]"""
+def linear_wgrad(dy, x, out: torch.Tensor, dbias: Optional[torch.Tensor] = None):
+    """out[N,K] (fp32) += dy[M,N]^T x[M,K];  dbias[N] (fp32, optional) += column sums of dy, from the same kernel"""
     M, N = dy.shape
-    return gemm(dy, x, M=N, N=x.shape[1], K=M, a_major=_lib.MAJOR_MN, b_major=_lib.MAJOR_MN, out=out, accumulate=True)
+    return gemm(dy, x, M=N, N=x.shape[1], K=M, a_major=_lib.MAJOR_MN, b_major=_lib.MAJOR_MN, out=out, accumulate=True,
+                a_rowsum=dbias)
 
 
 def embed_fwd(pv, pa, gv, bv, ga, ba, pos, B, T, drop_p=0.0, seed=0, site=0):
@@ -153,9 +159,11 @@ def mha_fwd(qkv, mask, B, T, H, d, want_probs=False, drop_p=0.0, seed=0, site=0)
     return out, probs
 
 
-def mha_bwd(qkv, mask, dout, B, T, H, d, drop_p=0.0, seed=0, site=0):
+def mha_bwd(qkv, mask, dout, B, T, H, d, drop_p=0.0, seed=0, site=0, dbias=None):
+    """dbias (optional fp32 [3*H*d]) accumulates the column sums of dqkv (gradient of in_proj_bias)."""
     dqkv = torch.empty_like(qkv)
-    call("mmer_mha_bwd", _p(qkv), _p(mask), _p(dout), _p(dqkv), B, T, H, d, _dt(qkv), drop_p, seed, site, _stream())
+    call("mmer_mha_bwd", _p(qkv), _p(mask), _p(dout), _p(dqkv), _f32(dbias), B, T, H, d, _dt(qkv), drop_p, seed, site,
+         _stream())
     return dqkv
 
 

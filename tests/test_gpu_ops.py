@@ -128,6 +128,22 @@ def test_gemm_cta_pair_matches_single_cta_and_reference(shape, majors):
             assert rel(a, refs[i]) < 6e-3
 
 
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(69632 + 24, 1536, 512), (4096, 512, 512), (4096 + 8, 2048, 512), (300, 136, 72),
+                                   (65536, 512, 768)])
+def test_gemm_wgrad_bias_gradient_from_row_sums(dt, shape):
+    """dW += dY^T X and db += colsum(dY) from ONE kernel: an extra N=16 MMA against a tile of ones accumulates the
+    row sums of the A operand (CTA pairs and single CTAs, split-K, ragged reduction length)."""
+    Mtok, N, K = shape
+    dy, x = rnd(Mtok, N, dt=dt, seed=18, scale=0.05), rnd(Mtok, K, dt=dt, seed=19)
+    out = torch.full((N, K), 0.5, device=DEV)
+    db = torch.full((N,), -0.25, device=DEV)
+    ops.linear_wgrad(dy, x, out, dbias=db)
+    # fp32 mode accumulates up to 69656 products per element in fp32: 2e-4 of the largest entry
+    assert rel(out, (dy.double().t() @ x.double()) + 0.5) < (2e-4 if dt == torch.float32 else 4e-3)
+    assert rel(db, dy.double().sum(0) - 0.25) < (2e-5 if dt == torch.float32 else 1e-4)
+
+
 def test_gemm_cta_pair_wgrad_split_k():
     Mtok, N, K = 69632 + 24, 1536, 512     # dW[N,K] += dY^T X at the cfg2 in_proj shape, ragged reduction length
     dy, x = rnd(Mtok, N, dt=torch.bfloat16, seed=8, scale=0.05), rnd(Mtok, K, dt=torch.bfloat16, seed=9)
@@ -315,8 +331,11 @@ def test_mha_fwd_bwd(dt, T, H, d, use_mask):
         assert float(probs.masked_select(full.view(B, 1, 1, S).expand_as(probs)).abs().max()) == 0.0
     do = rnd(B * S, F, dt=dt, seed=2)
     ref.backward(do.double().view(B, S, F))
-    dqkv = ops.mha_bwd(qkv, mk, do, B, T, H, d)
+    dbias = torch.full((3 * F,), 0.25, device=DEV)
+    dqkv = ops.mha_bwd(qkv, mk, do, B, T, H, d, dbias=dbias)
     assert rel(dqkv.view(B, S, 3 * F), qr.grad) < tol(dt)
+    # fused in_proj bias gradient: accumulates the column sums of what was stored
+    assert rel(dbias, dqkv.double().sum(0) + 0.25) < (1e-5 if dt == torch.float32 else 2e-3)
 
 
 @pytest.mark.parametrize("B,T", [(64, 16), (3, 70)])
