@@ -289,12 +289,12 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
     MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h2, P(m, g[MMER_G_C8_W]), w.g_h2, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
                                B, Hd, m->classes, d.dt, st));
     MMER_TRY(mmer_add_ln_bwd(w.g_h2, nullptr, w.h2p, w.st_h2, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), w.g_h2p, nullptr,
-                             G(m, g[MMER_G_C5_W]), G(m, g[MMER_G_C5_B]), nullptr, B, Hd, d.dt, 1, 0.f, 0, d.pc,
+                             G(m, g[MMER_G_C5_W]), G(m, g[MMER_G_C5_B]), G(m, g[MMER_G_C4_B]), B, Hd, d.dt, 1, 0.f, 0, d.pc,
                              201, d.seed, st));
-    MMER_TRY(lin_wgrad(m, w.g_h2p, w.h1, B, Hd, Hd, g[MMER_G_C4_W], g[MMER_G_C4_B], st));
+    MMER_TRY(lin_wgrad(m, w.g_h2p, w.h1, B, Hd, Hd, g[MMER_G_C4_W], -1, st));
     MMER_TRY(lin_dgrad(m, w.g_h2p, B, Hd, g[MMER_G_C4_W], Hd, w.g_h1, nullptr, nullptr, 0.f, st));
     MMER_TRY(mmer_add_ln_bwd(w.g_h1, nullptr, w.h1p, w.st_h1, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, nullptr,
-                             G(m, g[MMER_G_C1_W]), G(m, g[MMER_G_C1_B]), nullptr, B, Hd, d.dt, 1, 0.f, 0, d.pc,
+                             G(m, g[MMER_G_C1_W]), G(m, g[MMER_G_C1_B]), G(m, g[MMER_G_C0_B]), B, Hd, d.dt, 1, 0.f, 0, d.pc,
                              200, d.seed, st));
   } else {
     MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h1, P(m, g[MMER_G_C8_W]), w.g_h1, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
@@ -302,7 +302,7 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
     MMER_TRY(mmer_bn_bwd(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
                          G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st));
   }
-  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], g[MMER_G_C0_B], st));
+  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], m->variant == 2 ? -1 : g[MMER_G_C0_B], st));
   MMER_TRY(lin_dgrad(m, w.g_h1p, B, Hd, g[MMER_G_C0_W], F, w.g_fused, nullptr, nullptr, 0.f, st));
   return 0;
 }
@@ -323,24 +323,25 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     // norm2 <- linear2
     void* d_f2 = pf > 0.f ? w.g_f2 : w.g_z2;
     MMER_TRY(mmer_add_ln_bwd(w.g_x, L.x1, L.f2, L.st2, P(m, o[MMER_L_N2_W]), nullptr, w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
-                             G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), nullptr, M, F, d.dt, 0, pf,
+                             G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, 0, pf,
                              site_layer(l, 3), 0.f, 0, d.seed, st));
-    MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], st));
-    // through ReLU (+ its dropout): gate on the stored post-activation.  Every bias gradient is the row sum of the
-    // matching weight-gradient GEMM's A operand (a_rowsum): no separate column-sum pass over the gradients
+    MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], -1, st));
+    // through ReLU (+ its dropout): gate on the stored post-activation.  No gradient tensor is re-read for a bias
+    // gradient: the kernels that produce dY sum its columns where that is free (add_ln_bwd, mha_bwd); for linear1 and
+    // the two input projections the weight-gradient GEMM adds the row sums of its A operand (a_rowsum)
     MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, L.h, relu_gate_scale, st));
     MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], st));
     MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
     // norm1 <- attention
     void* d_ao = pf > 0.f ? w.g_ao : w.g_z1;
     MMER_TRY(mmer_add_ln_bwd(w.g_x1, xin, L.ao, L.st1, P(m, o[MMER_L_N1_W]), nullptr, w.g_z1, pf > 0.f ? w.g_ao : nullptr,
-                             G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), nullptr, M, F, d.dt, 0, pf,
+                             G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, 0, pf,
                              site_layer(l, 1), 0.f, 0, d.seed, st));
-    MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], st));
+    MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], -1, st));
     MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
-    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, nullptr, B, T, m->heads, F / m->heads, d.dt, pf,
+    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf,
                           d.seed, site_layer(l, 0), st));
-    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], o[MMER_L_IN_B], st));
+    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], -1, st));
     MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));
   }
   const void* dpv = w.g_pv;

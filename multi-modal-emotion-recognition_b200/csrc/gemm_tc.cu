@@ -365,7 +365,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       PROF_DECL(3);
       for (int item = unit; item < total_items; item += num_units) {
         const int split = (item / p.num_n) / p.num_m;
-        const bool do_rowsum = want_rowsum && (item % p.num_n) == 0;
+        const int rs_nblk = item % p.num_n;   // the tiles of one row block share the row-sum work: k-block kb goes to
+                                               // the tile with n_blk == kb % num_n, every tile adds its partial sums
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         PROF_TICK(2);
@@ -373,6 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         PROF_TICK(0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        bool rs_started = false;
         for (int kb = kb0; kb < kb1; ++kb) {
           PROF_TICK(2);
           mbar_wait(bar_full + 8 * stage, phase);
@@ -387,11 +389,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16<CG>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
                           (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (do_rowsum) {
+          if (want_rowsum && (kb % p.num_n) == rs_nblk) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_bf16<CG>(tmem_base + 256u, adesc + (uint64_t)(k * a_adv), ones_desc + (uint64_t)(k * 2), idesc_rs,
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+                            (rs_started || k > 0) ? 1u : 0u);
+            rs_started = true;
           }
           umma_commit<CG>(bar_empty + 8 * stage);  // frees the smem stage (in both CTAs) when these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -667,7 +670,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (want_rowsum && n_blk == 0 && hsel == 0) {
+      bool rs_any = false;
+      if (want_rowsum) {
+        const int split = (item / p.num_n) / p.num_m;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        // first k-block >= kb0 that is congruent to n_blk modulo num_n
+        const int first = kb0 + ((n_blk - kb0 % p.num_n) + p.num_n) % p.num_n;
+        rs_any = first < kb1;
+      }
+      if (rs_any && hsel == 0) {
         uint32_t rs;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rs) : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + 256u));
         tmem_ld_wait();
