@@ -255,7 +255,19 @@ typedef struct mmer_model {
   const void* fused_in;  /* stage 2: classifier input [B,fused] dtype */
   const void* dfused_in; /* stage 1 backward: gradient of the fused embedding [B,fused] dtype */
   void* dfused_out;      /* stage 2 backward: optional gradient w.r.t. fused_in */
+  /* Data-parallel overlap (stage 0 backward only): grad_events[k] (cudaEvent_t) is recorded on the stream as soon as
+   * gradient bucket k of the flat buffer is final, in the order  classifier + out_norm | layer L-1 | ... | layer 0 |
+   * projections, input norms and pos_embed.  n_grad_events must be 0 or layers + 2.  The caller waits for event k on a
+   * communication stream and all-reduces bucket k while backward continues. */
+  void* const* grad_events;
+  int32_t n_grad_events;
+  int32_t reserved2;
 } mmer_model;
+
+/* Plain event plumbing for callers that only hold raw stream handles (the events above). */
+int mmer_event_create(void** event_out);
+int mmer_event_destroy(void* event);
+int mmer_stream_wait_event(void* stream, void* event);
 
 int64_t mmer_workspace_bytes(const mmer_model* m);
 int mmer_model_forward(const mmer_model* m, void* stream);

@@ -54,7 +54,8 @@ class Model(C.Structure):
                 ("logits", C.c_void_p), ("probs", C.c_void_p), ("fused_out", C.c_void_p), ("attn_probs", C.c_void_p),
                 ("dlogits", C.c_void_p), ("dvideo", C.c_void_p), ("daudio", C.c_void_p),
                 ("stage", C.c_int32), ("reserved", C.c_int32),
-                ("fused_in", C.c_void_p), ("dfused_in", C.c_void_p), ("dfused_out", C.c_void_p)]
+                ("fused_in", C.c_void_p), ("dfused_in", C.c_void_p), ("dfused_out", C.c_void_p),
+                ("grad_events", C.POINTER(C.c_void_p)), ("n_grad_events", C.c_int32), ("reserved2", C.c_int32)]
 
 
 _P, _I64, _I, _F, _U64, _U32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_uint32
@@ -64,6 +65,9 @@ SIGNATURES = {
     "mmer_version": [],
     "mmer_last_error": [],
     "mmer_debug_set": [_I, _I],
+    "mmer_event_create": [C.POINTER(C.c_void_p)],
+    "mmer_event_destroy": [_P],
+    "mmer_stream_wait_event": [_P, _P],
     "mmer_debug_get": [_I],
     "mmer_launch_count": [],
     "mmer_gemm": [C.POINTER(GemmArgs), _P],

@@ -50,6 +50,24 @@ int mmer_debug_set(int key, int value) {
   return 0;
 }
 int64_t mmer_launch_count(void) { return (int64_t)mmer::launch_count(); }
+int mmer_event_create(void** event_out) {
+  MMER_CHECK_ARG(event_out != nullptr, "event_create: null pointer");
+  cudaEvent_t ev;
+  cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) return mmer::cuda_fail(e, "cudaEventCreateWithFlags");
+  *event_out = (void*)ev;
+  return 0;
+}
+int mmer_event_destroy(void* event) {
+  if (event == nullptr) return 0;
+  cudaError_t e = cudaEventDestroy((cudaEvent_t)event);
+  return e == cudaSuccess ? 0 : mmer::cuda_fail(e, "cudaEventDestroy");
+}
+int mmer_stream_wait_event(void* stream, void* event) {
+  MMER_CHECK_ARG(event != nullptr, "stream_wait_event: null event");
+  cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0);
+  return e == cudaSuccess ? 0 : mmer::cuda_fail(e, "cudaStreamWaitEvent");
+}
 int mmer_debug_get(int key) { return (key < 0 || key >= 16) ? 0 : mmer::g_debug[key]; }
 
 }  // extern "C"

@@ -307,6 +307,13 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
   return 0;
 }
 
+// gradient bucket k of the flat buffer is final: tell the data-parallel caller (see mmer_model.grad_events)
+static int bucket_done(const mmer_model* m, int k, cudaStream_t st) {
+  if (m->stage != 0 || m->n_grad_events == 0) return 0;
+  cudaError_t e = cudaEventRecord((cudaEvent_t)m->grad_events[k], st);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaEventRecord(grad bucket)");
+}
+
 static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaStream_t st) {
   const Dims d(m);
   const int64_t B = d.B, T = d.T, F = d.F, M = d.M, Mv = d.Mv, FF = d.FF;
@@ -315,6 +322,7 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
   MMER_TRY(mmer_pool_ln_bwd(dfused, w.pooled, w.st_o, m->variant == 2 ? P(m, g[MMER_G_ON_W]) : nullptr, d.mask, w.g_x,
                             m->variant == 2 ? G(m, g[MMER_G_ON_W]) : nullptr,
                             m->variant == 2 ? G(m, g[MMER_G_ON_B]) : nullptr, B, T, F, d.dt, st));
+  MMER_TRY(bucket_done(m, 0, st));   // classifier + out_norm
   const float relu_gate_scale = pf > 0.f ? make_drop(pf, d.seed, 0).scale : 1.f;
   for (int l = m->layers - 1; l >= 0; --l) {
     const int64_t* o = m->off_l[l];
@@ -342,6 +350,7 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf,
                           d.seed, site_layer(l, 0), st));
     MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], -1, st));
+    MMER_TRY(bucket_done(m, 1 + (m->layers - 1 - l), st));   // every gradient of layer l is final
     MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));
   }
   const void* dpv = w.g_pv;
@@ -360,6 +369,7 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
   }
   MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], g[MMER_G_BV], st));
   MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], g[MMER_G_BA], st));
+  MMER_TRY(bucket_done(m, m->layers + 1, st));   // projections, input norms, pos_embed
   if (m->dvideo) MMER_TRY(lin_dgrad(m, dpv, Mv, F, g[MMER_G_WV], m->video_dim, m->dvideo, nullptr, nullptr, 0.f, st));
   if (m->daudio) MMER_TRY(lin_dgrad(m, dpa, B, F, g[MMER_G_WA], m->audio_dim, m->daudio, nullptr, nullptr, 0.f, st));
   return 0;
@@ -373,6 +383,8 @@ int model_backward(const mmer_model* m, cudaStream_t st) {
   MMER_CHECK_ARG(m->stage == 2 || (m->video && m->audio), "model_backward: video/audio must be set");
   MMER_CHECK_ARG(m->stage != 1 || m->dfused_in, "model_backward: stage 1 needs dfused_in");
   MMER_CHECK_ARG(m->stage != 2 || m->fused_in, "model_backward: stage 2 needs fused_in");
+  MMER_CHECK_ARG(m->n_grad_events == 0 || (m->n_grad_events == m->layers + 2 && m->grad_events != nullptr),
+                 "model_backward: n_grad_events must be 0 or layers + 2");
   Ws w;
   carve(m, m->workspace, &w);
   if (m->stage != 1) {

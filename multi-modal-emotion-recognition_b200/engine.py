@@ -19,6 +19,9 @@ from ._lib import BF16, F32, G, L, MmerError, Model
 
 PAD = 64  # every parameter starts on a 256-byte boundary of the fp32 buffer
 
+# parameters whose gradients become final LAST in backward (token assembly and the two input projections)
+EMBED_SLOTS = ("POS", "WV", "BV", "WA", "BA", "NV_W", "NV_B", "NA_W", "NA_B")
+
 
 def _pad(n: int) -> int:
     return (n + PAD - 1) // PAD * PAD
@@ -33,7 +36,13 @@ class ParamContext:
         self.g_slots = g_slots
         self.l_slots = l_slots
         self.bn_buffers = bn_buffers or []   # [(module, 'running_mean'), (module, 'running_var'), ...] in engine order
-        self.params: List[nn.Parameter] = list(g_slots.values()) + [p for d in l_slots for p in d.values()]
+        # flat layout = reverse order of gradient completion in backward:  embed | layer 0 | ... | layer L-1 | head.
+        # Each group is one contiguous range, so the data-parallel all-reduce can go out bucket by bucket while
+        # backward is still running (see bucket_ranges / mmer_model.grad_events).
+        self.embed_params = [p for n, p in g_slots.items() if n in EMBED_SLOTS]
+        self.layer_params = [list(d.values()) for d in l_slots]
+        self.head_params = [p for n, p in g_slots.items() if n not in EMBED_SLOTS]
+        self.params: List[nn.Parameter] = self.embed_params + [p for d in self.layer_params for p in d] + self.head_params
         self.flat: Optional[torch.Tensor] = None
         self.grads: Optional[torch.Tensor] = None
         self.shadow: Optional[torch.Tensor] = None
@@ -43,9 +52,10 @@ class ParamContext:
         self.shadow_fresh = False
 
     # ------------------------------------------------------------------ layout
-    def _build(self, device: torch.device) -> None:
+    def layout(self) -> Tuple[Dict[int, int], int]:
+        """Element offset of every parameter in the flat buffers, and the buffer length (device independent)."""
         off = 0
-        offsets = {}
+        offsets: Dict[int, int] = {}
         for p in self.params:
             if id(p) in offsets:
                 continue
@@ -53,6 +63,26 @@ class ParamContext:
                 raise MmerError("parameters must be float32 masters (bf16 compute uses an internal shadow copy)")
             offsets[id(p)] = off
             off += _pad(p.numel())
+        return offsets, off
+
+    def bucket_ranges(self) -> List[Tuple[int, int]]:
+        """[lo, hi) element ranges of the flat gradient buffer in the order backward completes them:
+        head (classifier + out_norm), layer L-1, ..., layer 0, embed.  They tile the buffer exactly."""
+        offsets, total = self.layout()
+        starts = []
+        for group in [self.embed_params] + self.layer_params + [self.head_params]:
+            starts.append(min((offsets[id(p)] for p in group), default=None))
+        # an empty group (e.g. a classifier-only module tree) collapses onto its successor
+        bounds = []
+        nxt = total
+        for st in reversed(starts):
+            lo = nxt if st is None else st
+            bounds.append((lo, nxt))
+            nxt = lo
+        return bounds   # already in completion order: head first, embed last
+
+    def _build(self, device: torch.device) -> None:
+        offsets, off = self.layout()
         flat = torch.zeros(off, device=device, dtype=torch.float32)
         grads = torch.zeros(off, device=device, dtype=torch.float32)
         with torch.no_grad():

@@ -32,6 +32,69 @@ def allreduce_flat_gradients(flat: torch.Tensor, group=None) -> float:
     return 1.0 / world
 
 
+def allreduce_buckets(flat: torch.Tensor, ranges, group=None) -> float:
+    """The same sum as ``allreduce_flat_gradients``, issued bucket by bucket (``ranges`` = [lo, hi) element ranges
+    in the order backward completes them).  On GPUs ``OverlappedAllReduce`` launches each bucket as soon as its
+    gradients are final; this plain version is the host logic the gloo CPU tests exercise."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    for lo, hi in ranges:
+        if hi > lo:
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+class OverlappedAllReduce:
+    """NCCL all-reduce of the flat gradient buffer overlapped with backward.
+
+    ``mmer_model_backward`` records one CUDA event per gradient bucket as soon as that bucket is final
+    (classifier + out_norm, then the encoder layers from last to first, then the input projections).  A side
+    stream waits for event k and all-reduces bucket k over NVLink while the remaining backward kernels run on
+    the main stream; Adam waits for the side stream."""
+
+    def __init__(self, ctx: ParamContext, n_layers: int, device, group=None):
+        self.ctx, self.group = ctx, group
+        self.n = n_layers + 2
+        lib = _lib.load()
+        self.events = (C.c_void_p * self.n)()
+        for k in range(self.n):
+            ev = C.c_void_p()
+            _lib.check(lib.mmer_event_create(C.byref(ev)), "mmer_event_create")
+            self.events[k] = ev
+        self.stream = torch.cuda.Stream(device=device)
+        self.world = dist.get_world_size(group)
+
+    def attach(self, m) -> None:
+        m.grad_events = C.cast(self.events, C.POINTER(C.c_void_p))
+        m.n_grad_events = self.n
+
+    def reduce(self) -> float:
+        """Call right after mmer_model_backward has been enqueued on the current stream."""
+        lib = _lib.load()
+        ranges = self.ctx.bucket_ranges()
+        assert len(ranges) == self.n
+        grads = self.ctx.grads
+        side = C.c_void_p(self.stream.cuda_stream)
+        for k, (lo, hi) in enumerate(ranges):
+            _lib.check(lib.mmer_stream_wait_event(side, self.events[k]), "mmer_stream_wait_event")
+            if hi > lo:
+                with torch.cuda.stream(self.stream):
+                    dist.all_reduce(grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        return 1.0 / self.world
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for ev in self.events:
+                lib.mmer_event_destroy(ev)
+        except Exception:
+            pass
+
+
 class FusedAdam(torch.optim.Optimizer):
     """Adam over the flat parameter buffer of an mmer_b200 model: one kernel per step."""
 
@@ -94,7 +157,7 @@ class FusedTrainStep:
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  loss: str = "focal", gamma: float = 2.0, alpha: Optional[torch.Tensor] = None,
                  clip_grad_norm: Optional[float] = None, compute_dtype: torch.dtype = torch.bfloat16,
-                 process_group=None):
+                 process_group=None, overlap_allreduce: bool = True):
         self.model = model
         self.engine: Engine = model._engine
         self.ctx: ParamContext = self.engine.ctx
@@ -106,6 +169,8 @@ class FusedTrainStep:
         self.compute_dtype = compute_dtype
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.overlap = overlap_allreduce
+        self._overlapped: Optional[OverlappedAllReduce] = None
         self._key = None
         self._ws = None
         self.launch_count = 0
@@ -164,7 +229,14 @@ class FusedTrainStep:
                                          float(self.gamma), _lib.REDUCE_MEAN, self._loss.data_ptr(), None,
                                          self._dlogits.data_ptr(), self._scratch.data_ptr(), B,
                                          self.engine.cfg["classes"], 1.0, stream), "mmer_loss_fwd_bwd")
+        if self.world > 1 and self.overlap:
+            if self._overlapped is None or self._overlapped.ctx.grads is not ctx.grads:
+                self._overlapped = OverlappedAllReduce(ctx, self.engine.cfg["layers"], video.device, self.group)
+            self._overlapped.attach(m)
         _lib.check(lib.mmer_model_backward(C.byref(m), stream), "mmer_model_backward")
-        scale = allreduce_flat_gradients(ctx.grads, self.group) if self.world > 1 else 1.0
+        if self.world > 1 and self.overlap:
+            scale = self._overlapped.reduce()
+        else:
+            scale = allreduce_flat_gradients(ctx.grads, self.group) if self.world > 1 else 1.0
         self.opt.step(grad_scale=scale)
         return self._loss, self._probs

@@ -163,6 +163,70 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from mmer_b200.trainer import allreduce_buckets, allreduce_flat_gradients
+    import mmer_b200 as mm
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    model = mm.MultimodalEmotionModel(video_dim=48, audio_dim=40, fused_dim=64, max_seq_len=5, fusion_num_layers=2,
+                                      fusion_num_heads=2, classifier_hidden_dim=32)
+    ctx = model._engine.ctx
+    _, total = ctx.layout()
+    ranges = ctx.bucket_ranges()
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(total, generator=g, dtype=torch.float64)
+    a, b = flat.clone(), flat.clone()
+    s1 = allreduce_flat_gradients(a, None)
+    s2 = allreduce_buckets(b, ranges, None)
+    q.put((rank, bool(torch.equal(a, b)), s1, s2))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_tile_the_flat_buffer_in_backward_order():
+    """Flat layout = embed | layer 0 | ... | layer L-1 | head; bucket_ranges() lists them in the order backward
+    finishes them (head, layers last to first, embed): contiguous, disjoint, covering every parameter."""
+    import mmer_b200 as mm
+    model = mm.MultimodalEmotionModel(max_seq_len=17, fusion_num_layers=3, classifier_hidden_dim=512)
+    ctx = model._engine.ctx
+    offsets, total = ctx.layout()
+    ranges = ctx.bucket_ranges()
+    assert len(ranges) == 3 + 2
+    assert ranges[0][1] == total and ranges[-1][0] == 0
+    for (lo, hi), (lo2, hi2) in zip(ranges[1:], ranges[:-1]):
+        assert hi == lo2 and lo < hi                      # contiguous, descending: completion order
+    named = dict(model.named_parameters())
+
+    def bucket_of(name):
+        o = offsets[id(named[name])]
+        return next(k for k, (lo, hi) in enumerate(ranges) if lo <= o < hi)
+
+    assert bucket_of("classifier.net.8.weight") == 0 and bucket_of("fusion.out_norm.weight") == 0
+    assert bucket_of("fusion.transformer.layers.2.linear1.weight") == 1
+    assert bucket_of("fusion.transformer.layers.0.self_attn.in_proj_weight") == 3
+    assert bucket_of("fusion.pos_embed") == 4 and bucket_of("fusion.video_proj.weight") == 4
+    for n, p in named.items():                            # every parameter lies wholly inside one bucket
+        o = offsets[id(p)]
+        k = bucket_of(n)
+        assert o + p.numel() <= ranges[k][1]
+
+
+def test_bucketed_allreduce_equals_single_allreduce_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, same, s1, s2 in res:
+        assert same and s1 == s2 == 0.5
+
+
 def test_data_parallel_gradient_average_equals_global_batch_gloo():
     """Equal shards + per-rank mean loss + (sum all-reduce) * 1/world == global-batch gradient
     (SURVEY.md 8e), checked with two gloo ranks on CPU."""
