@@ -51,44 +51,76 @@ head_out_fwd_kernel(const T* __restrict__ h, const float* __restrict__ W, const 
   }
 }
 
-// one warp per sample: dh = dlogits W ; dW += dlogits^T h ; db += colsum(dlogits)
+// dh = dlogits W ; dW += dlogits^T h ; db += colsum(dlogits).  Warp w of a CTA owns the 256-column slab
+// (w % nslab) of K and every (8/nslab)-th row of the CTA's row range: the lane's 8 columns of dW stay in registers
+// for up to 8 classes at a time (8 x 8 accumulators); warps are combined through shared-memory atomics and each
+// CTA adds its partial dW with one fp32 atomic per element, so the per-row traffic is the 16-byte read of h and
+// the 16-byte write of dh.
+static constexpr int HOB_WARPS = 8, HOB_CC = 8;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(HOB_WARPS * 32)
 head_out_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ h, const float* __restrict__ W,
-                    T* __restrict__ dh, float* __restrict__ dW, float* __restrict__ db, int B, int K, int C) {
-  extern __shared__ float sW[];  // [C][K] partial dW, then [C] partial db
-  float* sdb = sW + (size_t)C * K;
-  for (int i = threadIdx.x; i < C * K + C; i += blockDim.x) sW[i] = 0.f;
-  __syncthreads();
+                    T* __restrict__ dh, float* __restrict__ dW, float* __restrict__ db, int B, int K, int C,
+                    int rows_per_cta) {
+  extern __shared__ float sW[];   // [min(C, 8)][K] partial dW of the current class group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int row = blockIdx.x * 8 + warp; row < B; row += gridDim.x * 8) {
-    float dl[MAXC];
+  const int nslab = (K + 255) / 256;
+  const int slab = warp % nslab, rgroup = warp / nslab, ngroups = HOB_WARPS / nslab;
+  const int row0 = blockIdx.x * rows_per_cta, row1 = min(B, row0 + rows_per_cta);
+  if (warp == 0 && lane < C) {
+    float s = 0.f;
+    for (int row = row0; row < row1; ++row) s += dlogits[(long long)row * C + lane];
+    atomicAdd(db + lane, s);
+  }
+  const int k = slab * 256 + lane * 8;
+  const bool active = rgroup < ngroups && k < K;
+  for (int c0 = 0; c0 < C; c0 += HOB_CC) {
+    const int cc = min(HOB_CC, C - c0);
+    for (int i = threadIdx.x; i < cc * K; i += blockDim.x) sW[i] = 0.f;
+    __syncthreads();
+    if (active) {
+      float acc[HOB_CC][8], wv[HOB_CC][8];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) dl[c] = c < C ? dlogits[(long long)row * C + c] : 0.f;
-    if (lane < C) atomicAdd(sdb + lane, dlogits[(long long)row * C + lane]);
-    for (int k = lane * 8; k < K; k += 256) {
-      float hv[8], o[8];
-      load8(h + (long long)row * K + k, hv);
+      for (int c = 0; c < HOB_CC; ++c) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        for (int j = 0; j < 8; ++j) { acc[c][j] = 0.f; wv[c][j] = 0.f; }
+        if (c < cc) load8(W + (long long)(c0 + c) * K + k, wv[c]);
+      }
+      for (int row = row0 + rgroup; row < row1; row += ngroups) {
+        float hv[8], o[8], dl[HOB_CC];
+        load8(h + (long long)row * K + k, hv);
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        if (c < C) {
-          float wv[8];
-          load8(W + (long long)c * K + k, wv);
+        for (int c = 0; c < HOB_CC; ++c) dl[c] = (c < cc) ? __ldg(dlogits + (long long)row * C + c0 + c) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < HOB_CC; ++c)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            o[j] = fmaf(dl[c], wv[j], o[j]);
-            atomicAdd(sW + c * K + k + j, dl[c] * hv[j]);
+            acc[c][j] = fmaf(dl[c], hv[j], acc[c][j]);
+            o[j] = fmaf(dl[c], wv[c][j], o[j]);
           }
+        if (dh != nullptr) {
+          if (c0 > 0) {   // more than HOB_CC classes: add to what the earlier class groups wrote
+            float prev[8];
+            load8(dh + (long long)row * K + k, prev);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += prev[j];
+          }
+          store8(dh + (long long)row * K + k, o);
         }
       }
-      if (dh != nullptr) store8(dh + (long long)row * K + k, o);
+#pragma unroll
+      for (int c = 0; c < HOB_CC; ++c)
+        if (c < cc) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(sW + c * K + k + j, acc[c][j]);
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cc * K; i += blockDim.x) atomicAdd(dW + (long long)c0 * K + i, sW[i]);
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C * K; i += blockDim.x) atomicAdd(dW + i, sW[i]);
-  if (threadIdx.x < C) atomicAdd(db + threadIdx.x, sdb[threadIdx.x]);
 }
 
 // sum of class weights of the batch labels (denominator of the weighted CE mean)
@@ -185,17 +217,28 @@ int mmer_head_out_bwd(const float* dlogits, const void* h, const float* W, void*
                       int64_t K, int64_t C, int dtype, void* stream) {
   MMER_CHECK_ARG(dlogits && h && W && dW && db, "head_out_bwd: null pointer");
   MMER_CHECK_ARG(C >= 1 && C <= MAXC && K % 8 == 0, "head_out_bwd: need C <= 16 and K %% 8 == 0");
-  const size_t smem = ((size_t)C * K + C) * sizeof(float);
-  MMER_CHECK_ARG(smem <= 48 * 1024, "head_out_bwd: C*K too large (%lld)", (long long)(C * K));
   if (B <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  long long want = (B + 7) / 8;
-  long long cap = sm_count();
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  MMER_CHECK_ARG(K <= 2048, "head_out_bwd: K above 2048 unsupported");
+  const int nslab = (int)((K + 255) / 256);
+  const int ngroups = HOB_WARPS / nslab;                 // rows in flight per CTA
+  long long ctas = sm_count();
+  long long rows_per_cta = (B + ctas - 1) / ctas;
+  if (rows_per_cta < ngroups) rows_per_cta = ngroups;
+  const unsigned grid = (unsigned)((B + rows_per_cta - 1) / rows_per_cta);
+  const size_t smem = (size_t)(C < HOB_CC ? C : HOB_CC) * K * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = dtype == MMER_BF16
+                        ? cudaFuncSetAttribute(head_out_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(head_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_out_bwd)");
+  }
   if (dtype == MMER_BF16)
-    head_out_bwd_kernel<bf16><<<grid, 256, smem, st>>>(dlogits, (const bf16*)h, W, (bf16*)dh, dW, db, (int)B, (int)K, (int)C);
+    head_out_bwd_kernel<bf16><<<grid, HOB_WARPS * 32, smem, st>>>(dlogits, (const bf16*)h, W, (bf16*)dh, dW, db, (int)B,
+                                                                   (int)K, (int)C, (int)rows_per_cta);
   else
-    head_out_bwd_kernel<float><<<grid, 256, smem, st>>>(dlogits, (const float*)h, W, (float*)dh, dW, db, (int)B, (int)K, (int)C);
+    head_out_bwd_kernel<float><<<grid, HOB_WARPS * 32, smem, st>>>(dlogits, (const float*)h, W, (float*)dh, dW, db, (int)B,
+                                                                    (int)K, (int)C, (int)rows_per_cta);
   MMER_LAUNCH_CHECK("head_out_bwd_kernel");
   return 0;
 }

@@ -217,7 +217,7 @@ add_ln_bwd_kernel(const T* __restrict__ dyp, const T* __restrict__ x, const T* _
 // position s, so pos_embed[s] and the LayerNorm parameter set (video / audio) are uniform.
 // ---------------------------------------------------------------------------------------
 template <typename T, int NCH>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
 embed_fwd_kernel(const T* __restrict__ pv, const T* __restrict__ pa, const float* __restrict__ gv,
                  const float* __restrict__ bv, const float* __restrict__ ga, const float* __restrict__ ba,
                  const float* __restrict__ pos, T* __restrict__ x0, float* __restrict__ stats, int B, int Tn, int F,
@@ -236,58 +236,82 @@ embed_fwd_kernel(const T* __restrict__ pv, const T* __restrict__ pa, const float
       if (gamma != nullptr) { load8(gamma + c, g[i]); load8(beta + c, be[i]); }
     }
   }
-  for (int b = blockIdx.x * ROW_WARPS + warp; b < B; b += gridDim.x * ROW_WARPS) {
-    const T* src = is_audio ? pa + (long long)b * F : pv + ((long long)b * Tn + s) * F;
-    const long long row = (long long)b * S + s;
-    float z[NCH][8];
-    float sm = 0.f;
+  // EMB_U rows per iteration: all of their 16-byte loads are issued before the first one is consumed, which is
+  // what keeps enough bytes in flight for an HBM-bound row kernel
+  constexpr int EMB_U = 4;
+  const int bstride = gridDim.x * ROW_WARPS;
+  for (int b0 = blockIdx.x * ROW_WARPS + warp; b0 < B; b0 += bstride * EMB_U) {
+    Raw8<T> zr[EMB_U][NCH];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = lane * 8 + i * 256;
-      if (c < F) { load8(src + c, z[i]); sm += sum8(z[i]); }
-      else {
+    for (int u = 0; u < EMB_U; ++u) {
+      const int b = b0 + u * bstride;
+      if (b < B) {
+        const T* src = is_audio ? pa + (long long)b * F : pv + ((long long)b * Tn + s) * F;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[i][j] = 0.f;
+        for (int i = 0; i < NCH; ++i) {
+          const int c = lane * 8 + i * 256;
+          if (c < F) zr[u][i].load(src + c);
+        }
       }
     }
-    float mean = 0.f, rstd = 1.f;
-    if (gamma != nullptr) {
-      mean = warp_sum(sm) / (float)F;
-      float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < EMB_U; ++u) {
+      const int b = b0 + u * bstride;
+      if (b >= B) break;
+      const long long row = (long long)b * S + s;
+      float z[NCH][8];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+        if (lane * 8 + i * 256 < F) zr[u][i].get(z[i]);
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (c < F) { sm += sum8(z[i]); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[i][j] = 0.f;
+        }
+      }
+      float mean = 0.f, rstd = 1.f;
+      if (gamma != nullptr) {
+        mean = warp_sum(sm) / (float)F;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c = lane * 8 + i * 256;
+          if (c < F) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = z[i][j] - mean; q += d * d; }
+          }
+        }
+        rstd = rsqrtf(warp_sum(q) / (float)F + LN_EPS);
+        if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+      }
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         const int c = lane * 8 + i * 256;
         if (c < F) {
+          const long long off = row * F + c;
+          float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float d = z[i][j] - mean; q += d * d; }
+          for (int j = 0; j < 8; ++j)
+            o[j] = (gamma != nullptr ? (z[i][j] - mean) * rstd * g[i][j] + be[i][j] : z[i][j]) + pe[i][j];
+          if (dc.thr) {
+            float f[8];
+            drop8(dc, (uint64_t)off, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] *= f[j];
+          }
+          store8(x0 + off, o);
         }
-      }
-      rstd = rsqrtf(warp_sum(q) / (float)F + LN_EPS);
-      if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
-    }
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = lane * 8 + i * 256;
-      if (c < F) {
-        const long long off = row * F + c;
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = (gamma != nullptr ? (z[i][j] - mean) * rstd * g[i][j] + be[i][j] : z[i][j]) + pe[i][j];
-        if (dc.thr) {
-          float f[8];
-          drop8(dc, (uint64_t)off, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] *= f[j];
-        }
-        store8(x0 + off, o);
       }
     }
   }
 }
 
 template <typename T, int NCH>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
 embed_bwd_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const T* __restrict__ pa,
                  const float* __restrict__ stats, const float* __restrict__ gv, const float* __restrict__ ga,
                  T* __restrict__ dpv, T* __restrict__ dpa, float* __restrict__ dgv, float* __restrict__ dbv,
@@ -306,29 +330,48 @@ embed_bwd_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const T* _
     for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; g[i][j] = 1.f; }
     if (c < F && gamma != nullptr) load8(gamma + c, g[i]);
   }
-  for (int b = blockIdx.x * ROW_WARPS + warp; b < B; b += gridDim.x * ROW_WARPS) {
+  // the next row's loads are in flight (as raw 16-byte registers) while the current row is processed
+  Raw8<T> nd[NCH], nz[NCH];
+  auto prefetch = [&](int b) {
+    if (b < B) {
+      const long long srow = is_audio ? (long long)b : (long long)b * Tn + s;
+      const T* src = (is_audio ? pa : pv) + srow * F;
+      const T* dsrc = dx0 + ((long long)b * S + s) * F;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (c < F) { nd[i].load(dsrc + c); nz[i].load(src + c); }
+      }
+    }
+  };
+  const int bstride = gridDim.x * ROW_WARPS;
+  prefetch(blockIdx.x * ROW_WARPS + warp);
+  for (int b = blockIdx.x * ROW_WARPS + warp; b < B; b += bstride) {
     const long long srow = is_audio ? (long long)b : (long long)b * Tn + s;
-    const T* src = (is_audio ? pa : pv) + srow * F;
     T* dst = (is_audio ? dpa : dpv) + srow * F;
     const long long row = (long long)b * S + s;
     float mean = 0.f, rstd = 1.f;
     if (gamma != nullptr) { mean = stats[row * 2]; rstd = stats[row * 2 + 1]; }
     float xh[NCH][8], gd[NCH][8];
     float s1 = 0.f, s2 = 0.f;
+    Raw8<T> cd[NCH], cz[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { cd[i] = nd[i]; cz[i] = nz[i]; }
+    prefetch(b + bstride);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = lane * 8 + i * 256;
       if (c < F) {
         const long long off = row * F + c;
         float d[8], z[8];
-        load8(dx0 + off, d);
+        cd[i].get(d);
         if (dc.thr) {
           float f[8];
           drop8(dc, (uint64_t)off, f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] *= f[j];
         }
-        load8(src + c, z);
+        cz[i].get(z);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           pb[i][j] += d[j];  // = dpos contribution = dbeta contribution

@@ -101,11 +101,34 @@ def bench_adam():
     timeit("adam (7.77M params, 30 B each)", [lambda: ops.adam_step(p, gr, m, v, sh, 3, 1e-4, weight_decay=1e-4)], n * 30, reps=50)
 
 
+def bench_embed():
+    gv, bv, ga, ba = (torch.ones(F, device=dev) for _ in range(4))
+    pos = torch.zeros(S, F, device=dev)
+    sets = [(rnd(B * T, F), rnd(B, F), rnd(M, F)) for _ in range(NBUF)]
+    dg = [torch.zeros(F, device=dev) for _ in range(4)]
+    dpos = torch.zeros(S, F, device=dev)
+    stats = ops.embed_fwd(sets[0][0], sets[0][1], gv, bv, ga, ba, pos, B, T)[1]
+    timeit("embed_fwd p=0.1", [lambda pv=pv, pa=pa: ops.embed_fwd(pv, pa, gv, bv, ga, ba, pos, B, T, drop_p=0.1, seed=1, site=1)
+                               for pv, pa, _ in sets], (B * T * F + B * F + M * F) * 2)
+    timeit("embed_bwd p=0.1", [lambda pv=pv, pa=pa, dx=dx: ops.embed_bwd(dx, pv, pa, stats, gv, ga, B, T, dg[0], dg[1], dg[2],
+                                                                         dg[3], dpos, drop_p=0.1, seed=1, site=1)
+                               for pv, pa, dx in sets], (2 * (B * T * F + B * F) + M * F) * 2)
+
+
+def bench_head():
+    Hd, Cn = 512, 6
+    h = rnd(B, Hd)
+    W, dW, db = torch.randn(Cn, Hd, device=dev), torch.zeros(Cn, Hd, device=dev), torch.zeros(Cn, device=dev)
+    dl = torch.randn(B, Cn, device=dev)
+    timeit("head_out_bwd (4096x512 -> 6)", [lambda: ops.head_out_bwd(dl, h, W, dW, db)], 2 * B * Hd * 2, reps=50)
+
+
 def main():
-    which = sys.argv[1:] or ["mha", "add_ln", "colsum", "adam"]
+    which = sys.argv[1:] or ["mha", "add_ln", "embed", "head", "adam"]
     print(torch.cuda.get_device_name(0), f"HBM peak {PEAK:.0f} GB/s (measured)")
     for w in which:
-        {"mha": bench_mha, "add_ln": bench_add_ln, "colsum": bench_colsum, "adam": bench_adam}[w]()
+        {"mha": bench_mha, "add_ln": bench_add_ln, "colsum": bench_colsum, "adam": bench_adam, "embed": bench_embed,
+         "head": bench_head}[w]()
 
 
 if __name__ == "__main__":
