@@ -161,6 +161,39 @@ def cpu_port_step_time(batch: int, steps: int, warmup: int, threads: int):
     return sum(times) / len(times)
 
 
+def torch_eager_gpu_rate(dev, dtype, steps=6, warmup=3):
+    """The reference architecture on STOCK torch.nn modules (what train2.py itself launches: cuBLAS, SDPA, one kernel
+    per elementwise op), same batch/shape, eager, fwd + FocalLoss + bwd + torch.optim.Adam.  A reported comparison
+    on the same GPU, not part of the product path."""
+    from oracle import eager_torch as E
+    torch.manual_seed(0)
+    model = E.EagerModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512, fusion_dropout=0.1,
+                         classifier_dropout=0.1).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    alpha = torch.tensor(ALPHA, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    v = torch.randn(B_PER_GPU, T, DV, generator=g).to(dev)
+    a = torch.randn(B_PER_GPU, DA, generator=g).to(dev)
+    y = torch.randint(0, NCLS, (B_PER_GPU,), generator=g).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+            _, logits = model(v, a, None)
+        loss = E.focal_loss(logits.float(), y, 2.0, alpha)
+        loss.backward()
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B_PER_GPU / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "what": "reference architecture on stock torch.nn (nn.TransformerEncoder, cuBLAS/SDPA), eager, "
+                    + ("autocast bf16" if dtype == torch.bfloat16 else "fp32") + ", same GPU, batch 4096"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -335,6 +368,11 @@ def run_ours(args):
         }
         out["roofline"] = time_dominant_kernel(dev, pk)
         if world == 1:
+            try:
+                out["torch_eager_gpu"] = {"bf16": torch_eager_gpu_rate(dev, torch.bfloat16),
+                                          "fp32": torch_eager_gpu_rate(dev, torch.float32)}
+            except Exception as exc:   # a comparison line must never take the bench down
+                out["torch_eager_gpu"] = {"error": repr(exc)[:200]}
             threads = os.cpu_count() or 1
             cb = 128
             dt = cpu_port_step_time(cb, 3, 1, threads)

@@ -162,3 +162,20 @@ def test_bf16_storage_noise_floor():
     assert float((l0 - l1).abs().max()) < 2e-2 * float(l0.abs().max())
     errs = {k: float((g0[k] - g1[k]).norm() / g0[k].norm()) for k in g0 if k.startswith("fusion.transformer")}
     assert 0.04 < min(errs.values()) and max(errs.values()) < 0.12, errs
+
+
+def test_stock_torch_restatement_matches_reference_golden():
+    """oracle/eager_torch.py (the reference architecture on stock torch.nn modules, used by bench.py as the
+    'what the reference launches on a GPU' comparison) reproduces the reference's golden logits."""
+    from oracle import eager_torch as E
+    for name in ("v2_b8_t5_mask", "v2_b4_t16_nomask"):
+        g, P, video, audio, mask, labels = load_case(name, "v2")
+        T = video.shape[1]
+        model = E.EagerModel(max_seq_len=T + 1, classifier_hidden_dim=512).eval()
+        model.load_state_dict(P, strict=True)
+        with torch.no_grad():
+            probs, logits = model(video, audio, mask)
+        np.testing.assert_allclose(logits.numpy(), g["eval/logits"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(probs.numpy(), g["eval/probs"], rtol=2e-4, atol=1e-6)
+        lf = E.focal_loss(logits, labels, 2.0, ALPHA.float())
+        np.testing.assert_allclose(float(lf), float(g["loss/focal_alpha"]), rtol=1e-4)
