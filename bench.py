@@ -214,29 +214,83 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def _timed(fns, reps):
+    """Average CUDA-event time (ms) of fns[i % n]() on the current stream, after one warm pass."""
+    for f in fns:
+        f()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        fns[i % len(fns)]()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def time_dominant_kernel(dev, pk):
-    """tcgen05 GEMM at the FFN1 forward shape of the workload, timed alone with CUDA events."""
+    """tcgen05 GEMM at the FFN1 forward shape of the workload (the step's largest single kernel), timed alone with
+    CUDA events over operand sets larger than L2.  `traffic` comes from the committed ncu --set full capture."""
     from mmer_b200 import ops
     M, K, N = B_PER_GPU * (T + 1), 512, 2048
     xs = [torch.randn(M, K, device=dev, dtype=torch.bfloat16) for _ in range(3)]   # 3 x 71 MB + outputs > L2
     w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
     bias = torch.zeros(N, device=dev)
     outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(3)]
-    for i in range(3):
-        ops.gemm(xs[i], w, M=M, N=N, K=K, bias=bias, relu=True, out=outs[i])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 30
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(reps):
-        ops.gemm(xs[i % 3], w, M=M, N=N, K=K, bias=bias, relu=True, out=outs[i % 3])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    ms = _timed([lambda i=i: ops.gemm(xs[i], w, M=M, N=N, K=K, bias=bias, relu=True, out=outs[i]) for i in range(3)], 30)
     tflops = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel<256,K,K> FFN1 fwd 69632x512x2048 +bias+ReLU",
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+            traffic = json.load(f)["traffic_bytes"]
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<256,K,K,pair,staged> FFN1 fwd 69632x512x2048 +bias+ReLU",
             "achieved": tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tflops / pk["tf_burst"],
-            "peak_source": pk["src"] + " bf16_tflops (burst: kernel timed alone)", "ms_per_launch": ms, "traffic": None}
+            "peak_source": pk["src"] + " bf16_tflops (burst: kernel timed alone)", "ms_per_launch": ms,
+            "algorithmic_flop_per_launch": 2.0 * M * N * K, "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_roofline_traffic.json"}
+
+
+def time_memory_bound_kernels(dev, pk):
+    """The step's HBM-bound kernels timed alone (CUDA events, 3 rotating buffer sets > L2): algorithmic bytes per
+    launch / time against the measured copy bandwidth.  Explains the part of the step the GEMM roofline does not."""
+    from mmer_b200 import ops
+    F, H, D = 512, 8, 64
+    B, S = B_PER_GPU, T + 1
+    M = B * S
+    bf = torch.bfloat16
+    rnd = lambda *s: torch.randn(*s, device=dev, dtype=bf)
+    out = []
+
+    def add(name, fns, nbytes, reps=20):
+        ms = _timed(fns, reps)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": gbs / pk["hbm"], "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes})
+
+    sets = [(rnd(M, 3 * F), rnd(M, F)) for _ in range(3)]
+    add("mha_fwd_mma_kernel (p=0.1)", [lambda q=q: ops.mha_fwd(q, None, B, T, H, D, drop_p=0.1, seed=1, site=1) for q, _ in sets],
+        M * 3 * F * 2 + M * F * 2)
+    add("mha_bwd_mma_kernel (p=0.1)", [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=0.1, seed=1, site=1)
+                                       for q, d in sets], 2 * M * 3 * F * 2 + M * F * 2)
+    del sets
+    gam, bet = torch.ones(F, device=dev), torch.zeros(F, device=dev)
+    dg, db, dbias = (torch.zeros(F, device=dev) for _ in range(3))
+    sets = [(rnd(M, F), rnd(M, F), rnd(M, F)) for _ in range(3)]
+    stats = ops.add_ln_fwd(sets[0][0], sets[0][1], gam, bet)[1]
+    add("add_ln_fwd_pipe_kernel (p=0.1)", [lambda x=x, a=a: ops.add_ln_fwd(x, a, gam, bet, drop_a_p=0.1, site_a=1, seed=1)
+                                           for x, a, _ in sets], 3 * M * F * 2)
+    add("add_ln_bwd_pipe_kernel (p=0.1)",
+        [lambda x=x, a=a, dy=dy: ops.add_ln_bwd(dy, x, a, stats, gam, bet, dg, db, dbias, drop_a_p=0.1, site_a=1, seed=1)
+         for x, a, dy in sets], 5 * M * F * 2)
+    del sets
+    n = 7_765_510
+    p_, g_, m_, v_ = (torch.randn(n, device=dev) for _ in range(4))
+    v_.abs_()
+    sh = torch.empty(n, device=dev, dtype=bf)
+    add("adam_kernel (7.77 M params)", [lambda: ops.adam_step(p_, g_, m_, v_, sh, 3, 1e-4, weight_decay=1e-4)], n * 30, reps=40)
+    return out
 
 
 def run_ours(args):
@@ -368,6 +422,7 @@ def run_ours(args):
         }
         out["roofline"] = time_dominant_kernel(dev, pk)
         if world == 1:
+            out["roofline_hbm_kernels"] = time_memory_bound_kernels(dev, pk)
             try:
                 out["torch_eager_gpu"] = {"bf16": torch_eager_gpu_rate(dev, torch.bfloat16),
                                           "fp32": torch_eager_gpu_rate(dev, torch.float32)}

@@ -277,9 +277,17 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
   const int g = lane >> 2, t = lane & 3;
   const float scale = rsqrtf((float)D);
   uint32_t phase = 0;
+#ifdef MMER_ATT_PROFILE
+  long long pt[4] = {0, 0, 0, 0}, pc = clock64();
+#define ATT_TICK(i) do { long long _n = clock64(); pt[i] += _n - pc; pc = _n; } while (0)
+#else
+#define ATT_TICK(i)
+#endif
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
   const uint32_t kvalid = key_valid_bits<NT>(mask, b, gm.Tn, S, t);
+  ATT_TICK(3);
   mbar_wait(bar_a, phase);
+  ATT_TICK(0);
   phase ^= 1;
 
   for (int h = warp; h < H; h += MMA_WARPS) {
@@ -425,8 +433,10 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
       store_tile<D>(smem + F * 2 + h * D * 2, gm.in_stride, mk * 16, S, lane, acck[mk]);
     __syncwarp();
   }
+  ATT_TICK(1);
   fence_async_smem();
   __syncthreads();
+  ATT_TICK(2);
   if (warp == 0) {
     for (int r = lane; r < S; r += 32) {
       bf16* drow = dqkv + ((long long)b * S + r) * 3 * F;
@@ -455,6 +465,10 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
   __syncthreads();   // rows drained by the stores and read by the column sums: the next sample may land
   if (warp == 0 && b + (int)gridDim.x < B) issue_loads(b + gridDim.x);
   }  // sample loop
+#ifdef MMER_ATT_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("mha_bwd warp %d: wait_load %lld compute %lld barrier %lld store+colsum+issue %lld\n", warp, pt[0], pt[1], pt[2], pt[3]);
+#endif
   if (dbias != nullptr) {
     __syncthreads();
     for (int c = threadIdx.x; c < 3 * F; c += blockDim.x) atomicAdd(dbias + c, colacc[c]);
