@@ -291,3 +291,105 @@ def test_torch_optimizer_and_clip_work_on_flat_views():
     for k, p in model.named_parameters():
         got = summarize(p.detach() - before[k])
         np.testing.assert_allclose(got[2:], g["delta1/" + k][2:], rtol=0, atol=3e-6, err_msg=k)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json full sizes
+def _full_size_model(T, layers=2):
+    torch.manual_seed(0)
+    return mm.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=layers, classifier_hidden_dim=512,
+                                     fusion_dropout=0.0, classifier_dropout=0.0).cuda()
+
+
+def test_cfg2_full_batch_is_sample_independent_and_matches_small_batches_bf16():
+    """cfg2 size (B=4096, T=16, bf16): the oracle cannot run this in seconds, so check the size-independent
+    properties the model has by construction (LayerNorm variant: no cross-sample coupling):
+    a permutation of the batch permutes logits bit for bit, and slices evaluated on their own give the same logits
+    (different GEMM tilings / CTA-pair vs single-CTA kernels) to bf16 tolerance."""
+    B, T = 4096, 16
+    model = _full_size_model(T).eval()
+    model.compute_dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    video = torch.randn(B, T, 768, generator=g).cuda().bfloat16()
+    audio = torch.randn(B, 1024, generator=g).cuda().bfloat16()
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None] >= lens[:, None]).cuda()
+    with torch.no_grad():
+        probs, logits, _ = model(video, audio, mask)
+        perm = torch.randperm(B, generator=g).cuda()
+        _, logits_p, _ = model(video[perm], audio[perm], mask[perm])
+        assert torch.equal(logits_p, logits[perm])
+        _, logits_s, _ = model(video[:96], audio[:96], mask[:96])
+    err = float((logits_s - logits[:96]).abs().max() / logits.abs().max())
+    assert err < 2e-2
+    assert float((logits_s.argmax(1) == logits[:96].argmax(1)).float().mean()) > 0.97
+    assert torch.allclose(probs.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+
+
+def test_cfg2_full_size_training_step_gradient_is_mean_of_shard_gradients_bf16():
+    """cfg2 size: the gradient of the mean loss over 4096 samples equals the average of the gradients over its four
+    1024-sample shards (the identity the data-parallel all-reduce relies on), to bf16 accumulation noise."""
+    B, T = 4096, 16
+    model = _full_size_model(T).train()
+    model.compute_dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(6)
+    video = torch.randn(B, T, 768, generator=g).cuda().bfloat16()
+    audio = torch.randn(B, 1024, generator=g).cuda().bfloat16()
+    labels = torch.randint(0, 6, (B,), generator=g).cuda()
+    crit = mm.FocalLoss(gamma=2.0, alpha=ALPHA.cuda())
+
+    def grad_of(sl):
+        model.zero_grad(set_to_none=True)
+        _, logits, _ = model(video[sl], audio[sl])
+        crit(logits, labels[sl]).backward()
+        return model._engine.ctx.grads.clone()
+
+    full = grad_of(slice(0, B))
+    parts = sum(grad_of(slice(i * 1024, (i + 1) * 1024)) for i in range(4)) / 4
+    rel_err = float((full - parts).norm() / full.norm())
+    assert rel_err < 2e-2, rel_err
+
+
+def test_cfg4_long_sequence_attention_weights_bf16():
+    """cfg4 (train2 variant, T=256, return_attn=True): rows of every attention map sum to 1, masked keys get exactly
+    zero weight, the audio row is the last row of the head-mean of the last layer, and bf16 agrees with the fp32
+    path on the argmax of the audio row for almost every sample."""
+    B, T = 16, 256
+    model = _full_size_model(T).eval()
+    g = torch.Generator().manual_seed(7)
+    video = torch.randn(B, T, 768, generator=g).cuda()
+    audio = torch.randn(B, 1024, generator=g).cuda()
+    lens = torch.randint(32, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None] >= lens[:, None]).cuda()
+    outs = {}
+    for dt in (torch.float32, torch.bfloat16):
+        model.compute_dtype = dt
+        with torch.no_grad():
+            probs, logits, attn = model(video.to(dt), audio.to(dt), mask, return_attn=True)
+        outs[dt] = (logits.float(), attn)
+        last = attn["layers"][-1]                       # (B, H, S, S)
+        assert torch.allclose(last.sum(-1), torch.ones_like(last.sum(-1)), atol=1e-4)
+        full = torch.cat([mask, torch.zeros(B, 1, dtype=torch.bool, device="cuda")], 1)
+        assert float(last.masked_select(full.view(B, 1, 1, T + 1).expand_as(last)).abs().max()) == 0.0
+        assert torch.allclose(attn["last_mean"], last.mean(1), atol=1e-6)
+        assert torch.equal(attn["audio_row"], attn["last_mean"][:, -1, :])
+    err = float((outs[torch.bfloat16][0] - outs[torch.float32][0]).abs().max() / outs[torch.float32][0].abs().max())
+    assert err < 5e-2
+    same = (outs[torch.bfloat16][1]["audio_row"].argmax(1) == outs[torch.float32][1]["audio_row"].argmax(1)).float().mean()
+    assert float(same) >= 0.8
+
+
+@pytest.mark.parametrize("B", [1, 8192])
+def test_cfg5_inference_batch_1_and_8192_bf16(B):
+    """cfg5: inference-only forward at batch 1 (serving latency shape, T=5 as in routers/infer.py:9) and batch 8192."""
+    T = 5 if B == 1 else 16
+    model = _full_size_model(T).eval()
+    model.compute_dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(8)
+    video = torch.randn(B, T, 768, generator=g).cuda().bfloat16()
+    audio = torch.randn(B, 1024, generator=g).cuda().bfloat16()
+    with torch.no_grad():
+        probs, logits, attn = model(video, audio)
+        assert attn is None and probs.shape == (B, 6) and bool(torch.isfinite(logits).all())
+        # the same sample inside a batch of copies gives the same logits
+        probs2, logits2, _ = model(video[:1].expand(3, -1, -1).contiguous(), audio[:1].expand(3, -1).contiguous())
+    assert float((logits2 - logits[:1]).abs().max()) < 2e-2 * float(logits.abs().max())
