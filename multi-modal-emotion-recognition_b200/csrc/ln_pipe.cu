@@ -427,4 +427,424 @@ int add_ln_bwd_pipe(const void* dy, const void* x, const void* a, const float* s
   LNP_DISPATCH(F, (bwd_launch<float, NCH>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, M, F, relu, da, ddy, st)));
 }
 
+// =========================================================================================================
+// Token assembly (train2.py:150-161): x0[b, s] = dropout(LN_v(pv[b, s]) + pos[s])  for s < T,
+//                                     x0[b, T] = dropout(LN_a(pa[b])    + pos[T])
+// on the same stage ring.  A tile is W consecutive OUTPUT rows r = b*S + s.  Their video sources are a contiguous
+// range of pv rows (row r maps to pv row r - b, and the audio row of a sample is exactly the gap between two
+// samples), their audio sources a contiguous range of pa rows, so a stage is filled by two bulk copies (three in
+// backward, with the gradient rows) regardless of where sample boundaries fall, and every warp has one row per tile.
+// =========================================================================================================
+// Tile walker: position of a tile's first row as (sample b0, position s0), advanced incrementally so that the
+// per-tile bookkeeping needs no 64-bit divisions.
+struct EmbedTile {
+  long long r0;      // first output row
+  int rows;          // output rows in the tile
+  int b0, s0;        // sample and position of r0
+  long long v0;      // first pv row
+  int nv;            // pv rows
+  int a0;            // first pa row (= b0: position s0 <= T, so sample b0's audio row is still ahead)
+  int na;            // pa rows
+};
+struct EmbedWalk {
+  long long r0, Mtot;
+  int b0, s0, W, S, Tn, step_b, step_s;
+  __device__ __forceinline__ void init(long long first_tile, long long tiles_step, int W_, long long Mtot_, int S_, int Tn_) {
+    W = W_; S = S_; Tn = Tn_; Mtot = Mtot_;
+    r0 = first_tile * W;
+    b0 = (int)(r0 / S);
+    s0 = (int)(r0 % S);
+    const long long step = tiles_step * W;
+    step_b = (int)(step / S);
+    step_s = (int)(step % S);
+  }
+  __device__ __forceinline__ bool valid() const { return r0 < Mtot; }
+  __device__ __forceinline__ void next() {
+    r0 += (long long)step_b * S + step_s;
+    b0 += step_b;
+    s0 += step_s;
+    if (s0 >= S) { s0 -= S; ++b0; }
+  }
+  __device__ __forceinline__ EmbedTile tile() const {
+    EmbedTile e;
+    e.r0 = r0;
+    const long long left = Mtot - r0;
+    e.rows = (int)(left < W ? left : W);
+    e.b0 = b0; e.s0 = s0;
+    int s1 = s0 + e.rows, b1 = b0;
+    b1 += s1 / S;
+    s1 -= (s1 / S) * S;
+    e.v0 = (long long)b0 * Tn + (s0 < Tn ? s0 : Tn);
+    e.nv = (int)((long long)b1 * Tn + (s1 < Tn ? s1 : Tn) - e.v0);
+    e.a0 = b0;
+    e.na = b1 - b0;
+    return e;
+  }
+};
+// sample and position of the tile's row w
+__device__ __forceinline__ void embed_row(const EmbedTile& e, int w, int S, int& b, int& s) {
+  s = e.s0 + w;
+  const int q = s / S;
+  b = e.b0 + q;
+  s -= q * S;
+}
+
+struct EmbedGeom {
+  long long Mtot;    // B * S output rows
+  int F, W, stages, S, Tn, with_grad;
+  uint32_t row_bytes, stage_bytes;   // stage = [W rows of sources][W rows of gradients (backward)]
+};
+
+template <typename T>
+__device__ __forceinline__ void embed_produce(const EmbedGeom& g, const T* pv, const T* pa, const T* dx0, uint32_t smem_a,
+                                              uint32_t full_a, uint32_t empty_a) {
+  int stage = 0;
+  uint32_t phase = 0;
+  EmbedWalk wk;
+  for (wk.init(blockIdx.x, gridDim.x, g.W, g.Mtot, g.S, g.Tn); wk.valid(); wk.next()) {
+    const EmbedTile e = wk.tile();
+    mbar_wait(empty_a + 8 * stage, phase ^ 1);
+    const uint32_t full = full_a + 8 * stage;
+    mbar_expect_tx(full, (uint32_t)(e.nv + e.na + (g.with_grad ? e.rows : 0)) * g.row_bytes);
+    const uint32_t base = smem_a + stage * g.stage_bytes;
+    if (e.nv > 0) bulk_g2s(base, pv + e.v0 * g.F, (uint32_t)e.nv * g.row_bytes, full);
+    if (e.na > 0) bulk_g2s(base + (uint32_t)e.nv * g.row_bytes, pa + (long long)e.a0 * g.F, (uint32_t)e.na * g.row_bytes, full);
+    if (g.with_grad) bulk_g2s(base + (uint32_t)g.W * g.row_bytes, dx0 + e.r0 * g.F, (uint32_t)e.rows * g.row_bytes, full);
+    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+  }
+}
+
+__device__ __forceinline__ LnSmem embed_setup(const EmbedGeom& g, uint8_t* smem) {
+  LnSmem s;
+  s.data = smem;
+  s.data_a = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * g.stage_bytes);
+  s.full_a = smem_u32(bars);
+  s.empty_a = smem_u32(bars + LNP_MAX_STAGES);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(s.full_a + 8 * i, 1);
+      mbar_init(s.empty_a + 8 * i, g.W);
+    }
+    mbar_init_fence();
+  }
+  __syncthreads();
+  return s;
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
+embed_fwd_pipe_kernel(const T* __restrict__ pv, const T* __restrict__ pa, const float* __restrict__ gv,
+                      const float* __restrict__ bv, const float* __restrict__ ga, const float* __restrict__ ba,
+                      const float* __restrict__ pos, T* __restrict__ x0, float* __restrict__ stats, EmbedGeom g, DropCfg dc) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LnSmem sm = embed_setup(g, smem);
+  const int F = g.F, S = g.S, Tn = g.Tn;
+  if (warp == g.W) {
+    if (lane == 0) embed_produce<T>(g, pv, pa, nullptr, sm.data_a, sm.full_a, sm.empty_a);
+    return;
+  }
+  float gmv[NCH][8], btv[NCH][8];   // LayerNorm parameters of the video tokens (16 of 17 rows)
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane * 8 + i * 256;
+    if (c < F) { load8(gv + c, gmv[i]); load8(bv + c, btv[i]); }
+  }
+  const float invF = 1.f / (float)F;
+  int stage = 0;
+  uint32_t phase = 0;
+  EmbedWalk wk;
+  for (wk.init(blockIdx.x, gridDim.x, g.W, g.Mtot, S, Tn); wk.valid(); wk.next()) {
+    const EmbedTile e = wk.tile();
+    const long long row = e.r0 + warp;
+    const bool have = warp < e.rows;
+    int b, s;
+    embed_row(e, warp, S, b, s);
+    const bool audio = s == Tn;
+    mbar_wait(sm.full_a + 8 * stage, phase);
+    float z[NCH][8];
+    float sum = 0.f;
+    if (have) {
+      const int slot = audio ? e.nv + (b - e.a0) : (int)((long long)b * Tn + s - e.v0);
+      const T* src = reinterpret_cast<const T*>(sm.data + (size_t)stage * g.stage_bytes) + (size_t)slot * F;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (c < F) { load8(src + c, z[i]); sum += sum8f(z[i]); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[i][j] = 0.f;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm.empty_a + 8 * stage);
+    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+    if (!have) continue;
+    const float mean = warp_sum(sum) * invF;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = z[i][j] - mean; q = fmaf(d, d, q); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invF + LNP_EPS);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+    const float nmr = -mean * rstd;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+        const long long off = row * F + c;
+        float pe[8], o[8], gg[8], bb[8];
+        load8(pos + (long long)s * F + c, pe);
+        if (audio) { load8(ga + c, gg); load8(ba + c, bb); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = fmaf(fmaf(z[i][j], rstd, nmr), audio ? gg[j] : gmv[i][j], audio ? bb[j] : btv[i][j]) + pe[j];
+        if (dc.thr) {
+          float f[8];
+          drop8(dc, (uint64_t)off, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= f[j];
+        }
+        store8(x0 + off, o);
+      }
+    }
+  }
+}
+
+// backward of the token assembly: dpv / dpa = LayerNorm backward of the (dropout-masked) gradient rows, dgamma of both
+// norms.  dbeta of both norms and dpos are column sums of the masked gradient per position: embed_dpos_kernel.
+template <typename T, int NCH>
+__global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
+embed_bwd_pipe_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const T* __restrict__ pa,
+                      const float* __restrict__ stats, const float* __restrict__ gv, const float* __restrict__ ga,
+                      T* __restrict__ dpv, T* __restrict__ dpa, float* __restrict__ dgv, float* __restrict__ dga,
+                      EmbedGeom g, DropCfg dc) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LnSmem sm = embed_setup(g, smem);
+  const int F = g.F, S = g.S, Tn = g.Tn;
+  const bool compute_warp = warp < g.W;
+  // audio rows are 1 in S: their dgamma partials go through shared-memory atomics instead of a second register set
+  float* sga = reinterpret_cast<float*>(smem + (size_t)g.stages * g.stage_bytes + 2 * LNP_MAX_STAGES * 8);
+  for (int c = threadIdx.x; c < F; c += blockDim.x) sga[c] = 0.f;
+  __syncthreads();
+  float pg[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pg[i][j] = 0.f;
+  if (!compute_warp) {
+    if (lane == 0) embed_produce<T>(g, pv, pa, dx0, sm.data_a, sm.full_a, sm.empty_a);
+  } else {
+    float gmv[NCH][8];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) load8(gv + c, gmv[i]);
+    }
+    const float invF = 1.f / (float)F;
+    int stage = 0;
+    uint32_t phase = 0;
+    EmbedWalk wk;
+    for (wk.init(blockIdx.x, gridDim.x, g.W, g.Mtot, S, Tn); wk.valid(); wk.next()) {
+      const EmbedTile e = wk.tile();
+      const long long row = e.r0 + warp;
+      const bool have = warp < e.rows;
+      int b, s;
+      embed_row(e, warp, S, b, s);
+      const bool audio = s == Tn;
+      float mean = 0.f, rstd = 0.f;
+      if (have) {
+        const float2 st = *reinterpret_cast<const float2*>(stats + row * 2);
+        mean = st.x;
+        rstd = st.y;
+      }
+      mbar_wait(sm.full_a + 8 * stage, phase);
+      float xh[NCH][8], gd[NCH][8];
+      float s1 = 0.f, s2 = 0.f;
+      if (have) {
+        const uint8_t* sb = sm.data + (size_t)stage * g.stage_bytes;
+        const int slot = audio ? e.nv + (b - e.a0) : (int)((long long)b * Tn + s - e.v0);
+        const T* sz = reinterpret_cast<const T*>(sb) + (size_t)slot * F;
+        const T* sd = reinterpret_cast<const T*>(sb + (size_t)g.W * g.row_bytes) + (size_t)warp * F;
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c = lane * 8 + i * 256;
+          if (c < F) {
+            float d[8], z[8], gg[8];
+            load8(sd + c, d);
+            if (dc.thr) {
+              float f[8];
+              drop8(dc, (uint64_t)(row * F + c), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] *= f[j];
+            }
+            load8(sz + c, z);
+            if (audio) load8(ga + c, gg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              xh[i][j] = fmaf(z[j], rstd, nmr);
+              const float dg = d[j] * xh[i][j];
+              if (audio) atomicAdd(sga + c + j, dg); else pg[i][j] += dg;
+              gd[i][j] = d[j] * (audio ? gg[j] : gmv[i][j]);
+              s1 += gd[i][j];
+              s2 = fmaf(gd[i][j], xh[i][j], s2);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.empty_a + 8 * stage);
+      if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      if (!have) continue;
+      const float c1r = warp_sum(s1) * invF * rstd;
+      const float c2r = warp_sum(s2) * invF * rstd;
+      T* dst = audio ? dpa + (long long)b * F : dpv + ((long long)b * Tn + s) * F;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (c < F) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[i][j], -c2r, fmaf(gd[i][j], rstd, -c1r));
+          store8(dst + c, o);
+        }
+      }
+    }
+  }
+  float* sred = reinterpret_cast<float*>(smem);
+  lnp_flush<NCH>(pg, dgv, F, g.W, sred, compute_warp);
+  for (int c = threadIdx.x; c < F; c += blockDim.x) atomicAdd(dga + c, sga[c]);
+}
+
+// dpos[s][c] += sum_b d[b,s,c];  dbeta_video[c] += the same for s < T;  dbeta_audio[c] += for s == T, with d the
+// dropout-masked gradient of the assembled tokens: a column sum of dx0 viewed as [B][S*F].
+template <typename T>
+__global__ void __launch_bounds__(256)
+embed_dpos_kernel(const T* __restrict__ dx0, float* __restrict__ dpos, float* __restrict__ dbv, float* __restrict__ dba,
+                  int B, int S, int F, DropCfg dc) {
+  __shared__ float sred[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long N = (long long)S * F;
+  const long long c = (long long)blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < N) {
+    for (int b = blockIdx.y * 8 + warp; b < B; b += gridDim.y * 8) {
+      float v[8];
+      const long long off = (long long)b * N + c;
+      load8(dx0 + off, v);
+      if (dc.thr) {
+        float f[8];
+        drop8(dc, (uint64_t)off, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sred[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const long long cc = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (cc < N) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sacc += sred[w][threadIdx.x];
+    if (dpos != nullptr) atomicAdd(dpos + cc, sacc);
+    const int s = (int)(cc / F), col = (int)(cc % F);
+    float* db = s == S - 1 ? dba : dbv;
+    if (db != nullptr) atomicAdd(db + col, sacc);
+  }
+}
+
+static int embed_geometry(long long B, long long T, long long F, int elt, int with_grad, EmbedGeom* g, size_t* smem_bytes) {
+  g->Mtot = B * (T + 1);
+  g->F = (int)F; g->S = (int)T + 1; g->Tn = (int)T; g->with_grad = with_grad;
+  g->row_bytes = (uint32_t)(F * elt);
+  const size_t budget = 200 * 1024;
+  const int arrays = with_grad ? 2 : 1;
+  int W = LNP_MAX_WARPS;
+  while (W > 1 && (size_t)2 * W * g->row_bytes * arrays > budget) --W;
+  if (g->Mtot < W) W = (int)g->Mtot;
+  g->W = W;
+  g->stage_bytes = (uint32_t)W * g->row_bytes * arrays;
+  int stages = (int)(budget / g->stage_bytes);
+  if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
+  MMER_CHECK_ARG(stages >= 2, "embed: row of %lld bytes does not fit the shared-memory pipeline", (long long)g->row_bytes);
+  g->stages = stages;
+  size_t data = (size_t)stages * g->stage_bytes;
+  const size_t red = (size_t)W * F * sizeof(float);
+  if (data < red) data = red;
+  *smem_bytes = data + 2 * LNP_MAX_STAGES * 8 + (size_t)F * sizeof(float) + 16;
+  return 0;
+}
+
+template <typename T, int NCH>
+static int embed_fwd_launch(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga,
+                            const float* ba, const float* pos, void* x0, float* stats, long long B, long long T_, long long F,
+                            DropCfg dc, cudaStream_t st) {
+  EmbedGeom g;
+  size_t smem;
+  MMER_TRY(embed_geometry(B, T_, F, sizeof(T), 0, &g, &smem));
+  static size_t configured = 0;
+  auto kern = embed_fwd_pipe_kernel<T, NCH>;
+  MMER_TRY(lnp_set_smem(kern, smem, &configured));
+  const long long tiles = (g.Mtot + g.W - 1) / g.W;
+  const long long cap = sm_count();
+  kern<<<(unsigned)(tiles < cap ? tiles : cap), (g.W + 1) * 32, smem, st>>>((const T*)pv, (const T*)pa, gv, bv, ga, ba, pos,
+                                                                            (T*)x0, stats, g, dc);
+  MMER_LAUNCH_CHECK("embed_fwd_pipe_kernel");
+  return 0;
+}
+template <typename T, int NCH>
+static int embed_bwd_launch(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv,
+                            const float* ga, void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba,
+                            float* dpos, long long B, long long T_, long long F, DropCfg dc, cudaStream_t st) {
+  EmbedGeom g;
+  size_t smem;
+  MMER_TRY(embed_geometry(B, T_, F, sizeof(T), 1, &g, &smem));
+  static size_t configured = 0;
+  auto kern = embed_bwd_pipe_kernel<T, NCH>;
+  MMER_TRY(lnp_set_smem(kern, smem, &configured));
+  const long long tiles = (g.Mtot + g.W - 1) / g.W;
+  const long long cap = sm_count();
+  kern<<<(unsigned)(tiles < cap ? tiles : cap), (g.W + 1) * 32, smem, st>>>((const T*)dx0, (const T*)pv, (const T*)pa, stats,
+                                                                            gv, ga, (T*)dpv, (T*)dpa, dgv, dga, g, dc);
+  MMER_LAUNCH_CHECK("embed_bwd_pipe_kernel");
+  const long long N = (T_ + 1) * F;
+  int gy = (int)((sm_count() * 4 + (N + 255) / 256 - 1) / ((N + 255) / 256));
+  if (gy < 1) gy = 1;
+  if (gy > (B + 7) / 8) gy = (int)((B + 7) / 8);
+  embed_dpos_kernel<T><<<dim3((unsigned)((N + 255) / 256), (unsigned)gy), 256, 0, st>>>((const T*)dx0, dpos, dbv, dba, (int)B,
+                                                                                        (int)T_ + 1, (int)F, dc);
+  MMER_LAUNCH_CHECK("embed_dpos_kernel");
+  return 0;
+}
+
+// LayerNorm variant of the token assembly (train2.py); the BatchNorm variant (no norm here) stays in rowops.cu
+int embed_fwd_pipe(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga, const float* ba,
+                   const float* pos, void* x0, float* stats, long long B, long long T, long long F, int dtype, DropCfg dc,
+                   cudaStream_t st) {
+  if (dtype == MMER_BF16) LNP_DISPATCH(F, (embed_fwd_launch<bf16, NCH>(pv, pa, gv, bv, ga, ba, pos, x0, stats, B, T, F, dc, st)));
+  LNP_DISPATCH(F, (embed_fwd_launch<float, NCH>(pv, pa, gv, bv, ga, ba, pos, x0, stats, B, T, F, dc, st)));
+}
+int embed_bwd_pipe(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv, const float* ga,
+                   void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos, long long B,
+                   long long T, long long F, int dtype, DropCfg dc, cudaStream_t st) {
+  if (dtype == MMER_BF16)
+    LNP_DISPATCH(F, (embed_bwd_launch<bf16, NCH>(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, B, T, F, dc, st)));
+  LNP_DISPATCH(F, (embed_bwd_launch<float, NCH>(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, B, T, F, dc, st)));
+}
+
 }  // namespace mmer

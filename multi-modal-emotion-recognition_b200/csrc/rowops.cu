@@ -16,6 +16,13 @@ int add_ln_bwd_pipe(const void* dy, const void* x, const void* a, const float* s
                     const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias, long long M,
                     long long F, int dtype, int relu, DropCfg da, DropCfg ddy, cudaStream_t st);
 
+int embed_fwd_pipe(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga, const float* ba,
+                   const float* pos, void* x0, float* stats, long long B, long long T, long long F, int dtype, DropCfg dc,
+                   cudaStream_t st);
+int embed_bwd_pipe(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv, const float* ga,
+                   void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos, long long B,
+                   long long T, long long F, int dtype, DropCfg dc, cudaStream_t st);
+
 static constexpr float LN_EPS = 1e-5f;
 static constexpr int ROW_WARPS = 8;  // warps per CTA for the row kernels
 
@@ -717,6 +724,8 @@ int mmer_embed_fwd(const void* pv, const void* pa, const float* gv, const float*
   if (B <= 0) return 0;
   DropCfg dc = make_drop(drop_p, seed, site);
   cudaStream_t st = (cudaStream_t)stream;
+  if (gv != nullptr && stats != nullptr)   // LayerNorm variant: bulk-copy pipelined kernel (ln_pipe.cu)
+    return embed_fwd_pipe(pv, pa, gv, bv, ga, ba, pos, x0, stats, B, T, F, dtype, dc, st);
   int gx = (int)((B + ROW_WARPS - 1) / ROW_WARPS);
   int cap = (sm_count() * 8) / (int)(T + 1) + 1;
   if (gx > cap) gx = cap;
@@ -741,6 +750,8 @@ int mmer_embed_bwd(const void* dx0, const void* pv, const void* pa, const float*
   if (B <= 0) return 0;
   DropCfg dc = make_drop(drop_p, seed, site);
   cudaStream_t st = (cudaStream_t)stream;
+  if (gv != nullptr && ga != nullptr && stats != nullptr && dgv && dga)
+    return embed_bwd_pipe(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, B, T, F, dtype, dc, st);
   int gx = (int)((B + ROW_WARPS - 1) / ROW_WARPS);
   int cap = (sm_count() * 2) / (int)(T + 1) + 1;
   if (gx > cap) gx = cap;

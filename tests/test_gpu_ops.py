@@ -244,8 +244,10 @@ def test_add_ln_dropout_consistency():
 
 # ----------------------------------------------------------------------------- token assembly / pooling
 @pytest.mark.parametrize("dt", DT)
-def test_embed_fwd_bwd(dt):
-    B, T, F = 9, 5, 512
+@pytest.mark.parametrize("B,T,F", [(9, 5, 512), (67, 16, 512), (40, 1, 256), (5, 31, 72), (3, 40, 1024)])
+def test_embed_fwd_bwd(dt, B, T, F):
+    """Tiles of 15 consecutive output rows cut through sample boundaries at every phase (T+1 = 6, 17, 2, 32, 41):
+    each tile's video rows and audio rows must come from the right contiguous source ranges."""
     pv, pa = rnd(B * T, F, dt=dt, seed=1), rnd(B, F, dt=dt, seed=2)
     gv, bv, ga, ba = rnd(F, seed=3) * .2 + 1, rnd(F, seed=4) * .2, rnd(F, seed=5) * .2 + 1, rnd(F, seed=6) * .2
     pos = rnd(T + 3, F, seed=7)
