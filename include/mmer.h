@@ -90,6 +90,11 @@ typedef struct mmer_gemm_args {
   uint32_t reserved;
   float* a_rowsum; /* optional fp32 [M]: += sum_k A[m][k].  Needs accumulate != 0 and an MN-major A: in a weight-gradient
                     * GEMM (A = dY^T) this is the bias gradient of the same Linear, produced by the same kernel */
+  /* 1 bit per output element (row-major, N/8 bytes per row; bf16 output, N % 64 == 0, ldd == N):
+   * relu_mask_out - written by a forward call: bit = stored value > 0 (after ReLU and dropout);
+   * gate_bits     - read by the matching dgrad call: acc *= bit ? gate_scale : 0.  16x less traffic than `gate`. */
+  uint8_t* relu_mask_out;
+  const uint8_t* gate_bits;
 } mmer_gemm_args;
 int mmer_gemm(const mmer_gemm_args* args, void* stream);
 

@@ -39,6 +39,7 @@ struct Carver {
 
 struct LayerWs {
   void *qkv, *att, *ao, *x1, *h, *f2, *x2;
+  uint8_t* hmask;   // bf16 mode: 1 bit per element of h (stored value > 0): the ReLU+dropout gate of backward
   float *st1, *st2;
 };
 struct Ws {
@@ -78,6 +79,7 @@ static void carve(const mmer_model* m, void* base, Ws* w) {
     L.ao = c.take(M * F * e);
     L.x1 = c.take(M * F * e);
     L.h = c.take(M * FF * e);
+    L.hmask = (m->dtype == MMER_BF16 && FF % 64 == 0) ? (uint8_t*)c.take(M * FF / 8) : nullptr;
     L.f2 = c.take(M * F * e);
     L.x2 = c.take(M * F * e);
     L.st1 = (float*)c.take(M * 2 * 4);
@@ -149,8 +151,9 @@ static inline const void* Wt(const mmer_model* m, int64_t off) {
 
 // y[M,N] = x[M,K] W[N,K]^T + b, optional relu / dropout
 static int lin_fwd(const mmer_model* m, const void* x, int64_t M, int64_t K, int64_t offW, int64_t offB, void* y,
-                   int64_t N, int relu, float drop_p, uint32_t site, cudaStream_t st) {
+                   int64_t N, int relu, float drop_p, uint32_t site, cudaStream_t st, uint8_t* mask_out = nullptr) {
   mmer_gemm_args a = {};
+  a.relu_mask_out = mask_out;
   a.A = x; a.B = Wt(m, offW); a.D = y; a.bias = P(m, offB);
   a.M = M; a.N = N; a.K = K; a.lda = K; a.ldb = K; a.ldd = N;
   a.a_major = MMER_MAJOR_K; a.b_major = MMER_MAJOR_K;
@@ -160,8 +163,10 @@ static int lin_fwd(const mmer_model* m, const void* x, int64_t M, int64_t K, int
 }
 // dx[M,K] = dy[M,N] W[N,K] (+ residual) (* gate)
 static int lin_dgrad(const mmer_model* m, const void* dy, int64_t M, int64_t N, int64_t offW, int64_t K, void* dx,
-                     const void* residual, const void* gate, float gate_scale, cudaStream_t st) {
+                     const void* residual, const void* gate, float gate_scale, cudaStream_t st,
+                     const uint8_t* gate_bits = nullptr) {
   mmer_gemm_args a = {};
+  a.gate_bits = gate_bits;
   a.A = dy; a.B = Wt(m, offW); a.D = dx; a.residual = residual; a.gate = gate; a.gate_scale = gate_scale;
   a.M = M; a.N = K; a.K = N; a.lda = N; a.ldb = K; a.ldd = K;
   a.a_major = MMER_MAJOR_K; a.b_major = MMER_MAJOR_MN;
@@ -226,7 +231,8 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
     MMER_TRY(lin_fwd(m, L.att, M, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], L.ao, F, 0, 0.f, 0, st));
     MMER_TRY(mmer_add_ln_fwd(x, L.ao, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]), L.x1, L.st1, M, F, d.dt, 0, d.pf,
                              site_layer(l, 1), 0.f, 0, d.seed, st));
-    MMER_TRY(lin_fwd(m, L.x1, M, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], L.h, FF, 1, d.pf, site_layer(l, 2), st));
+    MMER_TRY(lin_fwd(m, L.x1, M, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], L.h, FF, 1, d.pf, site_layer(l, 2), st,
+                     d.tr ? L.hmask : nullptr));
     MMER_TRY(lin_fwd(m, L.h, M, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], L.f2, F, 0, 0.f, 0, st));
     MMER_TRY(mmer_add_ln_fwd(L.x1, L.f2, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]), L.x2, L.st2, M, F, d.dt, 0, d.pf,
                              site_layer(l, 3), 0.f, 0, d.seed, st));
@@ -337,7 +343,9 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     // through ReLU (+ its dropout): gate on the stored post-activation.  No gradient tensor is re-read for a bias
     // gradient: the kernels that produce dY sum its columns where that is free (add_ln_bwd, mha_bwd); for linear1 and
     // the two input projections the weight-gradient GEMM adds the row sums of its A operand (a_rowsum)
-    MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, L.h, relu_gate_scale, st));
+    // the gate is read as the bit mask the forward epilogue wrote (1/16 of re-reading h) when there is one
+    const uint8_t* hmask = d.tr ? L.hmask : nullptr;   // written by the forward pass in training mode only
+    MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, hmask ? nullptr : L.h, relu_gate_scale, st, hmask));
     MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], st));
     MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
     // norm1 <- attention

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
 int gemm_simt(const mmer_gemm_args& a, cudaStream_t st) {
   MMER_CHECK_ARG(a.in_dtype == MMER_F32 && a.out_dtype == MMER_F32, "gemm_simt: fp32 in/out only");
   MMER_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm_simt: empty problem");
+  MMER_CHECK_ARG(a.relu_mask_out == nullptr && a.gate_bits == nullptr, "gemm_simt: bit masks are a bf16 (tcgen05) feature");
   SimtParams p;
   p.A = (const float*)a.A; p.B = (const float*)a.B; p.D = (float*)a.D;
   p.bias = a.bias; p.residual = (const float*)a.residual; p.gate = (const float*)a.gate;

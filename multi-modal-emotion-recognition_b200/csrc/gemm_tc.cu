@@ -169,6 +169,9 @@ struct GemmParams {
   int out_f32, accumulate, relu;
   int mn_swap;    // debug: swap LBO/SBO of MN-major descriptors
   float* rowsum;  // direct (accumulate) path: += sum_k A[m][k] per output row m
+  uint8_t* mask_out;          // staged path: 1 bit per output element, set where the stored value is > 0
+  const uint8_t* gate_bits;   // staged path: acc *= bit ? gate_scale : 0 (the mask a forward call wrote)
+  long long ldmask;           // bytes per row of either bit matrix (N / 8)
   int tma_store;  // bf16 output leaves through swizzled smem staging + TMA store (coalesced)
   int aux_mode;   // staged path only: 0 none, 1 residual add, 2 ReLU gate; the aux tile arrives by TMA
   DropCfg drop;
@@ -498,6 +501,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           aux_prefetched = false;
           __syncwarp();
           PROF_TICK(1);
+          // one 64-bit word = this row's gate bits for the 64 columns of the sub-tile (N is a multiple of 64 here)
+          uint2 gbits = make_uint2(0u, 0u);
+          if (p.gate_bits != nullptr && row_ok)
+            gbits = __ldg(reinterpret_cast<const uint2*>(p.gate_bits + row * p.ldmask + (col0 >> 3)));
+          uint2 mbits = make_uint2(0u, 0u);
           uint32_t r[2][32];
           tmem_ld32_nowait(trow + (uint32_t)(j * 64), r[0]);
           tmem_ld32_nowait(trow + (uint32_t)(j * 64 + 32), r[1]);
@@ -547,6 +555,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               }
+              if (p.gate_bits != nullptr) {
+                const uint32_t byte = ((h == 0 ? gbits.x : gbits.y) >> (8 * g)) & 0xFFu;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= ((byte >> i) & 1u) ? p.gate_scale : 0.f;
+              }
+              if (p.mask_out != nullptr) {
+                uint32_t byte = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) byte |= (v[i] > 0.f ? 1u : 0u) << i;
+                if (h == 0) mbits.x |= byte << (8 * g); else mbits.y |= byte << (8 * g);
+              }
               uint4 pk;
               __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
@@ -554,6 +573,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *reinterpret_cast<uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4)) = pk;
             }
           }
+          if (p.mask_out != nullptr && row_ok)
+            *reinterpret_cast<uint2*>(p.mask_out + row * p.ldmask + (col0 >> 3)) = mbits;
           PROF_TICK(3);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -812,6 +833,9 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
                      (reinterpret_cast<uintptr_t>(a.D) & 15) == 0,
                  "gemm_tc: pointers must be 16-byte aligned");
   MMER_CHECK_ARG(!a.accumulate || a.out_dtype == MMER_F32, "gemm_tc: accumulate needs fp32 output");
+  MMER_CHECK_ARG((a.relu_mask_out == nullptr && a.gate_bits == nullptr) ||
+                     (a.out_dtype == MMER_BF16 && !a.accumulate && a.N % 64 == 0 && a.ldd == a.N && a.gate == nullptr),
+                 "gemm_tc: bit masks need a dense bf16 output with N %% 64 == 0 and no gate tensor");
   MMER_CHECK_ARG(a.a_rowsum == nullptr || (a.accumulate && a.a_major == MMER_MAJOR_MN),
                  "gemm_tc: a_rowsum needs accumulate mode and an MN-major A (weight-gradient GEMM)");
   MMER_CHECK_ARG(!(a.a_major == MMER_MAJOR_MN && a.b_major == MMER_MAJOR_K), "gemm_tc: (MN,K) operand majors unused");
@@ -879,6 +903,7 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
   p.num_m = num_m; p.num_n = num_n; p.splits = splits; p.kb_total = kb_total; p.kb_per_split = kb_per;
   p.rowsum = a.a_rowsum;
+  p.mask_out = a.relu_mask_out; p.gate_bits = a.gate_bits; p.ldmask = a.N / 8;
   p.D = a.D; p.ldd = a.ldd; p.bias = a.bias; p.residual = a.residual; p.gate = a.gate; p.gate_scale = a.gate_scale;
   p.out_f32 = a.out_dtype == MMER_F32; p.accumulate = a.accumulate; p.relu = a.relu;
   p.mn_swap = g_debug[MMER_DEBUG_MN_SWAP];

@@ -45,7 +45,8 @@ def _f32(t: Optional[torch.Tensor]):
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_lib.MAJOR_K, b_major=_lib.MAJOR_K,
          bias=None, residual=None, gate=None, gate_scale=1.0, relu=False, drop_p=0.0, seed=0, site=0,
          out: Optional[torch.Tensor] = None, out_dtype=None, accumulate=False,
-         a_rowsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+         a_rowsum: Optional[torch.Tensor] = None, relu_mask_out: Optional[torch.Tensor] = None,
+         gate_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M,N] = epilogue(A[M,K] . B[N,K]^T); see mmer_gemm in include/mmer.h."""
     for t in (A, B, bias, residual, gate, out):
         if t is not None and not t.is_cuda:
@@ -68,6 +69,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_l
         if a_rowsum.dtype != torch.float32 or not a_rowsum.is_cuda:
             raise TypeError("a_rowsum must be a CUDA float32 tensor")
         a.a_rowsum = a_rowsum.data_ptr()
+    for name, t in (("relu_mask_out", relu_mask_out), ("gate_bits", gate_bits)):
+        if t is not None:
+            if t.dtype != torch.uint8 or not t.is_cuda or t.numel() != M * N // 8:
+                raise TypeError(f"{name} must be a CUDA uint8 tensor of M*N/8 bytes")
+            setattr(a, name, t.data_ptr())
     a.drop_p, a.gate_scale, a.seed, a.drop_site = float(drop_p), float(gate_scale), int(seed), int(site)
     call("mmer_gemm", C.byref(a), _stream())
     return out

@@ -144,6 +144,24 @@ def test_gemm_wgrad_bias_gradient_from_row_sums(dt, shape):
     assert rel(db, dy.double().sum(0) - 0.25) < (2e-5 if dt == torch.float32 else 1e-4)
 
 
+@pytest.mark.parametrize("shape", [(69632, 2048, 512), (1000, 192, 64), (4096 + 40, 512, 256)])
+def test_gemm_relu_bit_mask_round_trip(shape):
+    """Forward epilogue writes 1 bit per stored element (> 0 after bias, ReLU, dropout); the dgrad epilogue gated
+    by those bits must equal the one gated by the stored activation tensor itself."""
+    M, N, K = shape
+    x, w = rnd(M, K, dt=torch.bfloat16, seed=51), rnd(N, K, dt=torch.bfloat16, seed=52)
+    bias = rnd(N, seed=53)
+    mask = torch.zeros(M * N // 8, dtype=torch.uint8, device=DEV)
+    h = ops.gemm(x, w, M=M, N=N, K=K, bias=bias, relu=True, drop_p=0.1, seed=9, site=4, relu_mask_out=mask)
+    bits = (h > 0).view(M, N // 8, 8).to(torch.uint8)
+    packed = (bits << torch.arange(8, device=DEV, dtype=torch.uint8)).sum(-1).to(torch.uint8)
+    assert torch.equal(mask.view(M, N // 8), packed)
+    dy, w2 = rnd(M, K, dt=torch.bfloat16, seed=54), rnd(K, N, dt=torch.bfloat16, seed=55)   # dX[M,N] = dY[M,K] W2[K,N]
+    a = ops.gemm(dy, w2, M=M, N=N, K=K, b_major=_lib.MAJOR_MN, gate=h, gate_scale=1.0 / 0.9)
+    b = ops.gemm(dy, w2, M=M, N=N, K=K, b_major=_lib.MAJOR_MN, gate_bits=mask, gate_scale=1.0 / 0.9)
+    assert torch.equal(a, b)
+
+
 def test_gemm_cta_pair_wgrad_split_k():
     Mtok, N, K = 69632 + 24, 1536, 512     # dW[N,K] += dY^T X at the cfg2 in_proj shape, ragged reduction length
     dy, x = rnd(Mtok, N, dt=torch.bfloat16, seed=8, scale=0.05), rnd(Mtok, K, dt=torch.bfloat16, seed=9)

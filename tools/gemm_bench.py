@@ -55,6 +55,8 @@ def main():
         dxs = [torch.empty(m, k, device=dev, dtype=bf) for _ in range(NS)]
         aux = [rnd(m, k) for _ in range(NS)]
         gw = torch.zeros(n, k, device=dev)
+        gbits = torch.randint(0, 256, (m * k // 8,), device=dev, dtype=torch.uint8)
+        mbits = torch.zeros(m * n // 8, device=dev, dtype=torch.uint8)
         flop = 2.0 * m * n * k
         cases = [
             ("fwd +bias", lambda i: ops.gemm(xs[i % NS], w, M=m, N=n, K=k, bias=bias, out=ys[i % NS])),
@@ -65,6 +67,10 @@ def main():
                                                    residual=aux[i % NS], out=dxs[i % NS])),
             ("dgrad +gate", lambda i: ops.gemm(dys[i % NS], w, M=m, N=k, K=n, b_major=_lib.MAJOR_MN,
                                                gate=aux[i % NS], gate_scale=1.1, out=dxs[i % NS])),
+            ("dgrad +gate bits", (lambda i: ops.gemm(dys[i % NS], w, M=m, N=k, K=n, b_major=_lib.MAJOR_MN,
+                                                     gate_bits=gbits, gate_scale=1.1, out=dxs[i % NS])) if k % 64 == 0 else None),
+            ("fwd +bias+relu+drop+mask", (lambda i: ops.gemm(xs[i % NS], w, M=m, N=n, K=k, bias=bias, relu=True, drop_p=0.1, seed=1,
+                                                             site=1, out=ys[i % NS], relu_mask_out=mbits)) if n % 64 == 0 else None),
             ("wgrad", lambda i: ops.gemm(dys[i % NS], xs[i % NS], M=n, N=k, K=m, a_major=_lib.MAJOR_MN,
                                          b_major=_lib.MAJOR_MN, out=gw, accumulate=True)),
         ]
@@ -77,6 +83,8 @@ def main():
                 ("cuBLAS wgrad (dy^T@x)", lambda i: torch.matmul(dys[i % NS].t(), xs[i % NS])),
             ]
         for cname, fn in cases:
+            if fn is None:
+                continue
             ms = timeit(fn, reps)
             print(f"{name:11s} {cname:22s} M={m:6d} K={k:5d} N={n:5d}  {ms * 1e3:8.1f} us  {flop / ms / 1e9:8.1f} TFLOP/s",
                   flush=True)
