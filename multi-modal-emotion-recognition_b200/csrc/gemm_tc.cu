@@ -217,20 +217,13 @@ struct TileCfg {
   static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 8 <= 256, "barrier area");
 };
 
-// element-wise part of the staged epilogue on 8 consecutive accumulator columns of one row; `bias8` points at the
-// 8 bias values in shared memory (zero-filled beyond N), or is null
-__device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], const float* bias8, long long off) {
-  if (bias8 != nullptr) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias8);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (p.relu) {
+// ReLU and dropout of the staged epilogue on 8 consecutive accumulator columns of one row
+__device__ __forceinline__ void epi_math8(const GemmParams& p, bool relu, bool drop, float (&v)[8], long long off) {
+  if (relu) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
   }
-  if (p.drop.thr) {
+  if (drop) {
     float f[8];
     drop8(p.drop, (uint64_t)off, f);
 #pragma unroll
@@ -238,7 +231,12 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], co
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED>
+// Epilogue specialisation of the staged kernels: EPI < 0 decides everything at run time (any combination);
+// EPI >= 0 is a bit set fixed at compile time, which removes the predicated code of the unused features from the
+// per-element loop -- the epilogue warps are issue-bound, so instruction count is throughput here.
+enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_DROP = 4, EPI_MASK = 8, EPI_RES = 16, EPI_GATE = 32, EPI_GBITS = 64 };
+
+template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
@@ -284,6 +282,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.aux_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   }
   const bool want_rowsum = !STAGED && p.rowsum != nullptr;
+  const bool f_bias = EPI < 0 ? p.bias != nullptr : (EPI & EPI_BIAS) != 0;
+  const bool f_relu = EPI < 0 ? p.relu != 0 : (EPI & EPI_RELU) != 0;
+  const bool f_drop = EPI < 0 ? p.drop.thr != 0 : (EPI & EPI_DROP) != 0;
+  const bool f_mask = EPI < 0 ? p.mask_out != nullptr : (EPI & EPI_MASK) != 0;
+  const int f_aux = EPI < 0 ? p.aux_mode : ((EPI & EPI_RES) ? 1 : (EPI & EPI_GATE) ? 2 : 0);
+  const bool f_gbits = EPI < 0 ? p.gate_bits != nullptr : (EPI & EPI_GBITS) != 0;
+  (void)f_bias; (void)f_relu; (void)f_drop; (void)f_mask; (void)f_aux; (void)f_gbits;
   if (want_rowsum) {
     // bf16 ones: with them as the B operand an extra N = 16 MMA per k-step accumulates sum_k A[m][k] -- for a
     // weight-gradient GEMM (A = dY^T) that is the bias gradient of the same Linear, at 1/16 of the tile's MMA time
@@ -441,14 +446,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long row = (long long)row0 + lane;
       const bool row_ok = row < p.M;
       if (STAGED) {
-        if (p.aux_mode && lane < HALF / 64) {
+        if (f_aux && lane < HALF / 64) {
           // warm L2 with this tile's gate / residual sub-tiles while the MMAs of the tile are still running
           const int pc = n_blk * BN + hsel * HALF + lane * 64;
           if (pc < p.N && row0 < p.M)
             asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmX), "r"(pc), "r"(row0)
                          : "memory");
         }
-        if (p.bias) {
+        if (f_bias) {
           // the bias slice of this warp's column half (HALF <= 128 values: one float4 per lane) is fetched before
           // the wait for the accumulator and parked in shared memory after it (read back as broadcasts; zero beyond
           // N).  The four warps of a column half write identical values into the same slot; slots alternate with
@@ -473,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       PROF_TICK(0);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hsel * HALF);
-      if (STAGED && p.bias) {
+      if (STAGED && f_bias) {
         // the accumulator of this buffer is ready => every warp has left the tile that last used this bias slot
         if (lane * 4 < HALF) *reinterpret_cast<float4*>(bias_s + lane * 4) = bias_reg;
         bias_rd = bias_s;
@@ -493,7 +498,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the last store that read this staging tile has drained it
             if (C::EPI_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (p.aux_mode) {
+            if (f_aux) {
               mbar_expect_tx(auxbar, 4096);
               tma_load_2d(tile_u32, &tmX, auxbar, col0, row0);
             }
@@ -503,7 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           PROF_TICK(1);
           // one 64-bit word = this row's gate bits for the 64 columns of the sub-tile (N is a multiple of 64 here)
           uint2 gbits = make_uint2(0u, 0u);
-          if (p.gate_bits != nullptr && row_ok)
+          if (f_gbits && row_ok)
             gbits = __ldg(reinterpret_cast<const uint2*>(p.gate_bits + row * p.ldmask + (col0 >> 3)));
           uint2 mbits = make_uint2(0u, 0u);
           uint32_t r[2][32];
@@ -511,7 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32_nowait(trow + (uint32_t)(j * 64 + 32), r[1]);
           tmem_ld_wait();
           PROF_TICK(2);
-          if (p.aux_mode) {
+          if (f_aux) {
             mbar_wait(auxbar, aux_phase);
             aux_phase ^= 1;
           }
@@ -520,12 +525,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // bias values of the 32 columns first (broadcast reads), so that no shared-memory load has to be ordered
             // behind the staging-tile stores below
             float4 bv[8];
-            if (bias_rd != nullptr) {
+            if (f_bias) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) bv[g] = *reinterpret_cast<const float4*>(bias_rd + j * 64 + h * 32 + g * 4);
             }
             uint4 xr[4];
-            if (p.aux_mode) {
+            if (f_aux) {
 #pragma unroll
               for (int g = 0; g < 4; ++g)
                 xr[g] = *reinterpret_cast<const uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4));
@@ -536,17 +541,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h][g * 8 + i]);
-              if (bias_rd != nullptr) {
+              if (f_bias) {
                 v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
                 v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
               }
-              epi_math8(p, v, nullptr, row * p.ldd + col);
-              if (p.aux_mode) {
+              epi_math8(p, f_relu, f_drop, v, row * p.ldd + col);
+              if (f_aux) {
                 const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr[g]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 xf = __bfloat1622float2(xh[i]);
-                  if (p.aux_mode == 1) {
+                  if (f_aux == 1) {
                     v[2 * i] += xf.x;
                     v[2 * i + 1] += xf.y;
                   } else {
@@ -555,12 +560,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               }
-              if (p.gate_bits != nullptr) {
+              if (f_gbits) {
                 const uint32_t byte = ((h == 0 ? gbits.x : gbits.y) >> (8 * g)) & 0xFFu;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] *= ((byte >> i) & 1u) ? p.gate_scale : 0.f;
               }
-              if (p.mask_out != nullptr) {
+              if (f_mask) {
                 uint32_t byte = 0u;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) byte |= (v[i] > 0.f ? 1u : 0u) << i;
@@ -573,7 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *reinterpret_cast<uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4)) = pk;
             }
           }
-          if (p.mask_out != nullptr && row_ok)
+          if (f_mask && row_ok)
             *reinterpret_cast<uint2*>(p.mask_out + row * p.ldmask + (col0 >> 3)) = mbits;
           PROF_TICK(3);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -582,7 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmD, tile_u32, col0, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (C::EPI_BUFS == 2 && p.aux_mode) {
+          if (C::EPI_BUFS == 2 && f_aux) {
             // fetch the gate / residual tile of the NEXT sub-tile into the other staging tile now, so that its
             // latency is covered by this sub-tile's store and the next accumulator wait
             int ncol = col0 + 64, nrow = row0;
@@ -791,12 +796,12 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED>
+template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED, int EPI = -1>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                   const GemmParams& p, int grid, cudaStream_t st) {
   using C = TileCfg<BN, CG, STAGED>;
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, STAGED>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CG, STAGED, EPI>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
@@ -923,6 +928,21 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
     if (!amn && bmn) return launch<BN_, false, true, CG_, false>(ta, tb, td, tx, p, grid, st);                 \
     return launch<BN_, true, true, CG_, false>(ta, tb, td, tx, p, grid, st);                                   \
   } while (0)
+  if (cg == 2 && tma_store && g_debug[MMER_DEBUG_GENERIC_EPI] == 0) {
+    // the step's hot epilogues get their own instantiation (see EPI_* above); anything else runs the generic one
+    const int mode = (a.bias ? EPI_BIAS : 0) | (a.relu ? EPI_RELU : 0) | (p.drop.thr ? EPI_DROP : 0) |
+                     (a.relu_mask_out ? EPI_MASK : 0) | (p.aux_mode == 1 ? EPI_RES : 0) | (p.aux_mode == 2 ? EPI_GATE : 0) |
+                     (a.gate_bits ? EPI_GBITS : 0);
+    if (!amn && !bmn) {
+      if (mode == EPI_BIAS) return launch<256, false, false, 2, true, EPI_BIAS>(ta, tb, td, tx, p, grid, st);
+      if (mode == (EPI_BIAS | EPI_RELU | EPI_DROP | EPI_MASK))
+        return launch<256, false, false, 2, true, EPI_BIAS | EPI_RELU | EPI_DROP | EPI_MASK>(ta, tb, td, tx, p, grid, st);
+    } else if (!amn && bmn) {
+      if (mode == 0) return launch<256, false, true, 2, true, 0>(ta, tb, td, tx, p, grid, st);
+      if (mode == EPI_RES) return launch<256, false, true, 2, true, EPI_RES>(ta, tb, td, tx, p, grid, st);
+      if (mode == EPI_GBITS) return launch<256, false, true, 2, true, EPI_GBITS>(ta, tb, td, tx, p, grid, st);
+    }
+  }
   if (cg == 2) MMER_GEMM_LAUNCH(256, 2);
   if (bn == 256) MMER_GEMM_LAUNCH(256, 1);
   MMER_GEMM_LAUNCH(128, 1);

@@ -35,6 +35,8 @@ def timeit(fn, reps):
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20
+    if "--generic-epilogue" in sys.argv:
+        _lib.load().mmer_debug_set(_lib.DEBUG_GENERIC_EPI, 1)
     print(torch.cuda.get_device_name(0))
     NS = 3
     total_ms = 0.0
