@@ -11,9 +11,9 @@ dropout active as in the reference's training loop.  N>1: the same per-GPU batch
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same
 step driven from pinned HOST buffers (H2D of every step's inputs + D2H of its loss inside the timed
 region); `roofline` = the dominant kernel (tcgen05 GEMM at the FFN shape) timed live with CUDA
-events; `cpu_baseline` = the CPU oracle port on a bounded sample.  `--impl reference` times the CPU
-oracle port (the reference's own path restated on PyTorch-CPU primitives; the reference itself is
-a Python tree that does not travel to the GPU box) with all host threads.
+events; `cpu_baseline` = the reference's CPU path (its architecture on stock torch.nn modules, pinned to
+the reference's golden outputs) on a bounded sample.  `--impl reference` times that same CPU path
+with all host threads (the reference itself is a Python tree that does not travel to the GPU box).
 """
 from __future__ import annotations
 
@@ -139,23 +139,29 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------- CPU arms
 def cpu_port_step_time(batch: int, steps: int, warmup: int, threads: int):
-    """Times oracle.train_step (fwd + FocalLoss + bwd + Adam, fp32) on the host cores."""
-    from oracle import fusion_oracle as O
+    """The reference's own CPU path: its architecture on stock torch.nn modules (oracle/eager_torch.py, pinned to the
+    reference's golden outputs), fp32, eager, fwd + FocalLoss(alpha) + bwd + torch.optim.Adam on the host cores --
+    exactly what `python train2.py` executes per batch on a machine without a GPU (train2.py:570-579, 525)."""
+    from oracle import eager_torch as E
     torch.set_num_threads(threads)
-    import mmer_b200  # only for the module constructors: default init of the same architecture
     torch.manual_seed(0)
-    model = mmer_b200.MultimodalEmotionModel(max_seq_len=T + 1, classifier_hidden_dim=512)
-    P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = E.EagerModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512, fusion_dropout=0.1,
+                         classifier_dropout=0.1).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)
     g = torch.Generator().manual_seed(1234)
     video = torch.randn(batch, T, DV, generator=g)
     audio = torch.randn(batch, DA, generator=g)
     labels = torch.randint(0, NCLS, (batch,), generator=g)
     alpha = torch.tensor(ALPHA)
-    state, times = {}, []
+    times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        P, state, _, _, _ = O.train_step(P, state, i + 1, video, audio, None, labels, variant="v2", loss="focal",
-                                         alpha=alpha, lr=1e-4, weight_decay=1e-4)
+        opt.zero_grad(set_to_none=True)
+        _, logits = model(video, audio, None)
+        loss = E.focal_loss(logits, labels, 2.0, alpha)
+        loss.backward()
+        opt.step()
+        float(loss)                                   # the reference reads loss.item() every step (train2.py:579)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return sum(times) / len(times)
@@ -202,7 +208,7 @@ def run_reference(args):
     batch = 256
     dt = cpu_port_step_time(batch, args.steps, args.warmup, threads)
     val = batch / dt
-    sample = f"{args.steps} steps of batch {batch} (T={T}), fp32, torch CPU primitives"
+    sample = f"{args.steps} steps of batch {batch} (T={T}), fp32, stock torch.nn modules on the host cores"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -453,10 +459,11 @@ def run_ours(args):
             except Exception as exc:   # a comparison line must never take the bench down
                 out["torch_eager_gpu"] = {"error": repr(exc)[:200]}
             threads = os.cpu_count() or 1
-            cb = 128
+            cb = 256
             dt = cpu_port_step_time(cb, 3, 1, threads)
             out["cpu_baseline"] = {"value": cb / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": f"3 steps of batch {cb} (T={T}) of the same model, fp32, CPU oracle port"}
+                                   "sample": f"3 steps of batch {cb} (T={T}) of the same model, fp32, stock torch.nn modules (the "
+                                             "reference's own CPU path)"}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
