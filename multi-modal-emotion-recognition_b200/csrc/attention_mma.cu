@@ -20,6 +20,7 @@
 
 namespace mmer {
 
+extern int g_debug[16];
 static constexpr int MMA_WARPS = 8;
 static constexpr int SCR_STRIDE = 80;                 // bytes per scratch row (32 bf16 + 16 B pad: conflict-free ldmatrix)
 static constexpr int SCR_BYTES = 32 * SCR_STRIDE;     // per warp
@@ -28,6 +29,17 @@ struct MmaGeom {
   int S, F, Tn, H;
   uint32_t in_row, in_stride;   // bytes of one packed qkv row, padded smem stride
   uint32_t do_row, do_stride;   // bytes of one dO / out row, padded smem stride
+};
+
+// Byte offset of element (row, col) of a [rows][D] bf16 head tile in shared memory.
+struct PadAddr {      // row-padded packed rows (bulk-copied whole token rows): offset = row * stride + col * 2
+  uint32_t stride;
+  __device__ __forceinline__ uint32_t off(int row, int col) const { return (uint32_t)row * stride + (uint32_t)col * 2u; }
+};
+struct SwzAddr {      // one 128-byte row per token, 128B-swizzled as TMA writes it (D = 64): conflict-free ldmatrix
+  __device__ __forceinline__ uint32_t off(int row, int col) const {
+    return (uint32_t)row * 128u + (((((uint32_t)col >> 3) ^ (uint32_t)row) & 7u) << 4) + ((uint32_t)col & 7u) * 2u;
+  }
 };
 
 template <int NT>
@@ -47,8 +59,8 @@ __device__ __forceinline__ uint32_t key_valid_bits(const uint8_t* __restrict__ m
 
 // scores + masked softmax for one head: p[mt][nt][..] = softmax_j(q_i . k_j / sqrt(D)), fragment layout of the
 // m16n8 accumulators (row g / g+8, columns nt*8 + t*2 + {0,1}); invalid keys get exactly 0.
-template <int D, int MT, int NT>
-__device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, uint32_t stride, int S, int lane,
+template <int D, int MT, int NT, class AD>
+__device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, AD ad, int S, int lane,
                                                uint32_t kvalid, float (&p)[MT][NT][4]) {
   constexpr int KS = D / 16;
   uint32_t kf[NT][KS][2];
@@ -58,7 +70,7 @@ __device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, u
     for (int k2 = 0; k2 < KS / 2; ++k2) {
       const int row = min(nt * 8 + (lane & 7), S - 1);
       const int col = k2 * 32 + (lane >> 3) * 8;
-      ldsm_x4(kbase + row * stride + col * 2, kf[nt][2 * k2][0], kf[nt][2 * k2][1], kf[nt][2 * k2 + 1][0],
+      ldsm_x4(kbase + ad.off(row, col), kf[nt][2 * k2][0], kf[nt][2 * k2][1], kf[nt][2 * k2 + 1][0],
               kf[nt][2 * k2 + 1][1]);
     }
 #pragma unroll
@@ -72,7 +84,7 @@ __device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, u
       uint32_t a0, a1, a2, a3;
       const int row = min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
       const int col = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(qbase + row * stride + col * 2, a0, a1, a2, a3);
+      ldsm_x4(qbase + ad.off(row, col), a0, a1, a2, a3);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(p[mt][nt], a0, a1, a2, a3, kf[nt][ks][0], kf[nt][ks][1]);
     }
@@ -129,9 +141,9 @@ __device__ __forceinline__ void pack_rows(const float (&c)[MT][NT][4], uint32_t 
 }
 
 // acc[D/8][4] (+)= A-fragments(a, 16 x 16*KSTEPS) . X[rows 16*ks.. , D columns] with X row-major in smem (ldmatrix.trans)
-template <int D, int KSTEPS>
+template <int D, int KSTEPS, class AD>
 __device__ __forceinline__ void mma_rows_x(float (&acc)[D / 8][4], const uint32_t (&a)[KSTEPS][4], uint32_t xbase,
-                                           uint32_t stride, int S, int lane) {
+                                           AD ad, int S, int lane) {
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks)
 #pragma unroll
@@ -139,15 +151,15 @@ __device__ __forceinline__ void mma_rows_x(float (&acc)[D / 8][4], const uint32_
       uint32_t b0, b1, b2, b3;
       const int row = min(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
       const int col = n2 * 16 + (lane >> 4) * 8;
-      ldsm_x4_t(xbase + row * stride + col * 2, b0, b1, b2, b3);
+      ldsm_x4_t(xbase + ad.off(row, col), b0, b1, b2, b3);
       mma_bf16_16816(acc[2 * n2], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b0, b1);
       mma_bf16_16816(acc[2 * n2 + 1], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b2, b3);
     }
 }
 
 // store a 16 x D accumulator tile as bf16 rows (row0 + g, row0 + g + 8) of a smem matrix, rows >= S skipped
-template <int D>
-__device__ __forceinline__ void store_tile(uint8_t* base, uint32_t stride, int row0, int S, int lane,
+template <int D, class AD>
+__device__ __forceinline__ void store_tile(uint8_t* base, AD ad, int row0, int S, int lane,
                                            const float (&acc)[D / 8][4]) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -156,9 +168,55 @@ __device__ __forceinline__ void store_tile(uint8_t* base, uint32_t stride, int r
     if (row < S) {
 #pragma unroll
       for (int nd = 0; nd < D / 8; ++nd)
-        *reinterpret_cast<uint32_t*>(base + (size_t)row * stride + (nd * 8 + t * 2) * 2) =
-            pack_bf16x2(acc[nd][2 * r], acc[nd][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(base + ad.off(row, nd * 8 + t * 2)) = pack_bf16x2(acc[nd][2 * r], acc[nd][2 * r + 1]);
     }
+  }
+}
+
+// One head of the forward pass on fragments: S = Q K^T, masked softmax, dropout, O = P V.  q/k/v are shared-memory
+// addresses of [S][D] tiles laid out per the address policy `ad`; O (bf16) is written to o_ptr with the same policy.
+template <int D, int MT, int NT, class AD>
+__device__ __forceinline__ void mha_fwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint8_t* o_ptr, AD ad, int S,
+                                             int lane, uint32_t kvalid, long long bh, float* __restrict__ probs, DropCfg dc) {
+  const int g = lane >> 2, t = lane & 3;
+  float p[MT][NT][4];
+  scores_softmax<D, MT, NT>(qbase, kbase, ad, S, lane, kvalid, p);
+  if (probs != nullptr || dc.thr) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = mt * 16 + g + 8 * r;
+        if (i < S) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const int j = nt * 8 + t * 2;
+            if (probs != nullptr) {
+              if (j < S) probs[(bh * S + i) * S + j] = p[mt][nt][r * 2];
+              if (j + 1 < S) probs[(bh * S + i) * S + j + 1] = p[mt][nt][r * 2 + 1];
+            }
+            if (dc.thr) {
+              float f0, f1;
+              drop2(dc, att_drop_index(bh * S + i, j, NT * 8), f0, f1);
+              p[mt][nt][r * 2] *= f0;
+              p[mt][nt][r * 2 + 1] *= f1;
+            }
+          }
+        }
+      }
+  }
+  uint32_t pa[MT][(NT + 1) / 2][4];
+  pack_rows<MT, NT>(p, pa);
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float o[D / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
+    mma_rows_x<D, (NT + 1) / 2>(o, pa[mt], vbase, ad, S, lane);
+    store_tile<D>(o_ptr, ad, mt * 16, S, lane, o);   // O_h overwrites the dead Q_h slot
   }
 }
 
@@ -190,46 +248,8 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 
   for (int h = warp; h < H; h += MMA_WARPS) {
     const uint32_t qbase = in_a + h * D * 2, kbase = qbase + F * 2, vbase = kbase + F * 2;
-    float p[MT][NT][4];
-    scores_softmax<D, MT, NT>(qbase, kbase, gm.in_stride, S, lane, kvalid, p);
-    const long long bh = (long long)b * H + h;
-    if (probs != nullptr || dc.thr) {
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int i = mt * 16 + g + 8 * r;
-          if (i < S) {
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-              const int j = nt * 8 + t * 2;
-              if (probs != nullptr) {
-                if (j < S) probs[(bh * S + i) * S + j] = p[mt][nt][r * 2];
-                if (j + 1 < S) probs[(bh * S + i) * S + j + 1] = p[mt][nt][r * 2 + 1];
-              }
-              if (dc.thr) {
-                float f0, f1;
-                drop2(dc, att_drop_index(bh * S + i, j, NT * 8), f0, f1);
-                p[mt][nt][r * 2] *= f0;
-                p[mt][nt][r * 2 + 1] *= f1;
-              }
-            }
-          }
-        }
-    }
-    uint32_t pa[MT][(NT + 1) / 2][4];
-    pack_rows<MT, NT>(p, pa);
-    __syncwarp();
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float o[D / 8][4];
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
-      mma_rows_x<D, (NT + 1) / 2>(o, pa[mt], vbase, gm.in_stride, S, lane);
-      store_tile<D>(smem + h * D * 2, gm.in_stride, mt * 16, S, lane, o);   // O_h overwrites the dead Q_h slot
-    }
+    mha_fwd_head<D, MT, NT>(qbase, kbase, vbase, smem + h * D * 2, PadAddr{gm.in_stride}, S, lane, kvalid,
+                            (long long)b * H + h, probs, dc);
   }
   fence_async_smem();
   __syncthreads();
@@ -238,6 +258,157 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
     bulk_commit();
     bulk_wait_read0();
   }
+}
+
+// One head of the backward pass on fragments.  q/k/v tiles follow policy `ain`, the dO tile policy `ado`; `scr` is this
+// warp's transpose scratch.  Outputs overwrite dead operand tiles: dV -> dv_ptr (ain), dK -> dk_ptr (ain), dQ -> dq_ptr (ado).
+template <int D, int MT, int NT, class AIN, class ADO>
+__device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint32_t dobase, uint8_t* scr,
+                                             uint32_t scr_a, uint8_t* dq_ptr, uint8_t* dk_ptr, uint8_t* dv_ptr, AIN ain, ADO ado,
+                                             int S, int lane, uint32_t kvalid, long long bh, DropCfg dc) {
+  constexpr int KS = D / 16;
+  constexpr int MTK = (NT + 1) / 2;   // 16-row tiles over keys
+  const int g = lane >> 2, t = lane & 3;
+  const float scale = rsqrtf((float)D);
+  float p[MT][NT][4];
+  scores_softmax<D, MT, NT>(qbase, kbase, ain, S, lane, kvalid, p);
+  // dP = dO V^T
+  float dp[MT][NT][4];
+  {
+    uint32_t vf[NT][KS][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int k2 = 0; k2 < KS / 2; ++k2) {
+        const int row = min(nt * 8 + (lane & 7), S - 1);
+        const int col = k2 * 32 + (lane >> 3) * 8;
+        ldsm_x4(vbase + ain.off(row, col), vf[nt][2 * k2][0], vf[nt][2 * k2][1], vf[nt][2 * k2 + 1][0],
+                vf[nt][2 * k2 + 1][1]);
+      }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dp[mt][nt][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        const int row = min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
+        const int col = ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(dobase + ado.off(row, col), a0, a1, a2, a3);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(dp[mt][nt], a0, a1, a2, a3, vf[nt][ks][0], vf[nt][ks][1]);
+      }
+    }
+  }
+  // p <- Pd = P o dropout (what multiplied V in the forward pass); dp <- dS.  Query rows >= S are zeroed: they
+  // are reduction indices of dV and dK.
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = mt * 16 + g + 8 * r;
+      const bool row_ok = i < S;
+      float f[NT][2];
+      float dot = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        f[nt][0] = 1.f;
+        f[nt][1] = 1.f;
+        if (dc.thr && row_ok) drop2(dc, att_drop_index(bh * S + i, nt * 8 + t * 2, NT * 8), f[nt][0], f[nt][1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float dpm = dp[mt][nt][r * 2 + e] * f[nt][e];
+          dp[mt][nt][r * 2 + e] = dpm;
+          dot = fmaf(dpm, p[mt][nt][r * 2 + e], dot);
+        }
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = p[mt][nt][r * 2 + e];
+          dp[mt][nt][r * 2 + e] = row_ok ? pv * (dp[mt][nt][r * 2 + e] - dot) * scale : 0.f;
+          p[mt][nt][r * 2 + e] = row_ok ? pv * f[nt][e] : 0.f;
+        }
+    }
+  // ---- dV = Pd^T dO  (Pd^T through the scratch tile)
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        *reinterpret_cast<uint32_t*>(scr + (mt * 16 + g + 8 * r) * SCR_STRIDE + (nt * 8 + t * 2) * 2) =
+            pack_bf16x2(p[mt][nt][r * 2], p[mt][nt][r * 2 + 1]);
+  __syncwarp();
+#pragma unroll
+  for (int mk = 0; mk < MTK; ++mk) {
+    uint32_t a[MT][4];
+#pragma unroll
+    for (int kq = 0; kq < MT; ++kq) {
+      const int row = kq * 16 + (lane & 7) + (lane >> 4) * 8;         // query (reduction index)
+      const int col = mk * 16 + ((lane >> 3) & 1) * 8;                // key (output row)
+      ldsm_x4_t(scr_a + row * SCR_STRIDE + col * 2, a[kq][0], a[kq][1], a[kq][2], a[kq][3]);
+    }
+    float acc[D / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
+    mma_rows_x<D, MT>(acc, a, dobase, ado, S, lane);
+    store_tile<D>(dv_ptr, ain, mk * 16, S, lane, acc);   // dV_h -> dead V_h slot
+  }
+  // ---- dS^T through the same scratch tile (for dK); dS fragments stay in registers (for dQ)
+  uint32_t dsa[MT][(NT + 1) / 2][4];
+  pack_rows<MT, NT>(dp, dsa);
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        *reinterpret_cast<uint32_t*>(scr + (mt * 16 + g + 8 * r) * SCR_STRIDE + (nt * 8 + t * 2) * 2) =
+            pack_bf16x2(dp[mt][nt][r * 2], dp[mt][nt][r * 2 + 1]);
+  __syncwarp();
+  // ---- dQ = dS K -> dead dO_h slot
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float acc[D / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
+    mma_rows_x<D, (NT + 1) / 2>(acc, dsa[mt], kbase, ain, S, lane);
+    store_tile<D>(dq_ptr, ado, mt * 16, S, lane, acc);
+  }
+  // ---- dK = dS^T Q -> dead K_h slot
+  float acck[MTK][D / 8][4];
+#pragma unroll
+  for (int mk = 0; mk < MTK; ++mk) {
+    uint32_t a[MT][4];
+#pragma unroll
+    for (int kq = 0; kq < MT; ++kq) {
+      const int row = kq * 16 + (lane & 7) + (lane >> 4) * 8;
+      const int col = mk * 16 + ((lane >> 3) & 1) * 8;
+      ldsm_x4_t(scr_a + row * SCR_STRIDE + col * 2, a[kq][0], a[kq][1], a[kq][2], a[kq][3]);
+    }
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acck[mk][nd][i] = 0.f;
+    mma_rows_x<D, MT>(acck[mk], a, qbase, ain, S, lane);
+  }
+  __syncwarp();   // every lane has finished reading K_h (dQ) before it is overwritten
+#pragma unroll
+  for (int mk = 0; mk < MTK; ++mk)
+    store_tile<D>(dk_ptr, ain, mk * 16, S, lane, acck[mk]);
+  __syncwarp();
 }
 
 template <int D, int MT, int NT>
@@ -292,146 +463,9 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 
   for (int h = warp; h < H; h += MMA_WARPS) {
     const uint32_t qbase = in_a + h * D * 2, kbase = qbase + F * 2, vbase = kbase + F * 2, dobase = do_a + h * D * 2;
-    const long long bh = (long long)b * H + h;
-    float p[MT][NT][4];
-    scores_softmax<D, MT, NT>(qbase, kbase, gm.in_stride, S, lane, kvalid, p);
-    // dP = dO V^T
-    float dp[MT][NT][4];
-    {
-      uint32_t vf[NT][KS][2];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int k2 = 0; k2 < KS / 2; ++k2) {
-          const int row = min(nt * 8 + (lane & 7), S - 1);
-          const int col = k2 * 32 + (lane >> 3) * 8;
-          ldsm_x4(vbase + row * gm.in_stride + col * 2, vf[nt][2 * k2][0], vf[nt][2 * k2][1], vf[nt][2 * k2 + 1][0],
-                  vf[nt][2 * k2 + 1][1]);
-        }
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dp[mt][nt][i] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          uint32_t a0, a1, a2, a3;
-          const int row = min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
-          const int col = ks * 16 + (lane >> 4) * 8;
-          ldsm_x4(dobase + row * gm.do_stride + col * 2, a0, a1, a2, a3);
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(dp[mt][nt], a0, a1, a2, a3, vf[nt][ks][0], vf[nt][ks][1]);
-        }
-      }
-    }
-    // p <- Pd = P o dropout (what multiplied V in the forward pass); dp <- dS.  Query rows >= S are zeroed: they
-    // are reduction indices of dV and dK.
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i = mt * 16 + g + 8 * r;
-        const bool row_ok = i < S;
-        float f[NT][2];
-        float dot = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          f[nt][0] = 1.f;
-          f[nt][1] = 1.f;
-          if (dc.thr && row_ok) drop2(dc, att_drop_index(bh * S + i, nt * 8 + t * 2, NT * 8), f[nt][0], f[nt][1]);
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float dpm = dp[mt][nt][r * 2 + e] * f[nt][e];
-            dp[mt][nt][r * 2 + e] = dpm;
-            dot = fmaf(dpm, p[mt][nt][r * 2 + e], dot);
-          }
-        }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float pv = p[mt][nt][r * 2 + e];
-            dp[mt][nt][r * 2 + e] = row_ok ? pv * (dp[mt][nt][r * 2 + e] - dot) * scale : 0.f;
-            p[mt][nt][r * 2 + e] = row_ok ? pv * f[nt][e] : 0.f;
-          }
-      }
-    // ---- dV = Pd^T dO  (Pd^T through the scratch tile)
-    __syncwarp();
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-          *reinterpret_cast<uint32_t*>(scr + (mt * 16 + g + 8 * r) * SCR_STRIDE + (nt * 8 + t * 2) * 2) =
-              pack_bf16x2(p[mt][nt][r * 2], p[mt][nt][r * 2 + 1]);
-    __syncwarp();
-#pragma unroll
-    for (int mk = 0; mk < MTK; ++mk) {
-      uint32_t a[MT][4];
-#pragma unroll
-      for (int kq = 0; kq < MT; ++kq) {
-        const int row = kq * 16 + (lane & 7) + (lane >> 4) * 8;         // query (reduction index)
-        const int col = mk * 16 + ((lane >> 3) & 1) * 8;                // key (output row)
-        ldsm_x4_t(scr_a + row * SCR_STRIDE + col * 2, a[kq][0], a[kq][1], a[kq][2], a[kq][3]);
-      }
-      float acc[D / 8][4];
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
-      mma_rows_x<D, MT>(acc, a, dobase, gm.do_stride, S, lane);
-      store_tile<D>(smem + 2 * F * 2 + h * D * 2, gm.in_stride, mk * 16, S, lane, acc);   // dV_h -> dead V_h slot
-    }
-    // ---- dS^T through the same scratch tile (for dK); dS fragments stay in registers (for dQ)
-    uint32_t dsa[MT][(NT + 1) / 2][4];
-    pack_rows<MT, NT>(dp, dsa);
-    __syncwarp();
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-          *reinterpret_cast<uint32_t*>(scr + (mt * 16 + g + 8 * r) * SCR_STRIDE + (nt * 8 + t * 2) * 2) =
-              pack_bf16x2(dp[mt][nt][r * 2], dp[mt][nt][r * 2 + 1]);
-    __syncwarp();
-    // ---- dQ = dS K -> dead dO_h slot
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float acc[D / 8][4];
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
-      mma_rows_x<D, (NT + 1) / 2>(acc, dsa[mt], kbase, gm.in_stride, S, lane);
-      store_tile<D>(do_s + h * D * 2, gm.do_stride, mt * 16, S, lane, acc);
-    }
-    // ---- dK = dS^T Q -> dead K_h slot
-    float acck[MTK][D / 8][4];
-#pragma unroll
-    for (int mk = 0; mk < MTK; ++mk) {
-      uint32_t a[MT][4];
-#pragma unroll
-      for (int kq = 0; kq < MT; ++kq) {
-        const int row = kq * 16 + (lane & 7) + (lane >> 4) * 8;
-        const int col = mk * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4_t(scr_a + row * SCR_STRIDE + col * 2, a[kq][0], a[kq][1], a[kq][2], a[kq][3]);
-      }
-#pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acck[mk][nd][i] = 0.f;
-      mma_rows_x<D, MT>(acck[mk], a, qbase, gm.in_stride, S, lane);
-    }
-    __syncwarp();   // every lane has finished reading K_h (dQ) before it is overwritten
-#pragma unroll
-    for (int mk = 0; mk < MTK; ++mk)
-      store_tile<D>(smem + F * 2 + h * D * 2, gm.in_stride, mk * 16, S, lane, acck[mk]);
-    __syncwarp();
+    mha_bwd_head<D, MT, NT>(qbase, kbase, vbase, dobase, scr, scr_a, do_s + h * D * 2, smem + F * 2 + h * D * 2,
+                            smem + 2 * F * 2 + h * D * 2, PadAddr{gm.in_stride}, PadAddr{gm.do_stride}, S, lane, kvalid,
+                            (long long)b * H + h, dc);
   }
   ATT_TICK(1);
   fence_async_smem();
@@ -473,6 +507,207 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
     __syncthreads();
     for (int c = threadIdx.x; c < 3 * F; c += blockDim.x) atomicAdd(dbias + c, colacc[c]);
   }
+}
+
+// =========================================================================================================
+// Warp-pipelined variant for head size 64.  The unit of work is one (sample, head): its Q, K, V (and dO) tiles are
+// [S][64] bf16 = S rows of 128 B, fetched by ONE 2-D TMA box each straight from the packed activation matrices into
+// 128B-swizzled shared-memory tiles (conflict-free ldmatrix without padding), and results leave by TMA box stores.
+// Every warp runs its own load -> compute -> store loop on its own mbarrier, so an SM has as many independent
+// pipelines in flight as it has warps (16-24) instead of one per CTA: loads of some units overlap the math and the
+// stores of others.  A warp keeps the same head for all its units (grid stride is a multiple of H), so the in_proj
+// bias gradient accumulates in registers.
+// =========================================================================================================
+static constexpr int TMA_FWD_WARPS = 8;
+static constexpr int TMA_BWD_WARPS = 7;
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(TMA_FWD_WARPS * 32, 3)
+mha_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                   const uint8_t* __restrict__ mask, float* __restrict__ probs, int B, int Tn, int H, uint32_t tile_bytes,
+                   DropCfg dc) {
+  constexpr int D = 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int S = Tn + 1, F = H * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* my = smem + (size_t)warp * 3 * tile_bytes;            // Q | K | V tiles of this warp
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_FWD_WARPS * 3 * tile_bytes) + warp;
+  const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(my), k_a = q_a + tile_bytes, v_a = k_a + tile_bytes;
+  if (lane == 0) {
+    mbar_init(bar_a, 1);
+    mbar_init_fence();
+  }
+  __syncwarp();
+  const int t = lane & 3;
+  const long long units = (long long)B * H;
+  const long long stride = (long long)gridDim.x * TMA_FWD_WARPS;
+  uint32_t phase = 0;
+  for (long long u = (long long)blockIdx.x * TMA_FWD_WARPS + warp; u < units; u += stride) {
+    const int b = (int)(u / H), h = (int)(u % H);
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, 3u * (uint32_t)S * 128u);
+      tma_load_2d(q_a, &tm_qkv, bar_a, h * D, b * S);
+      tma_load_2d(k_a, &tm_qkv, bar_a, F + h * D, b * S);
+      tma_load_2d(v_a, &tm_qkv, bar_a, 2 * F + h * D, b * S);
+    }
+    const uint32_t kvalid = key_valid_bits<NT>(mask, b, Tn, S, t);
+    mbar_wait(bar_a, phase);
+    phase ^= 1;
+    mha_fwd_head<D, MT, NT>(q_a, k_a, v_a, my, SwzAddr{}, S, lane, kvalid, u, probs, dc);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tm_out, q_a, h * D, b * S);     // O_h sits in the Q tile
+      bulk_commit();
+      bulk_wait_read0();                            // the tile is reloaded next iteration
+    }
+    __syncwarp();
+  }
+}
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(TMA_BWD_WARPS * 32, 2)
+mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dqkv, const uint8_t* __restrict__ mask,
+                   float* __restrict__ dbias, int B, int Tn, int H, uint32_t tile_bytes, DropCfg dc) {
+  constexpr int D = 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int S = Tn + 1, F = H * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* my = smem + (size_t)warp * 4 * tile_bytes;            // Q | K | V | dO tiles of this warp
+  uint8_t* scr = smem + (size_t)TMA_BWD_WARPS * 4 * tile_bytes + (size_t)warp * SCR_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_BWD_WARPS * (4 * tile_bytes + SCR_BYTES)) + warp;
+  const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(my), k_a = q_a + tile_bytes, v_a = k_a + tile_bytes,
+                 do_a = v_a + tile_bytes, scr_a = smem_u32(scr);
+  if (lane == 0) {
+    mbar_init(bar_a, 1);
+    mbar_init_fence();
+  }
+  __syncwarp();
+  const int t = lane & 3;
+  const long long units = (long long)B * H;
+  const long long stride = (long long)gridDim.x * TMA_BWD_WARPS;   // host makes it a multiple of H: h is fixed per warp
+  float cs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};           // column sums of dQ | dK | dV, columns 2*lane, 2*lane+1
+  int my_h = -1;
+  uint32_t phase = 0;
+  const SwzAddr ad{};
+  for (long long u = (long long)blockIdx.x * TMA_BWD_WARPS + warp; u < units; u += stride) {
+    const int b = (int)(u / H), h = (int)(u % H);
+    my_h = h;
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, 4u * (uint32_t)S * 128u);
+      tma_load_2d(q_a, &tm_qkv, bar_a, h * D, b * S);
+      tma_load_2d(k_a, &tm_qkv, bar_a, F + h * D, b * S);
+      tma_load_2d(v_a, &tm_qkv, bar_a, 2 * F + h * D, b * S);
+      tma_load_2d(do_a, &tm_do, bar_a, h * D, b * S);
+    }
+    const uint32_t kvalid = key_valid_bits<NT>(mask, b, Tn, S, t);
+    mbar_wait(bar_a, phase);
+    phase ^= 1;
+    mha_bwd_head<D, MT, NT>(q_a, k_a, v_a, do_a, scr, scr_a, my + 3 * tile_bytes, my + tile_bytes, my + 2 * tile_bytes, ad, ad,
+                            S, lane, kvalid, u, dc);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tm_dqkv, do_a, h * D, b * S);            // dQ_h (dO tile)
+      tma_store_2d(&tm_dqkv, k_a, F + h * D, b * S);         // dK_h
+      tma_store_2d(&tm_dqkv, v_a, 2 * F + h * D, b * S);     // dV_h
+      bulk_commit();
+    }
+    if (dbias != nullptr) {
+      // column sums of what was stored, two columns per lane, while the stores drain
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const uint8_t* tile = my + (m == 0 ? 3 : m) * tile_bytes;
+        for (int r = 0; r < S; ++r) {
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tile + ad.off(r, 2 * lane)));
+          cs[m][0] += v.x;
+          cs[m][1] += v.y;
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+  }
+  if (dbias != nullptr && my_h >= 0) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      atomicAdd(dbias + m * F + my_h * D + 2 * lane, cs[m][0]);
+      atomicAdd(dbias + m * F + my_h * D + 2 * lane + 1, cs[m][1]);
+    }
+  }
+}
+
+template <typename K>
+static int tma_set_smem(K kern, size_t smem, size_t* configured) {
+  if (smem > *configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha tma)");
+    *configured = smem;
+  }
+  return 0;
+}
+
+template <int MT, int NT>
+static int fwd_tma_launch(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc,
+                          cudaStream_t st) {
+  const int S = Tn + 1, F = H * 64;
+  const uint32_t tile_bytes = (uint32_t)((S + 7) / 8) * 1024u;
+  CUtensorMap tq, to;
+  MMER_TRY(make_tma_map_bf16(&tq, qkv, (uint64_t)3 * F, (uint64_t)B * S, (uint64_t)3 * F, 64, (uint32_t)S));
+  MMER_TRY(make_tma_map_bf16(&to, out, (uint64_t)F, (uint64_t)B * S, (uint64_t)F, 64, (uint32_t)S));
+  const size_t smem = (size_t)TMA_FWD_WARPS * 3 * tile_bytes + TMA_FWD_WARPS * 8;
+  static size_t configured = 0;
+  static int bps = 0;
+  auto kern = mha_fwd_tma_kernel<MT, NT>;
+  if (smem > configured) bps = 0;
+  MMER_TRY(tma_set_smem(kern, smem, &configured));
+  if (bps == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TMA_FWD_WARPS * 32, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy(mha_fwd_tma)");
+    if (bps < 1) bps = 1;
+  }
+  const long long units = (long long)B * H;
+  long long grid = (units + TMA_FWD_WARPS - 1) / TMA_FWD_WARPS;
+  const long long cap = (long long)sm_count() * bps;
+  if (grid > cap) grid = cap;
+  kern<<<(unsigned)grid, TMA_FWD_WARPS * 32, smem, st>>>(tq, to, mask, probs, B, Tn, H, tile_bytes, dc);
+  MMER_LAUNCH_CHECK("mha_fwd_tma_kernel");
+  return 0;
+}
+template <int MT, int NT>
+static int bwd_tma_launch(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias, int B, int Tn,
+                          int H, DropCfg dc, cudaStream_t st) {
+  const int S = Tn + 1, F = H * 64;
+  const uint32_t tile_bytes = (uint32_t)((S + 7) / 8) * 1024u;
+  CUtensorMap tq, td, tg;
+  MMER_TRY(make_tma_map_bf16(&tq, qkv, (uint64_t)3 * F, (uint64_t)B * S, (uint64_t)3 * F, 64, (uint32_t)S));
+  MMER_TRY(make_tma_map_bf16(&td, dout, (uint64_t)F, (uint64_t)B * S, (uint64_t)F, 64, (uint32_t)S));
+  MMER_TRY(make_tma_map_bf16(&tg, dqkv, (uint64_t)3 * F, (uint64_t)B * S, (uint64_t)3 * F, 64, (uint32_t)S));
+  const size_t smem = (size_t)TMA_BWD_WARPS * (4 * tile_bytes + SCR_BYTES) + TMA_BWD_WARPS * 8;
+  static size_t configured = 0;
+  static int bps = 0;
+  auto kern = mha_bwd_tma_kernel<MT, NT>;
+  if (smem > configured) bps = 0;
+  MMER_TRY(tma_set_smem(kern, smem, &configured));
+  if (bps == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TMA_BWD_WARPS * 32, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy(mha_bwd_tma)");
+    if (bps < 1) bps = 1;
+  }
+  // total warps must be a multiple of H so that every warp keeps one head (register column sums)
+  const long long units = (long long)B * H;
+  long long grid = (units + TMA_BWD_WARPS - 1) / TMA_BWD_WARPS;
+  const long long cap = (long long)sm_count() * bps;
+  if (grid > cap) grid = cap;
+  if (dbias != nullptr) {
+    while (grid > 1 && (grid * TMA_BWD_WARPS) % H != 0) --grid;
+    MMER_CHECK_ARG((grid * TMA_BWD_WARPS) % H == 0 || units <= grid * TMA_BWD_WARPS,
+                   "mha_bwd: cannot tile %d heads over %d-warp CTAs for the fused bias gradient", H, TMA_BWD_WARPS);
+  }
+  kern<<<(unsigned)grid, TMA_BWD_WARPS * 32, smem, st>>>(tq, td, tg, mask, dbias, B, Tn, H, tile_bytes, dc);
+  MMER_LAUNCH_CHECK("mha_bwd_tma_kernel");
+  return 0;
 }
 
 static MmaGeom make_geom(int Tn, int H, int D) {
@@ -554,6 +789,12 @@ int mha_fwd_mma(const void* qkv, const uint8_t* mask, void* out, float* probs, i
   const MmaGeom g = make_geom(Tn, H, d);
   MMER_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "mha_fwd: qkv/out must be 16-byte aligned");
+  if (d == 64 && !g_debug[MMER_DEBUG_ATT_ROWS]) {   // warp-pipelined TMA-tile kernels
+    if (g.S <= 8) return fwd_tma_launch<1, 1>(qkv, mask, out, probs, B, Tn, H, dc, st);
+    if (g.S <= 16) return fwd_tma_launch<1, 2>(qkv, mask, out, probs, B, Tn, H, dc, st);
+    if (g.S <= 24) return fwd_tma_launch<2, 3>(qkv, mask, out, probs, B, Tn, H, dc, st);
+    return fwd_tma_launch<2, 4>(qkv, mask, out, probs, B, Tn, H, dc, st);
+  }
   return d == 64 ? fwd_d<64>(qkv, mask, out, probs, B, g, dc, st) : fwd_d<32>(qkv, mask, out, probs, B, g, dc, st);
 }
 // dbias (optional): += column sums of dqkv, i.e. the gradient of in_proj_bias
@@ -563,6 +804,12 @@ int mha_bwd_mma(const void* qkv, const uint8_t* mask, const void* dout, void* dq
   MMER_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0,
                  "mha_bwd: qkv/dout/dqkv must be 16-byte aligned");
+  if (d == 64 && !g_debug[MMER_DEBUG_ATT_ROWS]) {
+    if (g.S <= 8) return bwd_tma_launch<1, 1>(qkv, mask, dout, dqkv, dbias, B, Tn, H, dc, st);
+    if (g.S <= 16) return bwd_tma_launch<1, 2>(qkv, mask, dout, dqkv, dbias, B, Tn, H, dc, st);
+    if (g.S <= 24) return bwd_tma_launch<2, 3>(qkv, mask, dout, dqkv, dbias, B, Tn, H, dc, st);
+    return bwd_tma_launch<2, 4>(qkv, mask, dout, dqkv, dbias, B, Tn, H, dc, st);
+  }
   return d == 64 ? bwd_d<64>(qkv, mask, dout, dqkv, dbias, B, g, dc, st)
                  : bwd_d<32>(qkv, mask, dout, dqkv, dbias, B, g, dc, st);
 }

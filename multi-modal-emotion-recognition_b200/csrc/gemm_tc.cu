@@ -30,23 +30,12 @@ static constexpr int UMMA_K = 16;
 int g_debug[16] = {0};
 
 // ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
 // 2-CTA pair: the copy lands in this CTA's shared memory, its bytes are counted on the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1)
-               : "memory");
 }
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -767,7 +756,7 @@ struct MapKeyHash {
 };
 
 // 2-D bf16 tensor map: inner dimension d0 (contiguous), outer d1 with row stride ld elements.
-static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
+int make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{ptr, d0, d1, ld, b0, b1};
@@ -881,14 +870,14 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
 
   CUtensorMap ta, tb;
   if (a.a_major == MMER_MAJOR_K) {
-    MMER_TRY(make_map(&ta, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, BM));
+    MMER_TRY(make_tma_map_bf16(&ta, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, 64, BM));
   } else {
-    MMER_TRY(make_map(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, BK));
+    MMER_TRY(make_tma_map_bf16(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64, BK));
   }
   if (a.b_major == MMER_MAJOR_K) {
-    MMER_TRY(make_map(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(bn / cg)));
+    MMER_TRY(make_tma_map_bf16(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64, (uint32_t)(bn / cg)));
   } else {
-    MMER_TRY(make_map(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, BK));
+    MMER_TRY(make_tma_map_bf16(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, 64, BK));
   }
 
   CUtensorMap td = ta, tx = ta;  // placeholders when the staged store / aux tile are not used
@@ -898,8 +887,8 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   if (tma_store) {
     MMER_CHECK_ARG(aux == nullptr || (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
                    "gemm_tc: gate/residual must be 16-byte aligned");
-    MMER_TRY(make_map(&td, a.D, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
-    if (aux) MMER_TRY(make_map(&tx, aux, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
+    MMER_TRY(make_tma_map_bf16(&td, a.D, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
+    if (aux) MMER_TRY(make_tma_map_bf16(&tx, aux, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldd, 64, 32));
   }
 
   GemmParams p;

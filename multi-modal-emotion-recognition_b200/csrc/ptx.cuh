@@ -1,5 +1,6 @@
 // Inline-PTX wrappers shared by the sm_100a kernels: mbarriers, bulk (TMA) copies, ldmatrix, mma.sync.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -60,6 +61,19 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // make generic-proxy shared-memory writes visible to the async proxy (TMA) before it reads them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------ 2-D tiled TMA (tensor maps)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ warp-level tensor-core path (small tiles)
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -89,5 +103,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// host: 2-D bf16 tensor map, 128B swizzle; inner dimension d0 (contiguous) with box b0 (<= 64), outer d1 with row stride
+// ld elements and box b1.  Cached by (pointer, dims).  Defined in gemm_tc.cu.
+int make_tma_map_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1);
 
 }  // namespace mmer

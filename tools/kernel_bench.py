@@ -60,15 +60,15 @@ def bench_mha():
     sets = [(rnd(M, 3 * F), rnd(M, F)) for _ in range(NBUF)]
     fb = M * 3 * F * 2 + M * F * 2
     bb = 2 * M * 3 * F * 2 + M * F * 2
-    for simt in (0, 1):
-        lib.mmer_debug_set(_lib.DEBUG_ATT_SIMT, simt)
-        tag = "simt" if simt else "mma"
+    for variant in ("tma-tile", "bulk-row"):
+        lib.mmer_debug_set(_lib.DEBUG_ATT_ROWS, 0 if variant == "tma-tile" else 1)
+        tag = variant
         for p in (0.0, 0.1):
             timeit(f"mha_fwd[{tag}] p={p}", [lambda q=q: ops.mha_fwd(q, None, B, T, H, D, drop_p=p, seed=1, site=1)
                                              for q, _ in sets], fb)
             timeit(f"mha_bwd[{tag}] p={p}", [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=p, seed=1, site=1)
                                              for q, d in sets], bb)
-    lib.mmer_debug_set(_lib.DEBUG_ATT_SIMT, 0)
+    lib.mmer_debug_set(_lib.DEBUG_ATT_ROWS, 0)
 
 
 def bench_add_ln():
