@@ -114,8 +114,16 @@ def test_fp32_training_step_matches_reference_golden(name, variant, loss, clip):
             if "tracked" in k:
                 assert int(val) == int(g["bn_after_fwd/" + k])
     before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    # A bias that feeds straight into a BatchNorm has an analytically ZERO gradient (train.py:66-74,125: the batch
+    # mean removes it).  What either implementation holds there is summation-order noise (~1e-9), which Adam's first
+    # step g / (|g| + 1e-8) turns into an O(lr) update of arbitrary sign: not comparable, so check smallness instead.
+    zero_grad_keys = {"fusion.video_proj.bias", "fusion.audio_proj.bias", "classifier.fc1.bias"} if variant == "v1" else set()
+    for k in zero_grad_keys:
+        assert float(dict(model.named_parameters())[k].grad.abs().max()) < 1e-6, k
     opt.step()
     for k, p in model.named_parameters():
+        if k in zero_grad_keys:
+            continue
         ref = g["delta1/" + k]
         got = summarize(p.detach() - before[k])
         np.testing.assert_allclose(got[2:], ref[2:], rtol=0, atol=3e-6, err_msg=k)
