@@ -8,8 +8,7 @@
 // warp-level tensor-core MMAs (m16n8k16, bf16 in, fp32 accumulate) on ldmatrix fragments:
 //   forward   S = Q K^T, masked softmax in the accumulator fragments (quad shuffles), dropout, O = P V
 //   backward  recompute P, dP = dO V^T, dS = P o (dP - rowsum(dP o P)) / sqrt(d), dV = Pd^T dO, dQ = dS K,
-//             dK = dS^T Q; the transposed operands (Pd^T, dS^T) go through a 2.5 KB per-warp scratch tile and
-//             ldmatrix.trans
+//             dK = dS^T Q; the transposed operands (Pd^T, dS^T) are built in registers with movmatrix
 // Results overwrite operand slots that are dead by then (O -> Q slot; dV -> V slot, dK -> K slot, dQ -> dO slot),
 // so whole token rows leave through bulk shared->global copies.  HBM traffic is the algorithmic minimum: every
 // input byte is read once, every output byte written once, all as >= 1 KB contiguous bursts.
@@ -22,8 +21,6 @@ namespace mmer {
 
 extern int g_debug[16];
 static constexpr int MMA_WARPS = 8;
-static constexpr int SCR_STRIDE = 80;                 // bytes per scratch row (32 bf16 + 16 B pad: conflict-free ldmatrix)
-static constexpr int SCR_BYTES = 32 * SCR_STRIDE;     // per warp
 
 struct MmaGeom {
   int S, F, Tn, H;
@@ -119,6 +116,14 @@ __device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, A
 #pragma unroll
         for (int e = 0; e < 2; ++e) p[mt][nt][r * 2 + e] *= inv;
     }
+}
+
+// A fragment (16 x 16, rows m, columns k) of X^T from the A fragment of X covering the same 16 x 16 block
+__device__ __forceinline__ void trans_frag(const uint32_t (&x)[4], uint32_t (&y)[4]) {
+  y[0] = movmatrix_t(x[0]);
+  y[1] = movmatrix_t(x[2]);
+  y[2] = movmatrix_t(x[1]);
+  y[3] = movmatrix_t(x[3]);
 }
 
 // accumulator fragments [MT][NT][4] of a (queries x keys) matrix -> bf16 A fragments over 16-key steps
@@ -260,11 +265,11 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
   }
 }
 
-// One head of the backward pass on fragments.  q/k/v tiles follow policy `ain`, the dO tile policy `ado`; `scr` is this
-// warp's transpose scratch.  Outputs overwrite dead operand tiles: dV -> dv_ptr (ain), dK -> dk_ptr (ain), dQ -> dq_ptr (ado).
+// One head of the backward pass on fragments.  q/k/v tiles follow policy `ain`, the dO tile policy `ado`.
+// Outputs overwrite dead operand tiles: dV -> dv_ptr (ain), dK -> dk_ptr (ain), dQ -> dq_ptr (ado).
 template <int D, int MT, int NT, class AIN, class ADO>
-__device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint32_t dobase, uint8_t* scr,
-                                             uint32_t scr_a, uint8_t* dq_ptr, uint8_t* dk_ptr, uint8_t* dv_ptr, AIN ain, ADO ado,
+__device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint32_t dobase,
+                                             uint8_t* dq_ptr, uint8_t* dk_ptr, uint8_t* dv_ptr, AIN ain, ADO ado,
                                              int S, int lane, uint32_t kvalid, long long bh, DropCfg dc) {
   constexpr int KS = D / 16;
   constexpr int MTK = (NT + 1) / 2;   // 16-row tiles over keys
@@ -335,26 +340,15 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
           p[mt][nt][r * 2 + e] = row_ok ? pv * f[nt][e] : 0.f;
         }
     }
-  // ---- dV = Pd^T dO  (Pd^T through the scratch tile)
-  __syncwarp();
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-        *reinterpret_cast<uint32_t*>(scr + (mt * 16 + g + 8 * r) * SCR_STRIDE + (nt * 8 + t * 2) * 2) =
-            pack_bf16x2(p[mt][nt][r * 2], p[mt][nt][r * 2 + 1]);
-  __syncwarp();
+  // ---- dV = Pd^T dO.  The A fragments of a transposed operand are the 8x8 blocks of the original's fragments,
+  // each transposed in registers (movmatrix) and with the two off-diagonal blocks swapped: no shared memory.
+  uint32_t pda[MT][(NT + 1) / 2][4];
+  pack_rows<MT, NT>(p, pda);
 #pragma unroll
   for (int mk = 0; mk < MTK; ++mk) {
     uint32_t a[MT][4];
 #pragma unroll
-    for (int kq = 0; kq < MT; ++kq) {
-      const int row = kq * 16 + (lane & 7) + (lane >> 4) * 8;         // query (reduction index)
-      const int col = mk * 16 + ((lane >> 3) & 1) * 8;                // key (output row)
-      ldsm_x4_t(scr_a + row * SCR_STRIDE + col * 2, a[kq][0], a[kq][1], a[kq][2], a[kq][3]);
-    }
+    for (int kq = 0; kq < MT; ++kq) trans_frag(pda[kq][mk], a[kq]);
     float acc[D / 8][4];
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd)
@@ -363,19 +357,9 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
     mma_rows_x<D, MT>(acc, a, dobase, ado, S, lane);
     store_tile<D>(dv_ptr, ain, mk * 16, S, lane, acc);   // dV_h -> dead V_h slot
   }
-  // ---- dS^T through the same scratch tile (for dK); dS fragments stay in registers (for dQ)
+  // ---- dS as A fragments (for dQ); its transpose is built the same way (for dK)
   uint32_t dsa[MT][(NT + 1) / 2][4];
   pack_rows<MT, NT>(dp, dsa);
-  __syncwarp();
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-        *reinterpret_cast<uint32_t*>(scr + (mt * 16 + g + 8 * r) * SCR_STRIDE + (nt * 8 + t * 2) * 2) =
-            pack_bf16x2(dp[mt][nt][r * 2], dp[mt][nt][r * 2 + 1]);
-  __syncwarp();
   // ---- dQ = dS K -> dead dO_h slot
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
@@ -393,11 +377,7 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
   for (int mk = 0; mk < MTK; ++mk) {
     uint32_t a[MT][4];
 #pragma unroll
-    for (int kq = 0; kq < MT; ++kq) {
-      const int row = kq * 16 + (lane & 7) + (lane >> 4) * 8;
-      const int col = mk * 16 + ((lane >> 3) & 1) * 8;
-      ldsm_x4_t(scr_a + row * SCR_STRIDE + col * 2, a[kq][0], a[kq][1], a[kq][2], a[kq][3]);
-    }
+    for (int kq = 0; kq < MT; ++kq) trans_frag(dsa[kq][mk], a[kq]);
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd)
 #pragma unroll
@@ -423,10 +403,9 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
   const size_t in_bytes = ((size_t)S * gm.in_stride + 15) & ~size_t(15);
   const size_t do_bytes = ((size_t)S * gm.do_stride + 15) & ~size_t(15);
   uint8_t* do_s = smem + in_bytes;
-  uint8_t* scr = do_s + do_bytes + warp * SCR_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(do_s + do_bytes + MMA_WARPS * SCR_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(do_s + do_bytes);
   float* colacc = reinterpret_cast<float*>(bar + 2);   // [3F] running column sums of dqkv (in_proj bias gradient)
-  const uint32_t bar_a = smem_u32(bar), in_a = smem_u32(smem), do_a = smem_u32(do_s), scr_a = smem_u32(scr);
+  const uint32_t bar_a = smem_u32(bar), in_a = smem_u32(smem), do_a = smem_u32(do_s);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
@@ -463,7 +442,7 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 
   for (int h = warp; h < H; h += MMA_WARPS) {
     const uint32_t qbase = in_a + h * D * 2, kbase = qbase + F * 2, vbase = kbase + F * 2, dobase = do_a + h * D * 2;
-    mha_bwd_head<D, MT, NT>(qbase, kbase, vbase, dobase, scr, scr_a, do_s + h * D * 2, smem + F * 2 + h * D * 2,
+    mha_bwd_head<D, MT, NT>(qbase, kbase, vbase, dobase, do_s + h * D * 2, smem + F * 2 + h * D * 2,
                             smem + 2 * F * 2 + h * D * 2, PadAddr{gm.in_stride}, PadAddr{gm.do_stride}, S, lane, kvalid,
                             (long long)b * H + h, dc);
   }
@@ -519,7 +498,7 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 // bias gradient accumulates in registers.
 // =========================================================================================================
 static constexpr int TMA_FWD_WARPS = 8;
-static constexpr int TMA_BWD_WARPS = 7;
+static constexpr int TMA_BWD_WARPS = 8;
 
 template <int MT, int NT>
 __global__ void __launch_bounds__(TMA_FWD_WARPS * 32, 3)
@@ -575,10 +554,9 @@ mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int S = Tn + 1, F = H * D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* my = smem + (size_t)warp * 4 * tile_bytes;            // Q | K | V | dO tiles of this warp
-  uint8_t* scr = smem + (size_t)TMA_BWD_WARPS * 4 * tile_bytes + (size_t)warp * SCR_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_BWD_WARPS * (4 * tile_bytes + SCR_BYTES)) + warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_BWD_WARPS * 4 * tile_bytes) + warp;
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(my), k_a = q_a + tile_bytes, v_a = k_a + tile_bytes,
-                 do_a = v_a + tile_bytes, scr_a = smem_u32(scr);
+                 do_a = v_a + tile_bytes;
   if (lane == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
@@ -604,7 +582,7 @@ mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const uint32_t kvalid = key_valid_bits<NT>(mask, b, Tn, S, t);
     mbar_wait(bar_a, phase);
     phase ^= 1;
-    mha_bwd_head<D, MT, NT>(q_a, k_a, v_a, do_a, scr, scr_a, my + 3 * tile_bytes, my + tile_bytes, my + 2 * tile_bytes, ad, ad,
+    mha_bwd_head<D, MT, NT>(q_a, k_a, v_a, do_a, my + 3 * tile_bytes, my + tile_bytes, my + 2 * tile_bytes, ad, ad,
                             S, lane, kvalid, u, dc);
     fence_async_smem();
     __syncwarp();
@@ -684,7 +662,7 @@ static int bwd_tma_launch(const void* qkv, const uint8_t* mask, const void* dout
   MMER_TRY(make_tma_map_bf16(&tq, qkv, (uint64_t)3 * F, (uint64_t)B * S, (uint64_t)3 * F, 64, (uint32_t)S));
   MMER_TRY(make_tma_map_bf16(&td, dout, (uint64_t)F, (uint64_t)B * S, (uint64_t)F, 64, (uint32_t)S));
   MMER_TRY(make_tma_map_bf16(&tg, dqkv, (uint64_t)3 * F, (uint64_t)B * S, (uint64_t)3 * F, 64, (uint32_t)S));
-  const size_t smem = (size_t)TMA_BWD_WARPS * (4 * tile_bytes + SCR_BYTES) + TMA_BWD_WARPS * 8;
+  const size_t smem = (size_t)TMA_BWD_WARPS * 4 * tile_bytes + TMA_BWD_WARPS * 8;
   static size_t configured = 0;
   static int bps = 0;
   auto kern = mha_bwd_tma_kernel<MT, NT>;
@@ -720,7 +698,7 @@ static MmaGeom make_geom(int Tn, int H, int D) {
 static size_t fwd_smem(const MmaGeom& g) { return (((size_t)g.S * g.in_stride + 15) & ~size_t(15)) + 16; }
 static size_t bwd_smem(const MmaGeom& g) {
   return (((size_t)g.S * g.in_stride + 15) & ~size_t(15)) + (((size_t)g.S * g.do_stride + 15) & ~size_t(15)) +
-         (size_t)MMA_WARPS * SCR_BYTES + 16 + (size_t)3 * g.F * sizeof(float);
+         16 + (size_t)3 * g.F * sizeof(float);
 }
 
 template <typename K>
