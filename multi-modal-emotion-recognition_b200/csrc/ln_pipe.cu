@@ -104,12 +104,20 @@ __device__ __forceinline__ LnSmem lnp_setup(const LnPipeGeom& g, uint8_t* smem) 
 // ---------------------------------------------------------------------------------------------------------
 // forward:  z = x + drop_a(a);  y = drop_y(relu?(LN(z) * gamma + beta));  stats = (mean, rstd)
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int NCH>
+// MODE < 0: every option decided at run time.  MODE >= 0: a bit set fixed at compile time (LNM_*), which strips the
+// predicated code of the unused options from the per-row loop of the hot instances (encoder sub-layers).
+enum : int { LNM_X = 1, LNM_RELU = 2, LNM_DROP_A = 4, LNM_DROP_Y = 8, LNM_DBIAS = 16 };
+
+template <typename T, int NCH, int MODE>
 __global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
 add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ stats, LnPipeGeom g, int relu,
+                       const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ stats, LnPipeGeom g, int relu_rt,
                        DropCfg da, DropCfg dy) {
   extern __shared__ __align__(128) uint8_t smem[];
+  const bool has_x = MODE < 0 ? g.narr > 1 : (MODE & LNM_X) != 0;
+  const bool relu = MODE < 0 ? relu_rt != 0 : (MODE & LNM_RELU) != 0;
+  const bool drop_a = MODE < 0 ? da.thr != 0 : (MODE & LNM_DROP_A) != 0;
+  const bool drop_y = MODE < 0 ? dy.thr != 0 : (MODE & LNM_DROP_Y) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LnSmem sm = lnp_setup(g, smem);
   const int F = g.F;
@@ -143,13 +151,13 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
         const int c = lane * 8 + i * 256;
         if (c < F) {
           load8(sa + c, z[i]);
-          if (da.thr) {
+          if (drop_a) {
             float f[8];
             drop8(da, (uint64_t)(row * F + c), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) z[i][j] *= f[j];
           }
-          if (g.narr > 1) {
+          if (has_x) {
             float xv[8];
             load8(sx + c, xv);
 #pragma unroll
@@ -190,7 +198,7 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
           o[j] = fmaf(fmaf(z[i][j], rstd, nmr), gm[i][j], bt[i][j]);
           if (relu) o[j] = fmaxf(o[j], 0.f);
         }
-        if (dy.thr) {
+        if (drop_y) {
           float f[8];
           drop8(dy, (uint64_t)off, f);
 #pragma unroll
@@ -208,17 +216,25 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
 //   da  = dz o dropmask_a                                                   (gradient of the sub-layer output)
 //   dgamma += sum_rows dy'*xhat, dbeta += sum_rows dy', dbias += sum_rows (stored da)
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int NCH>
+template <typename T, int NCH, int MODE>
 __global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
 add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const T* __restrict__ x,
                        const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                        T* __restrict__ dz, T* __restrict__ dap, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       float* __restrict__ dbias, LnPipeGeom g, int relu, DropCfg da, DropCfg dy) {
+                       float* __restrict__ dbias, LnPipeGeom g, int relu_rt, DropCfg da, DropCfg dy) {
   extern __shared__ __align__(128) uint8_t smem[];
+  const bool has_x = MODE < 0 ? g.narr > 2 : (MODE & LNM_X) != 0;
+  const bool relu = MODE < 0 ? relu_rt != 0 : (MODE & LNM_RELU) != 0;
+  const bool drop_a = MODE < 0 ? da.thr != 0 : (MODE & LNM_DROP_A) != 0;
+  const bool drop_y = MODE < 0 ? dy.thr != 0 : (MODE & LNM_DROP_Y) != 0;
+  const bool want_dbias = MODE < 0 ? dbias != nullptr : (MODE & LNM_DBIAS) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LnSmem sm = lnp_setup(g, smem);
   const int F = g.F;
   const bool compute_warp = warp < g.W;
+  float* sgamma = reinterpret_cast<float*>(smem + (size_t)g.stages * g.stage_bytes + 2 * LNP_MAX_STAGES * 8);
+  for (int c = threadIdx.x; c < F; c += blockDim.x) sgamma[c] = gamma[c];
+  __syncthreads();
   float pg[NCH][8], pb[NCH][8], pbias[NCH][8];
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
@@ -230,12 +246,6 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
       lnp_produce<T>(g, src, sm.data_a, sm.full_a, sm.empty_a);
     }
   } else {
-    float gm[NCH][8];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int c = lane * 8 + i * 256;
-      if (c < F) load8(gamma + c, gm[i]);
-    }
     const float invF = 1.f / (float)F;
     const long long tiles = (g.M + g.W - 1) / g.W;
     int stage = 0;
@@ -262,21 +272,22 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
           const int c = lane * 8 + i * 256;
           if (c < F) {
             const long long off = row * F + c;
-            float z[8], d[8];
+            float z[8], d[8], gm8[8];
+            load8(sgamma + c, gm8);     // gamma lives in shared memory: 16 registers fewer than a per-lane copy
             load8(sa + c, z);
-            if (da.thr) {
+            if (drop_a) {
               drop8(da, (uint64_t)off, fa[i]);
 #pragma unroll
               for (int j = 0; j < 8; ++j) z[j] *= fa[i][j];
             }
-            if (g.narr > 2) {
+            if (has_x) {
               float xv[8];
               load8(sx + c, xv);
 #pragma unroll
               for (int j = 0; j < 8; ++j) z[j] += xv[j];
             }
             load8(sdy + c, d);
-            if (dy.thr) {
+            if (drop_y) {
               float f[8];
               drop8(dy, (uint64_t)off, f);
 #pragma unroll
@@ -287,14 +298,14 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
               load8(beta + c, be);
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                if (!(fmaf(fmaf(z[j], rstd, nmr), gm[i][j], be[j]) > 0.f)) d[j] = 0.f;
+                if (!(fmaf(fmaf(z[j], rstd, nmr), gm8[j], be[j]) > 0.f)) d[j] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               xh[i][j] = fmaf(z[j], rstd, nmr);
               pg[i][j] = fmaf(d[j], xh[i][j], pg[i][j]);
               pb[i][j] += d[j];
-              gd[i][j] = d[j] * gm[i][j];
+              gd[i][j] = d[j] * gm8[j];
               s1 += gd[i][j];
               s2 = fmaf(gd[i][j], xh[i][j], s2);
             }
@@ -316,12 +327,12 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[i][j], -c2r, fmaf(gd[i][j], rstd, -c1r));
           store8(dz + off, o);
-          if (da.thr) {
+          if (drop_a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] *= fa[i][j];
             if (dap != nullptr) store8(dap + off, o);
           }
-          if (dbias != nullptr) {
+          if (want_dbias) {
             // bias gradient of the Linear that produced `a`: column sum of what is stored
 #pragma unroll
             for (int j = 0; j < 8; ++j) pbias[i][j] += round_as<T>(o[j]);
@@ -334,7 +345,7 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
   float* sred = reinterpret_cast<float*>(smem);
   lnp_flush<NCH>(pg, dgamma, F, g.W, sred, compute_warp);
   lnp_flush<NCH>(pb, dbeta, F, g.W, sred, compute_warp);
-  if (dbias != nullptr) lnp_flush<NCH>(pbias, dbias, F, g.W, sred, compute_warp);
+  if (want_dbias) lnp_flush<NCH>(pbias, dbias, F, g.W, sred, compute_warp);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -359,7 +370,7 @@ static int lnp_geometry(long long M, long long F, int elt, int narr, LnPipeGeom*
   size_t data = (size_t)stages * g->stage_bytes;
   const size_t red = (size_t)W * F * sizeof(float);   // reduction scratch of the backward kernel
   if (data < red) data = red;
-  *smem_bytes = data + 2 * LNP_MAX_STAGES * 8 + 16;
+  *smem_bytes = data + 2 * LNP_MAX_STAGES * 8 + (size_t)F * sizeof(float) + 16;   // + gamma copy (backward)
   return 0;
 }
 static int lnp_grid(const LnPipeGeom& g) {
@@ -377,17 +388,40 @@ static int lnp_set_smem(K kern, size_t smem, size_t* configured) {
   return 0;
 }
 
+template <typename T, int NCH, int MODE>
+static int fwd_launch_mode(const void* x, const void* a, const float* gamma, const float* beta, void* y, float* stats,
+                           const LnPipeGeom& g, size_t smem, int relu, DropCfg da, DropCfg dy, cudaStream_t st) {
+  static size_t configured = 0;
+  auto kern = add_ln_fwd_pipe_kernel<T, NCH, MODE>;
+  MMER_TRY(lnp_set_smem(kern, smem, &configured));
+  kern<<<lnp_grid(g), (g.W + 1) * 32, smem, st>>>((const T*)a, (const T*)x, gamma, beta, (T*)y, stats, g, relu, da, dy);
+  MMER_LAUNCH_CHECK("add_ln_fwd_pipe_kernel");
+  return 0;
+}
 template <typename T, int NCH>
 static int fwd_launch(const void* x, const void* a, const float* gamma, const float* beta, void* y, float* stats,
                       long long M, long long F, int relu, DropCfg da, DropCfg dy, cudaStream_t st) {
   LnPipeGeom g;
   size_t smem;
   MMER_TRY(lnp_geometry(M, F, sizeof(T), x ? 2 : 1, &g, &smem));
+  if (NCH == 2 && sizeof(T) == 2) {   // the encoder sub-layer instances of the bf16 step
+    const int mode = (x ? LNM_X : 0) | (relu ? LNM_RELU : 0) | (da.thr ? LNM_DROP_A : 0) | (dy.thr ? LNM_DROP_Y : 0);
+    if (mode == (LNM_X | LNM_DROP_A))
+      return fwd_launch_mode<T, NCH, LNM_X | LNM_DROP_A>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
+    if (mode == LNM_X) return fwd_launch_mode<T, NCH, LNM_X>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
+  }
+  return fwd_launch_mode<T, NCH, -1>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
+}
+template <typename T, int NCH, int MODE>
+static int bwd_launch_mode(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
+                           const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias,
+                           const LnPipeGeom& g, size_t smem, int relu, DropCfg da, DropCfg ddy, cudaStream_t st) {
   static size_t configured = 0;
-  auto kern = add_ln_fwd_pipe_kernel<T, NCH>;
+  auto kern = add_ln_bwd_pipe_kernel<T, NCH, MODE>;
   MMER_TRY(lnp_set_smem(kern, smem, &configured));
-  kern<<<lnp_grid(g), (g.W + 1) * 32, smem, st>>>((const T*)a, (const T*)x, gamma, beta, (T*)y, stats, g, relu, da, dy);
-  MMER_LAUNCH_CHECK("add_ln_fwd_pipe_kernel");
+  kern<<<lnp_grid(g), (g.W + 1) * 32, smem, st>>>((const T*)dy, (const T*)a, (const T*)x, stats, gamma, beta, (T*)dz,
+                                                   (T*)dap, dgamma, dbeta, dbias, g, relu, da, ddy);
+  MMER_LAUNCH_CHECK("add_ln_bwd_pipe_kernel");
   return 0;
 }
 template <typename T, int NCH>
@@ -397,13 +431,17 @@ static int bwd_launch(const void* dy, const void* x, const void* a, const float*
   LnPipeGeom g;
   size_t smem;
   MMER_TRY(lnp_geometry(M, F, sizeof(T), x ? 3 : 2, &g, &smem));
-  static size_t configured = 0;
-  auto kern = add_ln_bwd_pipe_kernel<T, NCH>;
-  MMER_TRY(lnp_set_smem(kern, smem, &configured));
-  kern<<<lnp_grid(g), (g.W + 1) * 32, smem, st>>>((const T*)dy, (const T*)a, (const T*)x, stats, gamma, beta, (T*)dz,
-                                                   (T*)dap, dgamma, dbeta, dbias, g, relu, da, ddy);
-  MMER_LAUNCH_CHECK("add_ln_bwd_pipe_kernel");
-  return 0;
+  if (NCH == 2 && sizeof(T) == 2) {
+    const int mode = (x ? LNM_X : 0) | (relu ? LNM_RELU : 0) | (da.thr ? LNM_DROP_A : 0) | (ddy.thr ? LNM_DROP_Y : 0) |
+                     (dbias ? LNM_DBIAS : 0);
+    if (mode == (LNM_X | LNM_DROP_A | LNM_DBIAS))
+      return bwd_launch_mode<T, NCH, LNM_X | LNM_DROP_A | LNM_DBIAS>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta,
+                                                                      dbias, g, smem, relu, da, ddy, st);
+    if (mode == (LNM_X | LNM_DBIAS))
+      return bwd_launch_mode<T, NCH, LNM_X | LNM_DBIAS>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, g, smem,
+                                                         relu, da, ddy, st);
+  }
+  return bwd_launch_mode<T, NCH, -1>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, g, smem, relu, da, ddy, st);
 }
 
 #define LNP_DISPATCH(F, CALL)                                    \
