@@ -638,12 +638,18 @@ embed_fwd_pipe_kernel(const T* __restrict__ pv, const T* __restrict__ pa, const 
       const int c = lane * 8 + i * 256;
       if (c < F) {
         const long long off = row * F + c;
-        float pe[8], o[8], gg[8], bb[8];
+        float pe[8], o[8];
         load8(pos + (long long)s * F + c, pe);
-        if (audio) { load8(ga + c, gg); load8(ba + c, bb); }
+        if (audio) {     // warp-uniform: 1 row in S
+          float gg[8], bb[8];
+          load8(ga + c, gg);
+          load8(ba + c, bb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = fmaf(fmaf(z[i][j], rstd, nmr), audio ? gg[j] : gmv[i][j], audio ? bb[j] : btv[i][j]) + pe[j];
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(z[i][j], rstd, nmr), gg[j], bb[j]) + pe[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(z[i][j], rstd, nmr), gmv[i][j], btv[i][j]) + pe[j];
+        }
         if (dc.thr) {
           float f[8];
           drop8(dc, (uint64_t)off, f);
@@ -726,15 +732,25 @@ embed_bwd_pipe_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const
               for (int j = 0; j < 8; ++j) d[j] *= f[j];
             }
             load8(sz + c, z);
-            if (audio) load8(ga + c, gg);
+            if (audio) {     // warp-uniform: 1 row in S
+              load8(ga + c, gg);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              xh[i][j] = fmaf(z[j], rstd, nmr);
-              const float dg = d[j] * xh[i][j];
-              if (audio) atomicAdd(sga + c + j, dg); else pg[i][j] += dg;
-              gd[i][j] = d[j] * (audio ? gg[j] : gmv[i][j]);
-              s1 += gd[i][j];
-              s2 = fmaf(gd[i][j], xh[i][j], s2);
+              for (int j = 0; j < 8; ++j) {
+                xh[i][j] = fmaf(z[j], rstd, nmr);
+                atomicAdd(sga + c + j, d[j] * xh[i][j]);
+                gd[i][j] = d[j] * gg[j];
+                s1 += gd[i][j];
+                s2 = fmaf(gd[i][j], xh[i][j], s2);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                xh[i][j] = fmaf(z[j], rstd, nmr);
+                pg[i][j] = fmaf(d[j], xh[i][j], pg[i][j]);
+                gd[i][j] = d[j] * gmv[i][j];
+                s1 += gd[i][j];
+                s2 = fmaf(gd[i][j], xh[i][j], s2);
+              }
             }
           }
         }
