@@ -341,7 +341,7 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
                              site_layer(l, 3), 0.f, 0, d.seed, st));
     MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], -1, st));
     // through ReLU (+ its dropout): gate on the stored post-activation.  No gradient tensor is re-read for a bias
-    // gradient: the kernels that produce dY sum its columns where that is free (add_ln_bwd, mha_bwd); for linear1 and
+    // gradient: add_ln_bwd sums the columns of what it stores while they are in registers; for in_proj, linear1 and
     // the two input projections the weight-gradient GEMM adds the row sums of its A operand (a_rowsum)
     // the gate is read as the bit mask the forward epilogue wrote (1/16 of re-reading h) when there is one
     const uint8_t* hmask = d.tr ? L.hmask : nullptr;   // written by the forward pass in training mode only
@@ -355,9 +355,9 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
                              site_layer(l, 1), 0.f, 0, d.seed, st));
     MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], -1, st));
     MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
-    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf,
+    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, nullptr, B, T, m->heads, F / m->heads, d.dt, pf,
                           d.seed, site_layer(l, 0), st));
-    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], -1, st));
+    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], o[MMER_L_IN_B], st));
     MMER_TRY(bucket_done(m, 1 + (m->layers - 1 - l), st));   // every gradient of layer l is final
     MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));
   }
