@@ -924,6 +924,8 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
                      (a.gate_bits ? EPI_GBITS : 0);
     if (!amn && !bmn) {
       if (mode == EPI_BIAS) return launch<256, false, false, 2, true, EPI_BIAS>(ta, tb, td, tx, p, grid, st);
+      if (mode == (EPI_BIAS | EPI_RELU))   // linear1 in eval mode (inference forward)
+        return launch<256, false, false, 2, true, EPI_BIAS | EPI_RELU>(ta, tb, td, tx, p, grid, st);
       if (mode == (EPI_BIAS | EPI_RELU | EPI_DROP | EPI_MASK))
         return launch<256, false, false, 2, true, EPI_BIAS | EPI_RELU | EPI_DROP | EPI_MASK>(ta, tb, td, tx, p, grid, st);
     } else if (!amn && bmn) {

@@ -44,10 +44,12 @@ def main():
         x, w, bias = rnd(M, 512), rnd(2048, 512), torch.zeros(2048, device=dev)
         out = torch.empty(M, 2048, device=dev, dtype=bf)
         fn = lambda: ops.gemm(x, w, M=M, N=2048, K=512, bias=bias, relu=True, drop_p=0.1, seed=1, site=1, out=out)
-    elif what == "gemm_relu":   # the kernel bench.py reports as `roofline` (FFN1 forward, bias + ReLU)
+    elif what == "gemm_relu":   # the kernel bench.py reports as `roofline` (FFN1 forward as the step launches it: bias + ReLU + dropout + 1-bit mask)
         x, w, bias = rnd(M, 512), rnd(2048, 512), torch.zeros(2048, device=dev)
         out = torch.empty(M, 2048, device=dev, dtype=bf)
-        fn = lambda: ops.gemm(x, w, M=M, N=2048, K=512, bias=bias, relu=True, out=out)
+        mask = torch.empty(M * 2048 // 8, device=dev, dtype=torch.uint8)
+        fn = lambda: ops.gemm(x, w, M=M, N=2048, K=512, bias=bias, relu=True, drop_p=0.1, seed=1, site=1, out=out,
+                              relu_mask_out=mask)
     elif what == "gemm_gate":
         dy, w, h = rnd(M, 512), rnd(512, 2048), rnd(M, 2048)
         out = torch.empty(M, 2048, device=dev, dtype=bf)
