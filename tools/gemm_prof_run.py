@@ -14,3 +14,16 @@ run("ffn1 fwd+bias K=512 N=2048", 512, 2048)
 run("ffn1 fwd+bias+relu+drop", 512, 2048, relu=True, drop_p=0.1, seed=1, site=1)
 run("ffn2 fwd+bias K=2048 N=512", 2048, 512)
 run("out_proj K=512 N=512", 512, 512)
+
+
+def run_wgrad(name, Ntok, Nout, Kin):
+    dy = torch.randn(Ntok, Nout, device=dev).to(bf); x = torch.randn(Ntok, Kin, device=dev).to(bf)
+    gw = torch.zeros(Nout, Kin, device=dev); db = torch.zeros(Nout, device=dev)
+    torch.cuda.synchronize()
+    print("==", name, flush=True)
+    ops.linear_wgrad(dy, x, gw, dbias=db)
+    torch.cuda.synchronize()
+
+
+run_wgrad("ffn1 wgrad (dW[2048,512], K=69632) + row sums", M, 2048, 512)
+run_wgrad("ffn2 wgrad (dW[512,2048])", M, 512, 2048)
