@@ -19,6 +19,10 @@ int mha_fwd_mma(const void* qkv, const uint8_t* mask, void* out, float* probs, i
 int mha_bwd_mma(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias, int B, int Tn, int H,
                 int d, DropCfg dc, cudaStream_t st);
 extern int g_debug[16];
+bool mha_long_supported(int Tn, int d, int dtype);
+int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc, cudaStream_t st);
+int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn, int H, DropCfg dc,
+                 cudaStream_t st);
 int mha_fwd_generic(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T, int64_t H,
                     int64_t d, int dtype, DropCfg dc, cudaStream_t st);
 int mha_bwd_generic(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int64_t B, int64_t T,
@@ -38,6 +42,8 @@ int mmer_mha_fwd(const void* qkv, const uint8_t* mask, void* out, float* probs, 
   if (B <= 0) return 0;
   DropCfg dc = make_drop(drop_p, seed, site);
   cudaStream_t st = (cudaStream_t)stream;
+  if (T + 1 > 32 && mha_long_supported((int)T, (int)d, dtype) && !g_debug[MMER_DEBUG_ATT_SIMT])
+    return mha_fwd_long(qkv, mask, out, probs, (int)B, (int)T, (int)H, dc, st);   // tensor-core tiles, S <= 384
   if (T + 1 > 32) return mha_fwd_generic(qkv, mask, out, probs, B, T, H, d, dtype, dc, st);
   const int SP = (int)((T + 1 + 3) & ~3LL);
   if (dtype == MMER_BF16 && !g_debug[MMER_DEBUG_ATT_SIMT])
@@ -56,7 +62,9 @@ int mmer_mha_bwd(const void* qkv, const uint8_t* mask, const void* dout, void* d
   cudaStream_t st = (cudaStream_t)stream;
   if (T + 1 <= 32 && dtype == MMER_BF16 && !g_debug[MMER_DEBUG_ATT_SIMT])   // in_proj bias gradient fused
     return mha_bwd_mma(qkv, mask, dout, dqkv, dbias_qkv, (int)B, (int)T, (int)H, (int)d, dc, st);
-  if (T + 1 > 32) {
+  if (T + 1 > 32 && mha_long_supported((int)T, (int)d, dtype) && !g_debug[MMER_DEBUG_ATT_SIMT]) {
+    MMER_TRY(mha_bwd_long(qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, dc, st));
+  } else if (T + 1 > 32) {
     MMER_TRY(mha_bwd_generic(qkv, mask, dout, dqkv, B, T, H, d, dtype, dc, st));
   } else {
     const int SP = (int)((T + 1 + 3) & ~3LL);

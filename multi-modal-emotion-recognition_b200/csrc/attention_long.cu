@@ -1,0 +1,483 @@
+// Long-sequence attention on tensor cores (bf16, head size 64, 32 < S = T+1 <= 384): the T = 256 interpretability
+// configuration of train2.py (BASELINE.json configs[3]; SDPA inside nn.MultiheadAttention, train2.py:173-176).
+//
+// One CTA per (sample, head), 8 warps.  Q, K, V (and dO in backward) of the head are [S][64] bf16 = S rows of 128 B:
+// they arrive as 2-D TMA boxes (64 rows + a tail box) into 128B-swizzled shared-memory tiles, and every product is a
+// warp-level m16n8k16 MMA on ldmatrix fragments of those tiles.  Nothing of size S x S is ever materialised:
+//   forward   a warp owns 16 query rows at a time; pass 1 walks the key blocks for the row maxima and sums (online),
+//             pass 2 recomputes the scores, normalises, (optionally writes the probabilities: return_attn), applies
+//             dropout and accumulates O = P V
+//   backward  pass A (per query tile): forward recomputation -> row statistics m, 1/l and D = dO . O in shared memory;
+//             pass B (per query tile): dS = P o (dP o f - D) / sqrt(d), dQ = dS K;
+//             pass C (per key tile, transposed domain so that no cross-warp reduction is needed):
+//             S^T = K Q^T, dP^T = V dO^T, dV = Pd^T dO, dK = dS^T Q
+// Scores are recomputed in every pass: attention is 8 % of the layer's FLOPs at T = 256 and the tensor pipe has room.
+// Dropout decisions are regenerated from (seed, site, row, key) exactly as in the other attention kernels.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mmer {
+
+static constexpr int AL_WARPS = 8;
+static constexpr int AL_D = 64;
+
+struct SwzRow {   // byte offset of (row, col) in a tile of 128-byte rows, 128B-swizzled (what TMA writes)
+  __device__ __forceinline__ uint32_t operator()(int row, int col) const {
+    return (uint32_t)row * 128u + (((((uint32_t)col >> 3) ^ (uint32_t)row) & 7u) << 4) + ((uint32_t)col & 7u) * 2u;
+  }
+};
+
+// A fragments (16 rows x 64 columns = 4 k-steps) of rows [r0, r0+16) of a tile
+__device__ __forceinline__ void load_a16(uint32_t tile_a, int r0, int lane, uint32_t (&a)[4][4]) {
+  const SwzRow off;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(tile_a + off(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 16 + (lane >> 4) * 8), a[ks][0], a[ks][1], a[ks][2],
+            a[ks][3]);
+}
+// c[nt][..] = A(16 x 64) . X[rows c0 .. c0+32)^T : 16 x 32 block of products against 32 rows of tile X
+__device__ __forceinline__ void block_nt(const uint32_t (&a)[4][4], uint32_t x_a, int c0, int lane, float (&c)[4][4]) {
+  const SwzRow off;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    uint32_t xf[4][2];
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2)
+      ldsm_x4(x_a + off(c0 + nt * 8 + (lane & 7), k2 * 32 + (lane >> 3) * 8), xf[2 * k2][0], xf[2 * k2][1], xf[2 * k2 + 1][0],
+              xf[2 * k2 + 1][1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) mma_bf16_16816(c[nt], a[ks][0], a[ks][1], a[ks][2], a[ks][3], xf[ks][0], xf[ks][1]);
+  }
+}
+// acc(16 x 64) += P(16 x 32, as two A fragments) . X[rows r0 .. r0+32) (X row-major: ldmatrix.trans)
+__device__ __forceinline__ void acc_rows(float (&acc)[8][4], const uint32_t (&pa)[2][4], uint32_t x_a, int r0, int lane) {
+  const SwzRow off;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(x_a + off(r0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, n2 * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(acc[2 * n2], pa[ks][0], pa[ks][1], pa[ks][2], pa[ks][3], b0, b1);
+      mma_bf16_16816(acc[2 * n2 + 1], pa[ks][0], pa[ks][1], pa[ks][2], pa[ks][3], b2, b3);
+    }
+}
+__device__ __forceinline__ void pack_block(const float (&c)[4][4], uint32_t (&a)[2][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    a[ks][0] = pack_bf16x2(c[2 * ks][0], c[2 * ks][1]);
+    a[ks][1] = pack_bf16x2(c[2 * ks][2], c[2 * ks][3]);
+    a[ks][2] = pack_bf16x2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+    a[ks][3] = pack_bf16x2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+  }
+}
+// 16 x 64 accumulator tile -> bf16 rows of a (non-swizzled) per-warp staging tile [16][64], then 16-byte coalesced
+// stores of the rows < nrows to global (row stride ld elements)
+__device__ __forceinline__ void store_tile_global(const float (&acc)[8][4], uint8_t* stage, bf16* __restrict__ dst, long long ld,
+                                                  int nrows, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+      *reinterpret_cast<uint32_t*>(stage + (g + 8 * r) * 144 + (nd * 8 + t * 2) * 2) = pack_bf16x2(acc[nd][2 * r], acc[nd][2 * r + 1]);
+  __syncwarp();
+  for (int idx = lane; idx < 16 * 8; idx += 32) {
+    const int r = idx >> 3, c8 = idx & 7;
+    if (r < nrows) *reinterpret_cast<uint4*>(dst + (long long)r * ld + c8 * 8) = *reinterpret_cast<const uint4*>(stage + r * 144 + c8 * 16);
+  }
+}
+
+struct LongGeom {
+  int B, Tn, S, SR, H, F;        // SR = S rounded up to 8: the rows TMA delivers per tile
+  int nfull, tail;               // 64-row TMA boxes and the rows of the tail box (multiple of 8, may be 0)
+  uint32_t tile_bytes;           // tile allocation: S rounded up to 32 rows of 128 B (rows >= SR are zero-filled)
+  uint32_t load_bytes;           // SR * 128
+};
+
+// loads tile `which` (0 Q, 1 K, 2 V of the packed qkv matrix; 3 = dO) of (b, h)
+__device__ __forceinline__ void load_head_tile(uint32_t dst, const CUtensorMap* m64, const CUtensorMap* mtail, uint32_t bar,
+                                               const LongGeom& g, int col, long long row0) {
+  for (int c = 0; c < g.nfull; ++c) tma_load_2d(dst + c * 8192, m64, bar, col, (int)(row0 + c * 64));
+  if (g.tail > 0) tma_load_2d(dst + g.nfull * 8192, mtail, bar, col, (int)(row0 + g.nfull * 64));
+}
+
+// rows [SR, tile rows) of `ntiles` consecutive tiles are never written by TMA: zero them (they are multiplied by
+// exactly-zero probabilities, which must not meet NaN bit patterns)
+__device__ __forceinline__ void zero_pad_rows(uint8_t* tiles, int ntiles, const LongGeom& g) {
+  const uint32_t pad = g.tile_bytes - g.load_bytes;
+  for (int i = threadIdx.x * 16; i < (int)(ntiles * pad); i += blockDim.x * 16) {
+    const int tl = i / (int)pad, o = i % (int)pad;
+    *reinterpret_cast<uint4*>(tiles + (size_t)tl * g.tile_bytes + g.load_bytes + o) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void fill_valid(uint8_t* valid, const uint8_t* __restrict__ mask, int b, const LongGeom& g) {
+  for (int j = threadIdx.x; j < g.SR + 32; j += blockDim.x) {
+    bool ok = j < g.S;
+    if (ok && j < g.Tn && mask != nullptr) ok = mask[(long long)b * g.Tn + j] == 0;
+    valid[j] = ok ? 1 : 0;
+  }
+}
+
+// online row statistics of one 16 x 32 score block (rows g and g+8 of the tile; quad-uniform maxima)
+__device__ __forceinline__ void stats_update(const float (&sc)[4][4], const uint8_t* valid, int key0, int t, float sl2,
+                                             float (&m)[2], float (&l)[2]) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float bm = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (valid[key0 + nt * 8 + t * 2 + e]) bm = fmaxf(bm, sc[nt][r * 2 + e]);
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+    const float mn = fmaxf(m[r], bm);
+    if (mn == -INFINITY) continue;            // nothing valid yet in this row
+    float add = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (valid[key0 + nt * 8 + t * 2 + e]) add += ex2_approx((sc[nt][r * 2 + e] - mn) * sl2);
+    l[r] = l[r] * ex2_approx((m[r] - mn) * sl2) + add;    // l is this lane's partial sum; m is shared by the quad
+    m[r] = mn;
+  }
+}
+
+__global__ void __launch_bounds__(AL_WARPS * 32, 2)
+mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
+                    const uint8_t* __restrict__ mask, bf16* __restrict__ out, float* __restrict__ probs, LongGeom g, DropCfg dc) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int S = g.S, H = g.H, F = g.F;
+  const long long bh = blockIdx.x;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + g.tile_bytes;
+  uint8_t* v_s = k_s + g.tile_bytes;
+  uint8_t* valid = v_s + g.tile_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + ((g.SR + 32 + 15) & ~15));
+  const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    mbar_init_fence();
+  }
+  fill_valid(valid, mask, b, g);
+  zero_pad_rows(q_s, 3, g);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_a, 3u * g.load_bytes);
+    const long long row0 = (long long)b * S;
+    load_head_tile(q_a, &m64, &mtail, bar_a, g, h * AL_D, row0);
+    load_head_tile(k_a, &m64, &mtail, bar_a, g, F + h * AL_D, row0);
+    load_head_tile(v_a, &m64, &mtail, bar_a, g, 2 * F + h * AL_D, row0);
+  }
+  mbar_wait(bar_a, 0);
+  const float sl2 = rsqrtf((float)AL_D) * 1.4426950408889634f;
+  const int dstride = att_drop_stride(S);
+  const int nkb = (S + 31) / 32;
+  for (int q0 = warp * 16; q0 < S; q0 += AL_WARPS * 16) {
+    uint32_t qa[4][4];
+    load_a16(q_a, q0, lane, qa);
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    for (int kb = 0; kb < nkb; ++kb) {
+      float sc[4][4];
+      block_nt(qa, k_a, kb * 32, lane, sc);
+      stats_update(sc, valid, kb * 32, t, sl2, m, l);
+    }
+    float inv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float s = l[r];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      inv[r] = 1.f / s;
+    }
+    float o[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      float sc[4][4];
+      block_nt(qa, k_a, kb * 32, lane, sc);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = q0 + gq + 8 * r;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int j = kb * 32 + nt * 8 + t * 2;
+          float p0 = valid[j] ? ex2_approx((sc[nt][r * 2] - m[r]) * sl2) * inv[r] : 0.f;
+          float p1 = valid[j + 1] ? ex2_approx((sc[nt][r * 2 + 1] - m[r]) * sl2) * inv[r] : 0.f;
+          if (i < S) {
+            if (probs != nullptr) {
+              if (j < S) probs[(bh * S + i) * S + j] = p0;
+              if (j + 1 < S) probs[(bh * S + i) * S + j + 1] = p1;
+            }
+            if (dc.thr) {
+              float f0, f1;
+              drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
+              p0 *= f0;
+              p1 *= f1;
+            }
+          }
+          sc[nt][r * 2] = p0;
+          sc[nt][r * 2 + 1] = p1;
+        }
+      }
+      uint32_t pa[2][4];
+      pack_block(sc, pa);
+      acc_rows(o, pa, v_a, kb * 32, lane);
+    }
+    // O overwrites this warp's own (now dead) Q rows, then leaves as 16-byte coalesced row stores
+    const SwzRow off;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        *reinterpret_cast<uint32_t*>(q_s + off(q0 + gq + 8 * r, nd * 8 + t * 2)) = pack_bf16x2(o[nd][2 * r], o[nd][2 * r + 1]);
+    __syncwarp();
+    for (int idx = lane; idx < 16 * 8; idx += 32) {
+      const int r = idx >> 3, c8 = idx & 7;
+      if (q0 + r < S)
+        *reinterpret_cast<uint4*>(out + ((long long)b * S + q0 + r) * F + h * AL_D + c8 * 8) =
+            *reinterpret_cast<const uint4*>(q_s + off(q0 + r, c8 * 8));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AL_WARPS * 32, 1)
+mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
+                    const __grid_constant__ CUtensorMap d64, const __grid_constant__ CUtensorMap dtail,
+                    const uint8_t* __restrict__ mask, bf16* __restrict__ dqkv, LongGeom g, DropCfg dc) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int S = g.S, H = g.H, F = g.F;
+  const long long bh = blockIdx.x;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + g.tile_bytes;
+  uint8_t* v_s = k_s + g.tile_bytes;
+  uint8_t* do_s = v_s + g.tile_bytes;
+  float* st_m = reinterpret_cast<float*>(do_s + g.tile_bytes);     // row maxima            [SR + 32]
+  float* st_i = st_m + g.SR + 32;                                   // 1 / row sums          [SR + 32]
+  float* st_d = st_i + g.SR + 32;                                   // D_i = dO_i . O_i      [SR + 32]
+  uint8_t* valid = reinterpret_cast<uint8_t*>(st_d + g.SR + 32);
+  uint8_t* stage = valid + ((g.SR + 32 + 15) & ~15) + warp * (16 * 144);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + ((g.SR + 32 + 15) & ~15) + AL_WARPS * 16 * 144);
+  const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), do_a = smem_u32(do_s);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    mbar_init_fence();
+  }
+  fill_valid(valid, mask, b, g);
+  zero_pad_rows(q_s, 4, g);
+  for (int j = threadIdx.x; j < g.SR + 32; j += blockDim.x) { st_m[j] = 0.f; st_i[j] = 0.f; st_d[j] = 0.f; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_a, 4u * g.load_bytes);
+    const long long row0 = (long long)b * S;
+    load_head_tile(q_a, &m64, &mtail, bar_a, g, h * AL_D, row0);
+    load_head_tile(k_a, &m64, &mtail, bar_a, g, F + h * AL_D, row0);
+    load_head_tile(v_a, &m64, &mtail, bar_a, g, 2 * F + h * AL_D, row0);
+    load_head_tile(do_a, &d64, &dtail, bar_a, g, h * AL_D, row0);
+  }
+  mbar_wait(bar_a, 0);
+  const float scale = rsqrtf((float)AL_D);
+  const float sl2 = scale * 1.4426950408889634f;
+  const int dstride = att_drop_stride(S);
+  const int nkb = (S + 31) / 32;
+  const SwzRow off;
+
+  // ---------------- pass A + B per query tile: statistics, then dQ
+  for (int q0 = warp * 16; q0 < S; q0 += AL_WARPS * 16) {
+    uint32_t qa[4][4], doa[4][4];
+    load_a16(q_a, q0, lane, qa);
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    for (int kb = 0; kb < nkb; ++kb) {
+      float sc[4][4];
+      block_nt(qa, k_a, kb * 32, lane, sc);
+      stats_update(sc, valid, kb * 32, t, sl2, m, l);
+    }
+    float inv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float s = l[r];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      inv[r] = 1.f / s;
+    }
+    // D_i = sum_j P_ij f_ij dP_ij  with dP_ij = dO_i . V_j   (equals dO_i . O_i; accumulated block by block)
+    load_a16(do_a, q0, lane, doa);
+    float dsum[2] = {0.f, 0.f};
+    for (int kb = 0; kb < nkb; ++kb) {
+      float sc[4][4], dp[4][4];
+      block_nt(qa, k_a, kb * 32, lane, sc);
+      block_nt(doa, v_a, kb * 32, lane, dp);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = q0 + gq + 8 * r;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int j = kb * 32 + nt * 8 + t * 2;
+          const float p0 = valid[j] ? ex2_approx((sc[nt][r * 2] - m[r]) * sl2) * inv[r] : 0.f;
+          const float p1 = valid[j + 1] ? ex2_approx((sc[nt][r * 2 + 1] - m[r]) * sl2) * inv[r] : 0.f;
+          float f0 = 1.f, f1 = 1.f;
+          if (dc.thr && i < S) drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
+          dsum[r] = fmaf(p0 * f0, dp[nt][r * 2], dsum[r]);
+          dsum[r] = fmaf(p1 * f1, dp[nt][r * 2 + 1], dsum[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
+      dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
+      const int i = q0 + gq + 8 * r;
+      if (t == 0) { st_m[i] = m[r]; st_i[i] = (i < S) ? inv[r] : 0.f; st_d[i] = dsum[r]; }
+    }
+    // dQ = dS K
+    float dq[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dq[nd][i] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      float sc[4][4], dp[4][4];
+      block_nt(qa, k_a, kb * 32, lane, sc);
+      block_nt(doa, v_a, kb * 32, lane, dp);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = q0 + gq + 8 * r;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int j = kb * 32 + nt * 8 + t * 2;
+          const float p0 = valid[j] ? ex2_approx((sc[nt][r * 2] - m[r]) * sl2) * inv[r] : 0.f;
+          const float p1 = valid[j + 1] ? ex2_approx((sc[nt][r * 2 + 1] - m[r]) * sl2) * inv[r] : 0.f;
+          float f0 = 1.f, f1 = 1.f;
+          if (dc.thr && i < S) drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
+          sc[nt][r * 2] = (i < S) ? p0 * (dp[nt][r * 2] * f0 - dsum[r]) * scale : 0.f;
+          sc[nt][r * 2 + 1] = (i < S) ? p1 * (dp[nt][r * 2 + 1] * f1 - dsum[r]) * scale : 0.f;
+        }
+      }
+      uint32_t dsa[2][4];
+      pack_block(sc, dsa);
+      acc_rows(dq, dsa, k_a, kb * 32, lane);
+    }
+    store_tile_global(dq, stage, dqkv + ((long long)b * S + q0) * 3 * F + h * AL_D, 3 * F, S - q0, lane);
+  }
+  __syncthreads();   // row statistics of every query are in shared memory
+
+  // ---------------- pass C per key tile (transposed domain): dV = Pd^T dO, dK = dS^T Q
+  const int nqb = (S + 31) / 32;
+  for (int k0 = warp * 16; k0 < S; k0 += AL_WARPS * 16) {
+    uint32_t ka[4][4], va[4][4];
+    load_a16(k_a, k0, lane, ka);
+    load_a16(v_a, k0, lane, va);
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { dk[nd][i] = 0.f; dv[nd][i] = 0.f; }
+    for (int qb = 0; qb < nqb; ++qb) {
+      float st[4][4], dpt[4][4], pd[4][4];
+      block_nt(ka, q_a, qb * 32, lane, st);     // S^T block: rows = keys k0.., columns = queries qb*32..
+      block_nt(va, do_a, qb * 32, lane, dpt);   // dP^T block
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int j = k0 + gq + 8 * r;
+        const bool jv = valid[j] != 0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = qb * 32 + nt * 8 + t * 2 + e;
+            const float p = (jv && i < S) ? ex2_approx((st[nt][r * 2 + e] - st_m[i]) * sl2) * st_i[i] : 0.f;
+            float f = 1.f;
+            if (dc.thr && i < S && j < S) f = drop1(dc, att_drop_index(bh * S + i, j, dstride));
+            pd[nt][r * 2 + e] = p * f;
+            st[nt][r * 2 + e] = p * (dpt[nt][r * 2 + e] * f - st_d[i]) * scale;
+          }
+      }
+      uint32_t a2[2][4];
+      pack_block(pd, a2);
+      acc_rows(dv, a2, do_a, qb * 32, lane);
+      pack_block(st, a2);
+      acc_rows(dk, a2, q_a, qb * 32, lane);
+    }
+    bf16* base = dqkv + ((long long)b * S + k0) * 3 * F + h * AL_D;
+    store_tile_global(dk, stage, base + F, 3 * F, S - k0, lane);
+    store_tile_global(dv, stage, base + 2 * F, 3 * F, S - k0, lane);
+  }
+  (void)off;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int long_geom(int B, int Tn, int H, LongGeom* g) {
+  g->B = B; g->Tn = Tn; g->S = Tn + 1; g->H = H; g->F = H * AL_D;
+  g->SR = (g->S + 7) & ~7;
+  g->nfull = g->SR / 64;
+  g->tail = g->SR - g->nfull * 64;
+  g->tile_bytes = (uint32_t)((g->S + 31) & ~31) * 128u;
+  g->load_bytes = (uint32_t)g->SR * 128u;
+  return 0;
+}
+static size_t long_smem(const LongGeom& g, int tiles, bool backward) {
+  size_t n = (size_t)tiles * g.tile_bytes + ((g.SR + 32 + 15) & ~15) + 16;
+  if (backward) n += (size_t)3 * (g.SR + 32) * sizeof(float) + (size_t)AL_WARPS * 16 * 144;
+  return n;
+}
+static int long_maps(const void* ptr, int cols_total, const LongGeom& g, CUtensorMap* m64, CUtensorMap* mtail) {
+  const uint64_t rows = (uint64_t)g.B * g.S;
+  MMER_TRY(make_tma_map_bf16(m64, ptr, (uint64_t)cols_total, rows, (uint64_t)cols_total, 64, g.nfull > 0 ? 64 : (uint32_t)g.tail));
+  MMER_TRY(make_tma_map_bf16(mtail, ptr, (uint64_t)cols_total, rows, (uint64_t)cols_total, 64, g.tail > 0 ? (uint32_t)g.tail : 64));
+  return 0;
+}
+
+bool mha_long_supported(int Tn, int d, int dtype) { return dtype == MMER_BF16 && d == AL_D && Tn + 1 > 32 && Tn + 1 <= 384; }
+
+int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc, cudaStream_t st) {
+  LongGeom g;
+  long_geom(B, Tn, H, &g);
+  CUtensorMap m64, mtail;
+  MMER_TRY(long_maps(qkv, 3 * g.F, g, &m64, &mtail));
+  const size_t smem = long_smem(g, 3, false);
+  MMER_CHECK_ARG(smem <= 232448, "mha_fwd(long): %lld bytes of shared memory needed", (long long)smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mha_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_fwd_long)");
+    configured = smem;
+  }
+  mha_fwd_long_kernel<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, g, dc);
+  MMER_LAUNCH_CHECK("mha_fwd_long_kernel");
+  return 0;
+}
+
+int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn, int H, DropCfg dc,
+                 cudaStream_t st) {
+  LongGeom g;
+  long_geom(B, Tn, H, &g);
+  CUtensorMap m64, mtail, d64, dtail;
+  MMER_TRY(long_maps(qkv, 3 * g.F, g, &m64, &mtail));
+  MMER_TRY(long_maps(dout, g.F, g, &d64, &dtail));
+  const size_t smem = long_smem(g, 4, true);
+  MMER_CHECK_ARG(smem <= 232448, "mha_bwd(long): %lld bytes of shared memory needed", (long long)smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mha_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_bwd_long)");
+    configured = smem;
+  }
+  mha_bwd_long_kernel<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, d64, dtail, mask, (bf16*)dqkv, g, dc);
+  MMER_LAUNCH_CHECK("mha_bwd_long_kernel");
+  return 0;
+}
+
+}  // namespace mmer

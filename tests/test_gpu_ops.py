@@ -327,7 +327,8 @@ def test_colsum(dt):
 # ----------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("T,H,d", [(16, 8, 64), (5, 8, 64), (1, 4, 32), (31, 2, 64), (10, 2, 32), (32, 2, 64),
-                                   (100, 2, 32), (256, 8, 64)])
+                                   (100, 2, 32), (256, 8, 64), (40, 2, 64), (63, 4, 64), (64, 2, 64), (300, 2, 64),
+                                   (383, 1, 64), (400, 1, 64)])
 @pytest.mark.parametrize("use_mask", [True, False])
 def test_mha_fwd_bwd(dt, T, H, d, use_mask):
     B, S, F = 7, T + 1, H * d
@@ -335,6 +336,12 @@ def test_mha_fwd_bwd(dt, T, H, d, use_mask):
     lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(5))
     mask = (torch.arange(T)[None] >= lens[:, None])
     mk = mask.to(DEV).view(torch.uint8) if use_mask else None
+    if T + 1 > 384 or (dt == torch.float32 and T + 1 > 352):
+        # beyond the shared-memory resident kernels (bf16 tensor-core tiles: S <= 384; fp32 FMA path: S <= ~350):
+        # rejected loudly, never a silent fallback
+        with pytest.raises(mm.MmerError):
+            ops.mha_fwd(qkv, mk, B, T, H, d, want_probs=True)
+        return
     out, probs = ops.mha_fwd(qkv, mk, B, T, H, d, want_probs=True)
     qr = qkv.double().view(B, S, 3 * F).requires_grad_(True)
     q, k, v = qr.split(F, dim=-1)
@@ -379,7 +386,8 @@ def test_mha_dropout_fwd_bwd_consistent(B, T):
     assert abs(num - ana) < 2e-3 * max(abs(num), 1.0)
 
 
-@pytest.mark.parametrize("T,H,d", [(16, 8, 64), (5, 8, 64), (31, 4, 32), (9, 16, 64), (23, 2, 64)])
+@pytest.mark.parametrize("T,H,d", [(16, 8, 64), (5, 8, 64), (31, 4, 32), (9, 16, 64), (23, 2, 64), (70, 2, 64),
+                                   (256, 2, 64)])
 @pytest.mark.parametrize("p", [0.0, 0.1])
 def test_mha_mma_kernels_match_fma_kernels_bf16(T, H, d, p):
     """bf16: the tensor-core (mma.sync) kernels and the FMA kernels regenerate the same dropout decisions from the
