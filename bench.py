@@ -10,8 +10,8 @@ dropout active as in the reference's training loop.  N>1: the same per-GPU batch
 
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same
 step driven from pinned HOST buffers (H2D of every step's inputs + D2H of its loss inside the timed
-region); `roofline` = the dominant kernel (tcgen05 GEMM at the FFN shape) timed live with CUDA
-events; `cpu_baseline` = the reference's CPU path (its architecture on stock torch.nn modules, pinned to
+region); `roofline` = the kernel with the largest share of the step (the tcgen05 weight-gradient GEMM) timed
+with CUDA events at the step's shapes; `cpu_baseline` = the reference's CPU path (its architecture on stock torch.nn modules, pinned to
 the reference's golden outputs) on a bounded sample.  `--impl reference` times that same CPU path
 with all host threads (the reference itself is a Python tree that does not travel to the GPU box).
 """
@@ -249,31 +249,72 @@ def _timed(fns, reps):
 
 
 def time_dominant_kernel(dev, pk):
-    """tcgen05 GEMM at the FFN1 forward shape of the workload (the step's largest single kernel), timed alone with
-    CUDA events over operand sets larger than L2.  `traffic` comes from the committed ncu --set full capture."""
+    """The kernel with the largest share of the step (24 % in profiles/r01_launches_step_v4.txt): the weight-gradient
+    tcgen05 GEMM, gemm_tc_kernel<256, MN, MN, pair, direct> -- split-K over the 69,632 token rows with fp32 atomics.
+    Its 10 launches per step are timed alone at the step's own shapes (CUDA events, graph replay, operand sets larger
+    than L2); achieved = their total algorithmic FLOPs / their total time.  `traffic` comes from the committed
+    ncu --set full capture of the linear1 launch."""
     from mmer_b200 import ops
-    M, K, N = B_PER_GPU * (T + 1), 512, 2048
-    xs = [torch.randn(M, K, device=dev, dtype=torch.bfloat16) for _ in range(3)]   # 3 x 71 MB + outputs > L2
-    w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
-    bias = torch.zeros(N, device=dev)
-    outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(3)]
-    masks = [torch.empty(M * N // 8, device=dev, dtype=torch.uint8) for _ in range(3)]
-    # exactly the call the training step makes for linear1: bias + ReLU + dropout 0.1 + the 1-bit ReLU mask for backward
-    ms = _timed([lambda i=i: ops.gemm(xs[i], w, M=M, N=N, K=K, bias=bias, relu=True, drop_p=0.1, seed=1, site=1,
-                                      out=outs[i], relu_mask_out=masks[i]) for i in range(3)], 30)
-    tflops = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+    M, Mv = B_PER_GPU * (T + 1), B_PER_GPU * T
+    bf = torch.bfloat16
+    # (rows, N_out, K_in, launches per step, bias gradient from the row sums as in the engine)
+    shapes = [(Mv, 512, DV, 1, False), (M, 1536, 512, 2, False), (M, 512, 512, 2, False), (M, 2048, 512, 2, True),
+              (M, 512, 2048, 2, False)]
+    tot_ms, tot_flop, per_shape = 0.0, 0.0, []
+    for rows, n, k, cnt, with_bias in shapes:
+        dys = [torch.randn(rows, n, device=dev, dtype=bf) for _ in range(2)]
+        xs = [torch.randn(rows, k, device=dev, dtype=bf) for _ in range(2)]
+        gw, gb = torch.zeros(n, k, device=dev), torch.zeros(n, device=dev)
+        ms = _timed([lambda i=i: ops.linear_wgrad(dys[i], xs[i], gw, dbias=gb if with_bias else None) for i in range(2)], 20)
+        flop = 2.0 * rows * n * k
+        per_shape.append({"dW": [n, k], "tokens": rows, "ms": ms, "tflops": flop / (ms * 1e-3) / 1e12, "per_step": cnt})
+        tot_ms += ms * cnt
+        tot_flop += flop * cnt
+        del dys, xs
+    tflops = tot_flop / (tot_ms * 1e-3) / 1e12
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
             traffic = json.load(f)["traffic_bytes"]
     except Exception:
         pass
-    return {"bound": "tensor",
-            "kernel": "gemm_tc_kernel<256,K,K,pair,staged,bias|relu|drop|mask> FFN1 fwd 69632x512x2048 as launched by the step",
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<256,MN,MN,pair,direct>: weight-gradient GEMMs of the step (split-K, fp32 atomics)",
             "achieved": tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tflops / pk["tf_burst"],
-            "peak_source": pk["src"] + " bf16_tflops (burst: kernel timed alone)", "ms_per_launch": ms,
-            "algorithmic_flop_per_launch": 2.0 * M * N * K, "traffic": traffic,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_roofline_traffic.json"}
+            "peak_source": pk["src"] + " bf16_tflops (burst: kernels timed alone)", "ms_per_launch": tot_ms / 9.0,
+            "launches_per_step": 9, "algorithmic_flop_per_step": tot_flop, "shapes": per_shape, "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the linear1 launch (dW[2048,512], 69,632 "
+                              "tokens), profiles/r01_roofline_traffic.json"}
+
+
+def time_other_gemms(dev, pk):
+    """The step's other hot tcgen05 GEMM instances, timed alone the same way (tensor-bound; burst peak)."""
+    from mmer_b200 import ops, _lib
+    M, K, N = B_PER_GPU * (T + 1), 512, 2048
+    bf = torch.bfloat16
+    xs = [torch.randn(M, K, device=dev, dtype=bf) for _ in range(3)]   # 3 x 71 MB + outputs > L2
+    w = torch.randn(N, K, device=dev, dtype=bf)
+    bias = torch.zeros(N, device=dev)
+    outs = [torch.empty(M, N, device=dev, dtype=bf) for _ in range(3)]
+    masks = [torch.empty(M * N // 8, device=dev, dtype=torch.uint8) for _ in range(3)]
+    res = []
+
+    def add(name, fns, flop):
+        ms = _timed(fns, 20)
+        tf = flop / (ms * 1e-3) / 1e12
+        res.append({"kernel": name, "bound": "tensor", "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                    "frac": tf / pk["tf_burst"], "ms_per_launch": ms})
+
+    flop = 2.0 * M * N * K
+    add("linear1 forward 69632x512->2048, bias+ReLU+dropout+1-bit mask (as the step launches it)",
+        [lambda i=i: ops.gemm(xs[i], w, M=M, N=N, K=K, bias=bias, relu=True, drop_p=0.1, seed=1, site=1, out=outs[i],
+                              relu_mask_out=masks[i]) for i in range(3)], flop)
+    add("linear1-shaped forward, bias only", [lambda i=i: ops.gemm(xs[i], w, M=M, N=N, K=K, bias=bias, out=outs[i])
+                                               for i in range(3)], flop)
+    wt = torch.randn(K, N, device=dev, dtype=bf)     # linear2.weight [512, 2048]: dX[M,2048] = dY[M,512] W
+    add("linear2 dgrad 69632x512->2048 gated by the ReLU bit mask",
+        [lambda i=i: ops.gemm(xs[i], wt, M=M, N=N, K=K, b_major=_lib.MAJOR_MN, gate_bits=masks[i], gate_scale=1.0 / 0.9,
+                              out=outs[i]) for i in range(3)], flop)
+    return res
 
 
 def time_memory_bound_kernels(dev, pk):
@@ -456,6 +497,7 @@ def run_ours(args):
         }
         out["roofline"] = time_dominant_kernel(dev, pk)
         if world == 1:
+            out["roofline_other_gemms"] = time_other_gemms(dev, pk)
             out["roofline_hbm_kernels"] = time_memory_bound_kernels(dev, pk)
             try:
                 out["torch_eager_gpu"] = {"bf16": torch_eager_gpu_rate(dev, torch.bfloat16),

@@ -109,10 +109,12 @@ int mmer_embed_fwd(const void* pv, const void* pa, const float* gv, const float*
                    const float* ba, const float* pos, void* x0, float* stats, int64_t B, int64_t T,
                    int64_t F, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
 /* backward: dpv, dpa get the LayerNorm input gradients; dgv.. dpos are ACCUMULATED (+=) */
+/* dbias_v / dbias_a (optional, fp32 [F]): += column sums of dpv / dpa as stored, i.e. the bias gradients of the two
+ * input projections (LayerNorm variant only; NULL otherwise). */
 int mmer_embed_bwd(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv,
                    const float* ga, void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba,
-                   float* dpos, int64_t B, int64_t T, int64_t F, int dtype, float drop_p, uint64_t seed,
-                   uint32_t site, void* stream);
+                   float* dpos, float* dbias_v, float* dbias_a, int64_t B, int64_t T, int64_t F, int dtype,
+                   float drop_p, uint64_t seed, uint32_t site, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Row kernel: z = x + dropout_a(a);  y = dropout_y(relu?(LayerNorm(z))).

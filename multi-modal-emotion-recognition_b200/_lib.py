@@ -72,7 +72,7 @@ SIGNATURES = {
     "mmer_launch_count": [],
     "mmer_gemm": [C.POINTER(GemmArgs), _P],
     "mmer_embed_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
-    "mmer_embed_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
+    "mmer_embed_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _U64, _U32, _P],
     "mmer_add_ln_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _U32, _F, _U32, _U64, _P],
     "mmer_add_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _F, _U32, _F, _U32, _U64, _P],
     "mmer_pool_ln_fwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],

@@ -341,8 +341,9 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
                              site_layer(l, 3), 0.f, 0, d.seed, st));
     MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], -1, st));
     // through ReLU (+ its dropout): gate on the stored post-activation.  No gradient tensor is re-read for a bias
-    // gradient: add_ln_bwd sums the columns of what it stores while they are in registers; for in_proj, linear1 and
-    // the two input projections the weight-gradient GEMM adds the row sums of its A operand (a_rowsum)
+    // gradient: add_ln_bwd, mha_bwd and embed_bwd sum the columns of what they store while it is on chip; for linear1
+    // (and the BatchNorm variant's projections) the weight-gradient GEMM adds the row sums of its A operand (a_rowsum),
+    // which costs that GEMM ~20 % and is therefore used only where no producer can do it
     // the gate is read as the bit mask the forward epilogue wrote (1/16 of re-reading h) when there is one
     const uint8_t* hmask = d.tr ? L.hmask : nullptr;   // written by the forward pass in training mode only
     MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, hmask ? nullptr : L.h, relu_gate_scale, st, hmask));
@@ -355,9 +356,9 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
                              site_layer(l, 1), 0.f, 0, d.seed, st));
     MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], -1, st));
     MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
-    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, nullptr, B, T, m->heads, F / m->heads, d.dt, pf,
+    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf,
                           d.seed, site_layer(l, 0), st));
-    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], o[MMER_L_IN_B], st));
+    MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], -1, st));
     MMER_TRY(bucket_done(m, 1 + (m->layers - 1 - l), st));   // every gradient of layer l is final
     MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));
   }
@@ -366,17 +367,17 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
   if (m->variant == 2) {
     MMER_TRY(mmer_embed_bwd(w.g_x, w.pv, w.pa, w.st_e, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NA_W]), w.g_pv, w.g_pa,
                             G(m, g[MMER_G_NV_W]), G(m, g[MMER_G_NV_B]), G(m, g[MMER_G_NA_W]), G(m, g[MMER_G_NA_B]),
-                            G(m, g[MMER_G_POS]), B, T, F, d.dt, pf, d.seed, 0, st));
+                            G(m, g[MMER_G_POS]), G(m, g[MMER_G_BV]), G(m, g[MMER_G_BA]), B, T, F, d.dt, pf, d.seed, 0, st));
   } else {
     MMER_TRY(mmer_embed_bwd(w.g_x, w.pvn, w.pan, w.st_e, nullptr, nullptr, w.g_pvn, w.g_pan, nullptr, nullptr, nullptr,
-                            nullptr, G(m, g[MMER_G_POS]), B, T, F, d.dt, 0.f, d.seed, 0, st));
+                            nullptr, G(m, g[MMER_G_POS]), nullptr, nullptr, B, T, F, d.dt, 0.f, d.seed, 0, st));
     MMER_TRY(mmer_bn_bwd(w.g_pvn, w.pv, w.st_bnv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), w.g_pv, G(m, g[MMER_G_NV_W]),
                          G(m, g[MMER_G_NV_B]), w.bn_scratch, Mv, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
     MMER_TRY(mmer_bn_bwd(w.g_pan, w.pa, w.st_bna, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), w.g_pa, G(m, g[MMER_G_NA_W]),
                          G(m, g[MMER_G_NA_B]), w.bn_scratch, B, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
   }
-  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], g[MMER_G_BV], st));
-  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], g[MMER_G_BA], st));
+  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], m->variant == 2 ? -1 : g[MMER_G_BV], st));
+  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], m->variant == 2 ? -1 : g[MMER_G_BA], st));
   MMER_TRY(bucket_done(m, m->layers + 1, st));   // projections, input norms, pos_embed
   if (m->dvideo) MMER_TRY(lin_dgrad(m, dpv, Mv, F, g[MMER_G_WV], m->video_dim, m->dvideo, nullptr, nullptr, 0.f, st));
   if (m->daudio) MMER_TRY(lin_dgrad(m, dpa, B, F, g[MMER_G_WA], m->audio_dim, m->daudio, nullptr, nullptr, 0.f, st));

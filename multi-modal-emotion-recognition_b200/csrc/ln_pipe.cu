@@ -669,7 +669,7 @@ __global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
 embed_bwd_pipe_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const T* __restrict__ pa,
                       const float* __restrict__ stats, const float* __restrict__ gv, const float* __restrict__ ga,
                       T* __restrict__ dpv, T* __restrict__ dpa, float* __restrict__ dgv, float* __restrict__ dga,
-                      EmbedGeom g, DropCfg dc) {
+                      float* __restrict__ dbias_v, float* __restrict__ dbias_a, EmbedGeom g, DropCfg dc) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LnSmem sm = embed_setup(g, smem);
@@ -677,13 +677,14 @@ embed_bwd_pipe_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const
   const bool compute_warp = warp < g.W;
   // audio rows are 1 in S: their dgamma partials go through shared-memory atomics instead of a second register set
   float* sga = reinterpret_cast<float*>(smem + (size_t)g.stages * g.stage_bytes + 2 * LNP_MAX_STAGES * 8);
-  for (int c = threadIdx.x; c < F; c += blockDim.x) sga[c] = 0.f;
+  float* sba = sga + F;     // audio rows' contribution to the audio projection's bias gradient
+  for (int c = threadIdx.x; c < 2 * F; c += blockDim.x) sga[c] = 0.f;
   __syncthreads();
-  float pg[NCH][8];
+  float pg[NCH][8], pbv[NCH][8];   // dgamma and projection-bias-gradient partials of the video rows
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) pg[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pbv[i][j] = 0.f; }
   if (!compute_warp) {
     if (lane == 0) embed_produce<T>(g, pv, pa, dx0, sm.data_a, sm.full_a, sm.empty_a);
   } else {
@@ -770,13 +771,26 @@ embed_bwd_pipe_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[i][j], -c2r, fmaf(gd[i][j], rstd, -c1r));
           store8(dst + c, o);
+          if (audio) {
+            if (dbias_a != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) atomicAdd(sba + c + j, round_as<T>(o[j]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pbv[i][j] += round_as<T>(o[j]);
+          }
         }
       }
     }
   }
   float* sred = reinterpret_cast<float*>(smem);
   lnp_flush<NCH>(pg, dgv, F, g.W, sred, compute_warp);
-  for (int c = threadIdx.x; c < F; c += blockDim.x) atomicAdd(dga + c, sga[c]);
+  if (dbias_v != nullptr) lnp_flush<NCH>(pbv, dbias_v, F, g.W, sred, compute_warp);
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    atomicAdd(dga + c, sga[c]);
+    if (dbias_a != nullptr) atomicAdd(dbias_a + c, sba[c]);
+  }
 }
 
 // dpos[s][c] += sum_b d[b,s,c];  dbeta_video[c] += the same for s < T;  dbeta_audio[c] += for s == T, with d the
@@ -840,7 +854,7 @@ static int embed_geometry(long long B, long long T, long long F, int elt, int wi
   size_t data = (size_t)stages * g->stage_bytes;
   const size_t red = (size_t)W * F * sizeof(float);
   if (data < red) data = red;
-  *smem_bytes = data + 2 * LNP_MAX_STAGES * 8 + (size_t)F * sizeof(float) + 16;
+  *smem_bytes = data + 2 * LNP_MAX_STAGES * 8 + (size_t)2 * F * sizeof(float) + 16;
   return 0;
 }
 
@@ -864,7 +878,8 @@ static int embed_fwd_launch(const void* pv, const void* pa, const float* gv, con
 template <typename T, int NCH>
 static int embed_bwd_launch(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv,
                             const float* ga, void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba,
-                            float* dpos, long long B, long long T_, long long F, DropCfg dc, cudaStream_t st) {
+                            float* dpos, float* dbias_v, float* dbias_a, long long B, long long T_, long long F, DropCfg dc,
+                            cudaStream_t st) {
   EmbedGeom g;
   size_t smem;
   MMER_TRY(embed_geometry(B, T_, F, sizeof(T), 1, &g, &smem));
@@ -874,7 +889,8 @@ static int embed_bwd_launch(const void* dx0, const void* pv, const void* pa, con
   const long long tiles = (g.Mtot + g.W - 1) / g.W;
   const long long cap = sm_count();
   kern<<<(unsigned)(tiles < cap ? tiles : cap), (g.W + 1) * 32, smem, st>>>((const T*)dx0, (const T*)pv, (const T*)pa, stats,
-                                                                            gv, ga, (T*)dpv, (T*)dpa, dgv, dga, g, dc);
+                                                                            gv, ga, (T*)dpv, (T*)dpa, dgv, dga, dbias_v, dbias_a,
+                                                                            g, dc);
   MMER_LAUNCH_CHECK("embed_bwd_pipe_kernel");
   const long long N = (T_ + 1) * F;
   int gy = (int)((sm_count() * 4 + (N + 255) / 256 - 1) / ((N + 255) / 256));
@@ -894,11 +910,13 @@ int embed_fwd_pipe(const void* pv, const void* pa, const float* gv, const float*
   LNP_DISPATCH(F, (embed_fwd_launch<float, NCH>(pv, pa, gv, bv, ga, ba, pos, x0, stats, B, T, F, dc, st)));
 }
 int embed_bwd_pipe(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv, const float* ga,
-                   void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos, long long B,
-                   long long T, long long F, int dtype, DropCfg dc, cudaStream_t st) {
+                   void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos, float* dbias_v,
+                   float* dbias_a, long long B, long long T, long long F, int dtype, DropCfg dc, cudaStream_t st) {
   if (dtype == MMER_BF16)
-    LNP_DISPATCH(F, (embed_bwd_launch<bf16, NCH>(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, B, T, F, dc, st)));
-  LNP_DISPATCH(F, (embed_bwd_launch<float, NCH>(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, B, T, F, dc, st)));
+    LNP_DISPATCH(F, (embed_bwd_launch<bf16, NCH>(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, dbias_v,
+                                                 dbias_a, B, T, F, dc, st)));
+  LNP_DISPATCH(F, (embed_bwd_launch<float, NCH>(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, dbias_v,
+                                                dbias_a, B, T, F, dc, st)));
 }
 
 }  // namespace mmer

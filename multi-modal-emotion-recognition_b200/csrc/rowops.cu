@@ -20,8 +20,8 @@ int embed_fwd_pipe(const void* pv, const void* pa, const float* gv, const float*
                    const float* pos, void* x0, float* stats, long long B, long long T, long long F, int dtype, DropCfg dc,
                    cudaStream_t st);
 int embed_bwd_pipe(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv, const float* ga,
-                   void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos, long long B,
-                   long long T, long long F, int dtype, DropCfg dc, cudaStream_t st);
+                   void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos, float* dbias_v,
+                   float* dbias_a, long long B, long long T, long long F, int dtype, DropCfg dc, cudaStream_t st);
 
 static constexpr float LN_EPS = 1e-5f;
 static constexpr int ROW_WARPS = 8;  // warps per CTA for the row kernels
@@ -743,15 +743,17 @@ int mmer_embed_fwd(const void* pv, const void* pa, const float* gv, const float*
 
 int mmer_embed_bwd(const void* dx0, const void* pv, const void* pa, const float* stats, const float* gv,
                    const float* ga, void* dpv, void* dpa, float* dgv, float* dbv, float* dga, float* dba, float* dpos,
-                   int64_t B, int64_t T, int64_t F, int dtype, float drop_p, uint64_t seed, uint32_t site,
-                   void* stream) {
+                   float* dbias_v, float* dbias_a, int64_t B, int64_t T, int64_t F, int dtype, float drop_p, uint64_t seed,
+                   uint32_t site, void* stream) {
   CHECK_ROW_SHAPE(F);
   MMER_CHECK_ARG(dx0 && pv && pa && dpv && dpa, "embed_bwd: null pointer");
   if (B <= 0) return 0;
   DropCfg dc = make_drop(drop_p, seed, site);
   cudaStream_t st = (cudaStream_t)stream;
   if (gv != nullptr && ga != nullptr && stats != nullptr && dgv && dga)
-    return embed_bwd_pipe(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, B, T, F, dtype, dc, st);
+    return embed_bwd_pipe(dx0, pv, pa, stats, gv, ga, dpv, dpa, dgv, dbv, dga, dba, dpos, dbias_v, dbias_a, B, T, F, dtype,
+                          dc, st);
+  MMER_CHECK_ARG(dbias_v == nullptr && dbias_a == nullptr, "embed_bwd: bias-gradient outputs need the LayerNorm variant");
   int gx = (int)((B + ROW_WARPS - 1) / ROW_WARPS);
   int cap = (sm_count() * 2) / (int)(T + 1) + 1;
   if (gx > cap) gx = cap;

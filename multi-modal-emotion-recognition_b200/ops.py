@@ -106,11 +106,14 @@ def embed_fwd(pv, pa, gv, bv, ga, ba, pos, B, T, drop_p=0.0, seed=0, site=0):
     return x0, stats
 
 
-def embed_bwd(dx0, pv, pa, stats, gv, ga, B, T, dgv, dbv, dga, dba, dpos, drop_p=0.0, seed=0, site=0):
+def embed_bwd(dx0, pv, pa, stats, gv, ga, B, T, dgv, dbv, dga, dba, dpos, drop_p=0.0, seed=0, site=0, dbias_v=None,
+              dbias_a=None):
+    """dbias_v / dbias_a (optional fp32 [F]) accumulate the column sums of dpv / dpa (input-projection bias gradients)."""
     F = pv.shape[-1]
     dpv, dpa = torch.empty_like(pv), torch.empty_like(pa)
     call("mmer_embed_bwd", _p(dx0), _p(pv), _p(pa), _f32(stats), _f32(gv), _f32(ga), _p(dpv), _p(dpa), _f32(dgv),
-         _f32(dbv), _f32(dga), _f32(dba), _f32(dpos), B, T, F, _dt(pv), drop_p, seed, site, _stream())
+         _f32(dbv), _f32(dga), _f32(dba), _f32(dpos), _f32(dbias_v), _f32(dbias_a), B, T, F, _dt(pv), drop_p, seed, site,
+         _stream())
     return dpv, dpa
 
 

@@ -280,10 +280,14 @@ def test_embed_fwd_bwd(dt, B, T, F):
     ref.backward(dx0.double().view(B, T + 1, F))
     dgv, dbv, dga, dba = (torch.zeros(F, device=DEV) for _ in range(4))
     dpos = torch.zeros(T + 3, F, device=DEV)
-    dpv, dpa = ops.embed_bwd(dx0, pv, pa, stats, gv, ga, B, T, dgv, dbv, dga, dba, dpos)
+    dbias_v, dbias_a = torch.full((F,), 0.5, device=DEV), torch.full((F,), -0.5, device=DEV)
+    dpv, dpa = ops.embed_bwd(dx0, pv, pa, stats, gv, ga, B, T, dgv, dbv, dga, dba, dpos, dbias_v=dbias_v, dbias_a=dbias_a)
     for got, want in ((dpv, pvr.grad), (dpa, par.grad), (dgv, gvr.grad), (dbv, bvr.grad), (dga, gar.grad),
                       (dba, bar.grad), (dpos, posr.grad)):
         assert rel(got, want) < tol(dt)
+    # fused bias gradients of the two input projections: column sums of what was stored, accumulated
+    assert rel(dbias_v - 0.5, dpv.double().sum(0)) < (1e-5 if dt == torch.float32 else 2e-3) + 1e-6 / max(1e-9, float(dpv.double().sum(0).abs().max()))
+    assert rel(dbias_a + 0.5, dpa.double().sum(0)) < (1e-5 if dt == torch.float32 else 2e-3) + 1e-6 / max(1e-9, float(dpa.double().sum(0).abs().max()))
 
 
 @pytest.mark.parametrize("dt", DT)

@@ -50,6 +50,10 @@ def main():
         mask = torch.empty(M * 2048 // 8, device=dev, dtype=torch.uint8)
         fn = lambda: ops.gemm(x, w, M=M, N=2048, K=512, bias=bias, relu=True, drop_p=0.1, seed=1, site=1, out=out,
                               relu_mask_out=mask)
+    elif what == "gemm_wgrad":   # linear1's weight gradient as the step launches it: dW[2048,512] += dY^T X, + row sums
+        dy, x = rnd(M, 2048), rnd(M, 512)
+        gw, gb = torch.zeros(2048, 512, device=dev), torch.zeros(2048, device=dev)
+        fn = lambda: ops.linear_wgrad(dy, x, gw, dbias=gb)
     elif what == "gemm_gate":
         dy, w, h = rnd(M, 512), rnd(512, 2048), rnd(M, 2048)
         out = torch.empty(M, 2048, device=dev, dtype=bf)
