@@ -516,6 +516,62 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ig(args):
+    """`--ig`: the explainability path (train2.py:776-838): Integrated Gradients, n_steps = 50 like the
+    reference's default, for the served shape (1 sample, 5 video frames) and a test-loader batch (128 x 16 frames).
+    Not the headline metric: one JSON line of its own, with the same algorithm on stock torch.nn autograd (what Captum
+    drives in the reference) timed beside it on the same GPU."""
+    import mmer_b200 as mm
+    from oracle import eager_torch as E
+    from oracle import ig_oracle
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    out = {"metric": "integrated_gradients_samples_per_s", "unit": "samples/s", "n_steps": 50, "cases": []}
+    for (b, t, dtype) in ((1, 5, torch.float32), (1, 5, torch.bfloat16), (128, 16, torch.float32), (128, 16, torch.bfloat16)):
+        torch.manual_seed(0)
+        model = mm.MultimodalEmotionModel(max_seq_len=t + 1, fusion_num_layers=2, classifier_hidden_dim=512).to(dev)
+        eager = E.EagerModel(max_seq_len=t + 1, fusion_num_layers=2, classifier_hidden_dim=512).to(dev).eval()
+        eager.load_state_dict(model.state_dict(), strict=True)
+        if dtype == torch.bfloat16:
+            model.compute_dtype = torch.bfloat16
+        g = torch.Generator(device="cpu").manual_seed(3)
+        v = torch.randn(b, t, DV, generator=g).to(dev)
+        a = torch.randn(b, DA, generator=g).to(dev)
+        mask = torch.zeros(b, t, dtype=torch.bool, device=dev)
+        mask[:, t - 1] = True
+
+        def ours():
+            return mm.compute_attributions(model, v, a, mask=mask, n_steps=50)
+
+        def stock():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+                fn = lambda vv, aa, mk: eager(vv, aa, mk)[1].float()  # noqa: E731
+                with torch.no_grad():
+                    tgt = fn(v, a, mask).argmax(-1)
+                return ig_oracle.integrated_gradients(fn, (v, a), (torch.zeros_like(v), torch.zeros_like(a)), mask, tgt, 50)
+
+        res = {}
+        for name, f in (("ours", ours), ("stock_torch_autograd", stock)):
+            for _ in range(max(3, args.warmup)):
+                r = f()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                r = f()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / args.steps
+            res[name + "_attr"] = r[0].float()
+        diff = float((res["ours_attr"] - res["stock_torch_autograd_attr"]).norm() / res["stock_torch_autograd_attr"].norm())
+        out["cases"].append({"batch": b, "frames": t, "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
+                             "ms_ours": res["ours"], "ms_stock_torch": res["stock_torch_autograd"],
+                             "samples_per_s_ours": b / (res["ours"] * 1e-3),
+                             "samples_per_s_stock_torch": b / (res["stock_torch_autograd"] * 1e-3),
+                             "rel_l2_diff": diff})
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,8 +581,11 @@ def main():
     ap.add_argument("--step-only", action="store_true",
                     help="profiling aid (ncu launch lists): only the device-resident training steps, no e2e / roofline / "
                          "baseline legs, so that every captured launch belongs to the step")
+    ap.add_argument("--ig", action="store_true", help="time the Integrated-Gradients path instead (its own JSON line)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ig:
+        run_ig(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

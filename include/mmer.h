@@ -260,7 +260,8 @@ typedef struct mmer_model {
   void* daudio;         /* optional [B,audio_dim] dtype */
   /* partial evaluation, for callers that use the sub-modules on their own */
   int32_t stage;        /* 0 whole model; 1 CrossModalFusion only (train2.py:128-193); 2 EmotionClassifier only */
-  int32_t reserved;
+  int32_t input_grads_only; /* backward: skip every weight-gradient GEMM (attribution wants dvideo/daudio only); grads
+                             * must still point at a scratch buffer of n_params floats for the small reductions */
   const void* fused_in;  /* stage 2: classifier input [B,fused] dtype */
   const void* dfused_in; /* stage 1 backward: gradient of the fused embedding [B,fused] dtype */
   void* dfused_out;      /* stage 2 backward: optional gradient w.r.t. fused_in */
@@ -272,6 +273,16 @@ typedef struct mmer_model {
   int32_t n_grad_events;
   int32_t reserved2;
 } mmer_model;
+
+/* Integrated Gradients around the model (captum.attr.IntegratedGradients.attribute as called at train2.py:826-834 and
+ * back-end/app/libs/inference.py:313-321; Captum's default method "gausslegendre", multiply_by_inputs = True).
+ * expand: out[k*n + i] = base[i] + alphas[k] * (x[i] - base[i])   (base NULL = zeros; step-major like Captum's cat)
+ * reduce: attr[i] = (x[i] - base[i]) * sum_k weights[k] * grads[k*n + i]            (attr fp32)
+ * n = n_per_step elements of one un-expanded tensor (multiple of 8); alphas / weights fp32 [n_steps] on the device. */
+int mmer_ig_expand(const void* x, const void* base, const float* alphas, void* out, int64_t n_per_step, int64_t n_steps,
+                   int in_dtype, int out_dtype, void* stream);
+int mmer_ig_reduce(const void* grads, const void* x, const void* base, const float* weights, float* attr,
+                   int64_t n_per_step, int64_t n_steps, int in_dtype, int grad_dtype, void* stream);
 
 /* Plain event plumbing for callers that only hold raw stream handles (the events above). */
 int mmer_event_create(void** event_out);

@@ -53,7 +53,7 @@ class Model(C.Structure):
                 ("video", C.c_void_p), ("audio", C.c_void_p), ("mask", C.c_void_p),
                 ("logits", C.c_void_p), ("probs", C.c_void_p), ("fused_out", C.c_void_p), ("attn_probs", C.c_void_p),
                 ("dlogits", C.c_void_p), ("dvideo", C.c_void_p), ("daudio", C.c_void_p),
-                ("stage", C.c_int32), ("reserved", C.c_int32),
+                ("stage", C.c_int32), ("input_grads_only", C.c_int32),
                 ("fused_in", C.c_void_p), ("dfused_in", C.c_void_p), ("dfused_out", C.c_void_p),
                 ("grad_events", C.POINTER(C.c_void_p)), ("n_grad_events", C.c_int32), ("reserved2", C.c_int32)]
 
@@ -65,6 +65,8 @@ SIGNATURES = {
     "mmer_version": [],
     "mmer_last_error": [],
     "mmer_debug_set": [_I, _I],
+    "mmer_ig_expand": [_P, _P, _P, _P, _I64, _I64, _I, _I, _P],
+    "mmer_ig_reduce": [_P, _P, _P, _P, _P, _I64, _I64, _I, _I, _P],
     "mmer_event_create": [C.POINTER(C.c_void_p)],
     "mmer_event_destroy": [_P],
     "mmer_stream_wait_event": [_P, _P],

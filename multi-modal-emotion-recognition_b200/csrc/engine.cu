@@ -176,6 +176,7 @@ static int lin_dgrad(const mmer_model* m, const void* dy, int64_t M, int64_t N, 
 // gW[N,K] += dy[M,N]^T x[M,K];  gb[N] += column sums of dy (offB < 0: no bias gradient wanted)
 static int lin_wgrad(const mmer_model* m, const void* dy, const void* x, int64_t M, int64_t N, int64_t K,
                      int64_t offW, int64_t offB, cudaStream_t st) {
+  if (m->input_grads_only) return 0;   // attribution: only the data gradients are wanted
   mmer_gemm_args a = {};
   a.A = dy; a.B = x; a.D = G(m, offW); a.a_rowsum = G(m, offB);
   a.M = N; a.N = K; a.K = M; a.lda = N; a.ldb = K; a.ldd = K;

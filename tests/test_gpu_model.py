@@ -401,3 +401,77 @@ def test_cfg5_inference_batch_1_and_8192_bf16(B):
         # the same sample inside a batch of copies gives the same logits
         probs2, logits2, _ = model(video[:1].expand(3, -1, -1).contiguous(), audio[:1].expand(3, -1).contiguous())
     assert float((logits2 - logits[:1]).abs().max()) < 2e-2 * float(logits.abs().max())
+
+
+# ---------------------------------------------------------------- Integrated Gradients (train2.py:776-866)
+def _ig_golden():
+    return np.load(os.path.join(GOLD, "ig_v2_b8_t5_mask.npz"))
+
+
+def test_compute_attributions_matches_reference_golden_fp32():
+    """compute_attributions (engine forward/backward + the expand / reduce kernels) against attributions of the
+    unmodified reference model class (tests/golden/make_golden_ig.py); fp32 tolerance 1e-4 of the largest value."""
+    ig = _ig_golden()
+    _, model, P, video, audio, mask, _ = build("v2_b8_t5_mask", "v2")
+    model.train()
+    before = {k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+    av, aa = mm.compute_attributions(model, video, audio, mask=mask, n_steps=int(ig["n_steps"]))
+    assert not model.training                                   # left in eval mode like the reference
+    assert av.shape == video.shape and aa.shape == audio.shape and av.is_cuda and av.dtype == torch.float32
+    scale = float(np.abs(ig["attr_video"]).max())
+    assert float(np.abs(av.cpu().numpy() - ig["attr_video"]).max()) < 1e-4 * scale
+    assert float(np.abs(aa.cpu().numpy() - ig["attr_audio"]).max()) < 1e-4 * scale
+    assert float(av[mask].abs().max()) == 0.0                   # padded frames: exactly zero
+    for k, p in model.named_parameters():                       # parameter gradients are not touched
+        assert (p.grad is None) == (before[k] is None) and (p.grad is None or torch.equal(p.grad, before[k]))
+    vi, ai = mm.aggregate_importances(av, aa)
+    assert vi.shape == (video.shape[0], video.shape[2]) and ai.shape == audio.shape
+
+
+def test_compute_attributions_targets_baselines_and_chunking():
+    from oracle import ig_oracle
+    _, model, P, video, audio, mask, labels = build("v2_b8_t5_mask", "v2")
+    P64 = {k: (t.double() if t.is_floating_point() else t) for k, t in P.items()}
+    fn = lambda v, a, mk: O.model_forward_v2(P64, v, a, mk)[1]  # noqa: E731
+    g = torch.Generator().manual_seed(5)
+    bv = (0.1 * torch.randn(video.shape, generator=g)).cuda()
+    ba = (0.1 * torch.randn(audio.shape, generator=g)).cuda()
+    n = 7
+    av, aa = mm.compute_attributions(model, video, audio, mask=mask, target=labels, n_steps=n, baseline=(bv, ba))
+    rv, ra = ig_oracle.integrated_gradients(fn, (video.cpu().double(), audio.cpu().double()),
+                                            (bv.cpu().double(), ba.cpu().double()), mask.cpu(), labels.cpu(), n)
+    scale = float(rv.abs().max())
+    assert float((av.cpu().double() - rv).abs().max()) < 1e-4 * scale
+    assert float((aa.cpu().double() - ra).abs().max()) < 1e-4 * scale
+    # Captum's internal_batch_size: the steps in chunks give the same sums
+    cv, ca = mm.compute_attributions(model, video, audio, mask=mask, target=labels, n_steps=n, baseline=(bv, ba),
+                                     internal_batch_size=3 * video.shape[0])
+    # (not bitwise: another batch size changes the GEMM tiling / split-K summation order; both are within 1e-4 of exact)
+    assert float((cv - av).abs().max()) < 2e-4 * scale and float((ca - aa).abs().max()) < 2e-4 * scale
+    # an int target is broadcast
+    iv, _ = mm.compute_attributions(model, video, audio, mask=mask, target=2, n_steps=3)
+    tv, _ = mm.compute_attributions(model, video, audio, mask=mask, target=torch.full((video.shape[0],), 2), n_steps=3)
+    assert torch.equal(iv, tv)
+    with pytest.raises(ValueError):
+        mm.compute_attributions(model, video, audio, mask=mask, baseline="mean")
+
+
+def test_compute_attributions_bf16_and_completeness():
+    """Completeness against the engine's own logits, and bf16 compute within 5e-2 of the fp32 attributions in l2 norm
+    (measured 1.4e-2: the bf16 gradient noise floor of tests/test_oracle_golden.py::test_bf16_storage_noise_floor,
+    averaged over the integration steps)."""
+    _, model, P, video, audio, mask, _ = build("v2_b8_t5_mask", "v2")
+    n = 64
+    av, aa = mm.compute_attributions(model, video, audio, mask=mask, n_steps=n)
+    model.eval()
+    with torch.no_grad():
+        _, lx, _ = model(video, audio, mask=mask)
+        _, l0, _ = model(torch.zeros_like(video), torch.zeros_like(audio), mask=mask)
+    tgt = lx.argmax(1, keepdim=True)
+    delta = (lx - l0).gather(1, tgt).squeeze(1)
+    gap = float((av.flatten(1).sum(1) + aa.sum(1) - delta).abs().max())
+    assert gap < 0.06, gap
+    model.compute_dtype = torch.bfloat16
+    bv_, ba_ = mm.compute_attributions(model, video, audio, mask=mask, target=tgt.squeeze(1), n_steps=n)
+    rel = float((bv_ - av).norm() / av.norm())
+    assert rel < 5e-2, rel

@@ -179,3 +179,61 @@ def test_stock_torch_restatement_matches_reference_golden():
         np.testing.assert_allclose(probs.numpy(), g["eval/probs"], rtol=2e-4, atol=1e-6)
         lf = E.focal_loss(logits, labels, 2.0, ALPHA.float())
         np.testing.assert_allclose(float(lf), float(g["loss/focal_alpha"]), rtol=1e-4)
+
+
+# ---------------------------------------------------------------- Integrated Gradients (train2.py:776-866)
+def _ig_case():
+    from oracle import ig_oracle
+    g = np.load(os.path.join(GOLD, "ig_v2_b8_t5_mask.npz"))
+    _, P, video, audio, mask, _ = load_case("v2_b8_t5_mask", "v2")
+    P64 = to64(P)
+    fn = lambda v, a, mk: O.model_forward_v2(P64, v, a, mk)[1]  # noqa: E731
+    return ig_oracle, g, fn, video.double(), audio.double(), mask
+
+
+def test_integrated_gradients_oracle_matches_reference_model_golden():
+    """The model restatement under the IG restatement == the unmodified reference model class under it
+    (tests/golden/make_golden_ig.py), including the predicted-class target rule."""
+    ig, g, fn, video, audio, mask = _ig_case()
+    logits = fn(video, audio, mask)
+    target = logits.argmax(dim=-1)
+    assert np.array_equal(target.numpy(), g["target"])
+    av, aa = ig.integrated_gradients(fn, (video, audio), (torch.zeros_like(video), torch.zeros_like(audio)), mask, target,
+                                     int(g["n_steps"]))
+    np.testing.assert_allclose(av.numpy(), g["attr_video"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(aa.numpy(), g["attr_audio"], rtol=0, atol=1e-9)
+    assert float(av[mask].abs().max()) == 0.0           # padded frames get exactly zero attribution
+
+
+def test_integrated_gradients_completeness_converges():
+    """sum(attr) -> f(x) - f(baseline) as n_steps grows (slowly: LayerNorm makes the zero baseline a sharp corner)."""
+    ig, g, fn, video, audio, mask = _ig_case()
+    target = torch.from_numpy(g["target"])
+    zero = (torch.zeros_like(video), torch.zeros_like(audio))
+    gaps = []
+    for n in (int(g["n_steps"]), 96):
+        av, aa = ig.integrated_gradients(fn, (video, audio), zero, mask, target, n)
+        gaps.append(float((av.flatten(1).sum(1) + aa.sum(1) - torch.from_numpy(g["delta"])).abs().max()))
+    assert gaps[1] < 0.4 * gaps[0] and gaps[1] < 0.05, gaps
+
+
+def test_gauss_legendre_schedule_and_aggregation():
+    from oracle import ig_oracle
+    from mmer_b200 import attribution as A
+    for n in (1, 2, 7, 50):
+        al, st = ig_oracle.gauss_legendre(n)
+        al2, st2 = A.gauss_legendre_schedule(n)
+        assert np.array_equal(np.asarray(al), al2) and np.array_equal(np.asarray(st), st2)
+        assert abs(sum(st) - 1.0) < 1e-12 and all(0 < x < 1 for x in al)
+        assert np.allclose(np.asarray(al) + np.asarray(al)[::-1], 1.0)
+    # degree-(2n-1) exactness of the rule: integral of alpha^3 over [0,1] with two nodes
+    al, st = ig_oracle.gauss_legendre(2)
+    assert abs(sum(s * a ** 3 for a, s in zip(al, st)) - 0.25) < 1e-12
+    av, aa = torch.randn(3, 4, 8), torch.randn(3, 16)
+    for fn in (ig_oracle.aggregate_importances, A.aggregate_importances):
+        vi, ai = fn(av, aa)
+        assert torch.equal(vi, av.abs().sum(1)) and torch.equal(ai, aa.abs())
+        vi, ai = fn(av, aa, abs_sum=False)
+        assert torch.equal(vi, av.sum(1)) and torch.equal(ai, aa)
+    with pytest.raises(ValueError):
+        A.compute_attributions(object(), av, aa, baseline="mean")
