@@ -55,6 +55,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_NO_PAIR 5     /* tcgen05 GEMM: never use CTA pairs (cta_group::2); A/B timing */
 #define MMER_DEBUG_GENERIC_EPI 6 /* tcgen05 GEMM: always the run-time-flag epilogue, never a specialised one; A/B timing */
 #define MMER_DEBUG_ATT_ROWS 7    /* bf16 short-sequence attention, d=64: CTA-per-sample bulk-row kernels instead of the warp-pipelined TMA-tile ones */
+#define MMER_DEBUG_NO_PDL 8      /* launch every kernel fully serialised (no programmatic dependent launch); A/B timing */
 #define MMER_DEBUG_ATT_SIMT 4    /* bf16 short-sequence attention: use the FMA kernels instead of the MMA ones (A/B timing) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);

@@ -16,7 +16,7 @@ F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
 LOSS_FOCAL, LOSS_WCE = 0, 1
 REDUCE_MEAN, REDUCE_SUM, REDUCE_NONE = 0, 1, 2
-DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT, DEBUG_DIRECT_STORE, DEBUG_ATT_SIMT, DEBUG_NO_PAIR, DEBUG_GENERIC_EPI, DEBUG_ATT_ROWS = 0, 1, 2, 3, 4, 5, 6, 7
+DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT, DEBUG_DIRECT_STORE, DEBUG_ATT_SIMT, DEBUG_NO_PAIR, DEBUG_GENERIC_EPI, DEBUG_ATT_ROWS, DEBUG_NO_PDL = 0, 1, 2, 3, 4, 5, 6, 7, 8
 MAX_LAYERS = 16
 G_NAMES = ["POS", "WV", "BV", "WA", "BA", "NV_W", "NV_B", "NA_W", "NA_B", "ON_W", "ON_B", "C0_W", "C0_B", "C1_W",
            "C1_B", "C4_W", "C4_B", "C5_W", "C5_B", "C8_W", "C8_B"]
@@ -114,6 +114,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
+    # A/B timing knobs without code changes: MMER_DEBUG="8=1,6=1" sets mmer_debug_set(8, 1) and (6, 1) at load
+    for item in filter(None, os.environ.get("MMER_DEBUG", "").split(",")):
+        k, v = item.split("=")
+        lib.mmer_debug_set(int(k), int(v))
     _lib = lib
     return lib
 

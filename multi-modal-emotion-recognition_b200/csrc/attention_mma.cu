@@ -512,11 +512,13 @@ mha_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* my = smem + (size_t)warp * 3 * tile_bytes;            // Q | K | V tiles of this warp
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_FWD_WARPS * 3 * tile_bytes) + warp;
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(my), k_a = q_a + tile_bytes, v_a = k_a + tile_bytes;
+  pdl_trigger();
   if (lane == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
   }
   __syncwarp();
+  pdl_wait();
   const int t = lane & 3;
   const long long units = (long long)B * H;
   const long long stride = (long long)gridDim.x * TMA_FWD_WARPS;
@@ -557,11 +559,13 @@ mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)TMA_BWD_WARPS * 4 * tile_bytes) + warp;
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(my), k_a = q_a + tile_bytes, v_a = k_a + tile_bytes,
                  do_a = v_a + tile_bytes;
+  pdl_trigger();
   if (lane == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
   }
   __syncwarp();
+  pdl_wait();
   const int t = lane & 3;
   const long long units = (long long)B * H;
   const long long stride = (long long)gridDim.x * TMA_BWD_WARPS;   // host makes it a multiple of H: h is fixed per warp
@@ -649,7 +653,9 @@ static int fwd_tma_launch(const void* qkv, const uint8_t* mask, void* out, float
   long long grid = (units + TMA_FWD_WARPS - 1) / TMA_FWD_WARPS;
   const long long cap = (long long)sm_count() * bps;
   if (grid > cap) grid = cap;
-  kern<<<(unsigned)grid, TMA_FWD_WARPS * 32, smem, st>>>(tq, to, mask, probs, B, Tn, H, tile_bytes, dc);
+  cudaError_t le = launch_dep(kern, dim3((unsigned)grid), dim3(TMA_FWD_WARPS * 32), smem, st, 1, tq, to, mask, probs, B, Tn, H,
+                              tile_bytes, dc);
+  if (le != cudaSuccess) return cuda_fail(le, "launch(mha_fwd_tma)");
   MMER_LAUNCH_CHECK("mha_fwd_tma_kernel");
   return 0;
 }
@@ -683,7 +689,9 @@ static int bwd_tma_launch(const void* qkv, const uint8_t* mask, const void* dout
     MMER_CHECK_ARG((grid * TMA_BWD_WARPS) % H == 0 || units <= grid * TMA_BWD_WARPS,
                    "mha_bwd: cannot tile %d heads over %d-warp CTAs for the fused bias gradient", H, TMA_BWD_WARPS);
   }
-  kern<<<(unsigned)grid, TMA_BWD_WARPS * 32, smem, st>>>(tq, td, tg, mask, dbias, B, Tn, H, tile_bytes, dc);
+  cudaError_t le = launch_dep(kern, dim3((unsigned)grid), dim3(TMA_BWD_WARPS * 32), smem, st, 1, tq, td, tg, mask, dbias, B, Tn, H,
+                              tile_bytes, dc);
+  if (le != cudaSuccess) return cuda_fail(le, "launch(mha_bwd_tma)");
   MMER_LAUNCH_CHECK("mha_bwd_tma_kernel");
   return 0;
 }

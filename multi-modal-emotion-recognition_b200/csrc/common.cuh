@@ -35,6 +35,46 @@ void count_launch(int n = 1);
     mmer::count_launch();                                         \
   } while (0)
 
+// ---------------------------------------------------------------------------
+// programmatic dependent launch
+// ---------------------------------------------------------------------------
+// pdl_trigger: the next kernel in the stream (if launched with launch_dep below) may start being scheduled once
+// every CTA of this grid has executed it; pdl_wait: block until the previous grid has completed and its memory is
+// visible.  Everything a kernel does before pdl_wait (barrier init, TMEM allocation, tensor-map prefetch) overlaps the
+// tail of its predecessor; no global memory is touched before it.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch with programmatic stream serialisation (pdl_trigger / pdl_wait above).  ONLY for kernels whose every
+// thread executes pdl_wait() before its first global-memory access.  cluster = 2 launches CTA pairs.
+extern int g_debug[16];
+template <typename... KA, typename... A>
+inline cudaError_t launch_dep(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                              A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (!g_debug[MMER_DEBUG_NO_PDL]) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+
 #define MMER_TRY(expr)            \
   do {                            \
     int _rc = (expr);             \

@@ -254,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent work unit (CTA or CTA pair)
   const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -289,6 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   const int total_items = p.num_m * p.num_n * p.splits;   // num_m counts (CG*128)-row blocks
 
@@ -796,24 +798,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_tc)");
     attr_done = true;
   }
-  if (CG == 1) {
-    kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, td, tx, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tx, p);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc, CTA pair)");
-  }
+  cudaError_t e = launch_dep(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), C::SMEM_BYTES, st, CG, ta, tb, td, tx, p);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_tc)");
   MMER_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }

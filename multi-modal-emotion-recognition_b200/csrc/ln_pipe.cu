@@ -87,6 +87,7 @@ __device__ __forceinline__ LnSmem lnp_setup(const LnPipeGeom& g, uint8_t* smem) 
   LnSmem s;
   s.data = smem;
   s.data_a = smem_u32(smem);
+  pdl_trigger();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * g.stage_bytes);
   s.full_a = smem_u32(bars);
   s.empty_a = smem_u32(bars + LNP_MAX_STAGES);
@@ -98,6 +99,7 @@ __device__ __forceinline__ LnSmem lnp_setup(const LnPipeGeom& g, uint8_t* smem) 
     mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();
   return s;
 }
 
@@ -394,7 +396,9 @@ static int fwd_launch_mode(const void* x, const void* a, const float* gamma, con
   static size_t configured = 0;
   auto kern = add_ln_fwd_pipe_kernel<T, NCH, MODE>;
   MMER_TRY(lnp_set_smem(kern, smem, &configured));
-  kern<<<lnp_grid(g), (g.W + 1) * 32, smem, st>>>((const T*)a, (const T*)x, gamma, beta, (T*)y, stats, g, relu, da, dy);
+  cudaError_t e = launch_dep(kern, dim3(lnp_grid(g)), dim3((g.W + 1) * 32), smem, st, 1, (const T*)a, (const T*)x, gamma, beta,
+                             (T*)y, stats, g, relu, da, dy);
+  if (e != cudaSuccess) return cuda_fail(e, "launch(add_ln_fwd_pipe)");
   MMER_LAUNCH_CHECK("add_ln_fwd_pipe_kernel");
   return 0;
 }
@@ -419,8 +423,9 @@ static int bwd_launch_mode(const void* dy, const void* x, const void* a, const f
   static size_t configured = 0;
   auto kern = add_ln_bwd_pipe_kernel<T, NCH, MODE>;
   MMER_TRY(lnp_set_smem(kern, smem, &configured));
-  kern<<<lnp_grid(g), (g.W + 1) * 32, smem, st>>>((const T*)dy, (const T*)a, (const T*)x, stats, gamma, beta, (T*)dz,
-                                                   (T*)dap, dgamma, dbeta, dbias, g, relu, da, ddy);
+  cudaError_t e = launch_dep(kern, dim3(lnp_grid(g)), dim3((g.W + 1) * 32), smem, st, 1, (const T*)dy, (const T*)a, (const T*)x,
+                             stats, gamma, beta, (T*)dz, (T*)dap, dgamma, dbeta, dbias, g, relu, da, ddy);
+  if (e != cudaSuccess) return cuda_fail(e, "launch(add_ln_bwd_pipe)");
   MMER_LAUNCH_CHECK("add_ln_bwd_pipe_kernel");
   return 0;
 }
@@ -553,6 +558,7 @@ __device__ __forceinline__ void embed_produce(const EmbedGeom& g, const T* pv, c
 }
 
 __device__ __forceinline__ LnSmem embed_setup(const EmbedGeom& g, uint8_t* smem) {
+  pdl_trigger();
   LnSmem s;
   s.data = smem;
   s.data_a = smem_u32(smem);
@@ -567,6 +573,7 @@ __device__ __forceinline__ LnSmem embed_setup(const EmbedGeom& g, uint8_t* smem)
     mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();
   return s;
 }
 
@@ -800,6 +807,8 @@ __global__ void __launch_bounds__(256)
 embed_dpos_kernel(const T* __restrict__ dx0, float* __restrict__ dpos, float* __restrict__ dbv, float* __restrict__ dba,
                   int B, int S, int F, DropCfg dc) {
   __shared__ float sred[8][256];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long N = (long long)S * F;
   const long long c = (long long)blockIdx.x * 256 + lane * 8;
@@ -870,8 +879,9 @@ static int embed_fwd_launch(const void* pv, const void* pa, const float* gv, con
   MMER_TRY(lnp_set_smem(kern, smem, &configured));
   const long long tiles = (g.Mtot + g.W - 1) / g.W;
   const long long cap = sm_count();
-  kern<<<(unsigned)(tiles < cap ? tiles : cap), (g.W + 1) * 32, smem, st>>>((const T*)pv, (const T*)pa, gv, bv, ga, ba, pos,
-                                                                            (T*)x0, stats, g, dc);
+  cudaError_t e = launch_dep(kern, dim3((unsigned)(tiles < cap ? tiles : cap)), dim3((g.W + 1) * 32), smem, st, 1, (const T*)pv,
+                             (const T*)pa, gv, bv, ga, ba, pos, (T*)x0, stats, g, dc);
+  if (e != cudaSuccess) return cuda_fail(e, "launch(embed_fwd_pipe)");
   MMER_LAUNCH_CHECK("embed_fwd_pipe_kernel");
   return 0;
 }
@@ -888,16 +898,17 @@ static int embed_bwd_launch(const void* dx0, const void* pv, const void* pa, con
   MMER_TRY(lnp_set_smem(kern, smem, &configured));
   const long long tiles = (g.Mtot + g.W - 1) / g.W;
   const long long cap = sm_count();
-  kern<<<(unsigned)(tiles < cap ? tiles : cap), (g.W + 1) * 32, smem, st>>>((const T*)dx0, (const T*)pv, (const T*)pa, stats,
-                                                                            gv, ga, (T*)dpv, (T*)dpa, dgv, dga, dbias_v, dbias_a,
-                                                                            g, dc);
+  cudaError_t e = launch_dep(kern, dim3((unsigned)(tiles < cap ? tiles : cap)), dim3((g.W + 1) * 32), smem, st, 1, (const T*)dx0,
+                             (const T*)pv, (const T*)pa, stats, gv, ga, (T*)dpv, (T*)dpa, dgv, dga, dbias_v, dbias_a, g, dc);
+  if (e != cudaSuccess) return cuda_fail(e, "launch(embed_bwd_pipe)");
   MMER_LAUNCH_CHECK("embed_bwd_pipe_kernel");
   const long long N = (T_ + 1) * F;
   int gy = (int)((sm_count() * 4 + (N + 255) / 256 - 1) / ((N + 255) / 256));
   if (gy < 1) gy = 1;
   if (gy > (B + 7) / 8) gy = (int)((B + 7) / 8);
-  embed_dpos_kernel<T><<<dim3((unsigned)((N + 255) / 256), (unsigned)gy), 256, 0, st>>>((const T*)dx0, dpos, dbv, dba, (int)B,
-                                                                                        (int)T_ + 1, (int)F, dc);
+  e = launch_dep(embed_dpos_kernel<T>, dim3((unsigned)((N + 255) / 256), (unsigned)gy), dim3(256), 0, st, 1, (const T*)dx0, dpos,
+                 dbv, dba, (int)B, (int)T_ + 1, (int)F, dc);
+  if (e != cudaSuccess) return cuda_fail(e, "launch(embed_dpos)");
   MMER_LAUNCH_CHECK("embed_dpos_kernel");
   return 0;
 }

@@ -12,6 +12,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_out_fwd_kernel(const T* __restrict__ h, const float* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ logits, float* __restrict__ probs, int B, int K, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -63,6 +65,8 @@ head_out_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ h, 
                     T* __restrict__ dh, float* __restrict__ dW, float* __restrict__ db, int B, int K, int C,
                     int rows_per_cta) {
   extern __shared__ float sW[];   // [min(C, 8)][K] partial dW of the current class group
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nslab = (K + 255) / 256;
   const int slab = warp % nslab, rgroup = warp / nslab, ngroups = HOB_WARPS / nslab;
@@ -207,8 +211,12 @@ int mmer_head_out_fwd(const void* h, const float* W, const float* b, float* logi
   if (B <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((B + 7) / 8);
-  if (dtype == MMER_BF16) head_out_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, W, b, logits, probs, (int)B, (int)K, (int)C);
-  else head_out_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)h, W, b, logits, probs, (int)B, (int)K, (int)C);
+  cudaError_t le;
+  if (dtype == MMER_BF16)
+    le = launch_dep(head_out_fwd_kernel<bf16>, dim3(grid), dim3(256), 0, st, 1, (const bf16*)h, W, b, logits, probs, (int)B, (int)K, (int)C);
+  else
+    le = launch_dep(head_out_fwd_kernel<float>, dim3(grid), dim3(256), 0, st, 1, (const float*)h, W, b, logits, probs, (int)B, (int)K, (int)C);
+  if (le != cudaSuccess) return cuda_fail(le, "launch(head_out_fwd)");
   MMER_LAUNCH_CHECK("head_out_fwd_kernel");
   return 0;
 }
@@ -233,12 +241,14 @@ int mmer_head_out_bwd(const float* dlogits, const void* h, const float* W, void*
                         : cudaFuncSetAttribute(head_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_out_bwd)");
   }
+  cudaError_t le;
   if (dtype == MMER_BF16)
-    head_out_bwd_kernel<bf16><<<grid, HOB_WARPS * 32, smem, st>>>(dlogits, (const bf16*)h, W, (bf16*)dh, dW, db, (int)B,
-                                                                   (int)K, (int)C, (int)rows_per_cta);
+    le = launch_dep(head_out_bwd_kernel<bf16>, dim3(grid), dim3(HOB_WARPS * 32), smem, st, 1, dlogits, (const bf16*)h, W, (bf16*)dh,
+                    dW, db, (int)B, (int)K, (int)C, (int)rows_per_cta);
   else
-    head_out_bwd_kernel<float><<<grid, HOB_WARPS * 32, smem, st>>>(dlogits, (const float*)h, W, (float*)dh, dW, db, (int)B,
-                                                                    (int)K, (int)C, (int)rows_per_cta);
+    le = launch_dep(head_out_bwd_kernel<float>, dim3(grid), dim3(HOB_WARPS * 32), smem, st, 1, dlogits, (const float*)h, W,
+                    (float*)dh, dW, db, (int)B, (int)K, (int)C, (int)rows_per_cta);
+  if (le != cudaSuccess) return cuda_fail(le, "launch(head_out_bwd)");
   MMER_LAUNCH_CHECK("head_out_bwd_kernel");
   return 0;
 }

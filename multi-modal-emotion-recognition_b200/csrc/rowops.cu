@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 pool_ln_fwd_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ pooled, T* __restrict__ fused,
                    float* __restrict__ stats, int B, int Tn, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int S = Tn + 1;
   for (int b = blockIdx.x * ROW_WARPS + warp; b < B; b += gridDim.x * ROW_WARPS) {
@@ -519,6 +521,8 @@ pool_ln_bwd_kernel(const T* __restrict__ dfused, const float* __restrict__ poole
                    const float* __restrict__ gamma, const uint8_t* __restrict__ mask, T* __restrict__ dx,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn, int F) {
   extern __shared__ float sred[];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int S = Tn + 1;
   float pg[NCH][8], pb[NCH][8], g[NCH][8];
@@ -778,13 +782,15 @@ int mmer_pool_ln_fwd(const void* x, const uint8_t* mask, const float* gamma, con
   MMER_CHECK_ARG(x && pooled && fused, "pool_ln_fwd: null pointer");
   if (B <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t le = cudaSuccess;
   if (dtype == MMER_BF16) {
-    DISPATCH_NCH(F, (pool_ln_fwd_kernel<bf16, NCH><<<row_grid(B), ROW_WARPS * 32, 0, st>>>(
-                        (const bf16*)x, mask, gamma, beta, pooled, (bf16*)fused, stats, (int)B, (int)T, (int)F)));
+    DISPATCH_NCH(F, (le = launch_dep(pool_ln_fwd_kernel<bf16, NCH>, dim3(row_grid(B)), dim3(ROW_WARPS * 32), 0, st, 1,
+                                     (const bf16*)x, mask, gamma, beta, pooled, (bf16*)fused, stats, (int)B, (int)T, (int)F)));
   } else {
-    DISPATCH_NCH(F, (pool_ln_fwd_kernel<float, NCH><<<row_grid(B), ROW_WARPS * 32, 0, st>>>(
-                        (const float*)x, mask, gamma, beta, pooled, (float*)fused, stats, (int)B, (int)T, (int)F)));
+    DISPATCH_NCH(F, (le = launch_dep(pool_ln_fwd_kernel<float, NCH>, dim3(row_grid(B)), dim3(ROW_WARPS * 32), 0, st, 1,
+                                     (const float*)x, mask, gamma, beta, pooled, (float*)fused, stats, (int)B, (int)T, (int)F)));
   }
+  if (le != cudaSuccess) return cuda_fail(le, "launch(pool_ln_fwd)");
   MMER_LAUNCH_CHECK("pool_ln_fwd_kernel");
   return 0;
 }
@@ -796,14 +802,18 @@ int mmer_pool_ln_bwd(const void* dfused, const float* pooled, const float* stats
   MMER_CHECK_ARG(dfused && pooled && dx, "pool_ln_bwd: null pointer");
   if (B <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t le = cudaSuccess;
   const size_t sm = (size_t)ROW_WARPS * F * sizeof(float);
   if (dtype == MMER_BF16) {
-    DISPATCH_NCH(F, (pool_ln_bwd_kernel<bf16, NCH><<<bwd_grid(B), ROW_WARPS * 32, sm, st>>>(
-                        (const bf16*)dfused, pooled, stats, gamma, mask, (bf16*)dx, dgamma, dbeta, (int)B, (int)T, (int)F)));
+    DISPATCH_NCH(F, (le = launch_dep(pool_ln_bwd_kernel<bf16, NCH>, dim3(bwd_grid(B)), dim3(ROW_WARPS * 32), sm, st, 1,
+                                     (const bf16*)dfused, pooled, stats, gamma, mask, (bf16*)dx, dgamma, dbeta, (int)B, (int)T,
+                                     (int)F)));
   } else {
-    DISPATCH_NCH(F, (pool_ln_bwd_kernel<float, NCH><<<bwd_grid(B), ROW_WARPS * 32, sm, st>>>(
-                        (const float*)dfused, pooled, stats, gamma, mask, (float*)dx, dgamma, dbeta, (int)B, (int)T, (int)F)));
+    DISPATCH_NCH(F, (le = launch_dep(pool_ln_bwd_kernel<float, NCH>, dim3(bwd_grid(B)), dim3(ROW_WARPS * 32), sm, st, 1,
+                                     (const float*)dfused, pooled, stats, gamma, mask, (float*)dx, dgamma, dbeta, (int)B, (int)T,
+                                     (int)F)));
   }
+  if (le != cudaSuccess) return cuda_fail(le, "launch(pool_ln_bwd)");
   MMER_LAUNCH_CHECK("pool_ln_bwd_kernel");
   return 0;
 }
