@@ -377,7 +377,9 @@ def run_ours(args):
     model = mmer_b200.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512,
                                              fusion_dropout=0.1, classifier_dropout=0.1).to(dev).train()
     step = mmer_b200.FusedTrainStep(model, lr=1e-4, weight_decay=1e-4, loss="focal", gamma=2.0,
-                                    alpha=torch.tensor(ALPHA), compute_dtype=torch.bfloat16)
+                                    alpha=torch.tensor(ALPHA), compute_dtype=torch.bfloat16,
+                                    overlap_allreduce=os.environ.get("MMER_DP_OVERLAP", "1") != "0",
+                                    dp_mode=os.environ.get("MMER_DP_MODE", "auto"))
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     NBUF = 3  # rotate distinct input batches; one step also streams > 2 GB of activations, far beyond the 126 MB L2
     host_v = [torch.randn(B_PER_GPU, T, DV, generator=g).to(torch.bfloat16).pin_memory() for _ in range(NBUF)]

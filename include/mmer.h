@@ -56,6 +56,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_GENERIC_EPI 6 /* tcgen05 GEMM: always the run-time-flag epilogue, never a specialised one; A/B timing */
 #define MMER_DEBUG_ATT_ROWS 7    /* bf16 short-sequence attention, d=64: CTA-per-sample bulk-row kernels instead of the warp-pipelined TMA-tile ones */
 #define MMER_DEBUG_NO_PDL 8      /* launch every kernel fully serialised (no programmatic dependent launch); A/B timing */
+#define MMER_DEBUG_RESERVE_SMS 9 /* size every persistent grid for (SMs - value): room for an NCCL kernel beside the step */
 #define MMER_DEBUG_ATT_SIMT 4    /* bf16 short-sequence attention: use the FMA kernels instead of the MMA ones (A/B timing) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);
@@ -190,6 +191,16 @@ int mmer_loss_fwd_bwd(const float* logits, const int64_t* labels, const float* a
 int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                    const float* sumsq, float max_norm, void* stream);
+/* Data-parallel variant over NVSwitch multicast (NVLS): gradient reduce-scatter + Adam on elements [lo, hi) + all-gather
+ * of the updated weights in ONE kernel.  g_mc / p_mc / shadow_mc are MULTICAST addresses of symmetric buffers (every rank
+ * maps the same layout): the kernel reads sum-over-ranks gradients with multimem.ld_reduce and writes the new fp32
+ * weights (+ bf16 shadow) to all ranks with multimem.st; p_local / m / v are this rank's own memory.  The reference has
+ * no distributed code (train2.py:570-579 is single-process); this replaces NCCL all-reduce + mmer_adam_step for a
+ * torchrun data-parallel job.  The caller issues a cross-rank barrier before (all gradients complete) and after (all
+ * weights landed).  grad_scale = 1 / world_size.  lo, hi multiples of 4. */
+int mmer_adam_step_multicast(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, void* shadow_mc,
+                             int64_t lo, int64_t hi, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             int64_t step, float grad_scale, void* stream);
 int mmer_grad_sumsq(const float* g, int64_t n, float* out /* zeroed by the call */, void* stream);
 int mmer_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 int mmer_cast_f32(const void* src_bf16, float* dst, int64_t n, void* stream);

@@ -16,7 +16,7 @@ F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
 LOSS_FOCAL, LOSS_WCE = 0, 1
 REDUCE_MEAN, REDUCE_SUM, REDUCE_NONE = 0, 1, 2
-DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT, DEBUG_DIRECT_STORE, DEBUG_ATT_SIMT, DEBUG_NO_PAIR, DEBUG_GENERIC_EPI, DEBUG_ATT_ROWS, DEBUG_NO_PDL = 0, 1, 2, 3, 4, 5, 6, 7, 8
+DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT, DEBUG_DIRECT_STORE, DEBUG_ATT_SIMT, DEBUG_NO_PAIR, DEBUG_GENERIC_EPI, DEBUG_ATT_ROWS, DEBUG_NO_PDL, DEBUG_RESERVE_SMS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 MAX_LAYERS = 16
 G_NAMES = ["POS", "WV", "BV", "WA", "BA", "NV_W", "NV_B", "NA_W", "NA_B", "ON_W", "ON_B", "C0_W", "C0_B", "C1_W",
            "C1_B", "C4_W", "C4_B", "C5_W", "C5_B", "C8_W", "C8_B"]
@@ -86,6 +86,7 @@ SIGNATURES = {
     "mmer_head_out_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
     "mmer_loss_fwd_bwd": [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _I64, _I64, _F, _P],
     "mmer_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _F, _P, _F, _P],
+    "mmer_adam_step_multicast": [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _I64, _F, _P],
     "mmer_grad_sumsq": [_P, _I64, _P, _P],
     "mmer_cast_bf16": [_P, _P, _I64, _P],
     "mmer_cast_f32": [_P, _P, _I64, _P],

@@ -35,7 +35,10 @@ int sm_count() {
     cached = n;
     cached_dev = dev;
   }
-  return cached;
+  // SMs left to a communication kernel that runs beside the step (data-parallel overlap): every persistent grid of
+  // this library is sized from this number, and a persistent grid that does not fit in one wave runs twice as long
+  const int reserve = g_debug[MMER_DEBUG_RESERVE_SMS];
+  return reserve > 0 && reserve < cached ? cached - reserve : cached;
 }
 
 }  // namespace mmer

@@ -53,6 +53,62 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Data-parallel step: gradient reduce-scatter + Adam on this rank's shard + parameter all-gather in ONE kernel over
+// NVSwitch multicast (NVLS) addresses.  g_mc / p_mc / shadow_mc are multicast pointers of symmetric buffers:
+//   multimem.ld_reduce  -- the switch returns the SUM over all ranks of the gradient words (no NCCL all-reduce);
+//   multimem.st         -- the updated fp32 weights and their bf16 shadow are written to every rank at once.
+// Each element is reduced and updated by exactly one rank, so all ranks hold bit-identical parameters by
+// construction; Adam's moments exist only for the rank's own shard.  The caller brackets the launch with a
+// cross-rank barrier on both sides (gradients complete before, parameters landed after).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void mc_st_b32x2(void* mc, uint32_t a, uint32_t b) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+adam_shard_mc_kernel(const float* __restrict__ p, float* __restrict__ p_mc, const float* __restrict__ g_mc,
+                     float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow_mc, long long lo, long long hi,
+                     float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps, float wd,
+                     float inv_sqrt_bc2, float grad_scale) {
+  const long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= hi) return;   // lo, hi and the buffer length are multiples of 4
+  float4 pv = *reinterpret_cast<const float4*>(p + i);
+  const float4 gv = mc_ld_reduce_add(g_mc + i);
+  float4 mv = *reinterpret_cast<float4*>(m + i);
+  float4 vv = *reinterpret_cast<float4*>(v + i);
+  float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {   // same arithmetic, in the same order, as adam_kernel
+    const float gr = fmaf(wd, pp[k], gg[k] * grad_scale);
+    mm[k] = fmaf(beta1, mm[k], omb1 * gr);
+    vq[k] = fmaf(beta2, vq[k], omb2 * gr * gr);
+    pp[k] -= lr_over_bc1 * mm[k] / (sqrtf(vq[k]) * inv_sqrt_bc2 + eps);
+  }
+  *reinterpret_cast<float4*>(m + i) = mv;
+  *reinterpret_cast<float4*>(v + i) = vv;
+  mc_st_f32x4(p_mc + i, pv);
+  if (shadow_mc != nullptr) {
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(pv.x, pv.y), h2 = __floats2bfloat162_rn(pv.z, pv.w);
+    mc_st_b32x2(shadow_mc + i, *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&h2));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   float s = 0.f;
@@ -106,6 +162,32 @@ int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
       (float)(1.0 - b2), eps, weight_decay,
       (float)(1.0 / sqrt(bc2)), grad_scale, sumsq, max_norm);
   MMER_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+
+int mmer_adam_step_multicast(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, void* shadow_mc,
+                             int64_t lo, int64_t hi, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             int64_t step, float grad_scale, void* stream) {
+  MMER_CHECK_ARG(p_local && p_mc && g_mc && m && v, "adam_multicast: null pointer");
+  MMER_CHECK_ARG(step >= 1, "adam_multicast: step counts from 1");
+  MMER_CHECK_ARG(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "adam_multicast: shard bounds must be multiples of 4");
+  MMER_CHECK_ARG(((reinterpret_cast<uintptr_t>(p_local) | reinterpret_cast<uintptr_t>(p_mc) | reinterpret_cast<uintptr_t>(g_mc) |
+                   reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(shadow_mc) & 7) == 0,
+                 "adam_multicast: buffers must be 16-byte aligned");
+  if (hi == lo) return 0;
+  char buf[32];
+  snprintf(buf, sizeof(buf), "%.7g", (double)beta1);
+  const double b1 = strtod(buf, nullptr);
+  snprintf(buf, sizeof(buf), "%.7g", (double)beta2);
+  const double b2 = strtod(buf, nullptr);
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
+  const long long nt = (hi - lo) / 4;
+  adam_shard_mc_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      p_local, p_mc, g_mc, m, v, (bf16*)shadow_mc, lo, hi, (float)(lr / bc1), beta1, beta2, (float)(1.0 - b1),
+      (float)(1.0 - b2), eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale);
+  MMER_LAUNCH_CHECK("adam_shard_mc_kernel");
   return 0;
 }
 

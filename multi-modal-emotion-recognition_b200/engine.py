@@ -109,6 +109,57 @@ class ParamContext:
         self.shadow_fresh = False
         self._ptrs = [p.data_ptr() for p in self.params] + [getattr(m, n).data_ptr() for m, n in self.bn_buffers]
 
+    def make_symmetric(self, group) -> bool:
+        """Data-parallel jobs: move master weights, gradients and the bf16 shadow into ONE symmetric-memory allocation
+        (same layout on every rank: flat fp32 | grads fp32 | shadow bf16) and rendezvous it over ``group``, so that the
+        fused reduce-scatter + Adam + all-gather kernel (``mmer_adam_step_multicast``) can address all ranks through the
+        NVSwitch multicast pointer.  Collective: every rank of the group must call it.  Returns False (and changes
+        nothing) when symmetric memory or multicast is not available on this system."""
+        import torch.distributed as dist
+        self.ensure()
+        n = self.flat.numel()
+        dev = self.flat.device
+        ok = 1
+        sym = hdl = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            sym = symm_mem.empty(2 * n + n // 2, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(sym, group if group is not None else dist.group.WORLD)
+            if int(hdl.multicast_ptr) == 0:
+                ok = 0
+        except Exception:   # no symmetric-memory support in this build / on this fabric
+            ok = 0
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            return False
+        flat, grads = sym[:n], sym[n:2 * n]
+        shadow = sym[2 * n:].view(torch.bfloat16)
+        with torch.no_grad():
+            flat.copy_(self.flat)
+            grads.copy_(self.grads)
+            for p in self.params:
+                o = self.offsets[id(p)]
+                p.data = flat[o:o + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    p.grad = grads[o:o + p.numel()].view(p.shape)
+        self.flat, self.grads, self.shadow = flat, grads, shadow
+        self.shadow_fresh = False
+        self._ptrs = [p.data_ptr() for p in self.params] + [getattr(m, nm).data_ptr() for m, nm in self.bn_buffers]
+        self.sym, self.sym_hdl = sym, hdl
+        self.sym_flat_ptr = flat.data_ptr()
+        return True
+
+    def multicast_ptrs(self):
+        """(weights, gradients, shadow) multicast addresses, or None when the storage is not (or no longer) symmetric."""
+        hdl = getattr(self, "sym_hdl", None)
+        if hdl is None or self.flat is None or self.flat.data_ptr() != self.sym_flat_ptr:
+            return None
+        n = self.flat.numel()
+        # the tensor may sit at an offset inside the rendezvoused block: same offset in the multicast mapping
+        base = int(hdl.multicast_ptr) + (self.sym.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
+        return base, base + 4 * n, base + 8 * n
+
     def ensure(self) -> None:
         """(Re)build the flat storage if parameters were moved or replaced (``.to()``, ``.cuda()``...)."""
         dev = self.params[0].device

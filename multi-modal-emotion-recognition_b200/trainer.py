@@ -157,7 +157,7 @@ class FusedTrainStep:
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  loss: str = "focal", gamma: float = 2.0, alpha: Optional[torch.Tensor] = None,
                  clip_grad_norm: Optional[float] = None, compute_dtype: torch.dtype = torch.bfloat16,
-                 process_group=None, overlap_allreduce: bool = True):
+                 process_group=None, overlap_allreduce: bool = True, dp_mode: str = "auto"):
         self.model = model
         self.engine: Engine = model._engine
         self.ctx: ParamContext = self.engine.ctx
@@ -171,6 +171,21 @@ class FusedTrainStep:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.overlap = overlap_allreduce
         self._overlapped: Optional[OverlappedAllReduce] = None
+        # data-parallel gradient exchange: "nvls" = one kernel doing reduce-scatter + Adam on this rank's shard +
+        # all-gather over NVSwitch multicast (mmer_adam_step_multicast); "nccl" = NCCL all-reduce (overlapped with
+        # backward or not) + the ordinary Adam kernel; "auto" = nvls when the fabric offers multicast and no gradient
+        # clipping is asked for (the clip norm needs the reduced gradient on every rank), else nccl
+        if dp_mode not in ("auto", "nvls", "nccl"):
+            raise ValueError("dp_mode must be auto, nvls or nccl")
+        self.dp_mode = "nccl"
+        if self.world > 1 and dp_mode != "nccl":
+            if clip_grad_norm is not None:
+                if dp_mode == "nvls":
+                    raise MmerError("dp_mode='nvls' does not support clip_grad_norm (use dp_mode='nccl')")
+            elif self.ctx.make_symmetric(process_group):
+                self.dp_mode = "nvls"
+            elif dp_mode == "nvls":
+                raise MmerError("dp_mode='nvls': symmetric memory / NVSwitch multicast is not available here")
         self._key = None
         self._ws = None
         self.launch_count = 0
@@ -198,6 +213,29 @@ class FusedTrainStep:
         if self.alpha is not None:
             self.alpha = self.alpha.to(device=dev, dtype=torch.float32).contiguous()
         self._key = (B, T, self.compute_dtype, self.ctx.flat.data_ptr())
+
+    def _nvls_adam(self, stream) -> None:
+        """barrier | reduce-scatter + Adam(shard) + all-gather in one kernel over the multicast addresses | barrier."""
+        ctx, opt = self.ctx, self.opt
+        n = ctx.flat.numel()
+        rank = dist.get_rank(self.group)
+        chunk = ((n + self.world - 1) // self.world + 3) // 4 * 4
+        lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+        if opt._m is None or getattr(opt, "_ctx_flat_ptr", 0) != ctx.flat.data_ptr():
+            opt._m = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
+            opt._v = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
+            opt._ctx_flat_ptr = ctx.flat.data_ptr()
+        g = opt.param_groups[0]
+        opt._step += 1
+        p_mc, g_mc, s_mc = ctx.multicast_ptrs()
+        use_shadow = ctx.shadow is not None and self.compute_dtype == torch.bfloat16
+        ctx.sym_hdl.barrier(channel=0)      # every rank's backward has finished: all gradients are complete
+        _lib.check(_lib.load().mmer_adam_step_multicast(
+            ctx.flat.data_ptr(), C.c_void_p(p_mc), C.c_void_p(g_mc), opt._m.data_ptr(), opt._v.data_ptr(),
+            C.c_void_p(s_mc) if use_shadow else None, lo, hi, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+            float(g["eps"]), float(g["weight_decay"]), opt._step, 1.0 / self.world, stream), "mmer_adam_step_multicast")
+        ctx.sym_hdl.barrier(channel=1)      # every rank's shard has landed everywhere: weights are complete
+        ctx.shadow_fresh = use_shadow
 
     @torch.no_grad()
     def step(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor], labels: torch.Tensor):
@@ -229,11 +267,17 @@ class FusedTrainStep:
                                          float(self.gamma), _lib.REDUCE_MEAN, self._loss.data_ptr(), None,
                                          self._dlogits.data_ptr(), self._scratch.data_ptr(), B,
                                          self.engine.cfg["classes"], 1.0, stream), "mmer_loss_fwd_bwd")
-        if self.world > 1 and self.overlap:
+        nvls = self.dp_mode == "nvls" and ctx.multicast_ptrs() is not None
+        if self.dp_mode == "nvls" and not nvls:
+            raise MmerError("the model's parameters were re-allocated after FusedTrainStep made them symmetric")
+        if self.world > 1 and self.overlap and not nvls:
             if self._overlapped is None or self._overlapped.ctx.grads is not ctx.grads:
                 self._overlapped = OverlappedAllReduce(ctx, self.engine.cfg["layers"], video.device, self.group)
             self._overlapped.attach(m)
         _lib.check(lib.mmer_model_backward(C.byref(m), stream), "mmer_model_backward")
+        if nvls:
+            self._nvls_adam(stream)
+            return self._loss, self._probs
         if self.world > 1 and self.overlap:
             scale = self._overlapped.reduce()
         else:

@@ -23,7 +23,7 @@ def run(overlap, rank, dev):
                                       classifier_dropout=0.0).to(dev).train()
     # lr = 0: the step leaves the weights alone, so the all-reduced gradient buffer of the LAST step can be compared
     step = mm.FusedTrainStep(model, lr=0.0, weight_decay=0.0, loss="focal", alpha=torch.tensor([1, 1, 1, 1, 1.2, 1.2]),
-                             compute_dtype=torch.bfloat16, overlap_allreduce=overlap)
+                             compute_dtype=torch.bfloat16, overlap_allreduce=overlap, dp_mode="nccl")
     g = torch.Generator().manual_seed(7 + rank)
     for _ in range(3):
         v = torch.randn(512, 16, 768, generator=g).to(dev).bfloat16()
