@@ -47,6 +47,13 @@ def allreduce_buckets(flat: torch.Tensor, ranges, group=None) -> float:
     return 1.0 / world
 
 
+def shard_range(n: int, world: int, rank: int):
+    """[lo, hi) of the flat buffer that ``rank`` reduces, updates and broadcasts in the multicast step: equal chunks
+    rounded up to 4 elements (one 16-byte multimem access), the last ranks possibly short or empty."""
+    chunk = ((n + world - 1) // world + 3) // 4 * 4
+    return min(n, rank * chunk), min(n, (rank + 1) * chunk)
+
+
 class OverlappedAllReduce:
     """NCCL all-reduce of the flat gradient buffer overlapped with backward.
 
@@ -219,8 +226,7 @@ class FusedTrainStep:
         ctx, opt = self.ctx, self.opt
         n = ctx.flat.numel()
         rank = dist.get_rank(self.group)
-        chunk = ((n + self.world - 1) // self.world + 3) // 4 * 4
-        lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+        lo, hi = shard_range(n, self.world, rank)
         if opt._m is None or getattr(opt, "_ctx_flat_ptr", 0) != ctx.flat.data_ptr():
             opt._m = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
             opt._v = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)

@@ -243,3 +243,16 @@ def test_data_parallel_gradient_average_equals_global_batch_gloo():
     for rank, err, scale in res:
         assert scale == 0.5
         assert err < 1e-10, (rank, err)
+
+
+def test_multicast_adam_shards_tile_the_flat_buffer():
+    """The fused NVLS step gives every element to exactly one rank, in 16-byte units."""
+    from mmer_b200.trainer import shard_range
+    for n in (64, 7_766_720, 4 * 1000 + 64, 128):
+        for world in (1, 2, 3, 4, 8, 16):
+            prev = 0
+            for r in range(world):
+                lo, hi = shard_range(n, world, r)
+                assert lo == prev and lo <= hi <= n and lo % 4 == 0 and (hi % 4 == 0 or hi == n)
+                prev = hi
+            assert prev == n
