@@ -57,6 +57,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_ATT_ROWS 7    /* bf16 short-sequence attention, d=64: CTA-per-sample bulk-row kernels instead of the warp-pipelined TMA-tile ones */
 #define MMER_DEBUG_NO_PDL 8      /* launch every kernel fully serialised (no programmatic dependent launch); A/B timing */
 #define MMER_DEBUG_RESERVE_SMS 9 /* size every persistent grid for (SMs - value): room for an NCCL kernel beside the step */
+#define MMER_DEBUG_FORCE_SPLITS 10 /* tcgen05 GEMM, accumulate mode: force the split-K factor; A/B timing */
 #define MMER_DEBUG_ATT_SIMT 4    /* bf16 short-sequence attention: use the FMA kernels instead of the MMA ones (A/B timing) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);
@@ -295,6 +296,21 @@ int mmer_ig_expand(const void* x, const void* base, const float* alphas, void* o
                    int in_dtype, int out_dtype, void* stream);
 int mmer_ig_reduce(const void* grads, const void* x, const void* base, const float* weights, float* attr,
                    int64_t n_per_step, int64_t n_steps, int in_dtype, int grad_dtype, void* stream);
+
+/* Batch assembly on the device, the step before the model in the reference's loop (train2.py:362-463):
+ * mmer_feature_stats: per-feature mean and unbiased std + eps over x[R, D] (train2.py:430-441: `all_video.mean(dim=0)`,
+ *   `all_video.std(dim=0) + 1e-6`); two passes, double accumulation; scratch = 2*D doubles.
+ * mmer_collate: the closure collate_fn (train2.py:418-440) over a feature set resident in HBM -- frames[total, Dv] with
+ *   offsets[N+1] (frame range of sample i), audio[N, Da], labels[N]; idx[B] selects the batch.  Writes
+ *   video_out[B, Tmax, Dv] = pad_sequence(..., padding_value=0) of (x - mean_v) / std_v (train2.py:443-447; mean/std
+ *   NULL = features already normalised), audio_out[B, Da], labels_out[B] and mask_out[B, Tmax] (1 = padded).
+ *   Tmax must be >= the longest selected sample (the caller knows the lengths); out_dtype MMER_F32 or MMER_BF16. */
+int mmer_feature_stats(const float* x, int64_t R, int64_t D, float eps, float* mean, float* std, double* scratch,
+                       void* stream);
+int mmer_collate(const float* frames, const int64_t* offsets, const float* audio, const int64_t* labels, const int64_t* idx,
+                 const float* mean_v, const float* std_v, const float* mean_a, const float* std_a, void* video_out,
+                 void* audio_out, int64_t* labels_out, uint8_t* mask_out, int64_t B, int64_t Tmax, int64_t Dv, int64_t Da,
+                 int out_dtype, void* stream);
 
 /* Plain event plumbing for callers that only hold raw stream handles (the events above). */
 int mmer_event_create(void** event_out);

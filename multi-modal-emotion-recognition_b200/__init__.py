@@ -14,7 +14,10 @@ from .modules import (CrossModalFusion, EmotionClassifier, FocalLoss, Multimodal
 from . import modules_v1 as v1  # noqa: F401
 from .trainer import FusedAdam, FusedTrainStep  # noqa: F401
 from .attribution import aggregate_importances, compute_attributions  # noqa: F401
+from .data import DeviceFeatureSet, DeviceLoader  # noqa: F401
+from . import data  # noqa: F401
 
 __all__ = ["FocalLoss", "WeightedCrossEntropyLoss", "CrossModalFusion", "EmotionClassifier",
            "MultimodalEmotionModel", "v1", "FusedAdam", "FusedTrainStep", "ops", "MmerError",
-           "compute_attributions", "aggregate_importances"]
+           "compute_attributions", "aggregate_importances",
+           "DeviceFeatureSet", "DeviceLoader", "data"]

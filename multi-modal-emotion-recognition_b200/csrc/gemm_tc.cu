@@ -850,6 +850,7 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
     const int max_by_k = kb_total / 8 > 0 ? kb_total / 8 : 1;  // at least 8 k-blocks per split
     if (want > max_by_k) want = max_by_k;
     splits = want;
+    if (g_debug[MMER_DEBUG_FORCE_SPLITS] > 0 && g_debug[MMER_DEBUG_FORCE_SPLITS] <= max_by_k) splits = g_debug[MMER_DEBUG_FORCE_SPLITS];
   }
   int kb_per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, kb_per);

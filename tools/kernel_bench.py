@@ -123,12 +123,56 @@ def bench_head():
     timeit("head_out_bwd (4096x512 -> 6)", [lambda: ops.head_out_bwd(dl, h, W, dW, db)], 2 * B * Hd * 2, reps=50)
 
 
+def bench_collate():
+    """Batch assembly (mmer_collate): 4096 samples of up to 16 frames gathered from a resident ragged feature set,
+    z-scored, padded and cast to bf16, against the reference's host collate_fn + .to(device) for the same batch."""
+    import time
+    import mmer_b200 as mm
+    from torch.nn.utils.rnn import pad_sequence
+    gen = torch.Generator().manual_seed(0)
+    n = 3 * B
+    lens = torch.randint(8, T + 1, (n,), generator=gen).tolist()
+    videos = [torch.randn(t, 768, generator=gen) for t in lens]
+    audios = [torch.randn(1024, generator=gen) for _ in range(n)]
+    labels = torch.randint(0, 6, (n,), generator=gen).tolist()
+    ds = mm.DeviceFeatureSet(videos, audios, labels)
+    batches = [list(range(k * B, (k + 1) * B)) for k in range(3)]
+    frames = [sum(lens[i] for i in b) for b in batches]
+    tmax = [max(lens[i] for i in b) for b in batches]
+    byts = sum(f * 768 * 4 + B * 1024 * 4 + B * tm * 768 * 2 + B * 1024 * 2 + B * tm for f, tm in zip(frames, tmax)) / 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for b in batches:
+        ds.collate(b, torch.bfloat16)
+    torch.cuda.synchronize()
+    reps = 12
+    e0.record()
+    for i in range(reps):
+        ds.collate(batches[i % 3], torch.bfloat16)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    print(f"{'collate (device, incl. host index upload)':34s} {us:8.1f} us   {byts / 1e6:8.1f} MB   {byts / us * 1e-3:7.0f} GB/s   "
+          f"{byts / us * 1e-3 / PEAK:5.2f} of measured HBM peak   {B / us:6.1f} M samples/s")
+    vm, vs, am, as_ = (t.cpu() for t in (ds.video_mean, ds.video_std, ds.audio_mean, ds.audio_std))
+    nv = [(v - vm) / vs for v in videos[:B]]
+    na = [(a - am) / as_ for a in audios[:B]]
+    t0 = time.perf_counter()
+    vp = pad_sequence(nv, batch_first=True, padding_value=0.0)
+    ap = torch.stack(na)
+    mk = pad_sequence([torch.zeros(len(v), dtype=torch.bool) for v in nv], batch_first=True, padding_value=True)
+    vp, ap, mk = vp.to(dev), ap.to(dev), mk.to(dev)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    print(f"{'reference collate_fn + .to(device)':34s} {ms * 1e3:8.1f} us   (host pad_sequence/stack of pre-normalised tensors, "
+          f"pageable H2D)   {B / ms / 1e3:6.3f} M samples/s")
+
+
 def main():
-    which = sys.argv[1:] or ["mha", "add_ln", "embed", "head", "adam"]
+    which = sys.argv[1:] or ["mha", "add_ln", "embed", "head", "adam", "collate"]
     print(torch.cuda.get_device_name(0), f"HBM peak {PEAK:.0f} GB/s (measured)")
     for w in which:
         {"mha": bench_mha, "add_ln": bench_add_ln, "colsum": bench_colsum, "adam": bench_adam, "embed": bench_embed,
-         "head": bench_head}[w]()
+         "head": bench_head, "collate": bench_collate}[w]()
 
 
 if __name__ == "__main__":
