@@ -312,6 +312,13 @@ int mmer_collate(const float* frames, const int64_t* offsets, const float* audio
                  void* audio_out, int64_t* labels_out, uint8_t* mask_out, int64_t B, int64_t Tmax, int64_t Dv, int64_t Da,
                  int out_dtype, void* stream);
 
+/* Evaluation bookkeeping of the validation / test loops (train2.py:593-607, 651-667, 724-741) without host round
+ * trips: predicted[b] = argmax_c probs[b, c] (first maximum, torch.max) and confusion[y * C + predicted] += 1 (int64,
+ * rows = true class like sklearn.metrics.confusion_matrix; the caller zeroes it at the start of an epoch).  predicted
+ * may be NULL.  Accuracy and macro / micro precision / recall / F1 follow from the matrix. */
+int mmer_eval_accumulate(const float* probs, const int64_t* labels, int64_t* predicted, int64_t* confusion, int64_t B,
+                         int64_t C, void* stream);
+
 /* Plain event plumbing for callers that only hold raw stream handles (the events above). */
 int mmer_event_create(void** event_out);
 int mmer_event_destroy(void* event);

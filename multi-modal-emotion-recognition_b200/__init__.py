@@ -16,8 +16,10 @@ from .trainer import FusedAdam, FusedTrainStep  # noqa: F401
 from .attribution import aggregate_importances, compute_attributions  # noqa: F401
 from .data import DeviceFeatureSet, DeviceLoader  # noqa: F401
 from . import data  # noqa: F401
+from .evaluation import EvalAccumulator, metrics_from_confusion  # noqa: F401
+from .inference import GraphedInference  # noqa: F401
 
 __all__ = ["FocalLoss", "WeightedCrossEntropyLoss", "CrossModalFusion", "EmotionClassifier",
            "MultimodalEmotionModel", "v1", "FusedAdam", "FusedTrainStep", "ops", "MmerError",
            "compute_attributions", "aggregate_importances",
-           "DeviceFeatureSet", "DeviceLoader", "data"]
+           "DeviceFeatureSet", "DeviceLoader", "data", "EvalAccumulator", "metrics_from_confusion", "GraphedInference"]

@@ -1,4 +1,5 @@
-"""Batch assembly (train2.py:296-492).
+"""The callers on either side of the model: batch assembly (train2.py:296-492) and evaluation
+bookkeeping (row N3; train2.py:593-667).
 
 CPU: the oracle restatement of load_data / collate_fn against what the unmodified reference returned for the same
 synthetic feature files (tests/golden/data_v2_small.npz), plus the host-side helpers of mmer_b200.data.
@@ -147,3 +148,56 @@ def test_collated_batch_feeds_the_model_at_full_width():
         loss, _ = step.step(v, a, m, y)
         losses.append(float(loss))
     assert len(losses) == 3 and all(np.isfinite(losses))
+
+
+# ------------------------------------------------------------------------------------------------ evaluation (N3)
+def _sk_metrics(y, p):
+    from sklearn.metrics import precision_recall_fscore_support
+    out = {}
+    for avg in ("macro", "micro"):
+        pr, rc, f1, _ = precision_recall_fscore_support(y, p, average=avg, zero_division=0)   # train2.py:633-644
+        out[avg + "_precision"], out[avg + "_recall"], out[avg + "_f1"] = pr, rc, f1
+    return out
+
+
+def test_metrics_from_confusion_equal_sklearn():
+    """Every number the reference logs per epoch, including absent classes and 0/0 cases."""
+    from sklearn.metrics import confusion_matrix
+    from mmer_b200.evaluation import metrics_from_confusion
+    rng = np.random.default_rng(0)
+    cases = [(rng.integers(0, 6, 500), rng.integers(0, 6, 500)),
+             (rng.integers(0, 3, 40), rng.integers(2, 6, 40)),            # classes never predicted / never true
+             (np.array([0, 0, 1, 1]), np.array([2, 2, 2, 2])),            # nothing right: 0/0 in F1
+             (np.array([4]), np.array([4]))]
+    for y, p in cases:
+        got = metrics_from_confusion(confusion_matrix(y, p, labels=list(range(6))))
+        for k, v in _sk_metrics(y, p).items():
+            assert abs(got[k] - v) < 1e-12, (k, got[k], v)
+        assert got["accuracy"] == 100.0 * float((y == p).sum()) / len(y) and got["total"] == len(y)
+
+
+@pytest.mark.gpu
+def test_eval_accumulator_matches_the_reference_loop():
+    """Three batches through EvalAccumulator == the reference's per-batch bookkeeping (train2.py:593-609) + sklearn."""
+    import mmer_b200 as mm
+    from sklearn.metrics import confusion_matrix
+    g = torch.Generator().manual_seed(0)
+    acc = mm.EvalAccumulator(6, keep_predictions=True)
+    all_p, all_y, losses = [], [], []
+    for B in (4096, 33, 1):
+        probs = torch.softmax(3 * torch.randn(B, 6, generator=g), dim=1)
+        probs[0, :] = 1.0 / 6                                             # an exact tie: first index, like torch.max
+        labels = torch.randint(0, 6, (B,), generator=g)
+        loss = torch.rand((), generator=g)
+        acc.update(probs.cuda(), labels.cuda(), loss.cuda())
+        all_p.extend(torch.max(probs, dim=1)[1].tolist())
+        all_y.extend(labels.tolist())
+        losses.append(float(loss))
+    out = acc.result()
+    np.testing.assert_array_equal(acc.confusion_matrix(), confusion_matrix(all_y, all_p, labels=list(range(6))))
+    assert acc.predictions().tolist() == all_p
+    assert out["total"] == len(all_y) and out["correct"] == sum(int(a == b) for a, b in zip(all_p, all_y))
+    assert abs(out["accuracy"] - 100.0 * out["correct"] / out["total"]) < 1e-9
+    assert abs(out["avg_loss"] - sum(losses) / 3) < 1e-6
+    for k, v in _sk_metrics(all_y, all_p).items():
+        assert abs(out[k] - v) < 1e-12, k

@@ -476,3 +476,29 @@ def test_compute_attributions_bf16_and_completeness():
     bv_, ba_ = mm.compute_attributions(model, video, audio, mask=mask, target=tgt.squeeze(1), n_steps=n)
     rel = float((bv_ - av).norm() / av.norm())
     assert rel < 5e-2, rel
+
+
+def test_graphed_inference_equals_eager_and_tracks_weight_updates():
+    """cfg5 serving shape (1 clip, 5 chunks) and a small batch: graph replay == eager forward, for new inputs, with and
+    without a mask, in fp32 and bf16 compute, and after the weights change."""
+    for cdt in (None, torch.bfloat16):
+        g, model, P, video, audio, mask, labels = build("v2_b8_t5_mask", "v2")
+        model.eval()
+        model.compute_dtype = cdt
+        run = mm.GraphedInference(model, batch=video.shape[0], frames=video.shape[1])
+        one = mm.GraphedInference(model, batch=1, frames=video.shape[1])
+        with torch.no_grad():
+            for v, a, m in ((video, audio, mask), (video.flip(0), audio * 0.5, None)):
+                pe, le, _ = model(v, a, mask=m)
+                pg, lg = run(v, a, m)
+                assert torch.equal(pe, pg) and torch.equal(le, lg)
+            pe, le, _ = model(video[:1], audio[:1], mask=mask[:1])
+            pg, lg = one(video[:1], audio[:1], mask[:1])
+            assert torch.equal(le, lg)
+            for p in model.parameters():
+                p.mul_(0.9)
+            pe, le, _ = model(video, audio, mask=mask)
+            pg, lg = run(video, audio, mask)
+            assert torch.equal(le, lg)
+        with pytest.raises(mm.MmerError):
+            run(video[:2], audio[:2])
