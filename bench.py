@@ -6,7 +6,8 @@
 Workload (N=1): BASELINE.json configs[1] -- MultimodalEmotionModel (train2.py variant: 2 encoder
 layers, hidden 512) training step in bf16, batch 4096, T=16, class-weighted FocalLoss + fused Adam,
 dropout active as in the reference's training loop.  N>1: the same per-GPU batch on every rank
-(weak scaling, global batch N*4096) with an NCCL gradient all-reduce.
+(weak scaling, global batch N*4096); the gradient exchange is fused into the optimizer kernel over NVSwitch multicast
+when the fabric offers it (trainer.FusedTrainStep dp_mode="auto"), else an NCCL all-reduce overlapped with backward.
 
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same
 step driven from pinned HOST buffers (H2D of every step's inputs + D2H of its loss inside the timed
@@ -486,6 +487,10 @@ def run_ours(args):
                                    "= fwd + FocalLoss(gamma=2, alpha) + bwd + fused Adam(lr 1e-4, wd 1e-4), dropout 0.1",
                        "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world, "T": T, "video_dim": DV,
                        "audio_dim": DA, "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none" if world == 1 else
+                                             "fused into the optimizer kernel over NVSwitch multicast (multimem reduce-scatter "
+                                             "+ Adam shard + all-gather)" if step.dp_mode == "nvls" else
+                                             "NCCL all-reduce of the flat gradient buffer, overlapped with backward"),
                        "l2": f"{NBUF} rotating input batches (109 MB each); each step streams >2 GB of activations "
                              "through HBM, far larger than the 126 MB L2"},
             "step_tflops": FLOP_PER_SAMPLE_TRAIN * B_PER_GPU * world / (ms_total / args.steps * 1e-3) / 1e12,

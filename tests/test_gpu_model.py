@@ -502,3 +502,61 @@ def test_graphed_inference_equals_eager_and_tracks_weight_updates():
             assert torch.equal(le, lg)
         with pytest.raises(mm.MmerError):
             run(video[:2], audio[:2])
+
+
+def test_reference_epoch_loop_runs_on_the_device_pieces():
+    """The body of the reference's train_model (train2.py:523-647) with the device-side pieces swapped in: DeviceLoader
+    for DataLoader + collate_fn + .to(device), FusedTrainStep for zero_grad/forward/criterion/backward/clip/step,
+    EvalAccumulator for the .item()/.cpu() bookkeeping; ReduceLROnPlateau, best-state copy and the checkpoint stay as
+    they are in the reference.  The trained weights then load into the reference architecture on stock torch.nn
+    (oracle/eager_torch.py) and give the same logits."""
+    from oracle import eager_torch as E
+    gen = torch.Generator().manual_seed(11)
+    n, T = 192, 6
+    labels = torch.randint(0, 6, (n,), generator=gen).tolist()
+    lens = torch.randint(2, T + 1, (n,), generator=gen).tolist()
+    proto_v, proto_a = torch.randn(6, 768, generator=gen), torch.randn(6, 1024, generator=gen)   # class-dependent means
+    videos = [proto_v[y] * 0.5 + torch.randn(t, 768, generator=gen) for y, t in zip(labels, lens)]
+    audios = [proto_a[y] * 0.5 + torch.randn(1024, generator=gen) for y in labels]
+    ds = mm.DeviceFeatureSet(videos, audios, labels)
+    train_idx, val_idx, _ = mm.data.stratified_split(labels)
+    class_weights = mm.data.balanced_class_weights([labels[i] for i in train_idx])
+    torch.manual_seed(0)
+    model = mm.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512,
+                                      fusion_dropout=0.1, classifier_dropout=0.1).cuda()
+    step = mm.FusedTrainStep(model, lr=3e-4, weight_decay=1e-4, loss="wce", alpha=class_weights, clip_grad_norm=1.0,
+                             compute_dtype=torch.float32)                               # train2.py:523-526,576
+    scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(step.opt, mode="min", factor=0.3, patience=0)
+    criterion = mm.WeightedCrossEntropyLoss(class_weights.cuda())
+    history, best, best_state = [], float("inf"), None
+    for epoch in range(4):
+        model.train()
+        train_loss = torch.zeros(1, device="cuda")
+        loader = ds.loader(train_idx, batch_size=32, shuffle=True)
+        for v, a, y, m in loader:
+            loss, _ = step.step(v, a, m, y)
+            train_loss += loss
+        model.eval()
+        acc = mm.EvalAccumulator(6)
+        with torch.no_grad():
+            for v, a, y, m in ds.loader(val_idx, batch_size=32):
+                probs, logits, _ = model(v, a, mask=m)
+                acc.update(probs, y, criterion(logits, y))
+        out = acc.result()
+        history.append((float(train_loss) / len(loader), out["avg_loss"], out["accuracy"], step.lr))
+        scheduler.step(out["avg_loss"] if epoch != 2 else 1e9)        # force one plateau: lr must drop by 0.3
+        if out["avg_loss"] < best:
+            best, best_state = out["avg_loss"], {k: t.clone() for k, t in model.state_dict().items()}
+    assert history[-1][0] < 0.7 * history[0][0], history                 # it learns the class prototypes
+    assert abs(step.lr - 3e-4 * 0.3) < 1e-12 and step.opt.param_groups[0]["lr"] == step.lr
+    assert out["total"] == len(val_idx) and 0.0 <= out["macro_f1"] <= 1.0 and history[-1][2] > 100.0 / 6
+    # checkpoint interchange with the reference architecture (same state_dict keys and shapes)
+    ref = E.EagerModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512).cuda().eval()
+    ref.load_state_dict(best_state, strict=True)
+    model.load_state_dict(best_state, strict=True)
+    model.eval()
+    v, a, y, m = ds.collate(val_idx[:16])
+    with torch.no_grad():
+        _, lo, _ = model(v, a, mask=m)
+        _, lr_ = ref(v, a, m)
+    assert float((lo - lr_).abs().max()) < 1e-4 * max(1.0, float(lr_.abs().max()))
