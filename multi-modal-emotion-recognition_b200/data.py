@@ -14,8 +14,7 @@ the stratified 80/10/10 split (train2.py:399-413) and the boosted balanced class
 from __future__ import annotations
 
 import ctypes as C
-import os
-from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+from typing import Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
