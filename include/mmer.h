@@ -198,10 +198,18 @@ int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
  * weights (+ bf16 shadow) to all ranks with multimem.st; p_local / m / v are this rank's own memory.  The reference has
  * no distributed code (train2.py:570-579 is single-process); this replaces NCCL all-reduce + mmer_adam_step for a
  * torchrun data-parallel job.  The caller issues a cross-rank barrier before (all gradients complete) and after (all
- * weights landed).  grad_scale = 1 / world_size.  lo, hi multiples of 4. */
+ * weights landed).  grad_scale = 1 / world_size.  lo, hi multiples of 4.
+ * Gradient clipping (train2.py:576) in this mode: mmer_grad_sumsq_multicast sums the squares of the REDUCED gradient over
+ * [lo, hi) into local_acc and publishes it into slot `rank` of a symmetric float array on every rank (slots_mc = its
+ * multicast address); after a barrier, mmer_adam_step_multicast with sumsq_slots (this rank's copy of the array) and
+ * n_slots = world size clips by min(1, max_norm / (sqrt(sum of slots) * grad_scale + 1e-6)), identical on all ranks.
+ * sumsq_slots NULL = no clipping. */
+int mmer_grad_sumsq_multicast(const float* g_mc, int64_t lo, int64_t hi, float* local_acc, float* slots_mc, int rank,
+                              void* stream);
 int mmer_adam_step_multicast(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, void* shadow_mc,
                              int64_t lo, int64_t hi, float lr, float beta1, float beta2, float eps, float weight_decay,
-                             int64_t step, float grad_scale, void* stream);
+                             int64_t step, float grad_scale, const float* sumsq_slots, int n_slots, float max_norm,
+                             void* stream);
 int mmer_grad_sumsq(const float* g, int64_t n, float* out /* zeroed by the call */, void* stream);
 int mmer_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 int mmer_cast_f32(const void* src_bf16, float* dst, int64_t n, void* stream);

@@ -89,7 +89,8 @@ SIGNATURES = {
     "mmer_head_out_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P],
     "mmer_loss_fwd_bwd": [_P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _I64, _I64, _F, _P],
     "mmer_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _F, _P, _F, _P],
-    "mmer_adam_step_multicast": [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _I64, _F, _P],
+    "mmer_adam_step_multicast": [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _I64, _F, _P, _I, _F, _P],
+    "mmer_grad_sumsq_multicast": [_P, _I64, _I64, _P, _P, _I, _P],
     "mmer_grad_sumsq": [_P, _I64, _P, _P],
     "mmer_cast_bf16": [_P, _P, _I64, _P],
     "mmer_cast_f32": [_P, _P, _I64, _P],

@@ -81,13 +81,45 @@ __device__ __forceinline__ void mc_st_b32x2(void* mc, uint32_t a, uint32_t b) {
                : "memory");
 }
 
+// clip_grad_norm_ in the multicast step: sum of squares of the REDUCED gradient over this rank's shard ...
+__global__ void __launch_bounds__(256)
+sumsq_shard_mc_kernel(const float* __restrict__ g_mc, long long lo, long long hi, float* __restrict__ out) {
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
+    const float4 v = mc_ld_reduce_add(g_mc + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float sw[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += sw[k];
+    atomicAdd(out, t);
+  }
+}
+// ... published into slot `rank` of a symmetric array on every rank; after a barrier each rank adds the slots in the
+// same order, so all ranks clip by the identical factor
+__global__ void publish_slot_mc_kernel(const float* __restrict__ local, float* __restrict__ slots_mc, int rank) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(slots_mc + rank), "f"(*local) : "memory");
+}
+
 __global__ void __launch_bounds__(256)
 adam_shard_mc_kernel(const float* __restrict__ p, float* __restrict__ p_mc, const float* __restrict__ g_mc,
                      float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow_mc, long long lo, long long hi,
                      float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps, float wd,
-                     float inv_sqrt_bc2, float grad_scale) {
+                     float inv_sqrt_bc2, float grad_scale, const float* __restrict__ sumsq_slots, int n_slots, float max_norm) {
   const long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= hi) return;   // lo, hi and the buffer length are multiples of 4
+  if (sumsq_slots != nullptr) {
+    // torch.nn.utils.clip_grad_norm_ on the averaged gradient: coef = max_norm / (total_norm + 1e-6), clamped to 1
+    float ss = 0.f;
+    for (int k = 0; k < n_slots; ++k) ss += sumsq_slots[k];
+    const float total = sqrtf(ss) * fabsf(grad_scale);
+    grad_scale *= fminf(max_norm / (total + 1e-6f), 1.f);
+  }
   float4 pv = *reinterpret_cast<const float4*>(p + i);
   const float4 gv = mc_ld_reduce_add(g_mc + i);
   float4 mv = *reinterpret_cast<float4*>(m + i);
@@ -165,9 +197,30 @@ int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
   return 0;
 }
 
+int mmer_grad_sumsq_multicast(const float* g_mc, int64_t lo, int64_t hi, float* local_acc, float* slots_mc, int rank,
+                              void* stream) {
+  MMER_CHECK_ARG(g_mc && local_acc && slots_mc && rank >= 0, "grad_sumsq_multicast: bad argument");
+  MMER_CHECK_ARG(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "grad_sumsq_multicast: shard bounds must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(local_acc, 0, sizeof(float), st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset(sumsq shard)");
+  if (hi > lo) {
+    long long want = ((hi - lo) / 4 + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    sumsq_shard_mc_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(g_mc, lo, hi, local_acc);
+    MMER_LAUNCH_CHECK("sumsq_shard_mc_kernel");
+  }
+  publish_slot_mc_kernel<<<1, 1, 0, st>>>(local_acc, slots_mc, rank);
+  MMER_LAUNCH_CHECK("publish_slot_mc_kernel");
+  return 0;
+}
+
 int mmer_adam_step_multicast(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, void* shadow_mc,
                              int64_t lo, int64_t hi, float lr, float beta1, float beta2, float eps, float weight_decay,
-                             int64_t step, float grad_scale, void* stream) {
+                             int64_t step, float grad_scale, const float* sumsq_slots, int n_slots, float max_norm,
+                             void* stream) {
+  MMER_CHECK_ARG(sumsq_slots == nullptr || (n_slots >= 1 && n_slots <= 64 && max_norm > 0.f),
+                 "adam_multicast: clipping needs 1..64 slots and a positive max_norm");
   MMER_CHECK_ARG(p_local && p_mc && g_mc && m && v, "adam_multicast: null pointer");
   MMER_CHECK_ARG(step >= 1, "adam_multicast: step counts from 1");
   MMER_CHECK_ARG(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "adam_multicast: shard bounds must be multiples of 4");
@@ -186,7 +239,7 @@ int mmer_adam_step_multicast(const float* p_local, float* p_mc, const float* g_m
   const long long nt = (hi - lo) / 4;
   adam_shard_mc_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       p_local, p_mc, g_mc, m, v, (bf16*)shadow_mc, lo, hi, (float)(lr / bc1), beta1, beta2, (float)(1.0 - b1),
-      (float)(1.0 - b2), eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale);
+      (float)(1.0 - b2), eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale, sumsq_slots, n_slots, max_norm);
   MMER_LAUNCH_CHECK("adam_shard_mc_kernel");
   return 0;
 }

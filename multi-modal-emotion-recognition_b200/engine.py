@@ -123,7 +123,7 @@ class ParamContext:
         sym = hdl = None
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            sym = symm_mem.empty(2 * n + n // 2, dtype=torch.float32, device=dev)
+            sym = symm_mem.empty(2 * n + n // 2 + 64, dtype=torch.float32, device=dev)   # + 64 slots for the clip norm
             hdl = symm_mem.rendezvous(sym, group if group is not None else dist.group.WORLD)
             if int(hdl.multicast_ptr) == 0:
                 ok = 0
@@ -134,7 +134,9 @@ class ParamContext:
         if int(flag.item()) == 0:
             return False
         flat, grads = sym[:n], sym[n:2 * n]
-        shadow = sym[2 * n:].view(torch.bfloat16)
+        shadow = sym[2 * n:2 * n + n // 2].view(torch.bfloat16)
+        self.sym_slots = sym[2 * n + n // 2:]
+        self.sym_slots.zero_()
         with torch.no_grad():
             flat.copy_(self.flat)
             grads.copy_(self.grads)
@@ -151,14 +153,15 @@ class ParamContext:
         return True
 
     def multicast_ptrs(self):
-        """(weights, gradients, shadow) multicast addresses, or None when the storage is not (or no longer) symmetric."""
+        """(weights, gradients, shadow, clip-norm slots) multicast addresses, or None when the storage is not (or no
+        longer) symmetric."""
         hdl = getattr(self, "sym_hdl", None)
         if hdl is None or self.flat is None or self.flat.data_ptr() != self.sym_flat_ptr:
             return None
         n = self.flat.numel()
         # the tensor may sit at an offset inside the rendezvoused block: same offset in the multicast mapping
         base = int(hdl.multicast_ptr) + (self.sym.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
-        return base, base + 4 * n, base + 8 * n
+        return base, base + 4 * n, base + 8 * n, base + 10 * n
 
     def ensure(self) -> None:
         """(Re)build the flat storage if parameters were moved or replaced (``.to()``, ``.cuda()``...)."""

@@ -179,16 +179,16 @@ class FusedTrainStep:
         self.overlap = overlap_allreduce
         self._overlapped: Optional[OverlappedAllReduce] = None
         # data-parallel gradient exchange: "nvls" = one kernel doing reduce-scatter + Adam on this rank's shard +
-        # all-gather over NVSwitch multicast (mmer_adam_step_multicast); "nccl" = NCCL all-reduce (overlapped with
-        # backward or not) + the ordinary Adam kernel; "auto" = nvls when the fabric offers multicast and no gradient
-        # clipping is asked for (the clip norm needs the reduced gradient on every rank), else nccl
+        # all-gather over NVSwitch multicast (mmer_adam_step_multicast; with clipping, the norm of the reduced gradient
+        # is summed shard-wise and exchanged through a symmetric slot array first); "nccl" = NCCL all-reduce (overlapped
+        # with backward or not) + the ordinary Adam kernel; "auto" = nvls when the fabric offers multicast, else nccl
         if dp_mode not in ("auto", "nvls", "nccl"):
             raise ValueError("dp_mode must be auto, nvls or nccl")
         self.dp_mode = "nccl"
         if self.world > 1 and dp_mode != "nccl":
-            if clip_grad_norm is not None:
+            if self.world > 64:
                 if dp_mode == "nvls":
-                    raise MmerError("dp_mode='nvls' does not support clip_grad_norm (use dp_mode='nccl')")
+                    raise MmerError("dp_mode='nvls' supports at most 64 ranks")
             elif self.ctx.make_symmetric(process_group):
                 self.dp_mode = "nvls"
             elif dp_mode == "nvls":
@@ -233,13 +233,23 @@ class FusedTrainStep:
             opt._ctx_flat_ptr = ctx.flat.data_ptr()
         g = opt.param_groups[0]
         opt._step += 1
-        p_mc, g_mc, s_mc = ctx.multicast_ptrs()
+        p_mc, g_mc, s_mc, slots_mc = ctx.multicast_ptrs()
         use_shadow = ctx.shadow is not None and self.compute_dtype == torch.bfloat16
+        lib = _lib.load()
         ctx.sym_hdl.barrier(channel=0)      # every rank's backward has finished: all gradients are complete
-        _lib.check(_lib.load().mmer_adam_step_multicast(
+        slots, max_norm = None, 0.0
+        if opt.max_grad_norm is not None:   # clip_grad_norm_ on the reduced gradient (train2.py:576)
+            if opt._sumsq is None:
+                opt._sumsq = torch.zeros(1, device=ctx.flat.device, dtype=torch.float32)
+            _lib.check(lib.mmer_grad_sumsq_multicast(C.c_void_p(g_mc), lo, hi, opt._sumsq.data_ptr(), C.c_void_p(slots_mc),
+                                                     rank, stream), "mmer_grad_sumsq_multicast")
+            ctx.sym_hdl.barrier(channel=0)  # every rank's partial sum has landed in everybody's slot array
+            slots, max_norm = ctx.sym_slots.data_ptr(), float(opt.max_grad_norm)
+        _lib.check(lib.mmer_adam_step_multicast(
             ctx.flat.data_ptr(), C.c_void_p(p_mc), C.c_void_p(g_mc), opt._m.data_ptr(), opt._v.data_ptr(),
             C.c_void_p(s_mc) if use_shadow else None, lo, hi, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-            float(g["eps"]), float(g["weight_decay"]), opt._step, 1.0 / self.world, stream), "mmer_adam_step_multicast")
+            float(g["eps"]), float(g["weight_decay"]), opt._step, 1.0 / self.world, slots, self.world, max_norm, stream),
+            "mmer_adam_step_multicast")
         ctx.sym_hdl.barrier(channel=1)      # every rank's shard has landed everywhere: weights are complete
         ctx.shadow_fresh = use_shadow
 

@@ -28,10 +28,10 @@ def make(mode, dev, dropout):
     return model
 
 
-def run(mode, rank, dev, nsteps):
+def run(mode, rank, dev, nsteps, clip=None):
     model = make(mode, dev, 0.0)
     step = mm.FusedTrainStep(model, lr=1e-2, weight_decay=1e-4, eps=1.0, loss="focal", alpha=torch.tensor([1, 1, 1, 1, 1.2, 1.2]),
-                             compute_dtype=torch.bfloat16, overlap_allreduce=False, dp_mode=mode)
+                             compute_dtype=torch.bfloat16, overlap_allreduce=False, dp_mode=mode, clip_grad_norm=clip)
     g = torch.Generator().manual_seed(7 + rank)
     for _ in range(nsteps):
         v = torch.randn(512, 16, 768, generator=g).to(dev).bfloat16()
@@ -89,7 +89,17 @@ def main():
         dist.broadcast(ref, src=0)
         agree = bool(torch.equal(ref, pa3))
         shadow_ok = bool(torch.equal(sa3, pa3.bfloat16()))
-        ok = upd1 < 1e-4 * moved1 and upd3 < 1e-2 * moved3 and agree and shadow_ok and moved1 > 1e-5
+        # gradient clipping (train2.py:576): the norm of the reduced gradient, exchanged through the symmetric slot array
+        pc, _, _, mode_c = run("nvls", rank, dev, 1, clip=0.05)
+        pd, _, _, _ = run("nccl", rank, dev, 1, clip=0.05)
+        updc, movedc = float((pd - pc).abs().max()), float((pd - p0).abs().max())
+        refc = pc.clone()
+        dist.broadcast(refc, src=0)
+        # (the clipped step moves the weights by ~3e-5: one fp32 ulp of a weight, 3.7e-9, is already 1e-4 of that)
+        clip_ok = mode_c == "nvls" and updc < max(1e-4 * movedc, 1e-8) and movedc < 0.5 * moved1 and bool(torch.equal(refc, pc))
+        print(f"rank {rank}: clip 0.05, 1 step: max |nvls - nccl| weights = {updc:.3e} of {movedc:.3e} moved "
+              f"(unclipped step moved {moved1:.3e}); ok: {clip_ok}", flush=True)
+        ok = upd1 < 1e-4 * moved1 and upd3 < 1e-2 * moved3 and agree and shadow_ok and moved1 > 1e-5 and clip_ok
         print(f"rank {rank}: 1 step: max |nvls - nccl| weights = {upd1:.3e} of {moved1:.3e} moved; 3 steps: {upd3:.3e} of "
               f"{moved3:.3e}; ranks bit-identical: {agree}; shadow == bf16(weights): {shadow_ok}; "
               f"loss {la3:.6f} / {lb3:.6f}; ok: {ok}", flush=True)
