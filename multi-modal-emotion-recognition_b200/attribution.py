@@ -27,6 +27,8 @@ from .engine import Engine, _compute_dtype
 
 __all__ = ["compute_attributions", "aggregate_importances", "gauss_legendre_schedule"]
 
+_MAX_EXPANDED = 32768   # samples per engine pass when the caller sets no internal_batch_size
+
 
 def gauss_legendre_schedule(n_steps: int) -> Tuple[np.ndarray, np.ndarray]:
     """(alphas, step sizes) of Captum's default "gausslegendre" approximation (captum/attr/_utils/approximation_methods.py
@@ -109,7 +111,8 @@ def compute_attributions(model, video_feats: torch.Tensor, audio_feats: torch.Te
     branch reads undefined globals (train2.py:815-819) and the served copy raises ValueError (inference.py:306-310) --
     or, beyond the reference, a ``(video_baseline, audio_baseline)`` pair of tensors shaped like the inputs.
     ``internal_batch_size`` (not in the reference's signature; Captum's name) bounds how many
-    of the n_steps * B expanded samples go through the model at once; None = all, like the reference.
+    of the n_steps * B expanded samples go through the model at once; None = all like the reference, in passes of at
+    most 32768 samples.
     """
     if isinstance(baseline, str) and baseline != "zeros":
         raise ValueError("Invalid baseline: only 'zeros' (or a pair of baseline tensors) is implemented")
@@ -153,7 +156,10 @@ def compute_attributions(model, video_feats: torch.Tensor, audio_feats: torch.Te
                 raise ValueError("target must have one entry per sample")
 
         alphas_np, steps_np = gauss_legendre_schedule(n_steps)
-        chunk = n_steps if internal_batch_size is None else max(1, int(internal_batch_size) // B)
+        # None = everything in one pass like the reference, up to _MAX_EXPANDED samples per pass (the workspace of the
+        # engine grows with the expanded batch); the sums over the chunks are the same attributions
+        limit = _MAX_EXPANDED if internal_batch_size is None else int(internal_batch_size)
+        chunk = min(n_steps, max(1, limit // B))
         v_attr = a_attr = None
         for k0 in range(0, n_steps, chunk):
             k1 = min(n_steps, k0 + chunk)
