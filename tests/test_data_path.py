@@ -201,3 +201,27 @@ def test_eval_accumulator_matches_the_reference_loop():
     assert abs(out["avg_loss"] - sum(losses) / 3) < 1e-6
     for k, v in _sk_metrics(all_y, all_p).items():
         assert abs(out[k] - v) < 1e-12, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dv,da,lens", [(10, 6, [3, 1, 4]), (16, 8, [5]), (12, 4, [2, 2, 2, 2]), (768, 1024, [1, 16, 7])])
+def test_collate_edge_shapes(dv, da, lens):
+    """Widths that are not multiples of 4 (scalar path), a single sample, no padding at all, one-frame samples; fp32 output
+    is bit-exact against pad_sequence / stack given the same statistics."""
+    import mmer_b200 as mm
+    g = torch.Generator().manual_seed(len(lens) * 100 + dv)
+    videos = [torch.randn(t, dv, generator=g) * 3 - 1 for t in lens]
+    audios = [torch.randn(da, generator=g) for _ in lens]
+    labels = list(range(len(lens)))
+    ds = mm.DeviceFeatureSet(videos, audios, labels, normalize=len(lens) > 1)
+    if len(lens) > 1:
+        vm, vs, am, as_ = D.global_stats(videos, audios)
+        ds.video_mean, ds.video_std, ds.audio_mean, ds.audio_std = vm.cuda(), vs.cuda(), am.cuda(), as_.cuda()
+        nv, na = [(v - vm) / vs for v in videos], [(a - am) / as_ for a in audios]
+    else:
+        nv, na = videos, audios
+    order = list(reversed(range(len(lens))))
+    v, a, y, m = ds.collate(order)
+    rv, ra, ry, rm = D.collate([(nv[i], na[i], labels[i]) for i in order])
+    assert torch.equal(v.cpu(), rv) and torch.equal(a.cpu(), ra) and torch.equal(y.cpu(), ry) and torch.equal(m.cpu(), rm)
+    assert ds.max_chunks == max(lens)
