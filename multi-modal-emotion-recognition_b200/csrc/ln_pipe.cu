@@ -252,14 +252,16 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
     const long long tiles = (g.M + g.W - 1) / g.W;
     int stage = 0;
     uint32_t phase = 0;
+    // (mean, rstd) of a row come from global memory: fetched one tile ahead, so that the ~1 us of DRAM latency is not
+    // exposed once per row when the data tile is already waiting in shared memory
+    float2 st_next = make_float2(0.f, 0.f);
+    if ((long long)blockIdx.x * g.W + warp < g.M)
+      st_next = *reinterpret_cast<const float2*>(stats + ((long long)blockIdx.x * g.W + warp) * 2);
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
       const long long row = t * g.W + warp;
-      float mean = 0.f, rstd = 0.f;
-      if (row < g.M) {
-        const float2 st = *reinterpret_cast<const float2*>(stats + row * 2);
-        mean = st.x;
-        rstd = st.y;
-      }
+      const float mean = st_next.x, rstd = st_next.y;
+      const long long row_next = (t + gridDim.x) * g.W + warp;
+      if (row_next < g.M) st_next = *reinterpret_cast<const float2*>(stats + row_next * 2);
       mbar_wait(sm.full_a + 8 * stage, phase);
       float xh[NCH][8], gd[NCH][8], fa[NCH][8];
       float s1 = 0.f, s2 = 0.f;
