@@ -256,3 +256,37 @@ def test_multicast_adam_shards_tile_the_flat_buffer():
                 assert lo == prev and lo <= hi <= n and lo % 4 == 0 and (hi % 4 == 0 or hi == n)
                 prev = hi
             assert prev == n
+
+
+def test_host_logic_properties_hypothesis():
+    """Property checks of the host-side pieces that decide who owns which bytes: the multicast shards, the gradient buckets
+    and the evaluation metrics (against scikit-learn)."""
+    from hypothesis import given, settings, strategies as st
+    from mmer_b200.trainer import shard_range
+    from mmer_b200.evaluation import metrics_from_confusion
+    from sklearn.metrics import confusion_matrix, precision_recall_fscore_support
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 1 << 24).map(lambda k: 64 * k), st.integers(1, 64))
+    def shards(n, world):
+        covered = 0
+        for r in range(world):
+            lo, hi = shard_range(n, world, r)
+            assert lo == covered and lo % 4 == 0 and hi % 4 == 0 and hi <= n
+            covered = hi
+        assert covered == n
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 5), st.integers(0, 5)), min_size=1, max_size=200))
+    def metrics(pairs):
+        y = [a for a, _ in pairs]
+        p = [b for _, b in pairs]
+        got = metrics_from_confusion(confusion_matrix(y, p, labels=list(range(6))))
+        for avg in ("macro", "micro"):
+            pr, rc, f1, _ = precision_recall_fscore_support(y, p, average=avg, zero_division=0)
+            assert abs(got[avg + "_precision"] - pr) < 1e-12 and abs(got[avg + "_recall"] - rc) < 1e-12
+            assert abs(got[avg + "_f1"] - f1) < 1e-12
+        assert got["correct"] == sum(int(a == b) for a, b in pairs)
+
+    shards()
+    metrics()
