@@ -159,7 +159,14 @@ class FusedAdam(torch.optim.Optimizer):
 
 
 class FusedTrainStep:
-    """zero_grad + forward + loss + backward + [all-reduce] + [clip] + Adam as one host call."""
+    """zero_grad + forward + loss + backward + [gradient exchange] + [clip] + Adam as one host call.
+
+    Under ``torch.distributed`` (one process per GPU) the ranks' gradients are averaged.  ``dp_mode="nvls"`` (what
+    "auto" picks on an NVSwitch node) does that inside the optimizer kernel: every rank reduces, updates and broadcasts
+    its own 1/world shard of the flat parameter buffer through multicast addresses, so after a step ``param.grad`` still
+    holds this rank's LOCAL gradient, Adam's moments exist only for the rank's shard, and all ranks hold bit-identical
+    weights.  ``dp_mode="nccl"`` all-reduces the flat gradient buffer (``param.grad`` = sum over ranks; the 1/world factor
+    is applied inside Adam) and keeps full optimizer state on every rank."""
 
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  loss: str = "focal", gamma: float = 2.0, alpha: Optional[torch.Tensor] = None,
