@@ -315,6 +315,13 @@ int mmer_ig_reduce(const void* grads, const void* x, const void* base, const flo
  *   Tmax must be >= the longest selected sample (the caller knows the lengths); out_dtype MMER_F32 or MMER_BF16. */
 int mmer_feature_stats(const float* x, int64_t R, int64_t D, float eps, float* mean, float* std, double* scratch,
                        void* stream);
+/* bf16-resident variant: mmer_normalize_rows z-scores (mean/std NULL = plain cast) and rounds x[R, D] to bf16 once;
+ * mmer_collate_bf16 then gathers / pads / masks 2-byte rows (same bits as mmer_collate with bf16 output). */
+int mmer_normalize_rows(const float* x, const float* mean, const float* std, void* out_bf16, int64_t R, int64_t D,
+                        void* stream);
+int mmer_collate_bf16(const void* frames_bf16, const int64_t* offsets, const void* audio_bf16, const int64_t* labels,
+                      const int64_t* idx, void* video_out, void* audio_out, int64_t* labels_out, uint8_t* mask_out,
+                      int64_t B, int64_t Tmax, int64_t Dv, int64_t Da, void* stream);
 int mmer_collate(const float* frames, const int64_t* offsets, const float* audio, const int64_t* labels, const int64_t* idx,
                  const float* mean_v, const float* std_v, const float* mean_a, const float* std_a, void* video_out,
                  void* audio_out, int64_t* labels_out, uint8_t* mask_out, int64_t B, int64_t Tmax, int64_t Dv, int64_t Da,

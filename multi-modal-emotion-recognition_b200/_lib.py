@@ -66,6 +66,8 @@ SIGNATURES = {
     "mmer_last_error": [],
     "mmer_debug_set": [_I, _I],
     "mmer_feature_stats": [_P, _I64, _I64, _F, _P, _P, _P, _P],
+    "mmer_normalize_rows": [_P, _P, _P, _P, _I64, _I64, _P],
+    "mmer_collate_bf16": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P],
     "mmer_collate": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, _P],
     "mmer_eval_accumulate": [_P, _P, _P, _P, _I64, _I64, _P],
     "mmer_ig_expand": [_P, _P, _P, _P, _I64, _I64, _I, _I, _P],

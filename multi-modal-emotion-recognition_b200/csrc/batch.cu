@@ -103,6 +103,51 @@ collate_kernel(const float* __restrict__ frames, const long long* __restrict__ o
   }
 }
 
+// ---- bf16-resident variant: the features are z-scored and rounded to bf16 ONCE (normalize_rows_kernel), after which a
+// batch is a pure gather of 2-byte rows -- half the bytes per batch and per resident sample; the values are the same
+// bits the fp32-resident path produces with bf16 output (same arithmetic, one rounding)
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ sd,
+                      bf16* __restrict__ out, long long R, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < R; row += (long long)gridDim.x * 8)
+    emit_row(out + row * D, x + row * D, mean, sd, D, lane, (D & 3) == 0);
+}
+
+__device__ __forceinline__ void copy_row_bf16(bf16* __restrict__ dst, const bf16* __restrict__ src, int D, int lane, bool vec) {
+  if (vec) {   // D % 8 == 0: 16-byte accesses
+    for (int c = lane * 8; c < D; c += 256)
+      *reinterpret_cast<uint4*>(dst + c) = src != nullptr ? *reinterpret_cast<const uint4*>(src + c) : make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (int c = lane; c < D; c += 32) dst[c] = src != nullptr ? src[c] : __float2bfloat16_rn(0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+collate_bf16_kernel(const bf16* __restrict__ frames, const long long* __restrict__ offsets, const bf16* __restrict__ audio,
+                    const long long* __restrict__ labels, const long long* __restrict__ idx, bf16* __restrict__ video_out,
+                    bf16* __restrict__ audio_out, long long* __restrict__ labels_out, uint8_t* __restrict__ mask_out, int B,
+                    int Tmax, int Dv, int Da) {
+  const long long rows_v = (long long)B * Tmax;
+  const long long rows = rows_v + B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    if (row < rows_v) {
+      const int b = (int)(row / Tmax), t = (int)(row % Tmax);
+      const long long s = idx[b];
+      const long long f0 = offsets[s], len = offsets[s + 1] - f0;
+      const bool real = t < len;
+      if (lane == 0) mask_out[row] = real ? 0 : 1;
+      copy_row_bf16(video_out + row * Dv, real ? frames + (f0 + t) * Dv : nullptr, Dv, lane, (Dv & 7) == 0);
+    } else {
+      const int b = (int)(row - rows_v);
+      const long long s = idx[b];
+      copy_row_bf16(audio_out + (long long)b * Da, audio + s * Da, Da, lane, (Da & 7) == 0);
+      if (lane == 0 && labels_out != nullptr) labels_out[b] = labels[s];
+    }
+  }
+}
+
 }  // namespace mmer
 
 using namespace mmer;
@@ -127,6 +172,39 @@ int mmer_feature_stats(const float* x, int64_t R, int64_t D, float eps, float* m
   MMER_LAUNCH_CHECK("feature_moment_kernel(ss)");
   feature_finalize_kernel<<<gx, 256, 0, st>>>(scratch, scratch + D, R, (int)D, eps, mean, std);
   MMER_LAUNCH_CHECK("feature_finalize_kernel");
+  return 0;
+}
+
+int mmer_normalize_rows(const float* x, const float* mean, const float* std, void* out_bf16, int64_t R, int64_t D,
+                        void* stream) {
+  MMER_CHECK_ARG(x && out_bf16 && (mean == nullptr) == (std == nullptr), "normalize_rows: bad pointers");
+  MMER_CHECK_ARG(R >= 0 && D >= 1, "normalize_rows: bad shape");
+  if (R == 0) return 0;
+  long long grid = (R + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  normalize_rows_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, mean, std, (bf16*)out_bf16, R, (int)D);
+  MMER_LAUNCH_CHECK("normalize_rows_kernel");
+  return 0;
+}
+
+int mmer_collate_bf16(const void* frames, const int64_t* offsets, const void* audio, const int64_t* labels,
+                      const int64_t* idx, void* video_out, void* audio_out, int64_t* labels_out, uint8_t* mask_out, int64_t B,
+                      int64_t Tmax, int64_t Dv, int64_t Da, void* stream) {
+  MMER_CHECK_ARG(frames && offsets && audio && idx && video_out && audio_out && mask_out, "collate_bf16: null pointer");
+  MMER_CHECK_ARG(labels_out == nullptr || labels != nullptr, "collate_bf16: labels_out needs labels");
+  MMER_CHECK_ARG(B >= 0 && Tmax >= 0 && Dv >= 1 && Da >= 1, "collate_bf16: bad shape");
+  if (B == 0) return 0;
+  const long long rows = B * Tmax + B;
+  long long grid = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  typedef const long long* LP;
+  collate_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)frames, (LP)offsets, (const bf16*)audio,
+                                                                       (LP)labels, (LP)idx, (bf16*)video_out, (bf16*)audio_out,
+                                                                       (long long*)labels_out, mask_out, (int)B, (int)Tmax,
+                                                                       (int)Dv, (int)Da);
+  MMER_LAUNCH_CHECK("collate_bf16_kernel");
   return 0;
 }
 

@@ -225,3 +225,26 @@ def test_collate_edge_shapes(dv, da, lens):
     rv, ra, ry, rm = D.collate([(nv[i], na[i], labels[i]) for i in order])
     assert torch.equal(v.cpu(), rv) and torch.equal(a.cpu(), ra) and torch.equal(y.cpu(), ry) and torch.equal(m.cpu(), rm)
     assert ds.max_chunks == max(lens)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dv,da", [(768, 1024), (20, 6)])
+def test_bf16_resident_set_gives_the_same_batches(dv, da):
+    """store_dtype=bfloat16 (normalise + round once, then 2-byte gathers) == bf16 batches of the fp32-resident set, bit
+    for bit, including padding, mask and labels; with and without normalisation."""
+    import mmer_b200 as mm
+    g = torch.Generator().manual_seed(dv)
+    n = 40
+    lens = torch.randint(1, 9, (n,), generator=g).tolist()
+    videos = [torch.randn(t, dv, generator=g) * 2 + 0.5 for t in lens]
+    audios = [torch.randn(da, generator=g) for _ in range(n)]
+    labels = torch.randint(0, 6, (n,), generator=g).tolist()
+    for normalize in (True, False):
+        a32 = mm.DeviceFeatureSet(videos, audios, labels, normalize=normalize)
+        a16 = mm.DeviceFeatureSet(videos, audios, labels, normalize=normalize, store_dtype=torch.bfloat16)
+        assert a16.frames.dtype == torch.bfloat16 and a16.frames.shape == a32.frames.shape
+        for idx in ([3, 17, 0, 39, 8], list(range(n))):
+            x, y = a32.collate(idx, torch.bfloat16), a16.collate(idx, torch.bfloat16)
+            assert all(torch.equal(p, q) for p, q in zip(x, y))
+        with pytest.raises(mm.MmerError):
+            a16.collate([0], torch.float32)
