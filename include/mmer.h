@@ -195,7 +195,8 @@ int mmer_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
 /* Data-parallel variant over NVSwitch multicast (NVLS): gradient reduce-scatter + Adam on elements [lo, hi) + all-gather
  * of the updated weights in ONE kernel.  g_mc / p_mc / shadow_mc are MULTICAST addresses of symmetric buffers (every rank
  * maps the same layout): the kernel reads sum-over-ranks gradients with multimem.ld_reduce and writes the new fp32
- * weights (+ bf16 shadow) to all ranks with multimem.st; p_local / m / v are this rank's own memory.  The reference has
+ * weights (+ bf16 shadow) to all ranks with multimem.st; p_local is this rank's own full weight buffer, m / v hold the
+ * moments of the rank's SHARD only (hi - lo elements, element lo first: ZeRO-1).  The reference has
  * no distributed code (train2.py:570-579 is single-process); this replaces NCCL all-reduce + mmer_adam_step for a
  * torchrun data-parallel job.  The caller issues a cross-rank barrier before (all gradients complete) and after (all
  * weights landed).  grad_scale = 1 / world_size.  lo, hi multiples of 4.

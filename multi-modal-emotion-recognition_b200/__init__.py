@@ -18,8 +18,10 @@ from .data import DeviceFeatureSet, DeviceLoader  # noqa: F401
 from . import data  # noqa: F401
 from .evaluation import EvalAccumulator, metrics_from_confusion  # noqa: F401
 from .inference import GraphedInference  # noqa: F401
+from .dpcheck import dp_selfcheck, weights_checksum  # noqa: F401
 
 __all__ = ["FocalLoss", "WeightedCrossEntropyLoss", "CrossModalFusion", "EmotionClassifier",
            "MultimodalEmotionModel", "v1", "FusedAdam", "FusedTrainStep", "ops", "MmerError",
            "compute_attributions", "aggregate_importances",
-           "DeviceFeatureSet", "DeviceLoader", "data", "EvalAccumulator", "metrics_from_confusion", "GraphedInference"]
+           "DeviceFeatureSet", "DeviceLoader", "data", "EvalAccumulator", "metrics_from_confusion", "GraphedInference",
+           "dp_selfcheck", "weights_checksum"]

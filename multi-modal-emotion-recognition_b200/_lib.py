@@ -129,6 +129,23 @@ def load() -> C.CDLL:
     return lib
 
 
+_bound_device: Optional[int] = None
+
+
+def bind_device(index: Optional[int]) -> None:
+    """One GPU per process (the torchrun model): the library caches per-kernel attributes (opt-in shared-memory sizes,
+    occupancy) that CUDA keeps per DEVICE, so the first device a process uses stays its only one.  A tensor on another
+    GPU raises instead of failing later inside a launch."""
+    global _bound_device
+    if index is None:
+        return
+    if _bound_device is None:
+        _bound_device = index
+    elif _bound_device != index:
+        raise MmerError(f"mmer_b200 is bound to cuda:{_bound_device} in this process (one GPU per process); got a tensor "
+                        f"on cuda:{index}")
+
+
 def last_error() -> str:
     return (load().mmer_last_error() or b"").decode("utf-8", "replace")
 

@@ -128,9 +128,12 @@ head_out_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ h, 
 }
 
 // sum of class weights of the batch labels (denominator of the weighted CE mean)
-__global__ void wce_den_kernel(const int64_t* __restrict__ labels, const float* __restrict__ w, float* den, int B) {
+__global__ void wce_den_kernel(const int64_t* __restrict__ labels, const float* __restrict__ w, float* den, int B, int C) {
   float s = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) s += w ? w[labels[i]] : 1.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    const int64_t y = labels[i];
+    s += (y < 0 || y >= C) ? NAN : (w ? w[y] : 1.f);   // out-of-range label: poison the loss, never read out of bounds
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) atomicAdd(den, s);
 }
@@ -154,12 +157,14 @@ loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) sum += c < C ? expf(x[c] - m) : 0.f;
     const float lse = m + logf(sum);
-    const int y = (int)labels[i];
+    const int64_t y64 = labels[i];
+    const bool bad_label = y64 < 0 || y64 >= C;   // torch device-asserts here; we return a NaN loss and NaN gradients
+    const int y = bad_label ? 0 : (int)y64;
     float xy = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) xy = (c == y) ? x[c] : xy;
     const float ce = lse - xy;
-    const float w = alpha ? alpha[y] : 1.f;
+    const float w = bad_label ? NAN : (alpha ? alpha[y] : 1.f);
     float dce;  // d(per-sample loss)/d(ce), before the reduction factor
     if (kind == MMER_LOSS_FOCAL) {
       const float pt = expf(-ce);
@@ -271,7 +276,7 @@ int mmer_loss_fwd_bwd(const float* logits, const int64_t* labels, const float* a
     MMER_CHECK_ARG(scratch != nullptr, "loss: weighted CE needs scratch");
     e = cudaMemsetAsync(scratch, 0, sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(den)");
-    wce_den_kernel<<<(unsigned)((B + 255) / 256 < 64 ? (B + 255) / 256 : 64), 256, 0, st>>>(labels, alpha, scratch, (int)B);
+    wce_den_kernel<<<(unsigned)((B + 255) / 256 < 64 ? (B + 255) / 256 : 64), 256, 0, st>>>(labels, alpha, scratch, (int)B, (int)C);
     MMER_LAUNCH_CHECK("wce_den_kernel");
     den = scratch;
   }

@@ -122,8 +122,8 @@ adam_shard_mc_kernel(const float* __restrict__ p, float* __restrict__ p_mc, cons
   }
   float4 pv = *reinterpret_cast<const float4*>(p + i);
   const float4 gv = mc_ld_reduce_add(g_mc + i);
-  float4 mv = *reinterpret_cast<float4*>(m + i);
-  float4 vv = *reinterpret_cast<float4*>(v + i);
+  float4 mv = *reinterpret_cast<float4*>(m + (i - lo));   // the moments exist for this rank's shard only (ZeRO-1)
+  float4 vv = *reinterpret_cast<float4*>(v + (i - lo));
   float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {   // same arithmetic, in the same order, as adam_kernel
@@ -132,8 +132,8 @@ adam_shard_mc_kernel(const float* __restrict__ p, float* __restrict__ p_mc, cons
     vq[k] = fmaf(beta2, vq[k], omb2 * gr * gr);
     pp[k] -= lr_over_bc1 * mm[k] / (sqrtf(vq[k]) * inv_sqrt_bc2 + eps);
   }
-  *reinterpret_cast<float4*>(m + i) = mv;
-  *reinterpret_cast<float4*>(v + i) = vv;
+  *reinterpret_cast<float4*>(m + (i - lo)) = mv;
+  *reinterpret_cast<float4*>(v + (i - lo)) = vv;
   mc_st_f32x4(p_mc + i, pv);
   if (shadow_mc != nullptr) {
     __nv_bfloat162 l2 = __floats2bfloat162_rn(pv.x, pv.y), h2 = __floats2bfloat162_rn(pv.z, pv.w);

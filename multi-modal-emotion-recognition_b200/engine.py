@@ -168,6 +168,7 @@ class ParamContext:
         dev = self.params[0].device
         if dev.type != "cuda":
             raise MmerError("mmer_b200 modules run on CUDA only (no CPU fallback): call model.cuda() first")
+        _lib.bind_device(dev.index if dev.index is not None else torch.cuda.current_device())
         ptrs = [p.data_ptr() for p in self.params] + [getattr(m, n).data_ptr() for m, n in self.bn_buffers]
         if self.flat is None or ptrs != self._ptrs or self.flat.device != dev:
             self._build(dev)
@@ -195,12 +196,31 @@ class ParamContext:
             if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * self.offsets[id(p)]:
                 p.grad = self.grad_view(p)
 
-    def refresh_shadow(self) -> None:
+    def param_versions(self) -> int:
+        """Sum of the autograd version counters of the parameters: changes on ``load_state_dict``, a stock
+        ``torch.optim`` step or any other in-place write through the Parameter objects.  (Writes through ``p.data``
+        carry their own counter and are NOT seen: call ``invalidate_shadow()`` after those.)"""
+        return sum(p._version for p in self.params)
+
+    def mark_shadow_written(self) -> None:
+        """The optimizer kernel has just written bf16(weights) into the shadow."""
+        self.shadow_fresh = self.shadow is not None
+        self._shadow_versions = self.param_versions()
+
+    def invalidate_shadow(self) -> None:
+        self.shadow_fresh = False
+
+    def refresh_shadow(self, trust_optimizer: bool = False) -> None:
+        """Make the bf16 shadow equal bf16(fp32 masters).  The cast kernel (one 47 MB pass, ~8 us) runs on EVERY call
+        unless ``trust_optimizer`` is set (only FusedTrainStep's own loop does that) AND the last writer of the shadow
+        was the fused Adam kernel AND no parameter was modified in place since (``load_state_dict``, ``torch.optim``).
+        Evaluation, attribution and graph-captured forwards therefore always read the live weights."""
         if self.shadow is None:
             self.shadow = torch.empty(self.flat.numel(), device=self.flat.device, dtype=torch.bfloat16)
             self.shadow_fresh = False
-        if not self.shadow_fresh:
+        if not (trust_optimizer and self.shadow_fresh and getattr(self, "_shadow_versions", -1) == self.param_versions()):
             ops.cast_bf16(self.flat, self.shadow)
+            self.shadow_fresh = False
 
     # ------------------------------------------------------------------ C struct
     def fill_offsets(self, m: Model) -> None:
@@ -251,9 +271,9 @@ class Engine:
             raise MmerError("mmer_workspace_bytes: " + _lib.last_error())
         return int(n)
 
-    def attach_shadow(self, m: Model) -> None:
+    def attach_shadow(self, m: Model, trust_optimizer: bool = False) -> None:
         if m.dtype == BF16:
-            self.ctx.refresh_shadow()
+            self.ctx.refresh_shadow(trust_optimizer)
             m.shadow = self.ctx.shadow.data_ptr()
 
     @staticmethod

@@ -29,6 +29,7 @@ def _p(t: Optional[torch.Tensor]):
         raise _lib.MmerError("mmer_b200 ops need CUDA tensors; there is no CPU fallback")
     if not t.is_contiguous():
         raise _lib.MmerError("mmer_b200 ops need contiguous tensors")
+    _lib.bind_device(t.device.index)
     return C.c_void_p(t.data_ptr())
 
 

@@ -103,7 +103,12 @@ class OverlappedAllReduce:
 
 
 class FusedAdam(torch.optim.Optimizer):
-    """Adam over the flat parameter buffer of an mmer_b200 model: one kernel per step."""
+    """Adam over the flat parameter buffer of an mmer_b200 model: one kernel per step.
+
+    ``state_dict()`` / ``load_state_dict()`` use ``torch.optim.Adam``'s own format (per-parameter ``step``, ``exp_avg``,
+    ``exp_avg_sq`` keyed by the parameter's index in ``model.parameters()`` order), so optimizer checkpoints move freely
+    between this class and the stock optimizer the reference constructs (train2.py:525).  In the multicast data-parallel
+    mode the moments exist for the rank's shard only; ``state_dict()`` is then a COLLECTIVE that gathers them."""
 
     def __init__(self, model_or_params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None):
@@ -118,6 +123,8 @@ class FusedAdam(torch.optim.Optimizer):
         self.max_grad_norm = max_grad_norm
         self._step = 0
         self._m = self._v = None
+        self._mkey = None            # (flat length, lo, hi) the moments were allocated for
+        self._shard = None           # (lo, hi, group) in the multicast data-parallel mode, else None
         self._sumsq = None
         self._ctx: Optional[ParamContext] = None
 
@@ -132,23 +139,62 @@ class FusedAdam(torch.optim.Optimizer):
             raise MmerError("FusedAdam must own exactly the parameters of the model")
         return ctx
 
+    def _moments(self, ctx: ParamContext):
+        """Adam's moments for [lo, hi) of the flat buffer (the whole buffer outside the multicast mode).  The flat layout
+        depends only on the parameter shapes, so the moments survive a re-allocation of the flat buffer (``model.to()``,
+        a sub-module call that re-points ``param.data``); they are reset (with the step count, and a warning) only when
+        the layout itself changed."""
+        n = ctx.flat.numel()
+        lo, hi = (self._shard[0], self._shard[1]) if self._shard is not None else (0, n)
+        key, dev = (n, lo, hi), ctx.flat.device
+        if self._m is not None and self._mkey != key:
+            if self._mkey[0] == n:                 # same layout, different shard (mode switch): re-slice
+                full_m, full_v = self._full_moments(ctx)
+                self._m, self._v = full_m[lo:hi].clone(), full_v[lo:hi].clone()
+            else:
+                import warnings
+                warnings.warn("FusedAdam: the parameter layout changed; optimizer state and step count are reset")
+                self._m = self._v = None
+                self._step = 0
+        if self._m is None:
+            self._m = torch.zeros(hi - lo, device=dev, dtype=torch.float32)
+            self._v = torch.zeros(hi - lo, device=dev, dtype=torch.float32)
+        elif self._m.device != dev:
+            self._m, self._v = self._m.to(dev), self._v.to(dev)
+        self._mkey = key
+        if self._sumsq is None or self._sumsq.device != dev:
+            self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        return self._m, self._v
+
+    def _full_moments(self, ctx: ParamContext):
+        """(m, v) over the whole flat buffer; gathers the shards in the multicast mode (collective)."""
+        n = self._mkey[0]
+        if self._mkey[1:] == (0, n):
+            return self._m, self._v
+        lo, hi = self._mkey[1:]
+        out = []
+        for t in (self._m, self._v):
+            full = torch.zeros(n, device=t.device, dtype=torch.float32)
+            full[lo:hi] = t
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self._shard[2] if self._shard is not None else None)
+            out.append(full)
+        return out[0], out[1]
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = closure() if closure is not None else None
         ctx = self._context()
-        if self._m is None or getattr(self, "_ctx_flat_ptr", 0) != ctx.flat.data_ptr():
-            self._m = torch.zeros_like(ctx.flat)
-            self._v = torch.zeros_like(ctx.flat)
-            self._sumsq = torch.zeros(1, device=ctx.flat.device, dtype=torch.float32)
-            self._ctx_flat_ptr = ctx.flat.data_ptr()
+        if self._shard is not None:
+            raise MmerError("this optimizer belongs to a multicast data-parallel FusedTrainStep: call its step()")
+        m, v = self._moments(ctx)
         g = self.param_groups[0]
         self._step += 1
         sumsq = None
         if self.max_grad_norm is not None:
             sumsq = ops.grad_sumsq(ctx.grads, self._sumsq)
-        ops.adam_step(ctx.flat, ctx.grads, self._m, self._v, ctx.shadow, self._step, g["lr"], g["betas"][0],
+        ops.adam_step(ctx.flat, ctx.grads, m, v, ctx.shadow, self._step, g["lr"], g["betas"][0],
                       g["betas"][1], g["eps"], g["weight_decay"], grad_scale, sumsq, self.max_grad_norm or 0.0)
-        ctx.shadow_fresh = ctx.shadow is not None
+        ctx.mark_shadow_written()
         return loss
 
     def zero_grad(self, set_to_none: bool = True):
@@ -156,6 +202,61 @@ class FusedAdam(torch.optim.Optimizer):
         ctx = self._context()
         ctx.grads.zero_()
         ctx.attach_grads()
+
+    # ------------------------------------------------------------------ checkpointing (torch.optim.Adam's format)
+    def state_dict(self):
+        plist = [p for g in self.param_groups for p in g["params"]]
+        groups, start = [], 0
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = list(range(start, start + len(g["params"])))
+            start += len(g["params"])
+            groups.append(d)
+        state = {}
+        if self._m is not None:
+            ctx = self._context()
+            m, v = self._full_moments(ctx)
+            for i, p in enumerate(plist):
+                o = ctx.offsets[id(p)]
+                state[i] = {"step": torch.tensor(float(self._step)),
+                            "exp_avg": m[o:o + p.numel()].view(p.shape).clone(),
+                            "exp_avg_sq": v[o:o + p.numel()].view(p.shape).clone()}
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        plist = [p for g in self.param_groups for p in g["params"]]
+        for g, sg in zip(self.param_groups, state_dict["param_groups"]):
+            if len(sg["params"]) != len(g["params"]):
+                raise ValueError("loaded state dict has a parameter group of a different size")
+            for k, val in sg.items():
+                if k != "params":
+                    g[k] = val
+        st = state_dict.get("state", {})
+        if not st:
+            self._m = self._v = None
+            self._step = 0
+            return
+        ctx = self._context()
+        n = ctx.flat.numel()
+        m = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
+        v = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
+        steps = set()
+        for i, p in enumerate(plist):
+            s = st.get(i, st.get(str(i)))
+            if s is None:
+                raise ValueError(f"optimizer state for parameter {i} is missing")
+            if tuple(s["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {i}: shape {tuple(s['exp_avg'].shape)} != parameter {tuple(p.shape)}")
+            o = ctx.offsets[id(p)]
+            m[o:o + p.numel()].copy_(s["exp_avg"].reshape(-1))
+            v[o:o + p.numel()].copy_(s["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(s["step"])))
+        if len(steps) != 1:
+            raise ValueError("FusedAdam keeps ONE step count for all parameters; the loaded state has several")
+        self._step = steps.pop()
+        lo, hi = (self._shard[0], self._shard[1]) if self._shard is not None else (0, n)
+        self._m, self._v, self._mkey = m[lo:hi].clone(), v[lo:hi].clone(), (n, lo, hi)
 
 
 class FusedTrainStep:
@@ -171,8 +272,9 @@ class FusedTrainStep:
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  loss: str = "focal", gamma: float = 2.0, alpha: Optional[torch.Tensor] = None,
                  clip_grad_norm: Optional[float] = None, compute_dtype: torch.dtype = torch.bfloat16,
-                 process_group=None, overlap_allreduce: bool = True, dp_mode: str = "auto"):
+                 process_group=None, overlap_allreduce: bool = True, dp_mode: str = "auto", check_labels: bool = False):
         self.model = model
+        self.check_labels = check_labels
         self.engine: Engine = model._engine
         self.ctx: ParamContext = self.engine.ctx
         self.opt = FusedAdam(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
@@ -200,6 +302,22 @@ class FusedTrainStep:
                 self.dp_mode = "nvls"
             elif dp_mode == "nvls":
                 raise MmerError("dp_mode='nvls': symmetric memory / NVSwitch multicast is not available here")
+        if self.world > 1:
+            if self.engine.cfg["variant"] == 1 and not getattr(model, "sync_batchnorm", False):
+                raise MmerError("the BatchNorm variant (train.py) is not invariant under data parallelism: per-rank batch "
+                                "statistics differ from the global-batch reference (SURVEY 8e).  Construct the model with "
+                                "sync_batchnorm=True or train it on one GPU")
+            # DistributedDataParallel semantics: every replica starts from rank 0's weights (and BatchNorm buffers)
+            self.ctx.ensure()
+            src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+            dist.broadcast(self.ctx.flat, src=src, group=process_group)
+            if self.ctx.bn_state is not None:
+                dist.broadcast(self.ctx.bn_state, src=src, group=process_group)
+            self.ctx.invalidate_shadow()
+            if self.dp_mode == "nvls":
+                n = self.ctx.flat.numel()
+                lo, hi = shard_range(n, self.world, dist.get_rank(process_group))
+                self.opt._shard = (lo, hi, process_group)
         self._key = None
         self._ws = None
         self.launch_count = 0
@@ -234,10 +352,7 @@ class FusedTrainStep:
         n = ctx.flat.numel()
         rank = dist.get_rank(self.group)
         lo, hi = shard_range(n, self.world, rank)
-        if opt._m is None or getattr(opt, "_ctx_flat_ptr", 0) != ctx.flat.data_ptr():
-            opt._m = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
-            opt._v = torch.zeros(n, device=ctx.flat.device, dtype=torch.float32)
-            opt._ctx_flat_ptr = ctx.flat.data_ptr()
+        m_sh, v_sh = opt._moments(ctx)
         g = opt.param_groups[0]
         opt._step += 1
         p_mc, g_mc, s_mc, slots_mc = ctx.multicast_ptrs()
@@ -246,38 +361,56 @@ class FusedTrainStep:
         ctx.sym_hdl.barrier(channel=0)      # every rank's backward has finished: all gradients are complete
         slots, max_norm = None, 0.0
         if opt.max_grad_norm is not None:   # clip_grad_norm_ on the reduced gradient (train2.py:576)
-            if opt._sumsq is None:
-                opt._sumsq = torch.zeros(1, device=ctx.flat.device, dtype=torch.float32)
             _lib.check(lib.mmer_grad_sumsq_multicast(C.c_void_p(g_mc), lo, hi, opt._sumsq.data_ptr(), C.c_void_p(slots_mc),
                                                      rank, stream), "mmer_grad_sumsq_multicast")
             ctx.sym_hdl.barrier(channel=0)  # every rank's partial sum has landed in everybody's slot array
             slots, max_norm = ctx.sym_slots.data_ptr(), float(opt.max_grad_norm)
         _lib.check(lib.mmer_adam_step_multicast(
-            ctx.flat.data_ptr(), C.c_void_p(p_mc), C.c_void_p(g_mc), opt._m.data_ptr(), opt._v.data_ptr(),
+            ctx.flat.data_ptr(), C.c_void_p(p_mc), C.c_void_p(g_mc), m_sh.data_ptr(), v_sh.data_ptr(),
             C.c_void_p(s_mc) if use_shadow else None, lo, hi, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
             float(g["eps"]), float(g["weight_decay"]), opt._step, 1.0 / self.world, slots, self.world, max_norm, stream),
             "mmer_adam_step_multicast")
         ctx.sym_hdl.barrier(channel=1)      # every rank's shard has landed everywhere: weights are complete
-        ctx.shadow_fresh = use_shadow
+        if use_shadow:
+            ctx.mark_shadow_written()
+        else:
+            ctx.invalidate_shadow()
 
     @torch.no_grad()
     def step(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor], labels: torch.Tensor):
-        """Runs one optimisation step; returns (loss [1] fp32 device tensor, probs (B,C))."""
+        """Runs one optimisation step; returns (loss [1] fp32 device tensor, probs (B,C)).  Both are PERSISTENT buffers
+        that the next ``step`` overwrites: ``.clone()`` (or ``.item()``) them before the next call if they are kept.
+        Inputs are validated for shape, dtype and device here, as ``ModelFn`` does.  An out-of-range label never reads
+        out of bounds: the loss kernel poisons the loss and the gradients with NaN (torch device-asserts there);
+        ``check_labels=True`` raises on the host instead (one host sync per step)."""
         if not video.is_cuda:
             raise MmerError("FusedTrainStep needs CUDA tensors (no CPU fallback)")
+        from .modules import _check_inputs
+        _check_inputs(self.model.fusion, video, audio, mask)
+        dev = video.device
+        if audio.device != dev or labels.device != dev:
+            raise MmerError("video, audio and labels must live on the same CUDA device")
         B, T = video.shape[0], video.shape[1]
+        if labels.dtype != torch.int64 or tuple(labels.shape) != (B,):
+            raise MmerError(f"labels must be an int64 tensor of shape ({B},) (train2.py:568), got {labels.dtype} "
+                            f"{tuple(labels.shape)}")
+        labels = labels.contiguous()
+        if self.check_labels:
+            lo, hi = int(labels.min()), int(labels.max())      # host sync: debugging aid, off by default
+            if lo < 0 or hi >= self.engine.cfg["classes"]:
+                raise MmerError(f"label out of range [0, {self.engine.cfg['classes']}): min {lo}, max {hi}")
         self.ctx.ensure()
         self._prepare(B, T, video.device)
         eng, ctx = self.engine, self.ctx
         m = eng.make(B, T, self.compute_dtype, True, self.model._p_fusion, self.model._p_classifier,
                      self.model._next_seed(), 0)
-        eng.attach_shadow(m)
+        eng.attach_shadow(m, trust_optimizer=True)
         v = video if video.dtype == self.compute_dtype else video.to(self.compute_dtype)
         a = audio if audio.dtype == self.compute_dtype else audio.to(self.compute_dtype)
         v, a = v.contiguous(), a.contiguous()
         m.video, m.audio = v.data_ptr(), a.data_ptr()
         if mask is not None:
-            mk = mask.contiguous().view(torch.uint8)
+            mk = mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
             m.mask, m.has_mask = mk.data_ptr(), 1
         m.workspace, m.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
         m.logits, m.probs, m.dlogits = self._logits.data_ptr(), self._probs.data_ptr(), self._dlogits.data_ptr()

@@ -128,3 +128,46 @@ def make_batch(B: int, T: int, tag: str = "x", video_dim=768, audio_dim=1024, cl
         lens = np.full(B, T, dtype=np.int64)
     mask = np.arange(T)[None, :] >= lens[:, None]
     return video, audio, mask, labels
+
+
+# ------------------------------------------------------------------ element-wise gradient fixtures
+FULL_GRAD_MAX = 65536          # tensors up to this many elements are stored whole in the golden files
+N_PROJ, N_PICK = 256, 4096     # larger ones: 256 seeded sparse +-1 projections of 4096 elements each
+
+
+def projection_plan(numel: int, tag: str):
+    """(index [N_PROJ, N_PICK] int64, sign [N_PROJ, N_PICK] float64) of the seeded projections of a tensor with
+    ``numel`` elements; the plan depends only on (numel, tag), so generator and tests rebuild it bit for bit."""
+    idx = det_ints(N_PROJ * N_PICK, tag + "/proj_idx", 0, numel - 1).reshape(N_PROJ, N_PICK)
+    sign = det_ints(N_PROJ * N_PICK, tag + "/proj_sign", 0, 1).reshape(N_PROJ, N_PICK).astype(np.float64) * 2.0 - 1.0
+    return idx, sign
+
+
+def project(flat: np.ndarray, tag: str) -> np.ndarray:
+    """The N_PROJ projections of a flattened float array (float64 accumulation)."""
+    flat = np.asarray(flat, dtype=np.float64).reshape(-1)
+    idx, sign = projection_plan(flat.size, tag)
+    return (flat[idx] * sign).sum(axis=1)
+
+
+def check_gradient_elementwise(g, name: str, grad: np.ndarray, rel: float) -> None:
+    """Compare one parameter gradient with the golden file ``g`` ELEMENT-WISE: the whole tensor (``gradfull/``) or
+    its 256 seeded projections (``gradproj/``).  ``rel`` is the allowed error relative to the tensor's rms value
+    (a projection of N_PICK elements carries sqrt(N_PICK) times that)."""
+    grad = np.asarray(grad, dtype=np.float64)
+    norm = float(g["grad/" + name][0])
+    rms = norm / np.sqrt(grad.size)
+    floor = 2e-6                      # analytically-zero gradients (biases in front of a BatchNorm) hold noise
+    if "gradfull/" + name in g.files:
+        ref = np.asarray(g["gradfull/" + name], dtype=np.float64)
+        assert ref.shape == grad.shape, name
+        err = np.abs(grad - ref)
+        tol = rel * max(rms, np.abs(ref).max() * 0.05) + floor
+        # a ReLU pre-activation that rounds to the other side of zero (fp32 reference vs fp64 oracle / other summation
+        # order) moves the few elements it feeds by one token's contribution: allow 0.2 % such elements, bounded
+        assert (err > tol).mean() <= 2e-3 and err.max() <= max(50 * tol, 0.1 * rms), (name, err.max(), rms)
+    else:
+        ref = np.asarray(g["gradproj/" + name], dtype=np.float64)
+        got = project(grad, name)
+        err = np.abs(got - ref).max()
+        assert err <= rel * rms * np.sqrt(N_PICK) + floor, (name, err, rms)

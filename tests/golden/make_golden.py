@@ -11,7 +11,9 @@ True)``, runs forward / loss / backward / optimizer step with the reference's ow
 (nn.TransformerEncoder, F.cross_entropy, nn.CrossEntropyLoss, optim.Adam,
 clip_grad_norm_) and stores the results as small .npz fixtures next to this script.
 Full gradients are 30 MB, so each parameter's gradient is stored as
-[l2 norm, sum, first 16 values].
+[l2 norm, sum, first 16 values] (``grad/<name>``), plus, element-wise: the whole tensor when it has at most
+detgen.FULL_GRAD_MAX elements (``gradfull/<name>``) and 256 seeded sparse +-1 projections otherwise
+(``gradproj/<name>``, plan in detgen.projection_plan).
 """
 import os
 import sys
@@ -142,6 +144,10 @@ def run_case(name, variant, ref_mod, B, T, use_mask, steps_cfg):
     out["grad_in/video_sum"], out["grad_in/audio_sum"] = summarize(video.grad), summarize(audio.grad)
     for k, p in model.named_parameters():
         out["grad/" + k] = summarize(p.grad)
+        if p.numel() <= detgen.FULL_GRAD_MAX:
+            out["gradfull/" + k] = p.grad.detach().numpy().copy()
+        else:
+            out["gradproj/" + k] = detgen.project(p.grad.detach().numpy(), k)
 
     # ---- optimizer step exactly as the reference training loop does it
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)

@@ -107,6 +107,8 @@ def test_fp32_training_step_matches_reference_golden(name, variant, loss, clip):
         got = summarize(p.grad)
         assert abs(got[0] - ref[0]) <= 2e-4 * ref[0] + 2e-6, k
         np.testing.assert_allclose(got[2:], ref[2:], rtol=0, atol=5e-4 * ref[0] + 2e-6, err_msg=k)
+        # element-wise: the whole tensor (<= 64 K elements) or 256 seeded sparse projections of it
+        detgen.check_gradient_elementwise(g, k, p.grad.detach().cpu().numpy(), rel=5e-3)
     if variant == "v1":
         for k, val in model.state_dict().items():
             if "running" in k:
