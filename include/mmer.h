@@ -293,7 +293,16 @@ typedef struct mmer_model {
    * communication stream and all-reduces bucket k while backward continues. */
   void* const* grad_events;
   int32_t n_grad_events;
-  int32_t reserved2;
+  /* SyncBatchNorm for the train.py variant under data parallelism (train.py:51-52,66-74,116,125 compute batch statistics
+   * over the WHOLE batch): bn_world > 1 makes every BatchNorm layer call bn_sync(bn_sync_user, buf, n, stream) on the
+   * host, while it enqueues its kernels, for each buffer of partial column sums; the callee must enqueue an in-place
+   * SUM all-reduce of buf[0..n) over the bn_world replicas on `stream` (ordered after what is already enqueued) and
+   * return 0.  Forward: sum(x), then sum((x - mean)^2) (two calls of C floats per layer); backward: [sum(dy),
+   * sum(dy * xhat)] (one call of 2C floats).  Row counts are multiplied by bn_world (equal shards).  bn_world <= 1 or
+   * bn_sync NULL: plain per-replica BatchNorm. */
+  int32_t bn_world;
+  int (*bn_sync)(void* user, float* buf, int64_t n, void* stream);
+  void* bn_sync_user;
 } mmer_model;
 
 /* Integrated Gradients around the model (captum.attr.IntegratedGradients.attribute as called at train2.py:826-834 and

@@ -55,7 +55,12 @@ class Model(C.Structure):
                 ("dlogits", C.c_void_p), ("dvideo", C.c_void_p), ("daudio", C.c_void_p),
                 ("stage", C.c_int32), ("input_grads_only", C.c_int32),
                 ("fused_in", C.c_void_p), ("dfused_in", C.c_void_p), ("dfused_out", C.c_void_p),
-                ("grad_events", C.POINTER(C.c_void_p)), ("n_grad_events", C.c_int32), ("reserved2", C.c_int32)]
+                ("grad_events", C.POINTER(C.c_void_p)), ("n_grad_events", C.c_int32), ("bn_world", C.c_int32),
+                ("bn_sync", C.c_void_p), ("bn_sync_user", C.c_void_p)]
+
+
+# int (*bn_sync)(void* user, float* buf, int64_t n, void* stream): SyncBatchNorm hook of mmer_model
+BN_SYNC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 _P, _I64, _I, _F, _U64, _U32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_uint32

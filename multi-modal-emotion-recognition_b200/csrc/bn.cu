@@ -120,9 +120,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums,
-                    T* __restrict__ dx, long long N, int C, int relu, int training, DropCfg dc) {
+                    T* __restrict__ dx, long long N, long long Nstat, int C, int relu, int training, DropCfg dc) {
   const long long total = N * C / 8;
-  const float invN = 1.f / (float)N;
+  const float invN = 1.f / (float)Nstat;   // rows the statistics were taken over (the global batch under SyncBatchNorm)
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long off = e * 8;
     const int c = (int)(off % C);
@@ -173,17 +173,32 @@ static unsigned ew_grid(long long N, long long C) {
   return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// SyncBatchNorm (mmer_model.bn_sync): all-reduce a buffer of partial column sums over the replicas, on the stream
+static int bn_sync_call(const BnSync* sy, float* buf, long long n, cudaStream_t st) {
+  if (sy == nullptr || sy->fn == nullptr || sy->world <= 1) return 0;
+  const int rc = sy->fn(sy->user, buf, (int64_t)n, (void*)st);
+  if (rc != 0) { set_error("bn_sync callback failed (%d)", rc); return MMER_ERR_ARG; }
+  return 0;
+}
+static long long bn_rows(const BnSync* sy, long long N) {
+  return (sy != nullptr && sy->fn != nullptr && sy->world > 1) ? N * sy->world : N;
+}
+
 template <typename T>
 static int bn_fwd_t(const void* x, const float* gamma, const float* beta, float* rm, float* rv, void* y, float* stats,
-                    long long N, long long C, int training, int relu, float momentum, DropCfg dc, cudaStream_t st) {
+                    long long N, long long C, int training, int relu, float momentum, DropCfg dc, cudaStream_t st,
+                    const BnSync* sy) {
   const unsigned cb = (unsigned)((C + 127) / 128);
   if (training) {
+    const long long Ng = bn_rows(sy, N);   // rows of the whole (global) batch
     cudaError_t e = cudaMemsetAsync(stats, 0, 2 * C * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "memset(bn stats)");
     bn_reduce_kernel<T, 0><<<reduce_grid(N, C), 256, 0, st>>>((const T*)x, nullptr, stats, nullptr, nullptr, stats, nullptr, N, (int)C, 0, dc);
-    bn_finalize_kernel<<<cb, 128, 0, st>>>(stats, rm, rv, N, (int)C, 0, momentum);
+    MMER_TRY(bn_sync_call(sy, stats, C, st));
+    bn_finalize_kernel<<<cb, 128, 0, st>>>(stats, rm, rv, Ng, (int)C, 0, momentum);
     bn_reduce_kernel<T, 1><<<reduce_grid(N, C), 256, 0, st>>>((const T*)x, nullptr, stats, nullptr, nullptr, stats + C, nullptr, N, (int)C, 0, dc);
-    bn_finalize_kernel<<<cb, 128, 0, st>>>(stats, rm, rv, N, (int)C, 1, momentum);
+    MMER_TRY(bn_sync_call(sy, stats + C, C, st));
+    bn_finalize_kernel<<<cb, 128, 0, st>>>(stats, rm, rv, Ng, (int)C, 1, momentum);
   } else {
     bn_finalize_kernel<<<cb, 128, 0, st>>>(stats, rm, rv, N, (int)C, 2, momentum);
   }
@@ -196,15 +211,43 @@ static int bn_fwd_t(const void* x, const float* gamma, const float* beta, float*
 template <typename T>
 static int bn_bwd_t(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
                     float* dgamma, float* dbeta, float* scratch, long long N, long long C, int relu, int training,
-                    DropCfg dc, cudaStream_t st) {
+                    DropCfg dc, cudaStream_t st, const BnSync* sy) {
   cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * C * sizeof(float), st);
   if (e != cudaSuccess) return cuda_fail(e, "memset(bn scratch)");
   bn_reduce_kernel<T, 2><<<reduce_grid(N, C), 256, 0, st>>>((const T*)x, (const T*)dy, stats, gamma, beta, scratch, scratch + C, N, (int)C, relu, dc);
-  bn_bwd_apply_kernel<T><<<ew_grid(N, C), 256, 0, st>>>((const T*)dy, (const T*)x, stats, gamma, beta, scratch, (T*)dx, N, (int)C, relu, training, dc);
+  // the parameter gradients take this replica's LOCAL sums (the gradient exchange adds the replicas later); the input
+  // gradient needs the sums over the whole batch
   bn_param_grad_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(scratch, dgamma, dbeta, (int)C);
+  if (training) MMER_TRY(bn_sync_call(sy, scratch, 2 * C, st));
+  bn_bwd_apply_kernel<T><<<ew_grid(N, C), 256, 0, st>>>((const T*)dy, (const T*)x, stats, gamma, beta, scratch, (T*)dx, N, training ? bn_rows(sy, N) : N, (int)C, relu, training, dc);
   MMER_LAUNCH_CHECK("bn_bwd");
   count_launch(2);
   return 0;
+}
+
+int bn_fwd_sync(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var, void* y,
+                float* stats_out, int64_t N, int64_t C, int dtype, int training, int relu, float momentum, float drop_p,
+                uint64_t seed, uint32_t site, cudaStream_t st, const BnSync* sy) {
+  MMER_CHECK_ARG(x && gamma && beta && y && stats_out, "bn_fwd: null pointer");
+  MMER_CHECK_ARG(C > 0 && C % 8 == 0, "bn_fwd: C must be a multiple of 8");
+  MMER_CHECK_ARG(training || (running_mean && running_var), "bn_fwd: eval mode needs running statistics");
+  if (N <= 0) return 0;
+  DropCfg dc = make_drop(drop_p, seed, site);
+  return dtype == MMER_BF16
+             ? bn_fwd_t<bf16>(x, gamma, beta, running_mean, running_var, y, stats_out, N, C, training, relu, momentum, dc, st, sy)
+             : bn_fwd_t<float>(x, gamma, beta, running_mean, running_var, y, stats_out, N, C, training, relu, momentum, dc, st, sy);
+}
+
+int bn_bwd_sync(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
+                float* dgamma, float* dbeta, float* scratch, int64_t N, int64_t C, int dtype, int training, int relu,
+                float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, const BnSync* sy) {
+  MMER_CHECK_ARG(dy && x && stats && gamma && beta && dx && scratch, "bn_bwd: null pointer");
+  MMER_CHECK_ARG(C > 0 && C % 8 == 0, "bn_bwd: C must be a multiple of 8");
+  if (N <= 0) return 0;
+  DropCfg dc = make_drop(drop_p, seed, site);
+  return dtype == MMER_BF16
+             ? bn_bwd_t<bf16>(dy, x, stats, gamma, beta, dx, dgamma, dbeta, scratch, N, C, relu, training, dc, st, sy)
+             : bn_bwd_t<float>(dy, x, stats, gamma, beta, dx, dgamma, dbeta, scratch, N, C, relu, training, dc, st, sy);
 }
 
 }  // namespace mmer
@@ -216,28 +259,15 @@ extern "C" {
 int mmer_bn_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var, void* y,
                 float* stats_out, int64_t N, int64_t C, int dtype, int training, int relu, float momentum,
                 float drop_p, uint64_t seed, uint32_t site, void* stream) {
-  MMER_CHECK_ARG(x && gamma && beta && y && stats_out, "bn_fwd: null pointer");
-  MMER_CHECK_ARG(C > 0 && C % 8 == 0, "bn_fwd: C must be a multiple of 8");
-  MMER_CHECK_ARG(training || (running_mean && running_var), "bn_fwd: eval mode needs running statistics");
-  if (N <= 0) return 0;
-  DropCfg dc = make_drop(drop_p, seed, site);
-  cudaStream_t st = (cudaStream_t)stream;
-  return dtype == MMER_BF16
-             ? bn_fwd_t<bf16>(x, gamma, beta, running_mean, running_var, y, stats_out, N, C, training, relu, momentum, dc, st)
-             : bn_fwd_t<float>(x, gamma, beta, running_mean, running_var, y, stats_out, N, C, training, relu, momentum, dc, st);
+  return bn_fwd_sync(x, gamma, beta, running_mean, running_var, y, stats_out, N, C, dtype, training, relu, momentum, drop_p,
+                     seed, site, (cudaStream_t)stream, nullptr);
 }
 
 int mmer_bn_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
                 float* dgamma, float* dbeta, float* scratch, int64_t N, int64_t C, int dtype, int training, int relu,
                 float drop_p, uint64_t seed, uint32_t site, void* stream) {
-  MMER_CHECK_ARG(dy && x && stats && gamma && beta && dx && scratch, "bn_bwd: null pointer");
-  MMER_CHECK_ARG(C > 0 && C % 8 == 0, "bn_bwd: C must be a multiple of 8");
-  if (N <= 0) return 0;
-  DropCfg dc = make_drop(drop_p, seed, site);
-  cudaStream_t st = (cudaStream_t)stream;
-  return dtype == MMER_BF16
-             ? bn_bwd_t<bf16>(dy, x, stats, gamma, beta, dx, dgamma, dbeta, scratch, N, C, relu, training, dc, st)
-             : bn_bwd_t<float>(dy, x, stats, gamma, beta, dx, dgamma, dbeta, scratch, N, C, relu, training, dc, st);
+  return bn_bwd_sync(dy, x, stats, gamma, beta, dx, dgamma, dbeta, scratch, N, C, dtype, training, relu, drop_p, seed, site,
+                     (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

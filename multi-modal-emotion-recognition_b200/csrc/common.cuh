@@ -75,6 +75,13 @@ inline cudaError_t launch_dep(void (*kern)(KA...), dim3 grid, dim3 block, size_t
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
 }
 
+// SyncBatchNorm hook (mmer_model.bn_sync / bn_sync_user / bn_world)
+struct BnSync {
+  int (*fn)(void* user, float* buf, int64_t n, void* stream);
+  void* user;
+  int world;
+};
+
 #define MMER_TRY(expr)            \
   do {                            \
     int _rc = (expr);             \

@@ -13,6 +13,12 @@ namespace mmer {
 
 int gemm_tc(const mmer_gemm_args& a, cudaStream_t st);
 int gemm_simt(const mmer_gemm_args& a, cudaStream_t st);
+int bn_fwd_sync(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var, void* y,
+                float* stats_out, int64_t N, int64_t C, int dtype, int training, int relu, float momentum, float drop_p,
+                uint64_t seed, uint32_t site, cudaStream_t st, const BnSync* sy);
+int bn_bwd_sync(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
+                float* dgamma, float* dbeta, float* scratch, int64_t N, int64_t C, int dtype, int training, int relu,
+                float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, const BnSync* sy);
 extern int g_debug[16];
 
 int gemm_dispatch(const mmer_gemm_args& a, cudaStream_t st) {
@@ -195,10 +201,12 @@ struct Dims {
   uint64_t seed;
   const uint8_t* mask;
   const int64_t* g;
+  BnSync sy;
   explicit Dims(const mmer_model* m)
       : B(m->B), T(m->T), S(m->T + 1), F(m->fused), Hd(m->hidden), FF(m->ffn), M((int64_t)m->B * (m->T + 1)),
         Mv((int64_t)m->B * m->T), dt(m->dtype), tr(m->training != 0), pf(tr ? m->p_fusion : 0.f),
-        pc(tr ? m->p_classifier : 0.f), seed(m->seed), mask(m->has_mask ? m->mask : nullptr), g(m->off_g) {}
+        pc(tr ? m->p_classifier : 0.f), seed(m->seed), mask(m->has_mask ? m->mask : nullptr), g(m->off_g),
+        sy{m->bn_sync, m->bn_sync_user, m->bn_world} {}
 };
 
 // CrossModalFusion.forward: projections -> token assembly -> encoder layers -> pooling (+ out_norm)
@@ -213,10 +221,10 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
                             P(m, g[MMER_G_NA_B]), P(m, g[MMER_G_POS]), w.x0, w.st_e, B, T, F, d.dt, d.pf, d.seed, 0, st));
   } else {
     float* bs = m->bn_state;
-    MMER_TRY(mmer_bn_fwd(w.pv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), bs, bs + F, w.pvn, w.st_bnv, Mv, F, d.dt, d.tr,
-                         0, 0.1f, 0.f, d.seed, 0, st));
-    MMER_TRY(mmer_bn_fwd(w.pa, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), bs + 2 * F, bs + 3 * F, w.pan, w.st_bna, B, F,
-                         d.dt, d.tr, 0, 0.1f, 0.f, d.seed, 0, st));
+    MMER_TRY(bn_fwd_sync(w.pv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), bs, bs + F, w.pvn, w.st_bnv, Mv, F, d.dt, d.tr,
+                         0, 0.1f, 0.f, d.seed, 0, st, &d.sy));
+    MMER_TRY(bn_fwd_sync(w.pa, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), bs + 2 * F, bs + 3 * F, w.pan, w.st_bna, B, F,
+                         d.dt, d.tr, 0, 0.1f, 0.f, d.seed, 0, st, &d.sy));
     MMER_TRY(mmer_embed_fwd(w.pvn, w.pan, nullptr, nullptr, nullptr, nullptr, P(m, g[MMER_G_POS]), w.x0, w.st_e, B, T, F,
                             d.dt, 0.f, d.seed, 0, st));
   }
@@ -265,8 +273,8 @@ static int head_forward(const mmer_model* m, Ws& w, const void* fused, cudaStrea
                                d.dt, st));
   } else {
     float* bs = m->bn_state + 4 * F;
-    MMER_TRY(mmer_bn_fwd(w.h1p, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), bs, bs + Hd, w.h1, w.st_fc, B, Hd, d.dt, d.tr,
-                         1, 0.1f, d.pc, d.seed, 200, st));
+    MMER_TRY(bn_fwd_sync(w.h1p, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), bs, bs + Hd, w.h1, w.st_fc, B, Hd, d.dt, d.tr,
+                         1, 0.1f, d.pc, d.seed, 200, st, &d.sy));
     MMER_TRY(mmer_head_out_fwd(w.h1, P(m, g[MMER_G_C8_W]), P(m, g[MMER_G_C8_B]), m->logits, m->probs, B, Hd, m->classes,
                                d.dt, st));
   }
@@ -306,8 +314,8 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
   } else {
     MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h1, P(m, g[MMER_G_C8_W]), w.g_h1, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
                                B, Hd, m->classes, d.dt, st));
-    MMER_TRY(mmer_bn_bwd(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
-                         G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st));
+    MMER_TRY(bn_bwd_sync(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
+                         G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st, &d.sy));
   }
   MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], m->variant == 2 ? -1 : g[MMER_G_C0_B], st));
   MMER_TRY(lin_dgrad(m, w.g_h1p, B, Hd, g[MMER_G_C0_W], F, w.g_fused, nullptr, nullptr, 0.f, st));
@@ -372,10 +380,10 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
   } else {
     MMER_TRY(mmer_embed_bwd(w.g_x, w.pvn, w.pan, w.st_e, nullptr, nullptr, w.g_pvn, w.g_pan, nullptr, nullptr, nullptr,
                             nullptr, G(m, g[MMER_G_POS]), nullptr, nullptr, B, T, F, d.dt, 0.f, d.seed, 0, st));
-    MMER_TRY(mmer_bn_bwd(w.g_pvn, w.pv, w.st_bnv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), w.g_pv, G(m, g[MMER_G_NV_W]),
-                         G(m, g[MMER_G_NV_B]), w.bn_scratch, Mv, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
-    MMER_TRY(mmer_bn_bwd(w.g_pan, w.pa, w.st_bna, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), w.g_pa, G(m, g[MMER_G_NA_W]),
-                         G(m, g[MMER_G_NA_B]), w.bn_scratch, B, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st));
+    MMER_TRY(bn_bwd_sync(w.g_pvn, w.pv, w.st_bnv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), w.g_pv, G(m, g[MMER_G_NV_W]),
+                         G(m, g[MMER_G_NV_B]), w.bn_scratch, Mv, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st, &d.sy));
+    MMER_TRY(bn_bwd_sync(w.g_pan, w.pa, w.st_bna, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), w.g_pa, G(m, g[MMER_G_NA_W]),
+                         G(m, g[MMER_G_NA_B]), w.bn_scratch, B, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st, &d.sy));
   }
   MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], m->variant == 2 ? -1 : g[MMER_G_BV], st));
   MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], m->variant == 2 ? -1 : g[MMER_G_BA], st));

@@ -264,6 +264,38 @@ class Engine:
             m.bn_state = self.ctx.bn_state.data_ptr()
         return m
 
+    def attach_bn_sync(self, m: Model, ws: torch.Tensor, owner, keep: list) -> None:
+        """SyncBatchNorm (train.py variant under data parallelism): when the owning module was built with
+        ``sync_batchnorm=True`` and a process group of more than one rank is up, every BatchNorm layer of the C engine
+        calls back here (on the host, while it enqueues its kernels) with a buffer of partial column sums inside the
+        workspace; the callback enqueues an in-place SUM all-reduce of that buffer on the current stream.  Nine tiny
+        all-reduces per training step (two per layer in forward, one in backward); none in eval mode."""
+        import torch.distributed as dist
+        if self.cfg["variant"] != 1 or not getattr(owner, "sync_batchnorm", False):
+            return
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        group = getattr(owner, "sync_group", None)
+        world = dist.get_world_size(group)
+        if world <= 1:
+            return
+        base, nbytes = ws.data_ptr(), ws.numel()
+
+        def cb(_user, buf, n, _stream):
+            try:
+                off = int(buf) - base
+                if off < 0 or off + 4 * n > nbytes:
+                    return -2
+                dist.all_reduce(ws[off:off + 4 * n].view(torch.float32), op=dist.ReduceOp.SUM, group=group)
+                return 0
+            except Exception:      # never unwind through the C frames
+                return -1
+
+        fn = _lib.BN_SYNC_FN(cb)
+        keep.append(fn)            # the ctypes thunk must outlive every call that may invoke it
+        m.bn_sync = C.cast(fn, C.c_void_p)
+        m.bn_world = world
+
     @staticmethod
     def workspace_bytes(m: Model) -> int:
         n = _lib.load().mmer_workspace_bytes(C.byref(m))
@@ -318,6 +350,8 @@ class ModelFn(torch.autograd.Function):
         ws = torch.empty(eng.workspace_bytes(m), device=dev, dtype=torch.uint8)
         m.workspace, m.workspace_bytes = ws.data_ptr(), ws.numel()
         keep = [ws]
+        if training:
+            eng.attach_bn_sync(m, ws, owner, keep)
         if stage != 2:
             v = video.detach().to(cdt).contiguous()
             a = audio.detach().to(cdt).contiguous()

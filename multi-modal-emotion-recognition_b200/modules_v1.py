@@ -103,10 +103,16 @@ class EmotionClassifier(nn.Module, _EngineOwner):
 class MultimodalEmotionModel(nn.Module, _EngineOwner):
     """train.py:133-142.  forward -> (probs, logits, attn_weights)."""
 
-    def __init__(self, video_dim=768, audio_dim=1024, fused_dim=512, num_classes=6, max_seq_len=101):
+    def __init__(self, video_dim=768, audio_dim=1024, fused_dim=512, num_classes=6, max_seq_len=101, *,
+                 sync_batchnorm: bool = False, sync_group=None):
+        """``sync_batchnorm`` (keyword-only, not in the reference signature): under ``torch.distributed`` the three
+        BatchNorm layers take their batch statistics over ALL replicas (equal shards), so that a data-parallel run
+        computes what the reference's single process computes on the global batch (train.py:66-74,125)."""
         super().__init__()
         self.fusion = CrossModalFusion(video_dim, audio_dim, fused_dim, dropout=0.01, max_seq_len=max_seq_len)
         self.classifier = EmotionClassifier(fused_dim, num_classes, dropout=0.01)
+        self.sync_batchnorm = bool(sync_batchnorm)
+        self.sync_group = sync_group
         self._init_owner()
 
     def _make_engine(self) -> Engine:

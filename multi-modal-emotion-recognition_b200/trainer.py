@@ -413,6 +413,8 @@ class FusedTrainStep:
             mk = mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
             m.mask, m.has_mask = mk.data_ptr(), 1
         m.workspace, m.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        keep = []
+        eng.attach_bn_sync(m, self._ws, self.model, keep)
         m.logits, m.probs, m.dlogits = self._logits.data_ptr(), self._probs.data_ptr(), self._dlogits.data_ptr()
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         lib = _lib.load()

@@ -103,7 +103,10 @@ def test_cfg2_full_size_training_step_matches_stock_fp32_reference_bf16(masked):
 
 
 def test_cfg2_full_size_fp32_mode_matches_stock_fp32_reference():
-    """The fp32 parity mode at the benchmarked size: 1e-4 on logits and loss, 1e-3 on every gradient tensor."""
+    """The fp32 parity mode at the benchmarked size: 1e-4 on logits and loss against the stock fp32 modules.  Gradients
+    are sums over 69,632 token rows, where two fp32 evaluations differ by their summation order (and a handful of ReLU
+    pre-activations that round to the other side of zero): the truth is the stock model in FLOAT64 on the same GPU,
+    and the product must be as close to it as the stock fp32 evaluation is (x3), and within 3e-3 per tensor."""
     B, T = 4096, 16
     model, ref = _pair(T, bf16=False)
     model.train()
@@ -113,19 +116,30 @@ def test_cfg2_full_size_fp32_mode_matches_stock_fp32_reference():
     _, lref = ref(video, audio, mask)
     loss_ref = E.focal_loss(lref, labels, 2.0, alpha)
     loss_ref.backward()
+    ref64 = E.EagerModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512, fusion_dropout=0.0,
+                         classifier_dropout=0.0).cuda().double().train()
+    ref64.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    _, l64 = ref64(video.double(), audio.double(), mask)
+    E.focal_loss(l64, labels, 2.0, alpha.double()).backward()
     probs, logits, _ = model(video, audio, mask=mask)
     loss = mm.FocalLoss(2.0, alpha)(logits, labels)
     loss.backward()
-    scale = float(lref.abs().max())
-    assert float((logits.detach() - lref.detach()).abs().max()) < 1e-4 * max(scale, 1.0)
+    scale = max(float(lref.detach().abs().max()), 1.0)
+    assert float((logits.detach() - lref.detach()).abs().max()) < 1e-4 * scale
+    assert float((logits.detach().double() - l64.detach()).abs().max()) < 1e-4 * scale
     assert abs(float(loss) - float(loss_ref)) < 1e-4 * float(loss_ref)
-    _argmax_equal_outside_ties(logits.detach(), lref.detach(), 1e-4 * max(scale, 1.0))
-    ref_grads = dict(ref.named_parameters())
+    _argmax_equal_outside_ties(logits.detach(), lref.detach(), 1e-4 * scale)
+    g32, g64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    worst = (0.0, 0.0, "")
     for k, p in model.named_parameters():
-        gr = ref_grads[k].grad
-        if float(gr.norm()) < 1e-7:
+        truth = g64[k].grad
+        if float(truth.norm()) < 1e-7:
             continue
-        assert float((p.grad - gr).norm() / gr.norm()) < 1e-3, k
+        ours = float((p.grad.double() - truth).norm() / truth.norm())
+        stock = float((g32[k].grad.double() - truth).norm() / truth.norm())
+        worst = max(worst, (ours, stock, k))
+        assert ours < 3e-3 and ours < 3 * stock + 1e-4, (k, ours, stock)
+    print(f"cfg2 fp32: worst gradient error vs float64 truth {worst[0]:.2e} (stock fp32: {worst[1]:.2e}) at {worst[2]}")
 
 
 def _attention_of_stock_model(ref, video, audio, mask):
@@ -267,6 +281,7 @@ def test_bf16_gradient_vs_storage_rounded_oracle():
     print(f"bf16 gradient: oracle-vs-oracle floor {floor:.4f}; GPU vs exact {d_exact:.4f}; GPU vs storage-rounded {d_round:.4f}")
     assert 0.02 < floor < 0.12
     assert d_exact < 1.25 * floor + 0.01
+    assert d_round < 1.25 * floor + 0.01      # measured: 0.065 vs a floor of 0.069 (closer to the emulation than the exact oracle is)
     assert d_round < 1.6 * floor + 0.01       # two independent realisations of the same flip noise: ~sqrt(2) x floor
     assert float((logits.detach().cpu().double() - l_round).abs().max()) < 2e-2 * float(l_exact.abs().max())
 
