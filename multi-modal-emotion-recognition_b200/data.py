@@ -190,6 +190,11 @@ class DeviceLoader:
     def __len__(self) -> int:
         return (len(self.indices) + self.batch_size - 1) // self.batch_size
 
+    @property
+    def dataset(self):
+        """``len(loader.dataset)`` as the reference's main() prints it (train2.py:956-960): the loader's sample indices."""
+        return self.indices
+
     def __iter__(self) -> Iterator:
         order = np.arange(len(self.indices))
         if self.shuffle:

@@ -11,7 +11,7 @@ path, both from the same initial weights and the same per-rank batches, and repo
                                   a 64-bit checksum AND by broadcasting rank 0's buffer),
 * ``max_abs_vs_nccl``             largest weight difference between the two exchanges, next to ``max_abs_moved`` (how far
                                   the step moved the weights): only the summation order of the gradients differs,
-* ``shadow_equals_bf16_weights``  the bf16 shadow the next forward reads equals bf16(fp32 weights) on this rank,
+* ``shadow_equals_bf16_weights``  (bf16 compute) the bf16 shadow the next forward reads equals bf16(fp32 weights),
 * ``checksums``                   the per-rank checksums themselves.
 
 Adam runs with eps = 1 here so that the update is a smooth function of the gradient: with 1e-8 the first step is
@@ -76,7 +76,7 @@ def dp_selfcheck(dev, group=None, samples: int = 512, frames: int = 16, dtype: t
     same = torch.tensor([int(torch.equal(ref, pa))], device=dev)
     dist.all_reduce(same, op=dist.ReduceOp.MIN, group=group)
     stats = torch.tensor([float((pa - pb).abs().max()), float((pa - p0).abs().max()),
-                          0.0 if (sa is None or torch.equal(sa, pa.bfloat16())) else 1.0, abs(loss_a - loss_b)],
+                          0.0 if (sa is None or dtype != torch.bfloat16 or torch.equal(sa, pa.bfloat16())) else 1.0, abs(loss_a - loss_b)],
                          device=dev, dtype=torch.float64)
     dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=group)
     checks = [int(x) for x in sums.tolist()]

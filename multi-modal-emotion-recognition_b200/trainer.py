@@ -433,6 +433,10 @@ class FusedTrainStep:
                 self._overlapped = OverlappedAllReduce(ctx, self.engine.cfg["layers"], video.device, self.group)
             self._overlapped.attach(m)
         _lib.check(lib.mmer_model_backward(C.byref(m), stream), "mmer_model_backward")
+        if self.engine.cfg["variant"] == 1:
+            # BatchNorm bookkeeping of a training-mode forward (train.py:66-74,125): the module path does this in forward()
+            self.model.fusion._count_batches()
+            self.model.classifier.bn_fc1.num_batches_tracked += 1
         if nvls:
             self._nvls_adam(stream)
             return self._loss, self._probs
