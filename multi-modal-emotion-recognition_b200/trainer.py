@@ -320,6 +320,7 @@ class FusedTrainStep:
                 self.opt._shard = (lo, hi, process_group)
         self._key = None
         self._ws = None
+        self._trace = None      # measure_barrier_wait: list of CUDA events around the synchronisation points
         self.launch_count = 0
 
     @property
@@ -358,23 +359,77 @@ class FusedTrainStep:
         p_mc, g_mc, s_mc, slots_mc = ctx.multicast_ptrs()
         use_shadow = ctx.shadow is not None and self.compute_dtype == torch.bfloat16
         lib = _lib.load()
+        tr = self._trace
+        mark = (lambda: tr.append(self._mark())) if tr is not None else (lambda: None)
+        mark()                              # [0] backward finished on this rank
         ctx.sym_hdl.barrier(channel=0)      # every rank's backward has finished: all gradients are complete
+        mark()                              # [1]
         slots, max_norm = None, 0.0
         if opt.max_grad_norm is not None:   # clip_grad_norm_ on the reduced gradient (train2.py:576)
             _lib.check(lib.mmer_grad_sumsq_multicast(C.c_void_p(g_mc), lo, hi, opt._sumsq.data_ptr(), C.c_void_p(slots_mc),
                                                      rank, stream), "mmer_grad_sumsq_multicast")
             ctx.sym_hdl.barrier(channel=0)  # every rank's partial sum has landed in everybody's slot array
             slots, max_norm = ctx.sym_slots.data_ptr(), float(opt.max_grad_norm)
+        mark()                              # [2]
         _lib.check(lib.mmer_adam_step_multicast(
             ctx.flat.data_ptr(), C.c_void_p(p_mc), C.c_void_p(g_mc), m_sh.data_ptr(), v_sh.data_ptr(),
             C.c_void_p(s_mc) if use_shadow else None, lo, hi, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
             float(g["eps"]), float(g["weight_decay"]), opt._step, 1.0 / self.world, slots, self.world, max_norm, stream),
             "mmer_adam_step_multicast")
+        mark()                              # [3]
         ctx.sym_hdl.barrier(channel=1)      # every rank's shard has landed everywhere: weights are complete
+        mark()                              # [4]
         if use_shadow:
             ctx.mark_shadow_written()
         else:
             ctx.invalidate_shadow()
+
+    @staticmethod
+    def _mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    @torch.no_grad()
+    def measure_barrier_wait(self, video, audio, mask, labels, steps: int = 10) -> dict:
+        """Where a data-parallel step waits (collective; every rank calls it): ``steps`` training steps with CUDA events
+        around the cross-rank synchronisation points, averaged per rank and gathered.  In the multicast mode:
+        ``pre_barrier_ms`` = wait until EVERY rank has finished backward (rank skew + barrier latency),
+        ``clip_ms`` = norm exchange (when clipping), ``adam_ms`` = the reduce-scatter + Adam + all-gather kernel,
+        ``post_barrier_ms`` = wait until every rank's shard has landed.  In the NCCL mode: ``exchange_ms`` = from the end
+        of backward to the start of Adam (the part of the bucketed all-reduce that backward did not hide)."""
+        names = ["pre_barrier_ms", "clip_ms", "adam_ms", "post_barrier_ms"]
+        acc = [0.0] * 4
+        step_ms = 0.0
+        for _ in range(steps):
+            self._trace = []
+            e0 = self._mark()
+            self.step(video, audio, mask, labels)
+            e1 = self._mark()
+            torch.cuda.synchronize()
+            tr, self._trace = self._trace, None
+            step_ms += e0.elapsed_time(e1)
+            if len(tr) == 5:
+                for i in range(4):
+                    acc[i] += tr[i].elapsed_time(tr[i + 1])
+            elif len(tr) == 2:
+                acc[0] += tr[0].elapsed_time(tr[1])
+        mine = [a / steps for a in acc] + [step_ms / steps]
+        out = {"mode": self.dp_mode, "steps": steps}
+        if self.world > 1:
+            t = torch.tensor(mine, device=video.device, dtype=torch.float32)
+            allv = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(allv, t, group=self.group)
+            rows = [[round(float(x), 4) for x in r.tolist()] for r in allv]
+        else:
+            rows = [[round(x, 4) for x in mine]]
+        keys = (names if self.dp_mode == "nvls" else ["exchange_ms", "_", "_", "_"]) + ["step_ms"]
+        for i, k in enumerate(keys):
+            if k != "_":
+                out[k + "_per_rank"] = [r[i] for r in rows]
+        waits = [r[0] + (r[3] if self.dp_mode == "nvls" else 0.0) for r in rows]
+        out["wait_ms_mean"], out["wait_ms_max"] = sum(waits) / len(waits), max(waits)
+        return out
 
     @torch.no_grad()
     def step(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor], labels: torch.Tensor):
@@ -440,9 +495,13 @@ class FusedTrainStep:
         if nvls:
             self._nvls_adam(stream)
             return self._loss, self._probs
+        if self._trace is not None:
+            self._trace.append(self._mark())
         if self.world > 1 and self.overlap:
             scale = self._overlapped.reduce()
         else:
             scale = allreduce_flat_gradients(ctx.grads, self.group) if self.world > 1 else 1.0
+        if self._trace is not None:
+            self._trace.append(self._mark())
         self.opt.step(grad_scale=scale)
         return self._loss, self._probs

@@ -76,3 +76,60 @@ def focal_loss(logits, targets, gamma=2.0, alpha=None):
     if alpha is not None:
         fl = alpha[targets] * fl
     return fl.mean()
+
+
+# ------------------------------------------------------------------------------------------------ train.py variant
+class EagerFusionV1(nn.Module):
+    """train.py:47-106 on stock modules: Linear -> BatchNorm1d over (B*T) -> +pos_embed -> 4-layer post-norm encoder ->
+    masked mean pooling (AdaptiveAvgPool1d without a mask)."""
+
+    def __init__(self, video_dim=768, audio_dim=1024, fused_dim=512, num_layers=4, num_heads=8, dropout=0.01, max_seq_len=101):
+        super().__init__()
+        self.video_proj = nn.Linear(video_dim, fused_dim)            # train.py:49
+        self.audio_proj = nn.Linear(audio_dim, fused_dim)            # train.py:50
+        self.bn_video = nn.BatchNorm1d(fused_dim)                    # train.py:51
+        self.bn_audio = nn.BatchNorm1d(fused_dim)                    # train.py:52
+        self.pos_embed = nn.Parameter(torch.randn(1, max_seq_len, fused_dim))           # train.py:53
+        layer = nn.TransformerEncoderLayer(d_model=fused_dim, nhead=num_heads, dim_feedforward=2048, dropout=dropout)
+        self.transformer = nn.TransformerEncoder(layer, num_layers=num_layers)          # train.py:54-57
+        self.pool = nn.AdaptiveAvgPool1d(1)                          # train.py:58
+
+    def forward(self, video_feats, audio_feats, mask=None):
+        b, t, _ = video_feats.shape
+        video = self.bn_video(self.video_proj(video_feats).transpose(1, 2)).transpose(1, 2)              # train.py:66-69
+        audio = self.bn_audio(self.audio_proj(audio_feats.unsqueeze(1)).transpose(1, 2)).transpose(1, 2)  # train.py:71-74
+        x = torch.cat([video, audio], dim=1) + self.pos_embed[:, :t + 1, :]                              # train.py:76-77
+        full = None
+        if mask is not None:
+            full = torch.cat([mask, torch.zeros(b, 1, dtype=torch.bool, device=mask.device)], dim=1)    # train.py:80-82
+        x = self.transformer(x.transpose(0, 1), src_key_padding_mask=full).transpose(0, 1)               # train.py:86-96
+        if full is not None:
+            keep = (~full).float().unsqueeze(-1)
+            return (x * keep).sum(1) / keep.sum(1).clamp(min=1e-6)                                       # train.py:100-102
+        return self.pool(x.transpose(1, 2)).squeeze(-1)                                                  # train.py:104
+
+
+class EagerClassifierV1(nn.Module):
+    def __init__(self, input_dim=512, num_classes=6, dropout=0.01):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim, input_dim // 2)             # train.py:115
+        self.bn_fc1 = nn.BatchNorm1d(input_dim // 2)                # train.py:116
+        self.dropout1 = nn.Dropout(dropout)
+        self.fc2 = nn.Linear(input_dim // 2, num_classes)           # train.py:118
+        self.dropout2 = nn.Dropout(dropout)                         # (unused by forward, present in the state-less tree)
+
+    def forward(self, fused):
+        logits = self.fc2(self.dropout1(F.relu(self.bn_fc1(self.fc1(fused)))))         # train.py:124-128
+        return F.softmax(logits, dim=-1), logits                    # train.py:129-130
+
+
+class EagerModelV1(nn.Module):
+    """train.py:133-142; state_dict keys equal the reference's (tests/test_oracle_golden.py pins it on the v1 goldens)."""
+
+    def __init__(self, video_dim=768, audio_dim=1024, fused_dim=512, num_classes=6, max_seq_len=101, dropout=0.01):
+        super().__init__()
+        self.fusion = EagerFusionV1(video_dim, audio_dim, fused_dim, dropout=dropout, max_seq_len=max_seq_len)
+        self.classifier = EagerClassifierV1(fused_dim, num_classes, dropout=dropout)
+
+    def forward(self, video_feats, audio_feats, mask=None):
+        return self.classifier(self.fusion(video_feats, audio_feats, mask))

@@ -183,6 +183,29 @@ def test_stock_torch_restatement_matches_reference_golden():
         np.testing.assert_allclose(float(lf), float(g["loss/focal_alpha"]), rtol=1e-4)
 
 
+def test_stock_torch_restatement_of_train_py_matches_reference_golden():
+    """oracle/eager_torch.py::EagerModelV1 (train.py's BatchNorm model on stock torch.nn; bench.py's cfg1 CPU leg)
+    reproduces the reference's golden logits in eval and train mode, its loss and its BatchNorm running statistics."""
+    from oracle import eager_torch as E
+    for name in ("v1_b8_t5_mask", "v1_b32_t16_cfg1"):
+        g, P, video, audio, mask, labels = load_case(name, "v1")
+        T = video.shape[1]
+        model = E.EagerModelV1(max_seq_len=T + 1, dropout=0.0)
+        model.load_state_dict(P, strict=True)
+        model.eval()
+        with torch.no_grad():
+            probs, logits = model(video, audio, mask)
+        np.testing.assert_allclose(logits.numpy(), g["eval/logits"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(probs.numpy(), g["eval/probs"], rtol=2e-4, atol=1e-6)
+        model.train()
+        probs, logits = model(video, audio, mask)
+        np.testing.assert_allclose(logits.detach().numpy(), g["train/logits"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(float(E.focal_loss(logits, labels, 2.0, None)), float(g["loss/focal"]), rtol=1e-4)
+        for k, val in model.state_dict().items():
+            if "running" in k:
+                np.testing.assert_allclose(val.numpy(), g["bn_after_fwd/" + k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
 # ---------------------------------------------------------------- Integrated Gradients (train2.py:776-866)
 def _ig_case():
     from oracle import ig_oracle
