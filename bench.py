@@ -689,11 +689,13 @@ def run_ours(args):
             out["dp_wait"] = dp_wait
         out["roofline"] = time_dominant_kernel(dev, pk)
         if world == 1:
-            out["sustained"] = sustained_leg(step, dev_v, dev_a, dev_y, NBUF, local, pk)
-            out["cfg4"] = bench_cfg4(dev, pk)
-            out["cfg5"] = bench_cfg5(dev, pk)
             out["roofline_other_gemms"] = time_other_gemms(dev, pk)
             out["roofline_hbm_kernels"] = time_memory_bound_kernels(dev, pk)
+            out["cfg4"] = bench_cfg4(dev, pk)
+            out["cfg5"] = bench_cfg5(dev, pk)
+            # last of the GPU legs: it leaves the GPU in its power-capped steady state (clocks ~1.5 GHz), which would
+            # slow the issue-bound kernels timed alone above
+            out["sustained"] = sustained_leg(step, dev_v, dev_a, dev_y, NBUF, local, pk)
             try:
                 out["torch_eager_gpu"] = {"bf16": torch_eager_gpu_rate(dev, torch.bfloat16),
                                           "fp32": torch_eager_gpu_rate(dev, torch.float32)}

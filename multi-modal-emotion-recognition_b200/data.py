@@ -197,9 +197,12 @@ class DeviceLoader:
 
     def __iter__(self) -> Iterator:
         order = np.arange(len(self.indices))
+        # every DataLoader iterator -- shuffled or not -- first draws its workers' base seed from the global RNG
+        # (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__); the validation and test passes of an epoch
+        # therefore advance the RNG that the NEXT epoch's training shuffle draws from (train2.py:564, 596, 658)
+        torch.empty((), dtype=torch.int64).random_()
         if self.shuffle:
-            # DataLoader.__iter__ first draws its workers' base seed from the global RNG, then RandomSampler its own seed
-            torch.empty((), dtype=torch.int64).random_()
+            # ... then RandomSampler its own seed
             seed = int(torch.empty((), dtype=torch.int64).random_().item())
             g = torch.Generator()
             g.manual_seed(seed)

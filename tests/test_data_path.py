@@ -73,6 +73,14 @@ def test_loader_shuffle_order_is_the_random_samplers():
     got = list(DeviceLoader(Recorder(), indices, 4, True, torch.float32))
     assert got == ref and len(got) == 3 and len(got[-1]) == 3
     assert list(DeviceLoader(Recorder(), indices, 4, False, torch.float32)) == [indices[0:4], indices[4:8], indices[8:]]
+    # an UNSHUFFLED pass also advances the global RNG exactly like a DataLoader pass (its iterator draws a base seed),
+    # so that the next epoch's shuffle matches the reference's (train2.py:564-667: train, val, test passes per epoch)
+    torch.manual_seed(7)
+    list(torch.utils.data.DataLoader(indices, batch_size=4, shuffle=False))
+    ref2 = [b.tolist() for b in torch.utils.data.DataLoader(indices, batch_size=4, shuffle=True)]
+    torch.manual_seed(7)
+    list(DeviceLoader(Recorder(), indices, 4, False, torch.float32))
+    assert list(DeviceLoader(Recorder(), indices, 4, True, torch.float32)) == ref2
 
 
 # ------------------------------------------------------------------------------------------------ GPU

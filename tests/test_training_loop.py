@@ -107,7 +107,8 @@ def test_host_batch_stager_delivers_every_batch_in_order_and_feeds_the_step():
 
     direct = losses([(v.cuda(), a.cuda(), None if m is None else m.cuda(), y.cuda()) for v, a, m, y in batches])
     staged = losses(mm.HostBatchStager("cuda", depth=2).pipeline(batches))
-    assert direct == staged                                         # same bits: staging changes nothing but where the data waits
+    # staging changes nothing but where the data waits (split-K fp32 atomics make two runs differ in the last bit)
+    np.testing.assert_allclose(staged, direct, rtol=1e-5)
 
 
 @pytest.mark.gpu
