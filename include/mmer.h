@@ -58,6 +58,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_NO_PDL 8      /* launch every kernel fully serialised (no programmatic dependent launch); A/B timing */
 #define MMER_DEBUG_RESERVE_SMS 9 /* size every persistent grid for (SMs - value): room for an NCCL kernel beside the step */
 #define MMER_DEBUG_FORCE_SPLITS 10 /* tcgen05 GEMM, accumulate mode: force the split-K factor; A/B timing */
+#define MMER_DEBUG_NO_LN_FUSE 11 /* engine: GEMM + separate add_ln kernels instead of the fused GEMM+LayerNorm kernel; A/B timing */
 #define MMER_DEBUG_ATT_SIMT 4    /* bf16 short-sequence attention: use the FMA kernels instead of the MMA ones (A/B timing) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);
@@ -137,6 +138,21 @@ int mmer_add_ln_bwd(const void* dy, const void* x, const void* a, const float* s
                     const float* beta, void* dz, void* da, float* dgamma, float* dbeta, float* dbias,
                     int64_t M, int64_t F, int dtype, int relu, float drop_a_p, uint32_t site_a,
                     float drop_y_p, uint32_t site_y, uint64_t seed, void* stream);
+/* The same backward after the FUSED forward below: `z` is the stored pre-LayerNorm sum x + dropout(sub-layer output)
+ * (what mmer_gemm_ln_fwd writes), so x and the sub-layer output are not re-read; the dropout mask (drop_a_p, site_a,
+ * seed) is regenerated only for da = dz o mask.  da may be NULL when drop_a_p == 0 (then da == dz). */
+int mmer_add_ln_bwd_z(const void* dy, const void* z, const float* stats, const float* gamma, void* dz, void* da,
+                      float* dgamma, float* dbeta, float* dbias, int64_t M, int64_t F, int dtype, float drop_a_p,
+                      uint32_t site_a, uint64_t seed, void* stream);
+/* Post-norm encoder sub-layer tail in ONE tcgen05 kernel (train2.py:111-118 -> nn.TransformerEncoderLayer,
+ * norm_first=False: `x = norm1(x + dropout1(sa_block(x)))`, `x = norm2(x + dropout2(ff_block(x)))`):
+ *   z = residual + dropout(a[M,K] . w[512,K]^T + bias)      y = LayerNorm(z) * gamma + beta      (bf16, N = 512)
+ * z_out [M,512] bf16 (input of mmer_add_ln_bwd_z), y_out [M,512] bf16, stats [M,2] fp32 (mean, rstd).  residual may be
+ * NULL.  y is computed from the bf16-rounded z, i.e. from exactly what backward reads.  Dropout mask = the counter hash
+ * of (seed, site, row * 512 + col), the same one mmer_add_ln_fwd / _bwd use. */
+int mmer_gemm_ln_fwd(const void* a, const void* w, const float* bias, const void* residual, const float* gamma,
+                     const float* beta, void* z_out, void* y_out, float* stats, int64_t M, int64_t K, float drop_p,
+                     uint32_t site, uint64_t seed, void* stream);
 
 /* Masked mean pooling over the S tokens of each sample + out_norm (train2.py:184-191;
  * train.py:100-104 without the norm: gamma == NULL).  mask [B,T] bytes, 1 = padded, or NULL. */

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmmer_sm100.so")
-SOURCES = ["api", "gemm_tc", "gemm_simt", "rowops", "attention", "attention_fwd_bf16", "attention_fwd_f32", "attention_bwd_bf16",
+SOURCES = ["api", "gemm_tc", "gemm_ln", "gemm_simt", "rowops", "attention", "attention_fwd_bf16", "attention_fwd_f32", "attention_bwd_bf16",
            "attention_bwd_f32", "attention_generic", "attention_mma", "attention_long", "ln_pipe", "loss_head", "optim", "bn", "attribution", "batch", "evalops",
            "engine"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -27,7 +27,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "attention_small.cuh"), os.path.join(CSRC, "ptx.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "attention_small.cuh"), os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "tc05.cuh"),
                os.path.join(HERE, "..", "include", "mmer.h")]
     jobs = []
     for s in SOURCES:

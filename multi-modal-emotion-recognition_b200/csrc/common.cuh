@@ -82,6 +82,17 @@ struct BnSync {
   int world;
 };
 
+// cudaFuncSetAttribute is a per-DEVICE setting: a per-kernel bit mask of the devices already configured (the Python layer
+// binds a process to one GPU, this keeps a raw C caller on several GPUs correct too)
+inline bool needs_func_attr(unsigned long long* done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done_mask & bit) return false;
+  *done_mask |= bit;
+  return true;
+}
+
 #define MMER_TRY(expr)            \
   do {                            \
     int _rc = (expr);             \

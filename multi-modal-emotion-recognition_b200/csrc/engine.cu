@@ -19,7 +19,18 @@ int bn_fwd_sync(const void* x, const float* gamma, const float* beta, float* run
 int bn_bwd_sync(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
                 float* dgamma, float* dbeta, float* scratch, int64_t N, int64_t C, int dtype, int training, int relu,
                 float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, const BnSync* sy);
+int gemm_ln_fwd(const void* A, const void* W, const float* bias, const void* residual, const float* gamma, const float* beta,
+                void* z_out, void* y_out, float* stats, long long M, long long K, DropCfg drop, cudaStream_t st);
 extern int g_debug[16];
+
+// Post-norm sub-layer tails (out_proj -> norm1, linear2 -> norm2) as ONE tcgen05 kernel (gemm_ln.cu) instead of a GEMM
+// plus add_ln_fwd: bf16, d_model = 512, at least one 256-row block.  Forward then stores z = x + dropout(sub-layer)
+// where the unfused path stores the sub-layer output, and backward reads it through mmer_add_ln_bwd_z; both directions
+// take this decision from the same (dtype, dims), so a forward / backward pair always agrees.
+static bool fuse_ln(const mmer_model* m) {
+  return m->dtype == MMER_BF16 && m->fused == 512 && m->ffn % 64 == 0 && (int64_t)m->B * (m->T + 1) >= 256 &&
+         g_debug[MMER_DEBUG_NO_LN_FUSE] == 0;
+}
 
 int gemm_dispatch(const mmer_gemm_args& a, cudaStream_t st) {
   if (a.in_dtype == MMER_BF16) return gemm_tc(a, st);
@@ -237,14 +248,24 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
     float* probs = m->attn_probs ? m->attn_probs + (int64_t)l * B * m->heads * SS : nullptr;
     MMER_TRY(mmer_mha_fwd(L.qkv, d.mask, L.att, probs, B, T, m->heads, F / m->heads, d.dt, d.pf, d.seed,
                           site_layer(l, 0), st));
-    MMER_TRY(lin_fwd(m, L.att, M, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], L.ao, F, 0, 0.f, 0, st));
-    MMER_TRY(mmer_add_ln_fwd(x, L.ao, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]), L.x1, L.st1, M, F, d.dt, 0, d.pf,
-                             site_layer(l, 1), 0.f, 0, d.seed, st));
+    if (fuse_ln(m)) {   // L.ao / L.f2 hold z1 / z2 (pre-LayerNorm sums) on this path
+      MMER_TRY(gemm_ln_fwd(L.att, Wt(m, o[MMER_L_OUT_W]), P(m, o[MMER_L_OUT_B]), x, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]),
+                           L.ao, L.x1, L.st1, M, F, make_drop(d.pf, d.seed, site_layer(l, 1)), st));
+    } else {
+      MMER_TRY(lin_fwd(m, L.att, M, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], L.ao, F, 0, 0.f, 0, st));
+      MMER_TRY(mmer_add_ln_fwd(x, L.ao, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]), L.x1, L.st1, M, F, d.dt, 0, d.pf,
+                               site_layer(l, 1), 0.f, 0, d.seed, st));
+    }
     MMER_TRY(lin_fwd(m, L.x1, M, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], L.h, FF, 1, d.pf, site_layer(l, 2), st,
                      d.tr ? L.hmask : nullptr));
-    MMER_TRY(lin_fwd(m, L.h, M, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], L.f2, F, 0, 0.f, 0, st));
-    MMER_TRY(mmer_add_ln_fwd(L.x1, L.f2, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]), L.x2, L.st2, M, F, d.dt, 0, d.pf,
-                             site_layer(l, 3), 0.f, 0, d.seed, st));
+    if (fuse_ln(m)) {
+      MMER_TRY(gemm_ln_fwd(L.h, Wt(m, o[MMER_L_FF2_W]), P(m, o[MMER_L_FF2_B]), L.x1, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]),
+                           L.f2, L.x2, L.st2, M, FF, make_drop(d.pf, d.seed, site_layer(l, 3)), st));
+    } else {
+      MMER_TRY(lin_fwd(m, L.h, M, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], L.f2, F, 0, 0.f, 0, st));
+      MMER_TRY(mmer_add_ln_fwd(L.x1, L.f2, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]), L.x2, L.st2, M, F, d.dt, 0, d.pf,
+                               site_layer(l, 3), 0.f, 0, d.seed, st));
+    }
     x = L.x2;
   }
   MMER_TRY(mmer_pool_ln_fwd(x, d.mask, m->variant == 2 ? P(m, g[MMER_G_ON_W]) : nullptr,
@@ -345,9 +366,15 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     const void* xin = l == 0 ? w.x0 : w.L[l - 1].x2;
     // norm2 <- linear2
     void* d_f2 = pf > 0.f ? w.g_f2 : w.g_z2;
-    MMER_TRY(mmer_add_ln_bwd(w.g_x, L.x1, L.f2, L.st2, P(m, o[MMER_L_N2_W]), nullptr, w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
-                             G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, 0, pf,
-                             site_layer(l, 3), 0.f, 0, d.seed, st));
+    if (fuse_ln(m)) {
+      MMER_TRY(mmer_add_ln_bwd_z(w.g_x, L.f2, L.st2, P(m, o[MMER_L_N2_W]), w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
+                                 G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, pf,
+                                 site_layer(l, 3), d.seed, st));
+    } else {
+      MMER_TRY(mmer_add_ln_bwd(w.g_x, L.x1, L.f2, L.st2, P(m, o[MMER_L_N2_W]), nullptr, w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
+                               G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, 0, pf,
+                               site_layer(l, 3), 0.f, 0, d.seed, st));
+    }
     MMER_TRY(lin_wgrad(m, d_f2, L.h, M, F, FF, o[MMER_L_FF2_W], -1, st));
     // through ReLU (+ its dropout): gate on the stored post-activation.  No gradient tensor is re-read for a bias
     // gradient: add_ln_bwd, mha_bwd and embed_bwd sum the columns of what they store while it is on chip; for linear1
@@ -360,9 +387,15 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
     // norm1 <- attention
     void* d_ao = pf > 0.f ? w.g_ao : w.g_z1;
-    MMER_TRY(mmer_add_ln_bwd(w.g_x1, xin, L.ao, L.st1, P(m, o[MMER_L_N1_W]), nullptr, w.g_z1, pf > 0.f ? w.g_ao : nullptr,
-                             G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, 0, pf,
-                             site_layer(l, 1), 0.f, 0, d.seed, st));
+    if (fuse_ln(m)) {
+      MMER_TRY(mmer_add_ln_bwd_z(w.g_x1, L.ao, L.st1, P(m, o[MMER_L_N1_W]), w.g_z1, pf > 0.f ? w.g_ao : nullptr,
+                                 G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, pf,
+                                 site_layer(l, 1), d.seed, st));
+    } else {
+      MMER_TRY(mmer_add_ln_bwd(w.g_x1, xin, L.ao, L.st1, P(m, o[MMER_L_N1_W]), nullptr, w.g_z1, pf > 0.f ? w.g_ao : nullptr,
+                               G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, 0, pf,
+                               site_layer(l, 1), 0.f, 0, d.seed, st));
+    }
     MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], -1, st));
     MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
     MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf,

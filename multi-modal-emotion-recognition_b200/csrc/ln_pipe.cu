@@ -108,7 +108,7 @@ __device__ __forceinline__ LnSmem lnp_setup(const LnPipeGeom& g, uint8_t* smem) 
 // ---------------------------------------------------------------------------------------------------------
 // MODE < 0: every option decided at run time.  MODE >= 0: a bit set fixed at compile time (LNM_*), which strips the
 // predicated code of the unused options from the per-row loop of the hot instances (encoder sub-layers).
-enum : int { LNM_X = 1, LNM_RELU = 2, LNM_DROP_A = 4, LNM_DROP_Y = 8, LNM_DBIAS = 16 };
+enum : int { LNM_X = 1, LNM_RELU = 2, LNM_DROP_A = 4, LNM_DROP_Y = 8, LNM_DBIAS = 16, LNM_ZIN = 32 };
 
 template <typename T, int NCH, int MODE>
 __global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
@@ -223,8 +223,11 @@ __global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
 add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const T* __restrict__ x,
                        const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                        T* __restrict__ dz, T* __restrict__ dap, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       float* __restrict__ dbias, LnPipeGeom g, int relu_rt, DropCfg da, DropCfg dy) {
+                       float* __restrict__ dbias, LnPipeGeom g, int relu_rt, DropCfg da, DropCfg dy, int zin_rt) {
   extern __shared__ __align__(128) uint8_t smem[];
+  // zin: `a` already holds z = x + dropout(sub-layer output) (written by the fused GEMM + LayerNorm forward, gemm_ln.cu);
+  // the dropout factors are then needed only for da = dz o mask
+  const bool zin = MODE < 0 ? zin_rt != 0 : (MODE & LNM_ZIN) != 0;
   const bool has_x = MODE < 0 ? g.narr > 2 : (MODE & LNM_X) != 0;
   const bool relu = MODE < 0 ? relu_rt != 0 : (MODE & LNM_RELU) != 0;
   const bool drop_a = MODE < 0 ? da.thr != 0 : (MODE & LNM_DROP_A) != 0;
@@ -281,8 +284,10 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
             load8(sa + c, z);
             if (drop_a) {
               drop8(da, (uint64_t)off, fa[i]);
+              if (!zin) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) z[j] *= fa[i][j];
+                for (int j = 0; j < 8; ++j) z[j] *= fa[i][j];
+              }
             }
             if (has_x) {
               float xv[8];
@@ -421,12 +426,12 @@ static int fwd_launch(const void* x, const void* a, const float* gamma, const fl
 template <typename T, int NCH, int MODE>
 static int bwd_launch_mode(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
                            const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias,
-                           const LnPipeGeom& g, size_t smem, int relu, DropCfg da, DropCfg ddy, cudaStream_t st) {
+                           const LnPipeGeom& g, size_t smem, int relu, DropCfg da, DropCfg ddy, cudaStream_t st, int zin) {
   static size_t configured = 0;
   auto kern = add_ln_bwd_pipe_kernel<T, NCH, MODE>;
   MMER_TRY(lnp_set_smem(kern, smem, &configured));
   cudaError_t e = launch_dep(kern, dim3(lnp_grid(g)), dim3((g.W + 1) * 32), smem, st, 1, (const T*)dy, (const T*)a, (const T*)x,
-                             stats, gamma, beta, (T*)dz, (T*)dap, dgamma, dbeta, dbias, g, relu, da, ddy);
+                             stats, gamma, beta, (T*)dz, (T*)dap, dgamma, dbeta, dbias, g, relu, da, ddy, zin);
   if (e != cudaSuccess) return cuda_fail(e, "launch(add_ln_bwd_pipe)");
   MMER_LAUNCH_CHECK("add_ln_bwd_pipe_kernel");
   return 0;
@@ -434,21 +439,27 @@ static int bwd_launch_mode(const void* dy, const void* x, const void* a, const f
 template <typename T, int NCH>
 static int bwd_launch(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
                       const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias, long long M,
-                      long long F, int relu, DropCfg da, DropCfg ddy, cudaStream_t st) {
+                      long long F, int relu, DropCfg da, DropCfg ddy, cudaStream_t st, int zin) {
   LnPipeGeom g;
   size_t smem;
   MMER_TRY(lnp_geometry(M, F, sizeof(T), x ? 3 : 2, &g, &smem));
   if (NCH == 2 && sizeof(T) == 2) {
     const int mode = (x ? LNM_X : 0) | (relu ? LNM_RELU : 0) | (da.thr ? LNM_DROP_A : 0) | (ddy.thr ? LNM_DROP_Y : 0) |
-                     (dbias ? LNM_DBIAS : 0);
+                     (dbias ? LNM_DBIAS : 0) | (zin ? LNM_ZIN : 0);
     if (mode == (LNM_X | LNM_DROP_A | LNM_DBIAS))
       return bwd_launch_mode<T, NCH, LNM_X | LNM_DROP_A | LNM_DBIAS>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta,
-                                                                      dbias, g, smem, relu, da, ddy, st);
+                                                                      dbias, g, smem, relu, da, ddy, st, zin);
     if (mode == (LNM_X | LNM_DBIAS))
       return bwd_launch_mode<T, NCH, LNM_X | LNM_DBIAS>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, g, smem,
-                                                         relu, da, ddy, st);
+                                                         relu, da, ddy, st, zin);
+    if (mode == (LNM_ZIN | LNM_DROP_A | LNM_DBIAS))   // after the fused GEMM + LayerNorm forward (training step)
+      return bwd_launch_mode<T, NCH, LNM_ZIN | LNM_DROP_A | LNM_DBIAS>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta,
+                                                                        dbias, g, smem, relu, da, ddy, st, zin);
+    if (mode == (LNM_ZIN | LNM_DBIAS))
+      return bwd_launch_mode<T, NCH, LNM_ZIN | LNM_DBIAS>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, g,
+                                                           smem, relu, da, ddy, st, zin);
   }
-  return bwd_launch_mode<T, NCH, -1>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, g, smem, relu, da, ddy, st);
+  return bwd_launch_mode<T, NCH, -1>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, g, smem, relu, da, ddy, st, zin);
 }
 
 #define LNP_DISPATCH(F, CALL)                                    \
@@ -466,10 +477,10 @@ int add_ln_fwd_pipe(const void* x, const void* a, const float* gamma, const floa
 }
 int add_ln_bwd_pipe(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
                     const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias, long long M,
-                    long long F, int dtype, int relu, DropCfg da, DropCfg ddy, cudaStream_t st) {
+                    long long F, int dtype, int relu, DropCfg da, DropCfg ddy, cudaStream_t st, int zin) {
   if (dtype == MMER_BF16)
-    LNP_DISPATCH(F, (bwd_launch<bf16, NCH>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, M, F, relu, da, ddy, st)));
-  LNP_DISPATCH(F, (bwd_launch<float, NCH>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, M, F, relu, da, ddy, st)));
+    LNP_DISPATCH(F, (bwd_launch<bf16, NCH>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, M, F, relu, da, ddy, st, zin)));
+  LNP_DISPATCH(F, (bwd_launch<float, NCH>(dy, x, a, stats, gamma, beta, dz, dap, dgamma, dbeta, dbias, M, F, relu, da, ddy, st, zin)));
 }
 
 // =========================================================================================================

@@ -14,7 +14,7 @@ int add_ln_fwd_pipe(const void* x, const void* a, const float* gamma, const floa
                     long long M, long long F, int dtype, int relu, DropCfg da, DropCfg dy, cudaStream_t st);
 int add_ln_bwd_pipe(const void* dy, const void* x, const void* a, const float* stats, const float* gamma,
                     const float* beta, void* dz, void* dap, float* dgamma, float* dbeta, float* dbias, long long M,
-                    long long F, int dtype, int relu, DropCfg da, DropCfg ddy, cudaStream_t st);
+                    long long F, int dtype, int relu, DropCfg da, DropCfg ddy, cudaStream_t st, int zin);
 
 int embed_fwd_pipe(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga, const float* ba,
                    const float* pos, void* x0, float* stats, long long B, long long T, long long F, int dtype, DropCfg dc,
@@ -716,7 +716,18 @@ int mmer_add_ln_bwd(const void* dy, const void* x, const void* a, const float* s
   if (M <= 0) return 0;
   DropCfg dca = make_drop(drop_a_p, seed, site_a), dcy = make_drop(drop_y_p, seed, site_y);
   cudaStream_t st = (cudaStream_t)stream;
-  return add_ln_bwd_pipe(dy, x, a, stats, gamma, beta, dz, da, dgamma, dbeta, dbias, M, F, dtype, relu, dca, dcy, st);
+  return add_ln_bwd_pipe(dy, x, a, stats, gamma, beta, dz, da, dgamma, dbeta, dbias, M, F, dtype, relu, dca, dcy, st, 0);
+}
+
+int mmer_add_ln_bwd_z(const void* dy, const void* z, const float* stats, const float* gamma, void* dz, void* da,
+                      float* dgamma, float* dbeta, float* dbias, int64_t M, int64_t F, int dtype, float drop_a_p,
+                      uint32_t site_a, uint64_t seed, void* stream) {
+  CHECK_ROW_SHAPE(F);
+  MMER_CHECK_ARG(dy && z && gamma && dz && stats, "add_ln_bwd_z: null pointer");
+  if (M <= 0) return 0;
+  DropCfg dca = make_drop(drop_a_p, seed, site_a), none = make_drop(0.f, 0, 0);
+  return add_ln_bwd_pipe(dy, nullptr, z, stats, gamma, nullptr, dz, da, dgamma, dbeta, dbias, M, F, dtype, 0, dca, none,
+                         (cudaStream_t)stream, 1);
 }
 
 int mmer_embed_fwd(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga, const float* ba,

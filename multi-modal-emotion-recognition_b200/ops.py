@@ -137,6 +137,29 @@ def add_ln_bwd(dy, x, a, stats, gamma, beta, dgamma, dbeta, dbias=None, relu=Fal
     return dz, da
 
 
+def add_ln_bwd_z(dy, z, stats, gamma, dgamma, dbeta, dbias=None, drop_a_p=0.0, site_a=0, seed=0):
+    """Backward of y = LN(z) given the stored z = x + dropout(a) (see gemm_ln_fwd): returns (dz, da)."""
+    M, F = z.shape
+    dz = torch.empty_like(z)
+    da = torch.empty_like(z) if drop_a_p > 0 else None
+    call("mmer_add_ln_bwd_z", _p(dy), _p(z), _f32(stats), _f32(gamma), _p(dz), _p(da), _f32(dgamma), _f32(dbeta),
+         _f32(dbias), M, F, _dt(z), drop_a_p, site_a, seed, _stream())
+    return dz, da
+
+
+def gemm_ln_fwd(a, w, bias, residual, gamma, beta, drop_p=0.0, site=0, seed=0):
+    """(z, y, stats) = fused Linear + bias + dropout + residual + LayerNorm (N = 512, bf16); mmer_gemm_ln_fwd."""
+    M, K = a.shape
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or w.shape != (512, K):
+        raise TypeError("gemm_ln_fwd: bf16 a [M,K] and w [512,K]")
+    z = torch.empty((M, 512), device=a.device, dtype=torch.bfloat16)
+    y = torch.empty_like(z)
+    stats = torch.empty((M, 2), device=a.device, dtype=torch.float32)
+    call("mmer_gemm_ln_fwd", _p(a), _p(w), _f32(bias), _p(residual), _f32(gamma), _f32(beta), _p(z), _p(y), _p(stats), M, K,
+         drop_p, site, seed, _stream())
+    return z, y, stats
+
+
 def pool_ln_fwd(x, mask, gamma, beta, B, T):
     F = x.shape[-1]
     pooled = torch.empty((B, F), device=x.device, dtype=torch.float32)

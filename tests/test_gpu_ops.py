@@ -552,3 +552,83 @@ def test_bn_fwd_bwd(dt, relu):
     y2, _ = ops.bn_fwd(x, gamma, beta, rm, rv, training=False, relu=relu)
     ref2 = O.batch_norm(x.double(), gamma.double(), beta.double(), rm.double(), rv.double(), False)
     assert rel(y2, torch.relu(ref2) if relu else ref2) < tol(dt)
+
+
+# ----------------------------------------------------------------------------- fused Linear + dropout + residual + LayerNorm
+@pytest.mark.parametrize("M,K", [(256, 512), (69632, 512), (4096 + 8, 2048), (300, 64), (1000, 520)])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_gemm_ln_fwd_matches_fp64(M, K, with_res):
+    """mmer_gemm_ln_fwd (tcgen05 GEMM with the two-pass LayerNorm epilogue) against fp64 math on the same bf16 inputs:
+    z = res + a W^T + b, y = LN(z); ragged M (rows past the last full 256-row block), K not a multiple of 64, large
+    row means (|mean| ~ 8 std: the shifted-sum statistics must not cancel)."""
+    bf = torch.bfloat16
+    a = rnd(M, K, dt=bf, seed=1)
+    w = rnd(512, K, dt=bf, seed=2, scale=K ** -0.5)
+    bias = rnd(512, seed=3) * 0.5 + 4.0                      # a large common offset: exercises the pivot
+    res = rnd(M, 512, dt=bf, seed=4) if with_res else None
+    gamma, beta = rnd(512, seed=5) * 0.2 + 1, rnd(512, seed=6) * 0.2
+    z, y, stats = ops.gemm_ln_fwd(a, w, bias, res, gamma, beta)
+    zr = a.double() @ w.double().t() + bias.double()
+    if with_res:
+        zr = zr + res.double()
+    assert rel(z, zr) < 5e-3                                  # bf16 storage of z
+    mean, var = zr.mean(1), zr.var(1, unbiased=False)
+    assert float((stats[:, 0].double() - mean).abs().max()) < 2e-3 * float(zr.abs().max())
+    assert float((stats[:, 1].double() * torch.sqrt(var + 1e-5) - 1).abs().max()) < 5e-3
+    # y is LayerNorm of the STORED z with the stored statistics (what backward recomputes), and close to the exact one
+    zs = z.double()
+    y_from_stored = (zs - stats[:, :1].double()) * stats[:, 1:].double() * gamma.double() + beta.double()
+    assert rel(y, y_from_stored) < 5e-3
+    assert rel(y, O.layer_norm(zr, gamma.double(), beta.double())) < 2e-2
+
+
+def test_gemm_ln_fwd_dropout_and_z_backward_agree():
+    """Training path: the fused forward's dropout mask is the one mmer_add_ln_bwd_z regenerates, and that backward
+    equals autograd through y = LN(z) for the stored z."""
+    M, K, p = 4096 + 8, 512, 0.25
+    bf = torch.bfloat16
+    a, w = rnd(M, K, dt=bf, seed=1), rnd(512, K, dt=bf, seed=2, scale=K ** -0.5)
+    bias, res = rnd(512, seed=3), rnd(M, 512, dt=bf, seed=4)
+    gamma, beta = rnd(512, seed=5) * 0.2 + 1, rnd(512, seed=6) * 0.2
+    z, y, stats = ops.gemm_ln_fwd(a, w, bias, res, gamma, beta, drop_p=p, site=7, seed=99)
+    lin = a.double() @ w.double().t() + bias.double()
+    scale = 1 / (1 - round(p * 65536) / 65536)
+    # every element of z is either res (dropped) or res + scale * lin (kept)
+    kept = (z.double() - res.double() - scale * lin).abs() < 0.02 * (1 + lin.abs())
+    dropped = (z.double() - res.double()).abs() < 1e-6
+    assert bool((kept | dropped).all())
+    assert abs(float(kept.double().mean()) - (1 - p)) < 0.01
+    dy = rnd(M, 512, dt=bf, seed=8)
+    dg, db, dbias = (torch.zeros(512, device=DEV) for _ in range(3))
+    dz, da = ops.add_ln_bwd_z(dy, z, stats, gamma, dg, db, dbias, drop_a_p=p, site_a=7, seed=99)
+    zr = z.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    O.layer_norm(zr, gr, br).backward(dy.double())
+    assert rel(dz, zr.grad) < 2e-2 and rel(dg, gr.grad) < 2e-2 and rel(db, br.grad) < 2e-2
+    mask = da != 0
+    ambiguous = kept & dropped                                # lin == 0 exactly: cannot tell
+    assert bool(((mask == kept) | ambiguous | (dz == 0)).all())   # same mask in forward and backward
+    assert torch.allclose(da[mask].float(), (dz[mask].float() * scale), rtol=2e-2, atol=1e-6)
+    assert rel(dbias, da.double().sum(0)) < 2e-3
+    # without dropout da is not produced and dz is the whole gradient
+    z0, y0, st0 = ops.gemm_ln_fwd(a, w, bias, res, gamma, beta)
+    dz0, da0 = ops.add_ln_bwd_z(dy, z0, st0, gamma, dg, db, None)
+    assert da0 is None
+    z0r = z0.double().requires_grad_(True)
+    O.layer_norm(z0r, gamma.double(), beta.double()).backward(dy.double())
+    assert rel(dz0, z0r.grad) < 2e-2
+
+
+def test_gemm_ln_fwd_equals_unfused_kernels():
+    """Same inputs through the separate tcgen05 GEMM + add_ln_fwd kernels: the two paths differ only by where bf16
+    rounding happens (the sub-layer output vs the sum z)."""
+    M, K = 8192, 2048
+    bf = torch.bfloat16
+    a, w = rnd(M, K, dt=bf, seed=1), rnd(512, K, dt=bf, seed=2, scale=K ** -0.5)
+    bias, res = rnd(512, seed=3), rnd(M, 512, dt=bf, seed=4)
+    gamma, beta = rnd(512, seed=5) * 0.2 + 1, rnd(512, seed=6) * 0.2
+    z, y, stats = ops.gemm_ln_fwd(a, w, bias, res, gamma, beta)
+    sub = ops.gemm(a, w, M=M, N=512, K=K, bias=bias)
+    y2, st2 = ops.add_ln_fwd(res, sub, gamma, beta)
+    assert rel(y, y2) < 1e-2
+    assert float((stats - st2).abs().max()) < 1e-2

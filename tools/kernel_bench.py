@@ -167,12 +167,41 @@ def bench_collate():
           f"pageable H2D)   {B / ms / 1e3:6.3f} M samples/s")
 
 
+def bench_gemm_ln():
+    """Fused Linear + dropout + residual + LayerNorm (gemm_ln.cu) against the two kernels it replaces, at the two shapes
+    of the step (out_proj: K = 512, linear2: K = 2048), dropout 0.1 as in training."""
+    gam, bet, bias = torch.ones(F, device=dev), torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+    for K in (F, FF):
+        sets = [(rnd(M, K), rnd(M, F)) for _ in range(NBUF)]
+        w = rnd(F, K) * K ** -0.5
+        flop = 2.0 * M * F * K
+        byts = M * K * 2 + 3 * M * F * 2
+        us = timeit(f"gemm_ln_fwd K={K} (p=0.1)", [lambda a=a, r=r: ops.gemm_ln_fwd(a, w, bias, r, gam, bet, drop_p=0.1, site=1, seed=1)
+                                                   for a, r in sets], byts)
+        print(f"{'':34s} {flop / us * 1e-6:8.0f} TFLOP/s")
+        outs = [torch.empty(M, F, device=dev, dtype=bf) for _ in range(NBUF)]
+        us_g = timeit(f"  unfused: gemm K={K} bias", [lambda a=a, o=o: ops.gemm(a, w, M=M, N=F, K=K, bias=bias, out=o)
+                                                      for (a, _), o in zip(sets, outs)], M * K * 2 + M * F * 2)
+        us_l = timeit("  unfused: add_ln_fwd (p=0.1)", [lambda r=r, o=o: ops.add_ln_fwd(r, o, gam, bet, drop_a_p=0.1, site_a=1, seed=1)
+                                                        for (_, r), o in zip(sets, outs)], 3 * M * F * 2)
+        print(f"{'':34s} fused {us:.1f} us vs unfused {us_g + us_l:.1f} us")
+        del sets, outs
+    # backward that reads the stored z instead of x and the sub-layer output
+    dg, db, dbias = (torch.zeros(F, device=dev) for _ in range(3))
+    sets = [(rnd(M, F), rnd(M, F), rnd(M, F)) for _ in range(NBUF)]
+    stats = ops.add_ln_fwd(sets[0][0], sets[0][1], gam, bet)[1]
+    timeit("add_ln_bwd (x, a) (p=0.1)", [lambda x=x, a=a, dy=dy: ops.add_ln_bwd(dy, x, a, stats, gam, bet, dg, db, dbias, drop_a_p=0.1,
+                                                                               site_a=1, seed=1) for x, a, dy in sets], 5 * M * F * 2)
+    timeit("add_ln_bwd_z (p=0.1)", [lambda a=a, dy=dy: ops.add_ln_bwd_z(dy, a, stats, gam, dg, db, dbias, drop_a_p=0.1, site_a=1, seed=1)
+                                    for _, a, dy in sets], 4 * M * F * 2)
+
+
 def main():
-    which = sys.argv[1:] or ["mha", "add_ln", "embed", "head", "adam", "collate"]
+    which = sys.argv[1:] or ["mha", "add_ln", "embed", "head", "adam", "collate", "gemm_ln"]
     print(torch.cuda.get_device_name(0), f"HBM peak {PEAK:.0f} GB/s (measured)")
     for w in which:
         {"mha": bench_mha, "add_ln": bench_add_ln, "colsum": bench_colsum, "adam": bench_adam, "embed": bench_embed,
-         "head": bench_head, "collate": bench_collate}[w]()
+         "head": bench_head, "collate": bench_collate, "gemm_ln": bench_gemm_ln}[w]()
 
 
 if __name__ == "__main__":
