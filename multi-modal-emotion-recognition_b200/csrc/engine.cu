@@ -23,14 +23,24 @@ int gemm_ln_fwd(const void* A, const void* W, const float* bias, const void* res
                 void* z_out, void* y_out, float* stats, long long M, long long K, DropCfg drop, cudaStream_t st);
 extern int g_debug[16];
 
-// Post-norm sub-layer tails (out_proj -> norm1, linear2 -> norm2) as ONE tcgen05 kernel (gemm_ln.cu) instead of a GEMM
-// plus add_ln_fwd: bf16, d_model = 512, at least one 256-row block.  Forward then stores z = x + dropout(sub-layer)
-// where the unfused path stores the sub-layer output, and backward reads it through mmer_add_ln_bwd_z; both directions
-// take this decision from the same (dtype, dims), so a forward / backward pair always agrees.
-static bool fuse_ln(const mmer_model* m) {
-  return m->dtype == MMER_BF16 && m->fused == 512 && m->ffn % 64 == 0 && (int64_t)m->B * (m->T + 1) >= 256 &&
-         g_debug[MMER_DEBUG_NO_LN_FUSE] == 0;
+// Post-norm sub-layer tails (out_proj -> norm1, linear2 -> norm2), three ways (bf16, d_model = 512, M >= 256):
+//   0  GEMM -> a (sub-layer output), add_ln_fwd(x, a) -> y; backward re-reads x and a            (fp32 mode, small shapes)
+//   1  ONE tcgen05 kernel (gemm_ln.cu): GEMM + bias + dropout + residual + LayerNorm -> z, y, stats
+//   2  GEMM with the bias + dropout + residual epilogue -> z, add_ln_fwd(z) -> y (reads ONE tensor)
+// Modes 1 and 2 store the pre-LayerNorm sum z where mode 0 stores the sub-layer output, and backward reads it through
+// mmer_add_ln_bwd_z (4 tensor passes instead of 5).  Forward and backward take the decision from the same (dtype, dims,
+// debug knob), so a forward / backward pair always agrees.  Measured on B200 (profiles/r02_gemm_ln_*.txt): the fully
+// fused kernel is correct but not faster than mode 2 -- its epilogue traffic (residual tile in, z tile out, z back from
+// L2) goes through the same shared-memory ports that feed the MMAs -- so mode 2 is the default.
+static int ln_mode(const mmer_model* m) {
+  if (!(m->dtype == MMER_BF16 && m->fused == 512 && m->ffn % 64 == 0 && (int64_t)m->B * (m->T + 1) >= 256)) return 0;
+  const int k = g_debug[MMER_DEBUG_NO_LN_FUSE];   // 0 default, 1 force mode 0, 2 force the fully fused kernel
+  return k == 1 ? 0 : (k == 2 ? 1 : 2);
 }
+
+// z[M,N] = residual + dropout(x[M,K] W[N,K]^T + b)
+static int lin_fwd_res(const mmer_model* m, const void* x, int64_t M, int64_t K, int64_t offW, int64_t offB, const void* residual,
+                       void* z, int64_t N, float drop_p, uint32_t site, cudaStream_t st);
 
 int gemm_dispatch(const mmer_gemm_args& a, cudaStream_t st) {
   if (a.in_dtype == MMER_BF16) return gemm_tc(a, st);
@@ -178,6 +188,16 @@ static int lin_fwd(const mmer_model* m, const void* x, int64_t M, int64_t K, int
   a.drop_p = drop_p; a.seed = m->seed; a.drop_site = site;
   return gemm_dispatch(a, st);
 }
+static int lin_fwd_res(const mmer_model* m, const void* x, int64_t M, int64_t K, int64_t offW, int64_t offB, const void* residual,
+                       void* z, int64_t N, float drop_p, uint32_t site, cudaStream_t st) {
+  mmer_gemm_args a = {};
+  a.A = x; a.B = Wt(m, offW); a.D = z; a.bias = P(m, offB); a.residual = residual;
+  a.M = M; a.N = N; a.K = K; a.lda = K; a.ldb = K; a.ldd = N;
+  a.a_major = MMER_MAJOR_K; a.b_major = MMER_MAJOR_K;
+  a.in_dtype = m->dtype; a.out_dtype = m->dtype;
+  a.drop_p = drop_p; a.seed = m->seed; a.drop_site = site;
+  return gemm_dispatch(a, st);
+}
 // dx[M,K] = dy[M,N] W[N,K] (+ residual) (* gate)
 static int lin_dgrad(const mmer_model* m, const void* dy, int64_t M, int64_t N, int64_t offW, int64_t K, void* dx,
                      const void* residual, const void* gate, float gate_scale, cudaStream_t st,
@@ -248,9 +268,14 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
     float* probs = m->attn_probs ? m->attn_probs + (int64_t)l * B * m->heads * SS : nullptr;
     MMER_TRY(mmer_mha_fwd(L.qkv, d.mask, L.att, probs, B, T, m->heads, F / m->heads, d.dt, d.pf, d.seed,
                           site_layer(l, 0), st));
-    if (fuse_ln(m)) {   // L.ao / L.f2 hold z1 / z2 (pre-LayerNorm sums) on this path
+    const int lnm = ln_mode(m);   // modes 1 and 2: L.ao / L.f2 hold z1 / z2 (pre-LayerNorm sums)
+    if (lnm == 1) {
       MMER_TRY(gemm_ln_fwd(L.att, Wt(m, o[MMER_L_OUT_W]), P(m, o[MMER_L_OUT_B]), x, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]),
                            L.ao, L.x1, L.st1, M, F, make_drop(d.pf, d.seed, site_layer(l, 1)), st));
+    } else if (lnm == 2) {
+      MMER_TRY(lin_fwd_res(m, L.att, M, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], x, L.ao, F, d.pf, site_layer(l, 1), st));
+      MMER_TRY(mmer_add_ln_fwd(nullptr, L.ao, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]), L.x1, L.st1, M, F, d.dt, 0, 0.f, 0,
+                               0.f, 0, d.seed, st));
     } else {
       MMER_TRY(lin_fwd(m, L.att, M, F, o[MMER_L_OUT_W], o[MMER_L_OUT_B], L.ao, F, 0, 0.f, 0, st));
       MMER_TRY(mmer_add_ln_fwd(x, L.ao, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]), L.x1, L.st1, M, F, d.dt, 0, d.pf,
@@ -258,9 +283,13 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
     }
     MMER_TRY(lin_fwd(m, L.x1, M, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], L.h, FF, 1, d.pf, site_layer(l, 2), st,
                      d.tr ? L.hmask : nullptr));
-    if (fuse_ln(m)) {
+    if (lnm == 1) {
       MMER_TRY(gemm_ln_fwd(L.h, Wt(m, o[MMER_L_FF2_W]), P(m, o[MMER_L_FF2_B]), L.x1, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]),
                            L.f2, L.x2, L.st2, M, FF, make_drop(d.pf, d.seed, site_layer(l, 3)), st));
+    } else if (lnm == 2) {
+      MMER_TRY(lin_fwd_res(m, L.h, M, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], L.x1, L.f2, F, d.pf, site_layer(l, 3), st));
+      MMER_TRY(mmer_add_ln_fwd(nullptr, L.f2, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]), L.x2, L.st2, M, F, d.dt, 0, 0.f, 0,
+                               0.f, 0, d.seed, st));
     } else {
       MMER_TRY(lin_fwd(m, L.h, M, FF, o[MMER_L_FF2_W], o[MMER_L_FF2_B], L.f2, F, 0, 0.f, 0, st));
       MMER_TRY(mmer_add_ln_fwd(L.x1, L.f2, P(m, o[MMER_L_N2_W]), P(m, o[MMER_L_N2_B]), L.x2, L.st2, M, F, d.dt, 0, d.pf,
@@ -366,7 +395,7 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     const void* xin = l == 0 ? w.x0 : w.L[l - 1].x2;
     // norm2 <- linear2
     void* d_f2 = pf > 0.f ? w.g_f2 : w.g_z2;
-    if (fuse_ln(m)) {
+    if (ln_mode(m) != 0) {
       MMER_TRY(mmer_add_ln_bwd_z(w.g_x, L.f2, L.st2, P(m, o[MMER_L_N2_W]), w.g_z2, pf > 0.f ? w.g_f2 : nullptr,
                                  G(m, o[MMER_L_N2_W]), G(m, o[MMER_L_N2_B]), G(m, o[MMER_L_FF2_B]), M, F, d.dt, pf,
                                  site_layer(l, 3), d.seed, st));
@@ -387,7 +416,7 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
     // norm1 <- attention
     void* d_ao = pf > 0.f ? w.g_ao : w.g_z1;
-    if (fuse_ln(m)) {
+    if (ln_mode(m) != 0) {
       MMER_TRY(mmer_add_ln_bwd_z(w.g_x1, L.ao, L.st1, P(m, o[MMER_L_N1_W]), w.g_z1, pf > 0.f ? w.g_ao : nullptr,
                                  G(m, o[MMER_L_N1_W]), G(m, o[MMER_L_N1_B]), G(m, o[MMER_L_OUT_B]), M, F, d.dt, pf,
                                  site_layer(l, 1), d.seed, st));

@@ -5,21 +5,22 @@
 //
 // replaces a GEMM launch + add_ln_fwd_pipe_kernel (out_proj -> norm1 and linear2 -> norm2 of every layer).
 //
-// Structure = the CTA-pair GEMM of gemm_tc.cu (TMA producer warp, single-thread tcgen05.mma cta_group::2 issuer, eight
-// epilogue warps, fp32 accumulators double-buffered in the 512 TMEM columns) with a different tile order and a two-pass
-// epilogue.  A LayerNorm row needs all 512 output columns, i.e. BOTH 256-column accumulator tiles of a row block, so a
-// CTA pair walks row blocks (256 rows) and computes their two n-tiles back to back into the two TMEM buffers:
-//   pass 1 (per n-tile, the usual GEMM epilogue): tcgen05.ld -> + bias -> dropout -> + residual tile (prefetched by TMA)
-//           -> z; per-row shifted sums (pivot = the row's first value) accumulate in registers; bf16(z) leaves through
-//           the 128B-swizzled staging tile as a TMA store into the Z tensor (the backward kernel reads it instead of
-//           re-reading x and a).  The TMEM buffer is released right after its tcgen05.ld's: the MMAs of the next row
-//           block overlap everything below.
-//   row statistics: the two warps that share a TMEM lane quarter hold 256 columns each of the same 32 rows; they swap
+// Structure = the CTA-pair GEMM of gemm_tc.cu (TMA producer warp, single-thread tcgen05.mma cta_group::2 issuer, fp32
+// accumulators double-buffered in the 512 TMEM columns) with a different tile order and two groups of epilogue warps.
+// A LayerNorm row needs all 512 output columns, i.e. BOTH 256-column accumulator tiles of a row block, so a CTA pair
+// walks row blocks (256 rows) and computes their two n-tiles back to back into the two TMEM buffers:
+//   warps 2-9  (pass 1, the GEMM epilogue): tcgen05.ld (32 columns at a time) -> + bias -> dropout -> + residual tile
+//           (prefetched by TMA) -> z; per-row shifted sums (pivot = the row's first value) accumulate in registers;
+//           bf16(z) leaves through a 128B-swizzled staging tile as a TMA store into the Z tensor (which the backward
+//           kernel reads instead of re-reading x and a).  The TMEM buffer is released right after its last tcgen05.ld.
+//           The two warps that share a TMEM lane quarter hold 256 columns each of the same 32 rows: they swap
 //           (pivot, S1, S2) through shared memory behind a 64-thread named barrier and merge them (Chan), which gives
-//           mean / rstd without cancellation problems; (mean, rstd) go to the stats tensor for backward.
-//   pass 2: the warp's four bf16 z sub-tiles come back from L2 by TMA (they were written microseconds ago), are
-//           normalised in place -- y is computed from exactly the bf16 z that backward will see -- and leave as TMA
-//           stores into Y.
+//           mean / rstd without cancellation; (mean, rstd) go to shared memory and to the stats tensor for backward.
+//   warps 10-17 (pass 2, normalisers): once a row block's z tiles are complete in global memory (they are L2-resident,
+//           written microseconds ago) these warps stream them back with coalesced 16-byte loads -- a warp per row, a
+//           lane per 8 columns, gamma / beta in registers -- and write y = LN(bf16 z) with coalesced 16-byte stores.
+//           y is computed from exactly the bf16 z that backward will see.  No TMEM, no shared-memory tiles: their
+//           instructions fill the issue slots the latency-bound pass-1 warps leave idle, one row block behind them.
 // No S x 512 fp32 row ever lives in registers or shared memory, and the pipeline keeps 4 operand stages.
 #include <cuda.h>
 
@@ -33,20 +34,23 @@ namespace {
 
 constexpr int LN_N = 512;            // d_model: two 256-column accumulator tiles
 constexpr int LN_BN = 256;
-constexpr int LN_EPI_WARPS = 8;
-constexpr int LN_THREADS = 64 + 32 * LN_EPI_WARPS;
+constexpr int LN_EPI_WARPS = 8;      // pass-1 warps (TMEM readers): 2 per lane quarter, 128 of an n-tile's 256 columns each
+constexpr int LN_NRM_WARPS = 8;      // pass-2 warps (normalisers)
+constexpr int LN_THREADS = 64 + 32 * (LN_EPI_WARPS + LN_NRM_WARPS);
 constexpr int LN_A_BYTES = BM * BK * 2;                 // 16 KB: this CTA's 128 rows of A
 constexpr int LN_B_BYTES = (LN_BN / 2) * BK * 2;        // 16 KB: this CTA's half of the 256-row B tile
 constexpr int LN_STAGE_BYTES = LN_A_BYTES + LN_B_BYTES;
 constexpr int LN_STAGES = 4;
 constexpr int LN_TILE = 4096;                           // 32 rows x 64 bf16 columns, 128B-swizzled
-constexpr int LN_EPI_BYTES = LN_EPI_WARPS * 2 * LN_TILE;
+constexpr int LN_EPI_BYTES = LN_EPI_WARPS * 2 * LN_TILE; // two staging tiles per pass-1 warp
 constexpr int LN_VEC_BYTES = 3 * LN_N * 4;              // bias, gamma, beta
 constexpr int LN_XCH_BYTES = LN_EPI_WARPS * 32 * 16;    // (pivot, S1, S2, pad) per lane
-constexpr int LN_BAR_BYTES = 256;
-constexpr int LN_SMEM_BYTES = LN_STAGES * LN_STAGE_BYTES + LN_EPI_BYTES + LN_VEC_BYTES + LN_XCH_BYTES + LN_BAR_BYTES;
+constexpr int LN_RST_BYTES = 2 * BM * 8;                // (mean, rstd) of the CTA's 128 rows, two row blocks in flight
+constexpr int LN_BAR_BYTES = 512;
+constexpr int LN_SMEM_BYTES =
+    LN_STAGES * LN_STAGE_BYTES + LN_EPI_BYTES + LN_VEC_BYTES + LN_XCH_BYTES + LN_RST_BYTES + LN_BAR_BYTES;
 static_assert(LN_SMEM_BYTES <= 232448, "shared memory budget");
-static_assert((2 * LN_STAGES + 4 + LN_EPI_WARPS) * 8 + 8 <= LN_BAR_BYTES, "barrier area");
+static_assert((2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS + 4) * 8 + 8 <= LN_BAR_BYTES, "barrier area");
 constexpr float LN_EPS = 1e-5f;
 
 struct GemmLnParams {
@@ -57,7 +61,10 @@ struct GemmLnParams {
   const float* gamma;  // [512]
   const float* beta;   // [512]
   float* stats;        // [M][2] (mean, rstd)
+  const bf16* Z;       // [M][512]: written by pass 1 through tmZ, read back by pass 2
+  bf16* Y;             // [M][512]
   int has_residual;
+  int dbg;             // MMER_DEBUG_LN_VARIANT bits (A/B timing only): 1 no residual tile, 2 no z store, 4 no pass 2, 8 no epilogue math
   DropCfg drop;
 };
 
@@ -68,8 +75,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 template <bool DROP>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ,
-               const __grid_constant__ CUtensorMap tmY, const GemmLnParams p) {
+               const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, const GemmLnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) {
     if (threadIdx.x == 0) printf("mmer gemm_ln: dynamic shared memory is not 1024-byte aligned\n");
@@ -78,13 +84,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* epi_smem = smem + LN_STAGES * LN_STAGE_BYTES;
   float* vec_smem = reinterpret_cast<float*>(epi_smem + LN_EPI_BYTES);          // bias | gamma | beta
   float4* xch_smem = reinterpret_cast<float4*>(epi_smem + LN_EPI_BYTES + LN_VEC_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + LN_EPI_BYTES + LN_VEC_BYTES + LN_XCH_BYTES);
+  float2* rst_smem = reinterpret_cast<float2*>(epi_smem + LN_EPI_BYTES + LN_VEC_BYTES + LN_XCH_BYTES);   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + LN_EPI_BYTES + LN_VEC_BYTES + LN_XCH_BYTES + LN_RST_BYTES);
+  // bars: [0..S) full, [S..2S) empty, 2 tmem_full, 2 tmem_empty, 16 aux (one per residual staging tile), 2 z_ready, 2 z_done, tmem slot
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + LN_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * LN_STAGES);
   const uint32_t bar_tempty = smem_u32(bars + 2 * LN_STAGES + 2);
   const uint32_t bar_aux = smem_u32(bars + 2 * LN_STAGES + 4);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * LN_STAGES + 4 + LN_EPI_WARPS);
+  const uint32_t bar_zready = smem_u32(bars + 2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS);
+  const uint32_t bar_zdone = smem_u32(bars + 2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS + 2);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * LN_STAGES + 4 + 2 * LN_EPI_WARPS + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,15 +110,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, LN_EPI_WARPS * 2);   // the epilogue warps of both CTAs release the leader's issuer
+      mbar_init(bar_tempty + 8 * b, LN_EPI_WARPS * 2);   // the pass-1 warps of both CTAs release the leader's issuer
+      mbar_init(bar_zready + 8 * b, LN_EPI_WARPS);
+      mbar_init(bar_zdone + 8 * b, LN_NRM_WARPS);
     }
-    for (int w = 0; w < LN_EPI_WARPS; ++w) mbar_init(bar_aux + 8 * w, 1);
+    for (int w = 0; w < 2 * LN_EPI_WARPS; ++w) mbar_init(bar_aux + 8 * w, 1);   // one per staging tile
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
   }
   if (warp == 1) tmem_alloc<2>(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
@@ -169,205 +180,246 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..9)
-    const int ew = warp - 2;
-    const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int hsel = ew >> 2;        // which 128 of the n-tile's 256 columns
-    // bias / gamma / beta: 6 KB, read back as broadcasts
-    for (int i = threadIdx.x - 64; i < LN_N; i += 32 * LN_EPI_WARPS) {
+    // bias / gamma / beta: 6 KB of shared memory filled by the 16 epilogue warps
+    for (int i = threadIdx.x - 64; i < LN_N; i += 32 * (LN_EPI_WARPS + LN_NRM_WARPS)) {
       vec_smem[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
       vec_smem[LN_N + i] = __ldg(p.gamma + i);
       vec_smem[2 * LN_N + i] = __ldg(p.beta + i);
     }
-    named_bar_sync(1, 32 * LN_EPI_WARPS);
-    const float* bias_s = vec_smem;
-    const float* gamma_s = vec_smem + LN_N;
-    const float* beta_s = vec_smem + 2 * LN_N;
-    uint8_t* stg = epi_smem + ew * (2 * LN_TILE);
-    const uint32_t stg_u32 = smem_u32(stg);
-    const uint32_t auxbar = bar_aux + 8 * ew;
-    uint32_t aux_phase = 0;
-    uint32_t it = 0;                  // staging-tile parity
-    uint32_t tphase[2] = {0, 0};
-    const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
-    const bool has_res = p.has_residual != 0;
-
-    for (int rb = unit; rb < p.num_rb; rb += num_units) {
-      const int row0 = (rb * 2 + (int)rank) * BM + q * 32;
-      const long long row = (long long)row0 + lane;
-      const bool block_ok = row0 < p.M;      // rows past M: TMA clips the stores, the statistics are not written
-      float pivot = 0.f, s1 = 0.f, s2 = 0.f;
-      // ---------------------------------------------------------------- pass 1: z tiles + row sums
-      bool aux_ready = false;   // the residual tile of the NEXT sub-tile has already been requested
+    named_bar_sync(1, 32 * (LN_EPI_WARPS + LN_NRM_WARPS));
+    if (warp < 2 + LN_EPI_WARPS) {
+      // ===================================================== pass 1 (warps 2..9): z tiles + row statistics
+      const int ew = warp - 2;
+      const int q = warp & 3;          // TMEM lane quarter this warp may read
+      const int hsel = ew >> 2;        // which 128 of the n-tile's 256 columns
+      const float* bias_s = vec_smem;
+      uint8_t* stg = epi_smem + ew * (2 * LN_TILE);
+      const uint32_t stg_u32 = smem_u32(stg);
+      const uint32_t auxbar = bar_aux + 16 * ew;    // two barriers: one per staging tile
+      uint32_t aux_phase[2] = {0, 0};
+      uint32_t it = 0;                  // staging-tile parity
+      uint32_t tphase[2] = {0, 0};
+      const uint32_t tempty_leader = mapa_u32(bar_tempty, 0);
+      const bool has_res = p.has_residual != 0 && !(p.dbg & 1);
+      int iter = 0;                     // row blocks done by this CTA
+      bool pending = false;             // z_ready of the previous row block not signalled yet
+      bool aux_ready = false;           // the residual tile of the CURRENT sub-tile has already been requested
+      for (int rb = unit; rb < p.num_rb; rb += num_units, ++iter) {
+        const int par = iter & 1;
+        const int row0 = (rb * 2 + (int)rank) * BM + q * 32;
+        const long long row = (long long)row0 + lane;
+        const bool block_ok = row0 < p.M;      // rows past M: TMA clips the stores, the statistics are not written
+        float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+        if (has_res && lane < 4) {
+          // warm L2 with this warp's four residual tiles of the CTA's NEXT row block
+          const int nrow0 = ((rb + num_units) * 2 + (int)rank) * BM + q * 32;
+          if (nrow0 < p.M)
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmX),
+                         "r"((lane >> 1) * LN_BN + hsel * 128 + (lane & 1) * 64), "r"(nrow0)
+                         : "memory");
+        }
 #pragma unroll 1
-      for (int n = 0; n < 2; ++n) {
-        mbar_wait(bar_tfull + 8 * n, tphase[n]);
-        tphase[n] ^= 1;
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(n * LN_BN + hsel * 128);
+        for (int n = 0; n < 2; ++n) {
+          mbar_wait(bar_tfull + 8 * n, tphase[n]);
+          tphase[n] ^= 1;
+          tc_fence_after();
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(n * LN_BN + hsel * 128);
 #pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          const int col0 = n * LN_BN + hsel * 128 + j * 64;
-          const uint32_t tsel = it & 1u;
-          uint8_t* tile = stg + tsel * LN_TILE;
-          const uint32_t tile_u32 = stg_u32 + tsel * LN_TILE;
-          ++it;
-          if (lane == 0 && !aux_ready) {
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this tile has drained
-            if (has_res && block_ok) {
-              mbar_expect_tx(auxbar, LN_TILE);
-              tma_load_2d(tile_u32, &tmX, auxbar, col0, row0);
+          for (int j = 0; j < 2; ++j) {
+            const int col0 = n * LN_BN + hsel * 128 + j * 64;
+            const uint32_t tsel = it & 1u;
+            uint8_t* tile = stg + tsel * LN_TILE;
+            const uint32_t tile_u32 = stg_u32 + tsel * LN_TILE;
+            ++it;
+            if (lane == 0) {
+              // Residual tiles are requested a whole sub-tile ahead: at the top of sub-tile s the tile of s + 1 goes out
+              // into the OTHER staging tile (whose last reader, the z store of s - 1, has had a sub-tile's time to drain),
+              // so that a TMA load's ~1 us of latency is never waited for.
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              if (has_res && block_ok && !aux_ready) {            // the very first sub-tile of this warp
+                mbar_expect_tx(auxbar + 8 * tsel, LN_TILE);
+                tma_load_2d(tile_u32, &tmX, auxbar + 8 * tsel, col0, row0);
+              }
+              const bool last = (n == 1 && j == 1);
+              const int nrb = last ? rb + num_units : rb;
+              const int nrow0 = (nrb * 2 + (int)rank) * BM + q * 32;
+              const int ncol = last ? hsel * 128 : (j == 0 ? col0 + 64 : LN_BN + hsel * 128);
+              if (has_res && nrb < p.num_rb && nrow0 < p.M) {
+                mbar_expect_tx(auxbar + 8 * (tsel ^ 1u), LN_TILE);
+                tma_load_2d(stg_u32 + (tsel ^ 1u) * LN_TILE, &tmX, auxbar + 8 * (tsel ^ 1u), ncol, nrow0);
+              }
             }
-          }
-          aux_ready = false;
-          __syncwarp();
-          uint32_t r[2][32];
-          tmem_ld32_nowait(trow + (uint32_t)(j * 64), r[0]);
-          tmem_ld32_nowait(trow + (uint32_t)(j * 64 + 32), r[1]);
-          tmem_ld_wait();
-          if (j == 1) {
-            // both halves of this accumulator buffer are in registers: hand it back to the MMA issuer now
-            tc_fence_before();
+            {
+              const bool last = (n == 1 && j == 1);
+              const int nrb = last ? rb + num_units : rb;
+              aux_ready = has_res && nrb < p.num_rb && (nrb * 2 + (int)rank) * BM + q * 32 < p.M;
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * n);
-          }
-          if (has_res && block_ok) {
-            mbar_wait(auxbar, aux_phase);
-            aux_phase ^= 1;
-          }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float4 bv[8];
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32];
+              tmem_ld32(trow + (uint32_t)(j * 64 + h * 32), r);
+              if (j == 1 && h == 1) {
+                // the whole accumulator buffer has been read: hand it back to the MMA issuer now
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * n);
+              }
+              if (h == 0 && has_res && block_ok) {
+                mbar_wait(auxbar + 8 * tsel, aux_phase[tsel]);
+                aux_phase[tsel] ^= 1;
+              }
 #pragma unroll
-            for (int g = 0; g < 8; ++g) bv[g] = *reinterpret_cast<const float4*>(bias_s + col0 + h * 32 + g * 4);
-            uint4 xr[4];
+              for (int g = 0; g < 4; ++g) {
+                if (p.dbg & 8) break;
+                const int col = col0 + h * 32 + g * 8;
+                uint8_t* addr = tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
+                float v[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              xr[g] = make_uint4(0u, 0u, 0u, 0u);
-              if (has_res) xr[g] = *reinterpret_cast<const uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4));
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = 0.f;
+                if (has_res) {
+                  const uint4 xr = *reinterpret_cast<const uint4*>(addr);
+                  const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 xf = __bfloat1622float2(xh[i]);
+                    x[2 * i] = xf.x;
+                    x[2 * i + 1] = xf.y;
+                  }
+                }
+                if (DROP) {
+                  float f[8];
+                  drop8(p.drop, (uint64_t)(row * LN_N + col), f);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = fmaf(f[i], v[i], x[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += x[i];
+                }
+                if (n == 0 && j == 0 && h == 0 && g == 0) pivot = v[0];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float d = v[i] - pivot;
+                  s1 += d;
+                  s2 = fmaf(d, d, s2);
+                }
+                uint4 pk;
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                *reinterpret_cast<uint4*>(addr) = pk;
+              }
             }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + h * 32 + g * 8;
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h][g * 8 + i]);
-              v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
-              v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
-              if (DROP) {
-                float f[8];
-                drop8(p.drop, (uint64_t)(row * LN_N + col), f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= f[i];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && block_ok && !(p.dbg & 2)) {
+              tma_store_2d(&tmZ, tile_u32, col0, row0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (pending && n == 0 && j == 0) {
+              // every z store of the PREVIOUS row block has now been followed by a newer group: once at most one group
+              // is pending they are complete in global memory -> let the normaliser warps at that row block
+              if (lane == 0) {
+                if (block_ok) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // no newer group was committed
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive(bar_zready + 8 * (par ^ 1));
               }
-              const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr[g]);
+              pending = false;
+            }
+          }
+        }
+        // ---------------------------------------------------------------- row statistics (two warps per 32 rows)
+        xch_smem[ew * 32 + lane] = make_float4(pivot, s1, s2, 0.f);
+        // the (mean, rstd) slot of this parity was last read by the normalisers two row blocks ago
+        if (iter >= 2) mbar_wait(bar_zdone + 8 * par, (uint32_t)((iter >> 1) - 1) & 1u);
+        named_bar_sync(2 + q, 64);
+        const float4 o = xch_smem[(ew ^ 4) * 32 + lane];
+        const float inv_h = 1.f / 256.f;
+        const float mean_a = pivot + s1 * inv_h, m2_a = s2 - s1 * s1 * inv_h;
+        const float mean_b = o.x + o.y * inv_h, m2_b = o.z - o.y * o.y * inv_h;
+        const float delta = mean_b - mean_a;
+        const float mean = 0.5f * (mean_a + mean_b);
+        const float var = (m2_a + m2_b + delta * delta * 128.f) * (1.f / (float)LN_N);
+        const float rstd = rsqrtf(fmaxf(var, 0.f) + LN_EPS);
+        if (hsel == 0) {
+          rst_smem[par * BM + q * 32 + lane] = make_float2(mean, rstd);
+          if (row < p.M) *reinterpret_cast<float2*>(p.stats + row * 2) = make_float2(mean, rstd);
+        }
+        named_bar_sync(2 + q, 64);                       // xch slot reusable; (mean, rstd) written before either warp signals
+        pending = true;
+      }
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (pending) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          mbar_arrive(bar_zready + 8 * ((iter - 1) & 1));
+        }
+      }
+    } else {
+      // ===================================================== pass 2 (warps 10..17): y = LN(bf16 z), global -> global
+      const int pw = warp - 2 - LN_EPI_WARPS;
+      constexpr int ROWS = BM / LN_NRM_WARPS;    // 16 rows of the CTA's 128 per warp
+      float gm[2][8], bt[2][8];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 xf = __bfloat1622float2(xh[i]);
-                v[2 * i] += xf.x;
-                v[2 * i + 1] += xf.y;
-              }
-              if (n == 0 && j == 0 && h == 0 && g == 0) pivot = v[0];
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float d = v[i] - pivot;
-                s1 += d;
-                s2 = fmaf(d, d, s2);
-              }
+        for (int i = 0; i < 8; ++i) {
+          gm[c][i] = vec_smem[LN_N + c * 256 + lane * 8 + i];
+          bt[c][i] = vec_smem[2 * LN_N + c * 256 + lane * 8 + i];
+        }
+      int iter = 0;
+      for (int rb = unit; rb < p.num_rb; rb += num_units, ++iter) {
+        const int par = iter & 1;
+        mbar_wait(bar_zready + 8 * par, (uint32_t)(iter >> 1) & 1u);
+        const long long base = (long long)(rb * 2 + (int)rank) * BM + pw * ROWS;
+#pragma unroll 1
+        for (int r0 = 0; r0 < ROWS; r0 += 4) {
+          if (p.dbg & 4) break;
+          uint4 zr[4][2];
+          float2 st[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const long long row = base + r0 + k;
+            st[k] = rst_smem[par * BM + pw * ROWS + r0 + k];
+            if (row < p.M) {
+              const uint4* src = reinterpret_cast<const uint4*>(p.Z + row * LN_N);
+              zr[k][0] = __ldcg(src + lane);
+              zr[k][1] = __ldcg(src + 32 + lane);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const long long row = base + r0 + k;
+            if (row >= p.M) continue;
+            const float rstd = st[k].y, nmr = -st[k].x * st[k].y;
+            uint4* dst = reinterpret_cast<uint4*>(p.Y + row * LN_N);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const __nv_bfloat162* zh = reinterpret_cast<const __nv_bfloat162*>(&zr[k][c]);
               uint4 pk;
               __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              *reinterpret_cast<uint4*>(tile + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4)) = pk;
+              for (int i = 0; i < 4; ++i) {
+                const float2 zf = __bfloat1622float2(zh[i]);
+                hp[i] = __floats2bfloat162_rn(fmaf(fmaf(zf.x, rstd, nmr), gm[c][2 * i], bt[c][2 * i]),
+                                              fmaf(fmaf(zf.y, rstd, nmr), gm[c][2 * i + 1], bt[c][2 * i + 1]));
+              }
+              dst[c * 32 + lane] = pk;
             }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0 && block_ok) {
-            tma_store_2d(&tmZ, tile_u32, col0, row0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          // request the residual tile of the next sub-tile of THIS row block into the other staging tile
-          if (has_res && block_ok && !(n == 1 && j == 1)) {
-            const int ncol = (j == 0) ? col0 + 64 : LN_BN + hsel * 128;
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              mbar_expect_tx(auxbar, LN_TILE);
-              tma_load_2d(stg_u32 + (it & 1u) * LN_TILE, &tmX, auxbar, ncol, row0);
-            }
-            aux_ready = true;
-          }
-        }
-      }
-      // ---------------------------------------------------------------- row statistics (two warps per 32 rows)
-      xch_smem[ew * 32 + lane] = make_float4(pivot, s1, s2, 0.f);
-      named_bar_sync(2 + q, 64);
-      const float4 o = xch_smem[(ew ^ 4) * 32 + lane];
-      named_bar_sync(2 + q, 64);                       // the slot may be overwritten for the next row block
-      const float inv_h = 1.f / 256.f;
-      const float mean_a = pivot + s1 * inv_h, m2_a = s2 - s1 * s1 * inv_h;
-      const float mean_b = o.x + o.y * inv_h, m2_b = o.z - o.y * o.y * inv_h;
-      const float delta = mean_b - mean_a;
-      const float mean = 0.5f * (mean_a + mean_b);
-      const float var = (m2_a + m2_b + delta * delta * 128.f) * (1.f / (float)LN_N);
-      const float rstd = rsqrtf(fmaxf(var, 0.f) + LN_EPS);
-      const float nmr = -mean * rstd;
-      if (hsel == 0 && row < p.M) *reinterpret_cast<float2*>(p.stats + row * 2) = make_float2(mean, rstd);
-      // ---------------------------------------------------------------- pass 2: y = LN(bf16 z) from the tiles just stored
-      if (block_ok) {
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's z tiles are complete in global memory
-          mbar_expect_tx(auxbar, LN_TILE);
-          tma_load_2d(stg_u32 + (it & 1u) * LN_TILE, &tmZ, auxbar, hsel * 128, row0);
         }
         __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {                  // sub-tiles (n, j) = (k >> 1, k & 1)
-          const int col0 = (k >> 1) * LN_BN + hsel * 128 + (k & 1) * 64;
-          const uint32_t tsel = it & 1u;
-          uint8_t* tile = stg + tsel * LN_TILE;
-          const uint32_t tile_u32 = stg_u32 + tsel * LN_TILE;
-          ++it;
-          mbar_wait(auxbar, aux_phase);                // z tile k has landed (one load per barrier phase at a time)
-          aux_phase ^= 1;
-          if (k < 3 && lane == 0) {
-            // bring in the next z tile while this one is normalised; the other staging tile was last read by the y
-            // store of sub-tile k - 1
-            const int ncol = ((k + 1) >> 1) * LN_BN + hsel * 128 + ((k + 1) & 1) * 64;
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_expect_tx(auxbar, LN_TILE);
-            tma_load_2d(stg_u32 + (it & 1u) * LN_TILE, &tmZ, auxbar, ncol, row0);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint8_t* addr = tile + lane * 128 + ((c ^ (lane & 7)) << 4);
-            const uint4 zr = *reinterpret_cast<const uint4*>(addr);
-            const float4 g0 = *reinterpret_cast<const float4*>(gamma_s + col0 + c * 8);
-            const float4 g1 = *reinterpret_cast<const float4*>(gamma_s + col0 + c * 8 + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(beta_s + col0 + c * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(beta_s + col0 + c * 8 + 4);
-            const __nv_bfloat162* zh = reinterpret_cast<const __nv_bfloat162*>(&zr);
-            const float2 z0 = __bfloat1622float2(zh[0]), z1 = __bfloat1622float2(zh[1]);
-            const float2 z2 = __bfloat1622float2(zh[2]), z3 = __bfloat1622float2(zh[3]);
-            uint4 pk;
-            __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-            hp[0] = __floats2bfloat162_rn(fmaf(fmaf(z0.x, rstd, nmr), g0.x, b0.x), fmaf(fmaf(z0.y, rstd, nmr), g0.y, b0.y));
-            hp[1] = __floats2bfloat162_rn(fmaf(fmaf(z1.x, rstd, nmr), g0.z, b0.z), fmaf(fmaf(z1.y, rstd, nmr), g0.w, b0.w));
-            hp[2] = __floats2bfloat162_rn(fmaf(fmaf(z2.x, rstd, nmr), g1.x, b1.x), fmaf(fmaf(z2.y, rstd, nmr), g1.y, b1.y));
-            hp[3] = __floats2bfloat162_rn(fmaf(fmaf(z3.x, rstd, nmr), g1.z, b1.z), fmaf(fmaf(z3.y, rstd, nmr), g1.w, b1.w));
-            *reinterpret_cast<uint4*>(addr) = pk;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmY, tile_u32, col0, row0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
+        if (lane == 0) mbar_arrive(bar_zdone + 8 * par);
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -384,11 +436,10 @@ int gemm_ln_fwd(const void* A, const void* W, const float* bias, const void* res
   MMER_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(z_out) |
                    reinterpret_cast<uintptr_t>(y_out) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0,
                  "gemm_ln_fwd: pointers must be 16-byte aligned");
-  CUtensorMap ta, tb, tx, tz, ty;
+  CUtensorMap ta, tb, tx, tz;
   MMER_TRY(make_tma_map_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)K, 64, BM));
   MMER_TRY(make_tma_map_bf16(&tb, W, (uint64_t)K, (uint64_t)LN_N, (uint64_t)K, 64, LN_BN / 2));
   MMER_TRY(make_tma_map_bf16(&tz, z_out, (uint64_t)LN_N, (uint64_t)M, (uint64_t)LN_N, 64, 32));
-  MMER_TRY(make_tma_map_bf16(&ty, y_out, (uint64_t)LN_N, (uint64_t)M, (uint64_t)LN_N, 64, 32));
   tx = tz;
   if (residual) MMER_TRY(make_tma_map_bf16(&tx, residual, (uint64_t)LN_N, (uint64_t)M, (uint64_t)LN_N, 64, 32));
   GemmLnParams p;
@@ -396,7 +447,9 @@ int gemm_ln_fwd(const void* A, const void* W, const float* bias, const void* res
   p.num_rb = ceil_div(M, 2 * BM);
   p.kb_total = ceil_div(K, BK);
   p.bias = bias; p.gamma = gamma; p.beta = beta; p.stats = stats;
+  p.Z = reinterpret_cast<const bf16*>(z_out); p.Y = reinterpret_cast<bf16*>(y_out);
   p.has_residual = residual != nullptr;
+  p.dbg = g_debug[MMER_DEBUG_LN_VARIANT];
   p.drop = drop;
   const int pairs = sm_count() / 2;
   const int grid = (p.num_rb < pairs ? p.num_rb : pairs) * 2;
@@ -408,14 +461,14 @@ int gemm_ln_fwd(const void* A, const void* W, const float* bias, const void* res
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_ln)");
     }
-    e = launch_dep(kern, dim3((unsigned)grid), dim3(LN_THREADS), LN_SMEM_BYTES, st, 2, ta, tb, tx, tz, ty, p);
+    e = launch_dep(kern, dim3((unsigned)grid), dim3(LN_THREADS), LN_SMEM_BYTES, st, 2, ta, tb, tx, tz, p);
   } else {
     auto kern = gemm_ln_kernel<false>;
     if (needs_func_attr(&attr_done[1])) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_ln)");
     }
-    e = launch_dep(kern, dim3((unsigned)grid), dim3(LN_THREADS), LN_SMEM_BYTES, st, 2, ta, tb, tx, tz, ty, p);
+    e = launch_dep(kern, dim3((unsigned)grid), dim3(LN_THREADS), LN_SMEM_BYTES, st, 2, ta, tb, tx, tz, p);
   }
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_ln)");
   MMER_LAUNCH_CHECK("gemm_ln_kernel");

@@ -794,6 +794,12 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
         return launch<256, false, false, 2, true, EPI_BIAS | EPI_RELU>(ta, tb, td, tx, p, grid, st);
       if (mode == (EPI_BIAS | EPI_RELU | EPI_DROP | EPI_MASK))
         return launch<256, false, false, 2, true, EPI_BIAS | EPI_RELU | EPI_DROP | EPI_MASK>(ta, tb, td, tx, p, grid, st);
+      // z = residual + dropout(x W^T + b): the pre-LayerNorm sum of a post-norm sub-layer, written instead of the
+      // sub-layer output (engine.cu, ln_mode 2)
+      if (mode == (EPI_BIAS | EPI_DROP | EPI_RES))
+        return launch<256, false, false, 2, true, EPI_BIAS | EPI_DROP | EPI_RES>(ta, tb, td, tx, p, grid, st);
+      if (mode == (EPI_BIAS | EPI_RES))
+        return launch<256, false, false, 2, true, EPI_BIAS | EPI_RES>(ta, tb, td, tx, p, grid, st);
     } else if (!amn && bmn) {
       if (mode == 0) return launch<256, false, true, 2, true, 0>(ta, tb, td, tx, p, grid, st);
       if (mode == EPI_RES) return launch<256, false, true, 2, true, EPI_RES>(ta, tb, td, tx, p, grid, st);

@@ -420,6 +420,8 @@ static int fwd_launch(const void* x, const void* a, const float* gamma, const fl
     if (mode == (LNM_X | LNM_DROP_A))
       return fwd_launch_mode<T, NCH, LNM_X | LNM_DROP_A>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
     if (mode == LNM_X) return fwd_launch_mode<T, NCH, LNM_X>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
+    if (mode == 0)   // LayerNorm of a stored sum z (the GEMM epilogue already added bias, dropout and the residual)
+      return fwd_launch_mode<T, NCH, 0>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
   }
   return fwd_launch_mode<T, NCH, -1>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
 }

@@ -562,3 +562,45 @@ def test_reference_epoch_loop_runs_on_the_device_pieces():
         _, lo, _ = model(v, a, mask=m)
         _, lr_ = ref(v, a, m)
     assert float((lo - lr_).abs().max()) < 1e-4 * max(1.0, float(lr_.abs().max()))
+
+
+# ---------------------------------------------------------------- post-norm sub-layer tails: three kernel arrangements
+def test_layernorm_tail_modes_agree_bf16():
+    """engine.cu ln_mode: (0) GEMM -> a, add_ln(x, a); (1) the fully fused tcgen05 GEMM + LayerNorm kernel (gemm_ln.cu);
+    (2, default) GEMM with the residual epilogue -> z, LayerNorm(z).  Same model, same batch, same dropout seed: logits,
+    loss and every parameter gradient must agree to bf16 rounding, with and without dropout (the three arrangements draw
+    the SAME dropout mask: one counter hash of (seed, site, row * 512 + col))."""
+    from mmer_b200 import _lib
+    lib = _lib.load()
+    B, T = 64, 16                                   # M = 1088 >= 256: the fused arrangements are eligible
+    g = torch.Generator().manual_seed(3)
+    video = torch.randn(B, T, 768, generator=g).cuda().bfloat16()
+    audio = torch.randn(B, 1024, generator=g).cuda().bfloat16()
+    labels = torch.randint(0, 6, (B,), generator=g).cuda()
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None] >= lens[:, None]).cuda()
+    try:
+        for p_drop in (0.0, 0.2):
+            out = {}
+            for knob, name in ((1, "unfused"), (2, "fused kernel"), (0, "residual epilogue")):
+                lib.mmer_debug_set(_lib.DEBUG_NO_LN_FUSE, knob)
+                torch.manual_seed(0)
+                model = mm.MultimodalEmotionModel(max_seq_len=T + 1, classifier_hidden_dim=512, fusion_dropout=p_drop,
+                                                  classifier_dropout=0.0).cuda().train()
+                model.compute_dtype = torch.bfloat16
+                model.__dict__["_base_seed"] = 1234          # same dropout stream for the three runs
+                import mmer_b200.modules as M_
+                M_._seed_counter = __import__("itertools").count(77)
+                _, logits, _ = model(video, audio, mask=mask)
+                loss = mm.FocalLoss(2.0, ALPHA.cuda())(logits, labels)
+                loss.backward()
+                out[name] = (logits.detach().float().clone(), float(loss), model._engine.ctx.grads.clone())
+            ref = out["unfused"]
+            for name in ("fused kernel", "residual epilogue"):
+                lg, ls, gr = out[name]
+                assert float((lg - ref[0]).abs().max()) < 3e-2 * float(ref[0].abs().max()), (name, p_drop)
+                assert abs(ls - ref[1]) < 2e-2 * abs(ref[1]), (name, p_drop)
+                cos = float((gr * ref[2]).sum() / (gr.norm() * ref[2].norm()))
+                assert cos > 0.99 and abs(float(gr.norm() / ref[2].norm()) - 1) < 3e-2, (name, p_drop, cos)
+    finally:
+        lib.mmer_debug_set(_lib.DEBUG_NO_LN_FUSE, 0)
