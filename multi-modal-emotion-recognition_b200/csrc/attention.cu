@@ -20,13 +20,34 @@ int mha_bwd_mma(const void* qkv, const uint8_t* mask, const void* dout, void* dq
                 int d, DropCfg dc, cudaStream_t st);
 extern int g_debug[16];
 bool mha_long_supported(int Tn, int d, int dtype);
-int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc, cudaStream_t st);
+int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc, cudaStream_t st,
+                 float* lse);
 int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn, int H, DropCfg dc,
-                 cudaStream_t st);
+                 cudaStream_t st, const float* lse, const void* fwd_out);
 int mha_fwd_generic(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T, int64_t H,
                     int64_t d, int dtype, DropCfg dc, cudaStream_t st);
 int mha_bwd_generic(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int64_t B, int64_t T,
                     int64_t H, int64_t d, int dtype, DropCfg dc, cudaStream_t st);
+
+// Engine-side entry points: the same dispatch plus, for the long-sequence tensor-core kernels, the softmax statistics
+// (max, 1 / sum per query row; [B, H, S, 2] fp32) that forward can hand to backward together with its own output.
+int mha_fwd_ex(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T, int64_t H, int64_t d,
+               int dtype, float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, float* lse) {
+  if (lse != nullptr && B > 0 && T + 1 > 32 && mha_long_supported((int)T, (int)d, dtype) && !g_debug[MMER_DEBUG_ATT_SIMT])
+    return mha_fwd_long(qkv, mask, out, probs, (int)B, (int)T, (int)H, make_drop(drop_p, seed, site), st, lse);
+  return mmer_mha_fwd(qkv, mask, out, probs, B, T, H, d, dtype, drop_p, seed, site, (void*)st);
+}
+int mha_bwd_ex(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias_qkv, int64_t B, int64_t T,
+               int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, const float* lse,
+               const void* fwd_out) {
+  if (lse != nullptr && fwd_out != nullptr && B > 0 && T + 1 > 32 && mha_long_supported((int)T, (int)d, dtype) &&
+      !g_debug[MMER_DEBUG_ATT_SIMT]) {
+    MMER_TRY(mha_bwd_long(qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, make_drop(drop_p, seed, site), st, lse, fwd_out));
+    if (dbias_qkv != nullptr) return mmer_colsum(dqkv, dbias_qkv, B * (T + 1), 3 * H * d, 3 * H * d, dtype, (void*)st);
+    return 0;
+  }
+  return mmer_mha_bwd(qkv, mask, dout, dqkv, dbias_qkv, B, T, H, d, dtype, drop_p, seed, site, (void*)st);
+}
 
 }  // namespace mmer
 
@@ -43,7 +64,7 @@ int mmer_mha_fwd(const void* qkv, const uint8_t* mask, void* out, float* probs, 
   DropCfg dc = make_drop(drop_p, seed, site);
   cudaStream_t st = (cudaStream_t)stream;
   if (T + 1 > 32 && mha_long_supported((int)T, (int)d, dtype) && !g_debug[MMER_DEBUG_ATT_SIMT])
-    return mha_fwd_long(qkv, mask, out, probs, (int)B, (int)T, (int)H, dc, st);   // tensor-core tiles, S <= 384
+    return mha_fwd_long(qkv, mask, out, probs, (int)B, (int)T, (int)H, dc, st, nullptr);   // tensor-core tiles, S <= 384
   if (T + 1 > 32) return mha_fwd_generic(qkv, mask, out, probs, B, T, H, d, dtype, dc, st);
   const int SP = (int)((T + 1 + 3) & ~3LL);
   if (dtype == MMER_BF16 && !g_debug[MMER_DEBUG_ATT_SIMT])
@@ -63,7 +84,7 @@ int mmer_mha_bwd(const void* qkv, const uint8_t* mask, const void* dout, void* d
   if (T + 1 <= 32 && dtype == MMER_BF16 && !g_debug[MMER_DEBUG_ATT_SIMT])   // in_proj bias gradient fused
     return mha_bwd_mma(qkv, mask, dout, dqkv, dbias_qkv, (int)B, (int)T, (int)H, (int)d, dc, st);
   if (T + 1 > 32 && mha_long_supported((int)T, (int)d, dtype) && !g_debug[MMER_DEBUG_ATT_SIMT]) {
-    MMER_TRY(mha_bwd_long(qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, dc, st));
+    MMER_TRY(mha_bwd_long(qkv, mask, dout, dqkv, (int)B, (int)T, (int)H, dc, st, nullptr, nullptr));
   } else if (T + 1 > 32) {
     MMER_TRY(mha_bwd_generic(qkv, mask, dout, dqkv, B, T, H, d, dtype, dc, st));
   } else {

@@ -18,7 +18,8 @@
 
 namespace mmer {
 
-static constexpr int AL_WARPS = 8;
+static constexpr int AL_WARPS = 8;        // forward kernel (2 CTAs per SM)
+static constexpr int AL_BWD_MAX_WARPS = 9;   // backward: 222 registers per thread allow 9 warps (288 threads)
 static constexpr int AL_D = 64;
 
 struct SwzRow {   // byte offset of (row, col) in a tile of 128-byte rows, 128B-swizzled (what TMA writes)
@@ -150,7 +151,8 @@ __device__ __forceinline__ void stats_update(const float (&sc)[4][4], const uint
 
 __global__ void __launch_bounds__(AL_WARPS * 32, 2)
 mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
-                    const uint8_t* __restrict__ mask, bf16* __restrict__ out, float* __restrict__ probs, LongGeom g, DropCfg dc) {
+                    const uint8_t* __restrict__ mask, bf16* __restrict__ out, float* __restrict__ probs,
+                    float2* __restrict__ lse, LongGeom g, DropCfg dc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = g.S, H = g.H, F = g.F;
@@ -196,6 +198,8 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       inv[r] = 1.f / s;
+      // softmax statistics of the row for the backward kernel (saves it two of its four score recomputations)
+      if (lse != nullptr && t == 0 && q0 + gq + 8 * r < S) lse[bh * S + q0 + gq + 8 * r] = make_float2(m[r], inv[r]);
     }
     float o[8][4];
 #pragma unroll
@@ -252,10 +256,13 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AL_WARPS * 32, 1)
+// The backward kernel's warp count is a launch parameter: a warp owns 16-row query / key tiles, and S = 257 has 17 of
+// them -- 9 warps need two rounds per pass where 8 need three (17 / 8 = 2.1).
+__global__ void __launch_bounds__(AL_BWD_MAX_WARPS * 32, 1)
 mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
                     const __grid_constant__ CUtensorMap d64, const __grid_constant__ CUtensorMap dtail,
-                    const uint8_t* __restrict__ mask, bf16* __restrict__ dqkv, LongGeom g, DropCfg dc) {
+                    const uint8_t* __restrict__ mask, bf16* __restrict__ dqkv, const float2* __restrict__ lse,
+                    const bf16* __restrict__ fwd_out, LongGeom g, DropCfg dc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = g.S, H = g.H, F = g.F;
@@ -270,7 +277,8 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   float* st_d = st_i + g.SR + 32;                                   // D_i = dO_i . O_i      [SR + 32]
   uint8_t* valid = reinterpret_cast<uint8_t*>(st_d + g.SR + 32);
   uint8_t* stage = valid + ((g.SR + 32 + 15) & ~15) + warp * (16 * 144);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + ((g.SR + 32 + 15) & ~15) + AL_WARPS * 16 * 144);
+  const int nwarps = (int)(blockDim.x >> 5);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + ((g.SR + 32 + 15) & ~15) + AL_BWD_MAX_WARPS * 16 * 144);
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), do_a = smem_u32(do_s);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
@@ -296,16 +304,42 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   const SwzRow off;
 
   // ---------------- pass A + B per query tile: statistics, then dQ
-  for (int q0 = warp * 16; q0 < S; q0 += AL_WARPS * 16) {
+  for (int q0 = warp * 16; q0 < S; q0 += nwarps * 16) {
     uint32_t qa[4][4], doa[4][4];
     load_a16(q_a, q0, lane, qa);
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float inv[2];
+    float dsum[2] = {0.f, 0.f};
+    load_a16(do_a, q0, lane, doa);
+    if (lse != nullptr) {
+      // The forward kernel stored (max, 1 / sum) of every row, and D_i = sum_j P_ij f_ij dP_ij equals dO_i . O_i with
+      // the forward output O (dropout included): two of the four score recomputations disappear.
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = q0 + gq + 8 * r;
+        if (i < S) {
+          const float2 st = lse[bh * S + i];
+          m[r] = st.x;
+          inv[r] = st.y;
+          const bf16* orow = fwd_out + ((long long)b * S + i) * F + h * AL_D + t * 16;
+          float ov[16], dv[16];
+          load8(orow, *reinterpret_cast<float(*)[8]>(ov));
+          load8(orow + 8, *reinterpret_cast<float(*)[8]>(ov + 8));
+          load8(reinterpret_cast<const bf16*>(do_s + off(i, t * 16)), *reinterpret_cast<float(*)[8]>(dv));
+          load8(reinterpret_cast<const bf16*>(do_s + off(i, t * 16 + 8)), *reinterpret_cast<float(*)[8]>(dv + 8));
+#pragma unroll
+          for (int c = 0; c < 16; ++c) dsum[r] = fmaf(ov[c], dv[c], dsum[r]);
+        } else {
+          m[r] = 0.f;
+          inv[r] = 0.f;
+        }
+      }
+    } else {
     for (int kb = 0; kb < nkb; ++kb) {
       float sc[4][4];
       block_nt(qa, k_a, kb * 32, lane, sc);
       stats_update(sc, valid, kb * 32, t, sl2, m, l);
     }
-    float inv[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       float s = l[r];
@@ -314,8 +348,6 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       inv[r] = 1.f / s;
     }
     // D_i = sum_j P_ij f_ij dP_ij  with dP_ij = dO_i . V_j   (equals dO_i . O_i; accumulated block by block)
-    load_a16(do_a, q0, lane, doa);
-    float dsum[2] = {0.f, 0.f};
     for (int kb = 0; kb < nkb; ++kb) {
       float sc[4][4], dp[4][4];
       block_nt(qa, k_a, kb * 32, lane, sc);
@@ -334,6 +366,7 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
           dsum[r] = fmaf(p1 * f1, dp[nt][r * 2 + 1], dsum[r]);
         }
       }
+    }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -376,7 +409,7 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
 
   // ---------------- pass C per key tile (transposed domain): dV = Pd^T dO, dK = dS^T Q
   const int nqb = (S + 31) / 32;
-  for (int k0 = warp * 16; k0 < S; k0 += AL_WARPS * 16) {
+  for (int k0 = warp * 16; k0 < S; k0 += nwarps * 16) {
     uint32_t ka[4][4], va[4][4];
     load_a16(k_a, k0, lane, ka);
     load_a16(v_a, k0, lane, va);
@@ -430,7 +463,7 @@ static int long_geom(int B, int Tn, int H, LongGeom* g) {
 }
 static size_t long_smem(const LongGeom& g, int tiles, bool backward) {
   size_t n = (size_t)tiles * g.tile_bytes + ((g.SR + 32 + 15) & ~15) + 16;
-  if (backward) n += (size_t)3 * (g.SR + 32) * sizeof(float) + (size_t)AL_WARPS * 16 * 144;
+  if (backward) n += (size_t)3 * (g.SR + 32) * sizeof(float) + (size_t)AL_BWD_MAX_WARPS * 16 * 144;
   return n;
 }
 static int long_maps(const void* ptr, int cols_total, const LongGeom& g, CUtensorMap* m64, CUtensorMap* mtail) {
@@ -442,7 +475,8 @@ static int long_maps(const void* ptr, int cols_total, const LongGeom& g, CUtenso
 
 bool mha_long_supported(int Tn, int d, int dtype) { return dtype == MMER_BF16 && d == AL_D && Tn + 1 > 32 && Tn + 1 <= 384; }
 
-int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc, cudaStream_t st) {
+int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, int B, int Tn, int H, DropCfg dc, cudaStream_t st,
+                 float* lse) {
   LongGeom g;
   long_geom(B, Tn, H, &g);
   CUtensorMap m64, mtail;
@@ -455,13 +489,14 @@ int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, 
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_fwd_long)");
     configured = smem;
   }
-  mha_fwd_long_kernel<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, g, dc);
+  mha_fwd_long_kernel<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, reinterpret_cast<float2*>(lse), g, dc);
   MMER_LAUNCH_CHECK("mha_fwd_long_kernel");
   return 0;
 }
 
 int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, int B, int Tn, int H, DropCfg dc,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float* lse, const void* fwd_out) {
+  if (fwd_out == nullptr) lse = nullptr;   // the stored statistics are only useful together with the forward output
   LongGeom g;
   long_geom(B, Tn, H, &g);
   CUtensorMap m64, mtail, d64, dtail;
@@ -475,7 +510,11 @@ int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* d
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_bwd_long)");
     configured = smem;
   }
-  mha_bwd_long_kernel<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, d64, dtail, mask, (bf16*)dqkv, g, dc);
+  // fewest rounds over the 16-row tiles with 8 or 9 warps
+  const int ntile = (g.S + 15) / 16;
+  const int nw = ((ntile + 8) / 9 < (ntile + 7) / 8) ? 9 : 8;
+  mha_bwd_long_kernel<<<(unsigned)((long long)B * H), nw * 32, smem, st>>>(m64, mtail, d64, dtail, mask, (bf16*)dqkv, reinterpret_cast<const float2*>(lse),
+                                                                           (const bf16*)fwd_out, g, dc);
   MMER_LAUNCH_CHECK("mha_bwd_long_kernel");
   return 0;
 }

@@ -19,6 +19,11 @@ int bn_fwd_sync(const void* x, const float* gamma, const float* beta, float* run
 int bn_bwd_sync(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
                 float* dgamma, float* dbeta, float* scratch, int64_t N, int64_t C, int dtype, int training, int relu,
                 float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, const BnSync* sy);
+int mha_fwd_ex(const void* qkv, const uint8_t* mask, void* out, float* probs, int64_t B, int64_t T, int64_t H, int64_t d,
+               int dtype, float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, float* lse);
+int mha_bwd_ex(const void* qkv, const uint8_t* mask, const void* dout, void* dqkv, float* dbias_qkv, int64_t B, int64_t T,
+               int64_t H, int64_t d, int dtype, float drop_p, uint64_t seed, uint32_t site, cudaStream_t st, const float* lse,
+               const void* fwd_out);
 int gemm_ln_fwd(const void* A, const void* W, const float* bias, const void* residual, const float* gamma, const float* beta,
                 void* z_out, void* y_out, float* stats, long long M, long long K, DropCfg drop, cudaStream_t st);
 extern int g_debug[16];
@@ -68,6 +73,7 @@ struct LayerWs {
   void *qkv, *att, *ao, *x1, *h, *f2, *x2;
   uint8_t* hmask;   // bf16 mode: 1 bit per element of h (stored value > 0): the ReLU+dropout gate of backward
   float *st1, *st2;
+  float* lse;       // long-sequence attention: (max, 1 / sum) of every softmax row, forward -> backward
 };
 struct Ws {
   void *pv, *pa, *pvn, *pan, *x0;
@@ -111,6 +117,7 @@ static void carve(const mmer_model* m, void* base, Ws* w) {
     L.x2 = c.take(M * F * e);
     L.st1 = (float*)c.take(M * 2 * 4);
     L.st2 = (float*)c.take(M * 2 * 4);
+    L.lse = S > 32 ? (float*)c.take(B * (size_t)m->heads * S * 2 * 4) : nullptr;
   }
   w->pooled = (float*)c.take(B * F * 4);
   w->fused = c.take(B * F * e);
@@ -266,8 +273,8 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
     LayerWs& L = w.L[l];
     MMER_TRY(lin_fwd(m, x, M, F, o[MMER_L_IN_W], o[MMER_L_IN_B], L.qkv, 3 * F, 0, 0.f, 0, st));
     float* probs = m->attn_probs ? m->attn_probs + (int64_t)l * B * m->heads * SS : nullptr;
-    MMER_TRY(mmer_mha_fwd(L.qkv, d.mask, L.att, probs, B, T, m->heads, F / m->heads, d.dt, d.pf, d.seed,
-                          site_layer(l, 0), st));
+    MMER_TRY(mha_fwd_ex(L.qkv, d.mask, L.att, probs, B, T, m->heads, F / m->heads, d.dt, d.pf, d.seed, site_layer(l, 0), st,
+                        L.lse));
     const int lnm = ln_mode(m);   // modes 1 and 2: L.ao / L.f2 hold z1 / z2 (pre-LayerNorm sums)
     if (lnm == 1) {
       MMER_TRY(gemm_ln_fwd(L.att, Wt(m, o[MMER_L_OUT_W]), P(m, o[MMER_L_OUT_B]), x, P(m, o[MMER_L_N1_W]), P(m, o[MMER_L_N1_B]),
@@ -427,8 +434,8 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     }
     MMER_TRY(lin_wgrad(m, d_ao, L.att, M, F, F, o[MMER_L_OUT_W], -1, st));
     MMER_TRY(lin_dgrad(m, d_ao, M, F, o[MMER_L_OUT_W], F, w.g_att, nullptr, nullptr, 0.f, st));
-    MMER_TRY(mmer_mha_bwd(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf,
-                          d.seed, site_layer(l, 0), st));
+    MMER_TRY(mha_bwd_ex(L.qkv, d.mask, w.g_att, w.g_qkv, G(m, o[MMER_L_IN_B]), B, T, m->heads, F / m->heads, d.dt, pf, d.seed,
+                        site_layer(l, 0), st, L.lse, L.att));
     MMER_TRY(lin_wgrad(m, w.g_qkv, xin, M, 3 * F, F, o[MMER_L_IN_W], -1, st));
     MMER_TRY(bucket_done(m, 1 + (m->layers - 1 - l), st));   // every gradient of layer l is final
     MMER_TRY(lin_dgrad(m, w.g_qkv, M, 3 * F, o[MMER_L_IN_W], F, w.g_x, w.g_z1, nullptr, 0.f, st));

@@ -19,7 +19,7 @@ class EagerFusion(nn.Module):
         self.norm_video = nn.LayerNorm(fused_dim)                    # train2.py:104
         self.norm_audio = nn.LayerNorm(fused_dim)                    # train2.py:105
         self.pos_embed = nn.Parameter(torch.randn(1, max_seq_len, fused_dim) * 0.02)   # train2.py:108
-        layer = nn.TransformerEncoderLayer(d_model=fused_dim, nhead=num_heads, dim_feedforward=2048, dropout=dropout,
+        layer = nn.TransformerEncoderLayer(d_model=fused_dim, nhead=num_heads, dim_feedforward=4 * fused_dim, dropout=dropout,
                                            activation="relu", batch_first=False)       # train2.py:111-117
         self.transformer = nn.TransformerEncoder(layer, num_layers=num_layers)          # train2.py:118
         self.dropout_layer = nn.Dropout(dropout)
