@@ -366,6 +366,15 @@ int mmer_event_create(void** event_out);
 int mmer_event_destroy(void* event);
 int mmer_stream_wait_event(void* stream, void* event);
 
+/* Batch-1 serving forward as ONE launch (the live request of back-end/app/libs/inference.py:494-495: one clip window of
+ * <= 5 chunks): a single thread-block cluster walks the whole train2.py model in eval mode; weights stream once, split
+ * by output feature over the cluster's CTAs; activations are exchanged through `scratch` (mmer_serve_scratch_bytes(),
+ * fp32, stays L2-resident) between cluster barriers.  m: variant 2, dtype MMER_BF16, B == 1, T + 1 <= 16, fused 512,
+ * 8 heads; uses params, shadow, off_g / off_l, video [T, video_dim] and audio [audio_dim] (bf16), mask, logits, probs.
+ * Anything else (batches, longer clips, attention weights) goes through mmer_model_forward. */
+int64_t mmer_serve_scratch_bytes(void);
+int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream);
+
 int64_t mmer_workspace_bytes(const mmer_model* m);
 int mmer_model_forward(const mmer_model* m, void* stream);
 int mmer_model_backward(const mmer_model* m, void* stream);

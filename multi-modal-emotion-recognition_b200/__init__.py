@@ -17,12 +17,12 @@ from .attribution import aggregate_importances, compute_attributions  # noqa: F4
 from .data import DeviceFeatureSet, DeviceLoader  # noqa: F401
 from . import data  # noqa: F401
 from .evaluation import EvalAccumulator, metrics_from_confusion  # noqa: F401
-from .inference import GraphedInference  # noqa: F401
+from .inference import GraphedInference, ServingForward  # noqa: F401
 from .dpcheck import dp_selfcheck, weights_checksum  # noqa: F401
 from .training import HostBatchStager, bind_host_to_gpu, list_feature_pairs, load_data, train_model  # noqa: F401
 
 __all__ = ["FocalLoss", "WeightedCrossEntropyLoss", "CrossModalFusion", "EmotionClassifier",
            "MultimodalEmotionModel", "v1", "FusedAdam", "FusedTrainStep", "ops", "MmerError",
            "compute_attributions", "aggregate_importances",
-           "DeviceFeatureSet", "DeviceLoader", "data", "EvalAccumulator", "metrics_from_confusion", "GraphedInference",
+           "DeviceFeatureSet", "DeviceLoader", "data", "EvalAccumulator", "metrics_from_confusion", "GraphedInference", "ServingForward",
            "dp_selfcheck", "weights_checksum", "load_data", "train_model", "HostBatchStager", "list_feature_pairs", "bind_host_to_gpu"]

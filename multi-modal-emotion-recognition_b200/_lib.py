@@ -106,11 +106,14 @@ SIGNATURES = {
     "mmer_cast_f32": [_P, _P, _I64, _P],
     "mmer_bn_fwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _F, _F, _U64, _U32, _P],
     "mmer_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _F, _U64, _U32, _P],
+    "mmer_serve_scratch_bytes": [],
+    "mmer_serve_forward": [C.POINTER(Model), _P, _P],
     "mmer_workspace_bytes": [C.POINTER(Model)],
     "mmer_model_forward": [C.POINTER(Model), _P],
     "mmer_model_backward": [C.POINTER(Model), _P],
 }
-_RESTYPES = {"mmer_last_error": C.c_char_p, "mmer_workspace_bytes": C.c_int64, "mmer_launch_count": C.c_int64}
+_RESTYPES = {"mmer_last_error": C.c_char_p, "mmer_workspace_bytes": C.c_int64, "mmer_launch_count": C.c_int64,
+             "mmer_serve_scratch_bytes": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

@@ -1,0 +1,484 @@
+// Batch-1 serving forward as ONE launch: the live request shape of the reference's API
+// (back-end/app/libs/inference.py:494-495: `probs, logits, _ = fusion_model(video_feats_window[1, <=5, 768],
+// audio_feats[1, 1024], mask=mask)`, window_size 5 at routers/infer.py:9), for which the layer-by-layer engine is pure
+// launch latency (~30 launches, 135-180 us).
+//
+// One thread-block CLUSTER (16 CTAs when the device grants the non-portable size, else 8) walks the whole model
+// (train2.py:128-193, 235-238, 281-292 in eval mode): the 15.5 MB of bf16 weights stream once from L2 / HBM, split by
+// output feature across the CTAs; activations (S = T + 1 <= 16 tokens) live in shared memory and cross CTAs through a
+// small fp32 scratch in global memory (L2) between cluster barriers (11 for two layers).  Every Linear is a skinny GEMM
+// D[16 features x 8 tokens] on warp-level mma.sync m16n8k16: the weight rows arrive as 16-byte global loads straight into
+// A fragments (the contraction index is permuted identically for A and B, so a lane's 8 consecutive k values feed two
+// MMAs), the activations as 16-byte shared-memory loads into B fragments; k is split across warps when a CTA owns fewer
+// than 8 feature tiles, partial tiles are summed through shared memory together with bias / ReLU.
+// LayerNorm, residual adds, attention (one head per warp) and pooling are recomputed redundantly by every CTA from the
+// exchanged activations -- they are a few thousand elements.
+// tcgen05 has no role here: the matrices have 6 rows, the kernel is weight-bandwidth and barrier-latency bound.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mmer {
+
+namespace {
+
+constexpr int SV_THREADS = 256;
+constexpr int SV_WARPS = 8;
+constexpr int SV_MAXS = 16;            // tokens (T + 1)
+constexpr int SV_F = 512;              // d_model
+constexpr int SV_KMAX = 2048;          // widest GEMV input (linear2)
+constexpr int SV_LDX = SV_KMAX + 32;   // bf16 elements per activation row in shared memory: a 64-byte skew keeps the 16-byte
+constexpr int SV_LDA = SV_F + 32;      // B-fragment loads of a quarter warp (2 token rows x 4 k-chunks) on distinct banks
+constexpr float SV_EPS = 1e-5f;
+
+struct ServeParams {
+  int T, S, NT;                        // NT = token tiles of 8
+  int video_dim, audio_dim, ffn, hidden, classes, layers, heads;
+  const bf16* shadow;                  // bf16 weights (flat)
+  const float* params;                 // fp32 masters (biases, LayerNorm, pos_embed, output layer)
+  int64_t off_g[MMER_G_COUNT];
+  int64_t off_l[MMER_MAX_LAYERS][MMER_L_COUNT];
+  const bf16* video;                   // [T][video_dim]
+  const bf16* audio;                   // [audio_dim]
+  const uint8_t* mask;                 // [T] 1 = padded, or NULL
+  float* scratch;                      // fp32 exchange buffers (global, L2-resident)
+  float* logits;
+  float* probs;
+};
+
+// exchange buffers inside scratch (floats)
+constexpr int SC_PRE = 0;                                  // [16][512]  projections before LayerNorm
+constexpr int SC_QKV = SC_PRE + SV_MAXS * SV_F;            // [16][1536]
+constexpr int SC_AO = SC_QKV + SV_MAXS * 3 * SV_F;         // [16][512]
+constexpr int SC_H = SC_AO + SV_MAXS * SV_F;               // [16][2048]
+constexpr int SC_F2 = SC_H + SV_MAXS * SV_KMAX;            // [16][512]
+constexpr int SC_H1 = SC_F2 + SV_MAXS * SV_F;              // [2048] head hidden (pre-norm)
+constexpr int SC_H2 = SC_H1 + SV_KMAX;
+constexpr int SC_TOTAL = SC_H2 + SV_KMAX;
+
+struct Smem {
+  bf16 xs[SV_MAXS * SV_LDX];           // GEMV input, bf16
+  float xf[SV_MAXS * SV_F];            // residual stream, fp32
+  bf16 att[SV_MAXS * SV_LDA];          // attention output, bf16 (input of out_proj)
+  bf16 qkv[SV_WARPS][3 * SV_MAXS * 64];   // per head: q, k, v rows
+  float sc[SV_WARPS][SV_MAXS * SV_MAXS];  // per head: scores / probabilities
+  float part[SV_WARPS][2 * 16 * 8];    // partial D tiles of one round
+  float red[64];
+};
+
+__device__ __forceinline__ uint32_t sv_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t sv_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs; global writes before it are visible to every CTA after it
+__device__ __forceinline__ void sv_cluster_sync() {
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// out[s][n] = act(sum_k xs[s][k] W[n][k] + bias[n]) for n in [n0, n1), s < S.  xs: shared bf16 rows of ldx elements
+// (rows >= S are zero); W: global bf16 [N][K]; out: global fp32 rows of ldo elements.  (n1 - n0) % 16 == 0, K % 256 == 0
+// after the k-split.  Called by all threads of the CTA.
+template <int NT>
+__device__ void sv_linear(Smem& sm, const bf16* xs, int ldx, int K, const bf16* __restrict__ W, const float* __restrict__ bias,
+                          int n0, int n1, float* __restrict__ out, int ldo, int S, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tiles = (n1 - n0) >> 4;
+  int ksplit = 1;
+  while (ksplit * 2 * tiles <= SV_WARPS && (K / (ksplit * 2)) % 32 == 0) ksplit *= 2;
+  const int units = tiles * ksplit;
+  const int klen = K / ksplit;
+  for (int base = 0; base < units; base += SV_WARPS) {
+    const int u = base + warp;
+    if (u < units) {
+      const int tile = u / ksplit, ks = u - tile * ksplit;
+      const bf16* w0 = W + (long long)(n0 + tile * 16 + g) * K + ks * klen + t * 8;
+      const bf16* w1 = w0 + (long long)8 * K;
+      const bf16* x0 = xs + g * ldx + ks * klen + t * 8;
+      float c[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
+#pragma unroll 4
+      for (int kb = 0; kb < klen; kb += 32) {
+        const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(w0 + kb));
+        const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(w1 + kb));
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint4 b = *reinterpret_cast<const uint4*>(x0 + nt * 8 * ldx + kb);
+          mma_bf16_16816(c[nt], a0.x, a1.x, a0.y, a1.y, b.x, b.y);
+          mma_bf16_16816(c[nt], a0.z, a1.z, a0.w, a1.w, b.z, b.w);
+        }
+      }
+      float* pp = sm.part[warp];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        pp[(nt * 16 + g) * 8 + 2 * t] = c[nt][0];
+        pp[(nt * 16 + g) * 8 + 2 * t + 1] = c[nt][1];
+        pp[(nt * 16 + g + 8) * 8 + 2 * t] = c[nt][2];
+        pp[(nt * 16 + g + 8) * 8 + 2 * t + 1] = c[nt][3];
+      }
+    }
+    __syncthreads();
+    // tiles finished in this round: units [base, base + 8) -> tiles base / ksplit ...
+    const int round_units = min(SV_WARPS, units - base);
+    const int round_tiles = round_units / ksplit;
+    for (int e = threadIdx.x; e < round_tiles * 16 * 8 * NT; e += SV_THREADS) {
+      const int tok8 = e & 7, row = (e >> 3) & 15, nt = (e >> 7) % NT, tl = e / (128 * NT);
+      const int s = nt * 8 + tok8;
+      if (s < S) {
+        float v = 0.f;
+        for (int ks = 0; ks < ksplit; ++ks) v += sm.part[tl * ksplit + ks][(nt * 16 + row) * 8 + tok8];
+        const int n = n0 + (base / ksplit + tl) * 16 + row;
+        v += bias != nullptr ? __ldg(bias + n) : 0.f;
+        if (relu) v = fmaxf(v, 0.f);
+        out[(long long)s * ldo + n] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// rows of a global fp32 matrix (written by other CTAs) -> bf16 activation rows in shared memory; rows [S, rows_pad) zeroed
+__device__ void sv_stage_bf16(bf16* xs, int ldx, const float* __restrict__ src, int lds, int S, int rows_pad, int K) {
+  for (int i = threadIdx.x; i < rows_pad * (K / 4); i += SV_THREADS) {
+    const int s = i / (K / 4), c = (i - s * (K / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < S) v = __ldcg(reinterpret_cast<const float4*>(src + (long long)s * lds + c));
+    *reinterpret_cast<uint2*>(xs + s * ldx + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// row-wise LayerNorm over SV_F columns, a warp per row: y = LN(x (+ add)) * gamma + beta (+ pos); fp32 result into xf,
+// bf16 copy into xs.  x may alias xf (in place).
+__device__ void sv_ln_rows(Smem& sm, const float* x, int ldxr, bool x_global, const float* __restrict__ add, int S,
+                           const float* __restrict__ gamma_v, const float* __restrict__ beta_v, const float* __restrict__ gamma_a,
+                           const float* __restrict__ beta_a, int T_split, const float* __restrict__ pos, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < S; s += SV_WARPS) {
+    float v[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 128 + lane * 4;
+      float4 a = x_global ? __ldcg(reinterpret_cast<const float4*>(x + (long long)s * ldxr + c))
+                          : *reinterpret_cast<const float4*>(x + (long long)s * ldxr + c);
+      if (add != nullptr) {
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(add + (long long)s * SV_F + c));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+      sum += a.x + a.y + a.z + a.w;
+    }
+    const float mean = warp_sum(sum) * (1.f / SV_F);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / SV_F) + SV_EPS);
+    const float* gm = s < T_split ? gamma_v : gamma_a;
+    const float* bt = s < T_split ? beta_v : beta_a;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 128 + lane * 4;
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(gm + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bt + c));
+      float4 o;
+      o.x = (v[4 * i] - mean) * rstd * gg.x + bb.x;
+      o.y = (v[4 * i + 1] - mean) * rstd * gg.y + bb.y;
+      o.z = (v[4 * i + 2] - mean) * rstd * gg.z + bb.z;
+      o.w = (v[4 * i + 3] - mean) * rstd * gg.w + bb.w;
+      if (pos != nullptr) {
+        const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + (long long)s * SV_F + c));
+        o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
+      }
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(sm.xf + s * SV_F + c) = o;
+      *reinterpret_cast<uint2*>(sm.xs + s * SV_LDX + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+__device__ void sv_zero_pad_rows(bf16* xs, int ldx, int S, int rows_pad, int K) {
+  for (int i = threadIdx.x; i < (rows_pad - S) * (K / 8); i += SV_THREADS) {
+    const int s = S + i / (K / 8), c = (i % (K / 8)) * 8;
+    *reinterpret_cast<uint4*>(xs + s * ldx + c) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const ServeParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int rank = (int)sv_cluster_rank(), nc = (int)sv_cluster_size();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T, S = p.S, RP = 8 * NT;
+  const int64_t* g = p.off_g;
+  float* sc = p.scratch;
+  auto slice = [&](int N, int* a, int* b) { const int per = N / nc; *a = rank * per; *b = *a + per; };
+  int n0, n1;
+
+  // ---- phase 0: input projections (train2.py:150, 153), video rows then the audio row
+  for (int i = threadIdx.x; i < RP * (p.video_dim / 8); i += SV_THREADS) {
+    const int s = i / (p.video_dim / 8), c = (i % (p.video_dim / 8)) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (s < T) v = __ldg(reinterpret_cast<const uint4*>(p.video + (long long)s * p.video_dim + c));
+    *reinterpret_cast<uint4*>(sm.xs + s * SV_LDX + c) = v;
+  }
+  __syncthreads();
+  slice(SV_F, &n0, &n1);
+  sv_linear<NT>(sm, sm.xs, SV_LDX, p.video_dim, p.shadow + g[MMER_G_WV], p.params + g[MMER_G_BV], n0, n1, sc + SC_PRE, SV_F, T, false);
+  for (int i = threadIdx.x; i < 8 * (p.audio_dim / 8); i += SV_THREADS) {
+    const int s = i / (p.audio_dim / 8), c = (i % (p.audio_dim / 8)) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (s == 0) v = __ldg(reinterpret_cast<const uint4*>(p.audio + c));
+    *reinterpret_cast<uint4*>(sm.xs + s * SV_LDX + c) = v;
+  }
+  __syncthreads();
+  sv_linear<1>(sm, sm.xs, SV_LDX, p.audio_dim, p.shadow + g[MMER_G_WA], p.params + g[MMER_G_BA], n0, n1,
+               sc + SC_PRE + (long long)T * SV_F, SV_F, 1, false);
+  sv_cluster_sync();
+
+  // ---- token assembly (train2.py:151-160): LayerNorm per modality + positional embedding (dropout is identity in eval)
+  sv_zero_pad_rows(sm.xs, SV_LDX, S, RP, SV_KMAX);
+  sv_ln_rows(sm, sc + SC_PRE, SV_F, true, nullptr, S, p.params + g[MMER_G_NV_W], p.params + g[MMER_G_NV_B],
+             p.params + g[MMER_G_NA_W], p.params + g[MMER_G_NA_B], T, p.params + g[MMER_G_POS], false);
+  __syncthreads();
+
+  const int d = SV_F / p.heads;   // 64
+  for (int l = 0; l < p.layers; ++l) {
+    const int64_t* o = p.off_l[l];
+    // ---- packed in-projection (nn.MultiheadAttention.in_proj_weight)
+    slice(3 * SV_F, &n0, &n1);
+    sv_linear<NT>(sm, sm.xs, SV_LDX, SV_F, p.shadow + o[MMER_L_IN_W], p.params + o[MMER_L_IN_B], n0, n1, sc + SC_QKV, 3 * SV_F, S, false);
+    sv_cluster_sync();
+    // ---- attention, one head per warp (every CTA computes all heads: S <= 16)
+    for (int h = warp; h < p.heads; h += SV_WARPS) {
+      bf16* qh = sm.qkv[warp];
+      bf16* kh = qh + SV_MAXS * 64;
+      bf16* vh = kh + SV_MAXS * 64;
+      for (int i = lane; i < S * 16; i += 32) {          // 16 float4 per 64-wide row
+        const int s = i >> 4, c = (i & 15) * 4;
+        const float* row = sc + SC_QKV + (long long)s * 3 * SV_F + h * d + c;
+        const float4 q4 = __ldcg(reinterpret_cast<const float4*>(row));
+        const float4 k4 = __ldcg(reinterpret_cast<const float4*>(row + SV_F));
+        const float4 v4 = __ldcg(reinterpret_cast<const float4*>(row + 2 * SV_F));
+        *reinterpret_cast<uint2*>(qh + s * 64 + c) = make_uint2(pack_bf16x2(q4.x, q4.y), pack_bf16x2(q4.z, q4.w));
+        *reinterpret_cast<uint2*>(kh + s * 64 + c) = make_uint2(pack_bf16x2(k4.x, k4.y), pack_bf16x2(k4.z, k4.w));
+        *reinterpret_cast<uint2*>(vh + s * 64 + c) = make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+      }
+      __syncwarp();
+      float* ps = sm.sc[warp];
+      for (int idx = lane; idx < S * S; idx += 32) {
+        const int i = idx / S, j = idx - i * S;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < 64; c += 2) {
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qh + i * 64 + c));
+          const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kh + j * 64 + c));
+          acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+        }
+        const bool masked = (j < T) && p.mask != nullptr && p.mask[j] != 0;    // key padding mask; the audio token is never masked
+        ps[i * SV_MAXS + j] = masked ? -INFINITY : acc * rsqrtf((float)d);
+      }
+      __syncwarp();
+      if (lane < S) {
+        float mx = -INFINITY;
+        for (int j = 0; j < S; ++j) mx = fmaxf(mx, ps[lane * SV_MAXS + j]);
+        float den = 0.f;
+        for (int j = 0; j < S; ++j) { const float e = __expf(ps[lane * SV_MAXS + j] - mx); ps[lane * SV_MAXS + j] = e; den += e; }
+        const float inv = 1.f / den;
+        for (int j = 0; j < S; ++j) ps[lane * SV_MAXS + j] *= inv;
+      }
+      __syncwarp();
+      for (int i = 0; i < S; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < S; ++j) {
+          const float pj = ps[i * SV_MAXS + j];
+          const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vh + j * 64 + 2 * lane));
+          a0 = fmaf(pj, vv.x, a0);
+          a1 = fmaf(pj, vv.y, a1);
+        }
+        *reinterpret_cast<uint32_t*>(sm.att + i * SV_LDA + h * d + 2 * lane) = pack_bf16x2(a0, a1);
+      }
+      __syncwarp();
+    }
+    sv_zero_pad_rows(sm.att, SV_LDA, S, RP, SV_F);
+    __syncthreads();
+    // ---- out_proj, then x = norm1(x + attention) (post-norm layer, torch transformer.py:945-982)
+    slice(SV_F, &n0, &n1);
+    sv_linear<NT>(sm, sm.att, SV_LDA, SV_F, p.shadow + o[MMER_L_OUT_W], p.params + o[MMER_L_OUT_B], n0, n1, sc + SC_AO, SV_F, S, false);
+    sv_cluster_sync();
+    sv_ln_rows(sm, sm.xf, SV_F, false, sc + SC_AO, S, p.params + o[MMER_L_N1_W], p.params + o[MMER_L_N1_B], nullptr, nullptr, S,
+               nullptr, false);
+    __syncthreads();
+    // ---- feed-forward: linear1 + ReLU, linear2, x = norm2(x + ff)
+    slice(p.ffn, &n0, &n1);
+    sv_linear<NT>(sm, sm.xs, SV_LDX, SV_F, p.shadow + o[MMER_L_FF1_W], p.params + o[MMER_L_FF1_B], n0, n1, sc + SC_H, p.ffn, S, true);
+    sv_cluster_sync();
+    sv_stage_bf16(sm.xs, SV_LDX, sc + SC_H, p.ffn, S, RP, p.ffn);
+    __syncthreads();
+    slice(SV_F, &n0, &n1);
+    sv_linear<NT>(sm, sm.xs, SV_LDX, p.ffn, p.shadow + o[MMER_L_FF2_W], p.params + o[MMER_L_FF2_B], n0, n1, sc + SC_F2, SV_F, S, false);
+    sv_cluster_sync();
+    sv_ln_rows(sm, sm.xf, SV_F, false, sc + SC_F2, S, p.params + o[MMER_L_N2_W], p.params + o[MMER_L_N2_B], nullptr, nullptr, S,
+               nullptr, false);
+    __syncthreads();
+  }
+
+  // ---- masked mean pooling + out_norm (train2.py:184-191): row 0 of xf / xs becomes the fused embedding
+  {
+    float cnt = 0.f;
+    for (int s = 0; s < S; ++s) cnt += ((s < T) && p.mask != nullptr && p.mask[s] != 0) ? 0.f : 1.f;
+    const float inv = 1.f / fmaxf(cnt, 1e-6f);
+    float* pooled = sm.part[0];       // 512 floats: spans part[0] and part[1]
+    for (int c = threadIdx.x; c < SV_F; c += SV_THREADS) {
+      float a = 0.f;
+      for (int s = 0; s < S; ++s)
+        if (!((s < T) && p.mask != nullptr && p.mask[s] != 0)) a += sm.xf[s * SV_F + c];
+      pooled[c] = a * inv;
+    }
+    __syncthreads();
+    sv_zero_pad_rows(sm.xs, SV_LDX, 1, 8, SV_KMAX);
+    sv_ln_rows(sm, pooled, SV_F, false, nullptr, 1, p.params + g[MMER_G_ON_W], p.params + g[MMER_G_ON_B], nullptr, nullptr, 1,
+               nullptr, false);
+    __syncthreads();
+  }
+  // ---- classifier head (train2.py:217-229): Linear -> LayerNorm -> ReLU, twice, then Linear(hidden -> classes) + softmax
+  const int Hd = p.hidden;
+  slice(Hd, &n0, &n1);
+  sv_linear<1>(sm, sm.xs, SV_LDX, SV_F, p.shadow + g[MMER_G_C0_W], p.params + g[MMER_G_C0_B], n0, n1, sc + SC_H1, Hd, 1, false);
+  sv_cluster_sync();
+  // LayerNorm over Hd columns (a warp; Hd <= 2048), ReLU, into xs row 0
+  auto head_norm = [&](const float* src, const float* gm, const float* bt) {
+    if (warp == 0) {
+      float sum = 0.f;
+      for (int c = lane; c < Hd; c += 32) sum += __ldcg(src + c);
+      const float mean = warp_sum(sum) / (float)Hd;
+      float q = 0.f;
+      for (int c = lane; c < Hd; c += 32) { const float dd = __ldcg(src + c) - mean; q = fmaf(dd, dd, q); }
+      const float rstd = rsqrtf(warp_sum(q) / (float)Hd + SV_EPS);
+      for (int c = lane; c < Hd; c += 32) {
+        const float y = fmaxf((__ldcg(src + c) - mean) * rstd * __ldg(gm + c) + __ldg(bt + c), 0.f);
+        sm.xs[c] = __float2bfloat16_rn(y);
+        sm.xf[c] = y;
+      }
+    }
+    __syncthreads();
+  };
+  head_norm(sc + SC_H1, p.params + g[MMER_G_C1_W], p.params + g[MMER_G_C1_B]);
+  sv_linear<1>(sm, sm.xs, SV_LDX, Hd, p.shadow + g[MMER_G_C4_W], p.params + g[MMER_G_C4_B], n0, n1, sc + SC_H2, Hd, 1, false);
+  sv_cluster_sync();
+  if (rank == 0) {
+    head_norm(sc + SC_H2, p.params + g[MMER_G_C5_W], p.params + g[MMER_G_C5_B]);
+    // output layer in fp32 from the master weights (as the engine's head_out kernel), one class per warp
+    const float* W8 = p.params + g[MMER_G_C8_W];
+    for (int c = warp; c < p.classes; c += SV_WARPS) {
+      float a = 0.f;
+      for (int k = lane; k < Hd; k += 32) a = fmaf(sm.xf[k], __ldg(W8 + (long long)c * Hd + k), a);
+      a = warp_sum(a);
+      if (lane == 0) sm.red[c] = a + __ldg(p.params + g[MMER_G_C8_B] + c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mx = -INFINITY;
+      for (int c = 0; c < p.classes; ++c) mx = fmaxf(mx, sm.red[c]);
+      float den = 0.f;
+      for (int c = 0; c < p.classes; ++c) den += expf(sm.red[c] - mx);
+      for (int c = 0; c < p.classes; ++c) {
+        p.logits[c] = sm.red[c];
+        p.probs[c] = expf(sm.red[c] - mx) / den;
+      }
+    }
+  }
+  // no CTA may exit while a peer can still be inside a cluster barrier
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NT>
+static int serve_launch(const ServeParams& p, cudaStream_t st) {
+  auto kern = serve_forward_kernel<NT>;
+  static unsigned long long attr_done = 0ull;
+  static int cluster = 0;
+  const size_t smem = sizeof(Smem);
+  if (needs_func_attr(&attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(serve smem)");
+    // 16 CTAs need the non-portable cluster size; fall back to 8 when the device cannot co-schedule them
+    cluster = 8;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16);
+      cfg.blockDim = dim3(SV_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1) cluster = 16;
+    }
+    (void)cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cluster);
+  cfg.blockDim = dim3(SV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(serve_forward)");
+  MMER_LAUNCH_CHECK("serve_forward_kernel");
+  return 0;
+}
+
+}  // namespace
+
+}  // namespace mmer
+
+using namespace mmer;
+
+extern "C" {
+
+int64_t mmer_serve_scratch_bytes(void) { return (int64_t)SC_TOTAL * 4; }
+
+int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream) {
+  MMER_CHECK_ARG(m != nullptr && scratch != nullptr, "serve_forward: null pointer");
+  MMER_CHECK_ARG(m->variant == 2 && m->dtype == MMER_BF16, "serve_forward: the LayerNorm (train2.py) model in bf16 only");
+  MMER_CHECK_ARG(m->B == 1 && m->T >= 1 && m->T + 1 <= SV_MAXS, "serve_forward: one sample of at most %d frames (B=%d T=%d)",
+                 SV_MAXS - 1, m->B, m->T);
+  MMER_CHECK_ARG(m->fused == SV_F && m->heads == 8 && m->ffn % 256 == 0 && m->ffn <= SV_KMAX && m->video_dim % 256 == 0 &&
+                     m->video_dim <= SV_KMAX && m->audio_dim % 256 == 0 && m->audio_dim <= SV_KMAX && m->hidden % 256 == 0 &&
+                     m->hidden <= SV_KMAX && m->classes <= 16 && m->layers >= 1,
+                 "serve_forward: unsupported dimensions");
+  MMER_CHECK_ARG(m->params && m->shadow && m->video && m->audio && m->logits && m->probs, "serve_forward: null tensor");
+  ServeParams p;
+  p.T = m->T; p.S = m->T + 1; p.NT = (p.S + 7) / 8;
+  p.video_dim = m->video_dim; p.audio_dim = m->audio_dim; p.ffn = m->ffn; p.hidden = m->hidden; p.classes = m->classes;
+  p.layers = m->layers; p.heads = m->heads;
+  p.shadow = reinterpret_cast<const bf16*>(m->shadow);
+  p.params = m->params;
+  for (int i = 0; i < MMER_G_COUNT; ++i) p.off_g[i] = m->off_g[i];
+  for (int l = 0; l < MMER_MAX_LAYERS; ++l)
+    for (int i = 0; i < MMER_L_COUNT; ++i) p.off_l[l][i] = m->off_l[l][i];
+  p.video = reinterpret_cast<const bf16*>(m->video);
+  p.audio = reinterpret_cast<const bf16*>(m->audio);
+  p.mask = m->has_mask ? m->mask : nullptr;
+  p.scratch = reinterpret_cast<float*>(scratch);
+  p.logits = m->logits; p.probs = m->probs;
+  return p.NT == 1 ? serve_launch<1>(p, (cudaStream_t)stream) : serve_launch<2>(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

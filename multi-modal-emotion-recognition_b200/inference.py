@@ -13,7 +13,7 @@ import torch
 
 from ._lib import MmerError
 
-__all__ = ["GraphedInference"]
+__all__ = ["GraphedInference", "ServingForward"]
 
 
 class GraphedInference:
@@ -59,4 +59,76 @@ class GraphedInference:
             else:
                 self.mask.copy_(mask, non_blocking=True)
         self.graph.replay()
+        return self.probs.clone(), self.logits.clone()
+
+
+class ServingForward:
+    """The served call -- one clip window, ``probs, logits, _ = fusion_model(video[1, T, 768], audio[1, 1024], mask)``
+    (back-end/app/libs/inference.py:494-495, T <= window_size = 5) -- as ONE kernel launch: a thread-block cluster walks
+    the whole model (``mmer_serve_forward``, csrc/serve.cu) instead of ~30 launch-bound kernels.
+
+    ``run = ServingForward(model, frames=5); probs, logits = run(video, audio, mask)``.  bf16 weights (the shadow is
+    re-cast from the live fp32 parameters inside the captured graph, so ``load_state_dict`` between calls is picked up),
+    fp32 residual stream, eval mode.  Supports the LayerNorm (train2.py) model, batch 1, ``frames + 1 <= 16`` tokens;
+    other shapes use ``GraphedInference`` / the module call.  Returned tensors are copies."""
+
+    def __init__(self, model, frames: int, device="cuda", use_graph: bool = True):
+        import ctypes as C
+        from . import _lib
+        if not hasattr(model, "_engine") or model._engine.cfg["variant"] != 2:
+            raise MmerError("ServingForward needs the mmer_b200 LayerNorm (train2.py) model")
+        if not 1 <= frames <= 15:
+            raise MmerError("ServingForward serves one clip of 1..15 chunks")
+        dev = torch.device(device)
+        model.eval()
+        self.model, self.frames = model, frames
+        eng = model._engine
+        dv, da = eng.cfg["video_dim"], eng.cfg["audio_dim"]
+        self.video = torch.zeros((1, frames, dv), device=dev, dtype=torch.bfloat16)
+        self.audio = torch.zeros((1, da), device=dev, dtype=torch.bfloat16)
+        self.mask = torch.zeros((1, frames), device=dev, dtype=torch.bool)
+        self.logits = torch.zeros((1, eng.cfg["classes"]), device=dev, dtype=torch.float32)
+        self.probs = torch.zeros_like(self.logits)
+        lib = _lib.load()
+        self.scratch = torch.zeros(int(lib.mmer_serve_scratch_bytes()), device=dev, dtype=torch.uint8)
+        self._lib, self._C = lib, C
+
+        def launch():
+            m = eng.make(1, frames, torch.bfloat16, False, 0.0, 0.0, 0, 0)
+            eng.attach_shadow(m)                      # casts the live fp32 weights (captured in the graph)
+            m.video, m.audio = self.video.data_ptr(), self.audio.data_ptr()
+            m.mask, m.has_mask = self.mask.view(torch.uint8).data_ptr(), 1
+            m.logits, m.probs = self.logits.data_ptr(), self.probs.data_ptr()
+            _lib.check(lib.mmer_serve_forward(C.byref(m), C.c_void_p(self.scratch.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mmer_serve_forward")
+
+        self._launch = launch
+        self.graph = None
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):                    # first-call work (function attributes, cluster size probe) outside the graph
+                    launch()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            if use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    launch()
+
+    @torch.no_grad()
+    def __call__(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+        if tuple(video.shape) != tuple(self.video.shape) or tuple(audio.shape) != tuple(self.audio.shape):
+            raise MmerError(f"this server was built for video {tuple(self.video.shape)} / audio {tuple(self.audio.shape)}")
+        self.video.copy_(video, non_blocking=True)
+        self.audio.copy_(audio, non_blocking=True)
+        if mask is None:
+            self.mask.zero_()
+        else:
+            self.mask.copy_(mask, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
         return self.probs.clone(), self.logits.clone()

@@ -604,3 +604,50 @@ def test_layernorm_tail_modes_agree_bf16():
                 assert cos > 0.99 and abs(float(gr.norm() / ref[2].norm()) - 1) < 3e-2, (name, p_drop, cos)
     finally:
         lib.mmer_debug_set(_lib.DEBUG_NO_LN_FUSE, 0)
+
+
+# ---------------------------------------------------------------- batch-1 serving forward (one cluster kernel)
+@pytest.mark.parametrize("T,masked", [(5, False), (5, True), (1, False), (8, True), (15, True)])
+def test_serving_forward_single_launch_matches_module_and_stock_reference(T, masked):
+    """mmer_serve_forward (csrc/serve.cu) on the served shape (back-end/app/libs/inference.py:494-495): same logits as
+    the layer-by-layer bf16 engine and as the stock fp32 modules on bf16-rounded weights, to bf16 tolerance; argmax equal;
+    parameter changes between calls are picked up (the graph re-casts the shadow)."""
+    from oracle import eager_torch as E
+    torch.manual_seed(T)
+    model = mm.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512).cuda().eval()
+    ref = E.EagerModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512).cuda().eval()
+    last = "classifier.net.8.weight"
+    ref.load_state_dict({k: (v.bfloat16().float() if (v.dim() == 2 and k != last) else v) for k, v in model.state_dict().items()})
+    g = torch.Generator().manual_seed(100 + T)
+    video = torch.randn(1, T, 768, generator=g).bfloat16().cuda()
+    audio = torch.randn(1, 1024, generator=g).bfloat16().cuda()
+    mask = None
+    if masked:
+        mask = torch.zeros(1, T, dtype=torch.bool, device="cuda")
+        mask[0, T - max(1, T // 3):] = True
+    run = mm.ServingForward(model, frames=T)
+    probs, logits = run(video, audio, mask)
+    model.compute_dtype = torch.bfloat16
+    with torch.no_grad():
+        p_eng, l_eng, _ = model(video, audio, mask=mask)
+        p_ref, l_ref = ref(video.float(), audio.float(), mask)
+    scale = float(l_ref.abs().max())
+    assert float((logits - l_ref).abs().max()) < 2e-2 * scale, (logits, l_ref)
+    assert float((logits - l_eng).abs().max()) < 3e-2 * scale
+    assert float((probs - p_ref).abs().max()) < 2e-2
+    assert abs(float(probs.sum()) - 1.0) < 1e-5
+    top2 = l_ref.topk(2).values[0]
+    if float(top2[0] - top2[1]) > 3e-2 * scale:
+        assert int(logits.argmax()) == int(l_ref.argmax())
+    # same call again: identical bits; after an in-place parameter change: follows the module
+    probs2, logits2 = run(video, audio, mask)
+    assert torch.equal(logits2, logits)
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.mul_(1.05)
+        _, l_new, _ = model(video, audio, mask=mask)
+    _, logits3 = run(video, audio, mask)
+    assert float((logits3 - l_new).abs().max()) < 3e-2 * float(l_new.abs().max())
+    assert float((logits3 - logits).abs().max()) > 1e-4
+    with pytest.raises(mm.MmerError):
+        run(video[:, :-1] if T > 1 else torch.zeros(1, 2, 768, device="cuda"), audio, None)
