@@ -514,6 +514,7 @@ def bench_cfg5(dev, pk):
     srv = mm.ServingForward(m, frames=5)            # the whole forward as ONE cluster kernel (csrc/serve.cu)
     out["b1_t5_single_kernel_call_us"] = _event_ms(lambda: srv(v, a, mk), 200, warm=10) * 1e3
     out["b1_t5_single_kernel_graph_only_us"] = _event_ms(srv.graph.replay, 200, warm=10) * 1e3
+    out["b1_t5_single_kernel_phase_ns"] = srv.phase_times()
     torch.manual_seed(0)
     m = mm.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512).to(dev).eval()
     m.compute_dtype = torch.bfloat16

@@ -21,8 +21,9 @@ namespace mmer {
 
 namespace {
 
-constexpr int SV_THREADS = 256;
-constexpr int SV_WARPS = 8;
+constexpr int SV_THREADS = 512;
+constexpr int SV_WARPS = 16;          // enough warps that every skinny GEMM is ONE batch of weight loads per warp
+constexpr int SV_HEADS = 8;
 constexpr int SV_MAXS = 16;            // tokens (T + 1)
 constexpr int SV_F = 512;              // d_model
 constexpr int SV_KMAX = 2048;          // widest GEMV input (linear2)
@@ -53,14 +54,15 @@ constexpr int SC_H = SC_AO + SV_MAXS * SV_F;               // [16][2048]
 constexpr int SC_F2 = SC_H + SV_MAXS * SV_KMAX;            // [16][512]
 constexpr int SC_H1 = SC_F2 + SV_MAXS * SV_F;              // [2048] head hidden (pre-norm)
 constexpr int SC_H2 = SC_H1 + SV_KMAX;
-constexpr int SC_TOTAL = SC_H2 + SV_KMAX;
+constexpr int SC_STAMPS = SC_H2 + SV_KMAX;                 // 64 x int64: globaltimer at the phase boundaries (CTA 0)
+constexpr int SC_TOTAL = SC_STAMPS + 128;
 
 struct Smem {
   bf16 xs[SV_MAXS * SV_LDX];           // GEMV input, bf16
   float xf[SV_MAXS * SV_F];            // residual stream, fp32
   bf16 att[SV_MAXS * SV_LDA];          // attention output, bf16 (input of out_proj)
-  bf16 qkv[SV_WARPS][3 * SV_MAXS * 64];   // per head: q, k, v rows
-  float sc[SV_WARPS][SV_MAXS * SV_MAXS];  // per head: scores / probabilities
+  bf16 qkv[SV_HEADS][3 * SV_MAXS * 64];   // per head: q, k, v rows
+  float sc[SV_HEADS][SV_MAXS * SV_MAXS];  // per head: scores / probabilities
   float part[SV_WARPS][2 * 16 * 8];    // partial D tiles of one round
   float red[64];
 };
@@ -106,7 +108,7 @@ __device__ void sv_linear(Smem& sm, const bf16* xs, int ldx, int K, const bf16* 
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
       for (int kb = 0; kb < klen; kb += 32) {
         const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(w0 + kb));
         const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(w1 + kb));
@@ -148,11 +150,28 @@ __device__ void sv_linear(Smem& sm, const bf16* xs, int ldx, int K, const bf16* 
 
 // rows of a global fp32 matrix (written by other CTAs) -> bf16 activation rows in shared memory; rows [S, rows_pad) zeroed
 __device__ void sv_stage_bf16(bf16* xs, int ldx, const float* __restrict__ src, int lds, int S, int rows_pad, int K) {
-  for (int i = threadIdx.x; i < rows_pad * (K / 4); i += SV_THREADS) {
-    const int s = i / (K / 4), c = (i - s * (K / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s < S) v = __ldcg(reinterpret_cast<const float4*>(src + (long long)s * lds + c));
-    *reinterpret_cast<uint2*>(xs + s * ldx + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  // eight independent 16-byte loads in flight per thread (the whole tensor in one or two batches): a dependent batch of
+  // loads from L2 costs ~1 us here, so the loop must not serialise on them
+  const int per_row = K / 4, total = rows_pad * per_row;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * SV_THREADS) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * SV_THREADS;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total) {
+        const int s = i / per_row, c = (i - s * per_row) * 4;
+        if (s < S) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (long long)s * lds + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * SV_THREADS;
+      if (i < total) {
+        const int s = i / per_row, c = (i - s * per_row) * 4;
+        *reinterpret_cast<uint2*>(xs + s * ldx + c) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+      }
+    }
   }
 }
 
@@ -223,6 +242,19 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
   float* sc = p.scratch;
   auto slice = [&](int N, int* a, int* b) { const int per = N / nc; *a = rank * per; *b = *a + per; };
   int n0, n1;
+  // phase boundaries in ns (CTA 0, thread 0): a profile of the single launch for free (ServingForward.phase_times())
+  long long* stamps = reinterpret_cast<long long*>(sc + SC_STAMPS);
+  int n_stamp = 0;
+  auto stamp = [&]() {
+    if (rank == 0 && threadIdx.x == 0 && n_stamp < 63) {
+      long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      stamps[1 + n_stamp] = tns;
+      stamps[0] = n_stamp + 1;
+    }
+    ++n_stamp;
+  };
+  stamp();
 
   // ---- phase 0: input projections (train2.py:150, 153), video rows then the audio row
   for (int i = threadIdx.x; i < RP * (p.video_dim / 8); i += SV_THREADS) {
@@ -244,12 +276,14 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
   sv_linear<1>(sm, sm.xs, SV_LDX, p.audio_dim, p.shadow + g[MMER_G_WA], p.params + g[MMER_G_BA], n0, n1,
                sc + SC_PRE + (long long)T * SV_F, SV_F, 1, false);
   sv_cluster_sync();
+  stamp();   // 1: projections
 
   // ---- token assembly (train2.py:151-160): LayerNorm per modality + positional embedding (dropout is identity in eval)
   sv_zero_pad_rows(sm.xs, SV_LDX, S, RP, SV_KMAX);
   sv_ln_rows(sm, sc + SC_PRE, SV_F, true, nullptr, S, p.params + g[MMER_G_NV_W], p.params + g[MMER_G_NV_B],
              p.params + g[MMER_G_NA_W], p.params + g[MMER_G_NA_B], T, p.params + g[MMER_G_POS], false);
   __syncthreads();
+  stamp();   // 2: token assembly
 
   const int d = SV_F / p.heads;   // 64
   for (int l = 0; l < p.layers; ++l) {
@@ -258,31 +292,50 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
     slice(3 * SV_F, &n0, &n1);
     sv_linear<NT>(sm, sm.xs, SV_LDX, SV_F, p.shadow + o[MMER_L_IN_W], p.params + o[MMER_L_IN_B], n0, n1, sc + SC_QKV, 3 * SV_F, S, false);
     sv_cluster_sync();
-    // ---- attention, one head per warp (every CTA computes all heads: S <= 16)
+    stamp();   // +1: in_proj
+    // ---- attention (every CTA computes all heads: S <= 16).  q, k, v of all heads: one batch of loads by all threads
+    {
+      const int total = S * 3 * (SV_F / 4);             // float4 items of the [S][1536] matrix
+      for (int i0 = threadIdx.x; i0 < total; i0 += 6 * SV_THREADS) {
+        float4 v[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int i = i0 + u * SV_THREADS;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < total) v[u] = __ldcg(reinterpret_cast<const float4*>(sc + SC_QKV) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int i = i0 + u * SV_THREADS;
+          if (i < total) {
+            const int s = i / (3 * (SV_F / 4)), c = (i - s * (3 * (SV_F / 4))) * 4;   // column in [0, 1536)
+            const int which = c / SV_F, hc = c - which * SV_F, h = hc / 64, cc = hc - h * 64;
+            *reinterpret_cast<uint2*>(sm.qkv[h] + which * SV_MAXS * 64 + s * 64 + cc) =
+                make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+          }
+        }
+      }
+    }
+    __syncthreads();
     for (int h = warp; h < p.heads; h += SV_WARPS) {
-      bf16* qh = sm.qkv[warp];
+      bf16* qh = sm.qkv[h];
       bf16* kh = qh + SV_MAXS * 64;
       bf16* vh = kh + SV_MAXS * 64;
-      for (int i = lane; i < S * 16; i += 32) {          // 16 float4 per 64-wide row
-        const int s = i >> 4, c = (i & 15) * 4;
-        const float* row = sc + SC_QKV + (long long)s * 3 * SV_F + h * d + c;
-        const float4 q4 = __ldcg(reinterpret_cast<const float4*>(row));
-        const float4 k4 = __ldcg(reinterpret_cast<const float4*>(row + SV_F));
-        const float4 v4 = __ldcg(reinterpret_cast<const float4*>(row + 2 * SV_F));
-        *reinterpret_cast<uint2*>(qh + s * 64 + c) = make_uint2(pack_bf16x2(q4.x, q4.y), pack_bf16x2(q4.z, q4.w));
-        *reinterpret_cast<uint2*>(kh + s * 64 + c) = make_uint2(pack_bf16x2(k4.x, k4.y), pack_bf16x2(k4.z, k4.w));
-        *reinterpret_cast<uint2*>(vh + s * 64 + c) = make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
-      }
-      __syncwarp();
-      float* ps = sm.sc[warp];
+      float* ps = sm.sc[h];
       for (int idx = lane; idx < S * S; idx += 32) {
         const int i = idx / S, j = idx - i * S;
         float acc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 64; c += 2) {
-          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qh + i * 64 + c));
-          const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kh + j * 64 + c));
-          acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {              // 16-byte shared-memory loads: 8 per operand row
+          const uint4 qa = *reinterpret_cast<const uint4*>(qh + i * 64 + c);
+          const uint4 kb = *reinterpret_cast<const uint4*>(kh + j * 64 + c);
+          const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qa);
+          const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kb);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __bfloat1622float2(q2[e]), b = __bfloat1622float2(k2[e]);
+            acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+          }
         }
         const bool masked = (j < T) && p.mask != nullptr && p.mask[j] != 0;    // key padding mask; the audio token is never masked
         ps[i * SV_MAXS + j] = masked ? -INFINITY : acc * rsqrtf((float)d);
@@ -311,10 +364,12 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
     }
     sv_zero_pad_rows(sm.att, SV_LDA, S, RP, SV_F);
     __syncthreads();
+    stamp();   // +2: attention
     // ---- out_proj, then x = norm1(x + attention) (post-norm layer, torch transformer.py:945-982)
     slice(SV_F, &n0, &n1);
     sv_linear<NT>(sm, sm.att, SV_LDA, SV_F, p.shadow + o[MMER_L_OUT_W], p.params + o[MMER_L_OUT_B], n0, n1, sc + SC_AO, SV_F, S, false);
     sv_cluster_sync();
+    stamp();   // +3: out_proj
     sv_ln_rows(sm, sm.xf, SV_F, false, sc + SC_AO, S, p.params + o[MMER_L_N1_W], p.params + o[MMER_L_N1_B], nullptr, nullptr, S,
                nullptr, false);
     __syncthreads();
@@ -322,11 +377,14 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
     slice(p.ffn, &n0, &n1);
     sv_linear<NT>(sm, sm.xs, SV_LDX, SV_F, p.shadow + o[MMER_L_FF1_W], p.params + o[MMER_L_FF1_B], n0, n1, sc + SC_H, p.ffn, S, true);
     sv_cluster_sync();
+    stamp();   // +4: norm1 + linear1
     sv_stage_bf16(sm.xs, SV_LDX, sc + SC_H, p.ffn, S, RP, p.ffn);
     __syncthreads();
+    stamp();   // (staging of h)
     slice(SV_F, &n0, &n1);
     sv_linear<NT>(sm, sm.xs, SV_LDX, p.ffn, p.shadow + o[MMER_L_FF2_W], p.params + o[MMER_L_FF2_B], n0, n1, sc + SC_F2, SV_F, S, false);
     sv_cluster_sync();
+    stamp();   // +5: linear2
     sv_ln_rows(sm, sm.xf, SV_F, false, sc + SC_F2, S, p.params + o[MMER_L_N2_W], p.params + o[MMER_L_N2_B], nullptr, nullptr, S,
                nullptr, false);
     __syncthreads();
@@ -350,22 +408,35 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
                nullptr, false);
     __syncthreads();
   }
+  stamp();   // norm2 + pooling + out_norm
   // ---- classifier head (train2.py:217-229): Linear -> LayerNorm -> ReLU, twice, then Linear(hidden -> classes) + softmax
   const int Hd = p.hidden;
   slice(Hd, &n0, &n1);
   sv_linear<1>(sm, sm.xs, SV_LDX, SV_F, p.shadow + g[MMER_G_C0_W], p.params + g[MMER_G_C0_B], n0, n1, sc + SC_H1, Hd, 1, false);
   sv_cluster_sync();
+  stamp();   // head linear 0
   // LayerNorm over Hd columns (a warp; Hd <= 2048), ReLU, into xs row 0
   auto head_norm = [&](const float* src, const float* gm, const float* bt) {
+    // one coalesced pass from global (L2) into shared memory (values, gamma, beta: rows 4.., 8.., 12.. of the residual
+    // buffer, free after pooling; Hd <= 2048), then a warp normalises from there
+    float* buf = sm.xf + 4 * SV_F;
+    float* g_s = sm.xf + 8 * SV_F;
+    float* b_s = sm.xf + 12 * SV_F;
+    for (int c = threadIdx.x; c < Hd; c += SV_THREADS) {
+      buf[c] = __ldcg(src + c);
+      g_s[c] = __ldg(gm + c);
+      b_s[c] = __ldg(bt + c);
+    }
+    __syncthreads();
     if (warp == 0) {
       float sum = 0.f;
-      for (int c = lane; c < Hd; c += 32) sum += __ldcg(src + c);
+      for (int c = lane; c < Hd; c += 32) sum += buf[c];
       const float mean = warp_sum(sum) / (float)Hd;
       float q = 0.f;
-      for (int c = lane; c < Hd; c += 32) { const float dd = __ldcg(src + c) - mean; q = fmaf(dd, dd, q); }
+      for (int c = lane; c < Hd; c += 32) { const float dd = buf[c] - mean; q = fmaf(dd, dd, q); }
       const float rstd = rsqrtf(warp_sum(q) / (float)Hd + SV_EPS);
       for (int c = lane; c < Hd; c += 32) {
-        const float y = fmaxf((__ldcg(src + c) - mean) * rstd * __ldg(gm + c) + __ldg(bt + c), 0.f);
+        const float y = fmaxf((buf[c] - mean) * rstd * g_s[c] + b_s[c], 0.f);
         sm.xs[c] = __float2bfloat16_rn(y);
         sm.xf[c] = y;
       }
@@ -373,14 +444,17 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
     __syncthreads();
   };
   head_norm(sc + SC_H1, p.params + g[MMER_G_C1_W], p.params + g[MMER_G_C1_B]);
+  stamp();   // head norm 0
   sv_linear<1>(sm, sm.xs, SV_LDX, Hd, p.shadow + g[MMER_G_C4_W], p.params + g[MMER_G_C4_B], n0, n1, sc + SC_H2, Hd, 1, false);
   sv_cluster_sync();
+  stamp();   // head linear 1
   if (rank == 0) {
     head_norm(sc + SC_H2, p.params + g[MMER_G_C5_W], p.params + g[MMER_G_C5_B]);
     // output layer in fp32 from the master weights (as the engine's head_out kernel), one class per warp
     const float* W8 = p.params + g[MMER_G_C8_W];
     for (int c = warp; c < p.classes; c += SV_WARPS) {
       float a = 0.f;
+#pragma unroll 16
       for (int k = lane; k < Hd; k += 32) a = fmaf(sm.xf[k], __ldg(W8 + (long long)c * Hd + k), a);
       a = warp_sum(a);
       if (lane == 0) sm.red[c] = a + __ldg(p.params + g[MMER_G_C8_B] + c);
@@ -397,6 +471,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) serve_forward_kernel(const Serv
       }
     }
   }
+  stamp();   // head
   // no CTA may exit while a peer can still be inside a cluster barrier
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -93,9 +93,11 @@ class ServingForward:
         self.scratch = torch.zeros(int(lib.mmer_serve_scratch_bytes()), device=dev, dtype=torch.uint8)
         self._lib, self._C = lib, C
 
-        def launch():
+        def launch(cast: bool = True):
             m = eng.make(1, frames, torch.bfloat16, False, 0.0, 0.0, 0, 0)
-            eng.attach_shadow(m)                      # casts the live fp32 weights (captured in the graph)
+            if cast:
+                eng.attach_shadow(m)                  # casts the live fp32 weights into the bf16 shadow
+            m.shadow = eng.ctx.shadow.data_ptr()
             m.video, m.audio = self.video.data_ptr(), self.audio.data_ptr()
             m.mask, m.has_mask = self.mask.view(torch.uint8).data_ptr(), 1
             m.logits, m.probs = self.logits.data_ptr(), self.probs.data_ptr()
@@ -103,18 +105,42 @@ class ServingForward:
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mmer_serve_forward")
 
         self._launch = launch
-        self.graph = None
+        self.graph = self.graph_cast = None
+        self._cast_state = None       # (flat pointer, parameter versions) the shadow was last cast for
         with torch.no_grad():
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                for _ in range(2):                    # first-call work (function attributes, cluster size probe) outside the graph
+                for _ in range(2):                    # first-call work (function attributes, cluster size probe) outside the graphs
                     launch()
             torch.cuda.current_stream(dev).wait_stream(side)
             if use_graph:
+                # two graphs: shadow cast + kernel (after any parameter change), and the kernel alone (steady state)
+                self.graph_cast = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_cast):
+                    launch(True)
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
-                    launch()
+                    launch(False)
+
+    def _weights_state(self):
+        ctx = self.model._engine.ctx
+        return (ctx.flat.data_ptr() if ctx.flat is not None else 0, ctx.shadow.data_ptr() if ctx.shadow is not None else 0,
+                ctx.param_versions())
+
+    def refresh(self) -> None:
+        """Force a re-cast of the bf16 weights on the next call (needed only after writes through ``param.data``, which
+        carry no version counter; ``load_state_dict``, optimizer steps and in-place ops on the parameters are seen)."""
+        self._cast_state = None
+
+    def phase_times(self):
+        """Nanosecond offsets of the kernel's phase boundaries during the LAST call (stamped by CTA 0 from
+        ``%globaltimer``): projections, token assembly, then per layer in_proj / attention / out_proj / norm1+linear1 /
+        linear2, then norm2+pooling, head."""
+        st = self.scratch.view(torch.int64)[-16 * 4:]           # SC_STAMPS: the last 128 floats = 64 int64
+        st = st.cpu().tolist()
+        n = int(st[0])
+        return [t - st[1] for t in st[1:1 + n]]
 
     @torch.no_grad()
     def __call__(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor] = None
@@ -127,8 +153,11 @@ class ServingForward:
             self.mask.zero_()
         else:
             self.mask.copy_(mask, non_blocking=True)
+        state = self._weights_state()
+        fresh = state == self._cast_state
         if self.graph is not None:
-            self.graph.replay()
+            (self.graph if fresh else self.graph_cast).replay()
         else:
-            self._launch()
+            self._launch(not fresh)
+        self._cast_state = self._weights_state()
         return self.probs.clone(), self.logits.clone()
