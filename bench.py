@@ -39,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_PER_GPU, T, DV, DA, NCLS = 4096, 16, 768, 1024, 6
-LINEAR1_BIAS_FROM_WGRAD = True    # engine.cu: linear1's bias gradient = row sums of the wgrad GEMM's A operand
+LINEAR1_BIAS_FROM_WGRAD = False   # engine.cu: linear1's bias gradient now comes out of linear2's dgrad epilogue (d_colsum)
 ALPHA = [1.0, 1.0, 1.0, 1.0, 1.2, 1.2]
 METRIC, UNIT = "fusion_train_samples_per_s", "samples/s"
 # train2 model, L=2, T=16: 114.89 M MAC forward per sample; train = 3x (fwd + dgrad + wgrad); BASELINE.md section 3
@@ -355,6 +355,10 @@ def time_other_gemms(dev, pk):
     add("linear2 dgrad 69632x512->2048 gated by the ReLU bit mask",
         [lambda i=i: ops.gemm(xs[i], wt, M=M, N=N, K=K, b_major=_lib.MAJOR_MN, gate_bits=masks[i], gate_scale=1.0 / 0.9,
                               out=outs[i]) for i in range(3)], flop)
+    db1 = torch.zeros(N, device=dev)
+    add("linear2 dgrad + linear1 bias gradient (column sums in the epilogue; as the step launches it)",
+        [lambda i=i: ops.gemm(xs[i], wt, M=M, N=N, K=K, b_major=_lib.MAJOR_MN, gate_bits=masks[i], gate_scale=1.0 / 0.9,
+                              out=outs[i], d_colsum=db1) for i in range(3)], flop)
     return res
 
 

@@ -102,6 +102,11 @@ typedef struct mmer_gemm_args {
    * gate_bits     - read by the matching dgrad call: acc *= bit ? gate_scale : 0.  16x less traffic than `gate`. */
   uint8_t* relu_mask_out;
   const uint8_t* gate_bits;
+  /* optional fp32 [N]: += column sums of D as STORED (bf16 output through the staged epilogue; any other output path
+   * adds them with a separate pass).  For a data-gradient GEMM dX = dY W this is the bias gradient of the Linear that
+   * produced X -- linear1's bias gradient comes out of linear2's dgrad epilogue, where the gradient tile is in shared
+   * memory anyway, instead of a row-sum MMA in linear1's weight-gradient GEMM. */
+  float* d_colsum;
 } mmer_gemm_args;
 int mmer_gemm(const mmer_gemm_args* args, void* stream);
 

@@ -39,7 +39,8 @@ class GemmArgs(C.Structure):
                 ("a_major", C.c_int32), ("b_major", C.c_int32), ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
                 ("accumulate", C.c_int32), ("relu", C.c_int32), ("drop_p", C.c_float), ("gate_scale", C.c_float),
                 ("seed", C.c_uint64), ("drop_site", C.c_uint32), ("reserved", C.c_uint32),
-                ("a_rowsum", C.c_void_p), ("relu_mask_out", C.c_void_p), ("gate_bits", C.c_void_p)]
+                ("a_rowsum", C.c_void_p), ("relu_mask_out", C.c_void_p), ("gate_bits", C.c_void_p),
+                ("d_colsum", C.c_void_p)]
 
 
 class Model(C.Structure):

@@ -47,9 +47,17 @@ static int ln_mode(const mmer_model* m) {
 static int lin_fwd_res(const mmer_model* m, const void* x, int64_t M, int64_t K, int64_t offW, int64_t offB, const void* residual,
                        void* z, int64_t N, float drop_p, uint32_t site, cudaStream_t st);
 
+bool gemm_tc_stages_output(const mmer_gemm_args& a);
+
 int gemm_dispatch(const mmer_gemm_args& a, cudaStream_t st) {
-  if (a.in_dtype == MMER_BF16) return gemm_tc(a, st);
+  if (a.in_dtype == MMER_BF16) {
+    MMER_TRY(gemm_tc(a, st));
+    // column sums of D: free in the staged (TMA-store) epilogue, a separate pass otherwise
+    if (a.d_colsum != nullptr && !gemm_tc_stages_output(a)) return mmer_colsum(a.D, a.d_colsum, a.M, a.N, a.ldd, a.out_dtype, st);
+    return 0;
+  }
   MMER_TRY(gemm_simt(a, st));
+  if (a.d_colsum != nullptr) MMER_TRY(mmer_colsum(a.D, a.d_colsum, a.M, a.N, a.ldd, a.out_dtype, st));
   if (a.a_rowsum != nullptr) {
     // fp32 parity mode: the row sums of an MN-major A are the column sums of A as stored ([K][M])
     MMER_CHECK_ARG(a.a_major == MMER_MAJOR_MN, "gemm: a_rowsum needs an MN-major A");
@@ -208,9 +216,10 @@ static int lin_fwd_res(const mmer_model* m, const void* x, int64_t M, int64_t K,
 // dx[M,K] = dy[M,N] W[N,K] (+ residual) (* gate)
 static int lin_dgrad(const mmer_model* m, const void* dy, int64_t M, int64_t N, int64_t offW, int64_t K, void* dx,
                      const void* residual, const void* gate, float gate_scale, cudaStream_t st,
-                     const uint8_t* gate_bits = nullptr) {
+                     const uint8_t* gate_bits = nullptr, float* dx_colsum = nullptr) {
   mmer_gemm_args a = {};
   a.gate_bits = gate_bits;
+  a.d_colsum = m->input_grads_only ? nullptr : dx_colsum;
   a.A = dy; a.B = Wt(m, offW); a.D = dx; a.residual = residual; a.gate = gate; a.gate_scale = gate_scale;
   a.M = M; a.N = K; a.K = N; a.lda = N; a.ldb = K; a.ldd = K;
   a.a_major = MMER_MAJOR_K; a.b_major = MMER_MAJOR_MN;
@@ -418,8 +427,11 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     // which costs that GEMM ~20 % and is therefore used only where no producer can do it
     // the gate is read as the bit mask the forward epilogue wrote (1/16 of re-reading h) when there is one
     const uint8_t* hmask = d.tr ? L.hmask : nullptr;   // written by the forward pass in training mode only
-    MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, hmask ? nullptr : L.h, relu_gate_scale, st, hmask));
-    MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], o[MMER_L_FF1_B], st));
+    // linear1's bias gradient = column sums of g_h: taken from the staged tile in this GEMM's epilogue (it used to be a
+    // row-sum MMA inside linear1's weight-gradient GEMM, ~20 % of that kernel)
+    MMER_TRY(lin_dgrad(m, d_f2, M, F, o[MMER_L_FF2_W], FF, w.g_h, nullptr, hmask ? nullptr : L.h, relu_gate_scale, st, hmask,
+                       G(m, o[MMER_L_FF1_B])));
+    MMER_TRY(lin_wgrad(m, w.g_h, L.x1, M, FF, F, o[MMER_L_FF1_W], -1, st));
     MMER_TRY(lin_dgrad(m, w.g_h, M, FF, o[MMER_L_FF1_W], F, w.g_x1, w.g_z2, nullptr, 0.f, st));
     // norm1 <- attention
     void* d_ao = pf > 0.f ? w.g_ao : w.g_z1;

@@ -40,6 +40,7 @@ struct GemmParams {
   float* rowsum;  // direct (accumulate) path: += sum_k A[m][k] per output row m
   uint8_t* mask_out;          // staged path: 1 bit per output element, set where the stored value is > 0
   const uint8_t* gate_bits;   // staged path: acc *= bit ? gate_scale : 0 (the mask a forward call wrote)
+  float* colsum;              // staged path: += column sums of the stored bf16 tile (rows past M hold zeros)
   long long ldmask;           // bytes per row of either bit matrix (N / 8)
   int tma_store;  // bf16 output leaves through swizzled smem staging + TMA store (coalesced)
   int aux_mode;   // staged path only: 0 none, 1 residual add, 2 ReLU gate; the aux tile arrives by TMA
@@ -103,7 +104,7 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, bool relu, bool d
 // Epilogue specialisation of the staged kernels: EPI < 0 decides everything at run time (any combination);
 // EPI >= 0 is a bit set fixed at compile time, which removes the predicated code of the unused features from the
 // per-element loop -- the epilogue warps are issue-bound, so instruction count is throughput here.
-enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_DROP = 4, EPI_MASK = 8, EPI_RES = 16, EPI_GATE = 32, EPI_GBITS = 64 };
+enum : int { EPI_BIAS = 1, EPI_RELU = 2, EPI_DROP = 4, EPI_MASK = 8, EPI_RES = 16, EPI_GATE = 32, EPI_GBITS = 64, EPI_COLSUM = 128 };
 
 template <int BN, bool A_MN, bool B_MN, int CG, bool STAGED, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -158,6 +159,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool f_mask = EPI < 0 ? p.mask_out != nullptr : (EPI & EPI_MASK) != 0;
   const int f_aux = EPI < 0 ? p.aux_mode : ((EPI & EPI_RES) ? 1 : (EPI & EPI_GATE) ? 2 : 0);
   const bool f_gbits = EPI < 0 ? p.gate_bits != nullptr : (EPI & EPI_GBITS) != 0;
+  const bool f_colsum = EPI < 0 ? p.colsum != nullptr : (EPI & EPI_COLSUM) != 0;
+  (void)f_colsum;
   (void)f_bias; (void)f_relu; (void)f_drop; (void)f_mask; (void)f_aux; (void)f_gbits;
   if (want_rowsum) {
     // bf16 ones: with them as the B operand an extra N = 16 MMA per k-step accumulates sum_k A[m][k] -- for a
@@ -451,6 +454,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (f_mask && row_ok)
             *reinterpret_cast<uint2*>(p.mask_out + row * p.ldmask + (col0 >> 3)) = mbits;
+          if (f_colsum) {
+            // column sums of the tile just staged: lane l owns columns 2l, 2l+1 and walks the 32 rows (one 4-byte word
+            // per row; the 32 lanes read the 32 distinct words of a 128-byte row: conflict free).  Rows past M are zero
+            // (zero-filled A rows, no bias on this path), so no row predicate is needed.
+            __syncwarp();
+            float c0 = 0.f, c1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(tile + rr * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)rr & 7u)) << 4) +
+                                                                     ((uint32_t)lane & 3u) * 4u);
+              c0 += __uint_as_float(wv << 16);
+              c1 += __uint_as_float(wv & 0xFFFF0000u);
+            }
+            const int cc = col0 + 2 * lane;
+            if (cc < p.N) atomicAdd(p.colsum + cc, c0);
+            if (cc + 1 < p.N) atomicAdd(p.colsum + cc + 1, c1);
+          }
           PROF_TICK(3);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -683,6 +703,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   return 0;
 }
 
+// true when gemm_tc sends this problem's output through the staged (shared-memory + TMA store) epilogue
+bool gemm_tc_stages_output(const mmer_gemm_args& a) {
+  return a.out_dtype == MMER_BF16 && !a.accumulate && a.ldd % 8 == 0 && !(a.gate && a.residual) && !g_debug[MMER_DEBUG_DIRECT_STORE];
+}
+
 int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   MMER_CHECK_ARG(a.in_dtype == MMER_BF16, "gemm_tc: bf16 inputs only");
   MMER_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tc: empty problem M=%lld N=%lld K=%lld", (long long)a.M,
@@ -698,6 +723,8 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   MMER_CHECK_ARG(a.a_rowsum == nullptr || (a.accumulate && a.a_major == MMER_MAJOR_MN),
                  "gemm_tc: a_rowsum needs accumulate mode and an MN-major A (weight-gradient GEMM)");
   MMER_CHECK_ARG(!(a.a_major == MMER_MAJOR_MN && a.b_major == MMER_MAJOR_K), "gemm_tc: (MN,K) operand majors unused");
+  MMER_CHECK_ARG(a.d_colsum == nullptr || (a.bias == nullptr && a.residual == nullptr && !a.accumulate),
+                 "gemm_tc: d_colsum is for data-gradient GEMMs (no bias, no residual, no accumulation)");
 
   const int nsm = sm_count();
   // CTA pairs (cta_group::2, 256 x 256 tiles) whenever the problem offers enough of them to fill the machine;
@@ -764,6 +791,7 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
   p.num_m = num_m; p.num_n = num_n; p.splits = splits; p.kb_total = kb_total; p.kb_per_split = kb_per;
   p.rowsum = a.a_rowsum;
   p.mask_out = a.relu_mask_out; p.gate_bits = a.gate_bits; p.ldmask = a.N / 8;
+  p.colsum = tma_store ? a.d_colsum : nullptr;   // other output paths: a separate pass (gemm_dispatch)
   p.D = a.D; p.ldd = a.ldd; p.bias = a.bias; p.residual = a.residual; p.gate = a.gate; p.gate_scale = a.gate_scale;
   p.out_f32 = a.out_dtype == MMER_F32; p.accumulate = a.accumulate; p.relu = a.relu;
   p.mn_swap = g_debug[MMER_DEBUG_MN_SWAP];
@@ -787,7 +815,7 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
     // the step's hot epilogues get their own instantiation (see EPI_* above); anything else runs the generic one
     const int mode = (a.bias ? EPI_BIAS : 0) | (a.relu ? EPI_RELU : 0) | (p.drop.thr ? EPI_DROP : 0) |
                      (a.relu_mask_out ? EPI_MASK : 0) | (p.aux_mode == 1 ? EPI_RES : 0) | (p.aux_mode == 2 ? EPI_GATE : 0) |
-                     (a.gate_bits ? EPI_GBITS : 0);
+                     (a.gate_bits ? EPI_GBITS : 0) | (p.colsum ? EPI_COLSUM : 0);
     if (!amn && !bmn) {
       if (mode == EPI_BIAS) return launch<256, false, false, 2, true, EPI_BIAS>(ta, tb, td, tx, p, grid, st);
       if (mode == (EPI_BIAS | EPI_RELU))   // linear1 in eval mode (inference forward)
@@ -804,6 +832,8 @@ int gemm_tc(const mmer_gemm_args& a, cudaStream_t st) {
       if (mode == 0) return launch<256, false, true, 2, true, 0>(ta, tb, td, tx, p, grid, st);
       if (mode == EPI_RES) return launch<256, false, true, 2, true, EPI_RES>(ta, tb, td, tx, p, grid, st);
       if (mode == EPI_GBITS) return launch<256, false, true, 2, true, EPI_GBITS>(ta, tb, td, tx, p, grid, st);
+      if (mode == (EPI_GBITS | EPI_COLSUM))   // linear2 dgrad + linear1 bias gradient
+        return launch<256, false, true, 2, true, EPI_GBITS | EPI_COLSUM>(ta, tb, td, tx, p, grid, st);
     }
   }
   if (cg == 2) MMER_GEMM_LAUNCH(256, 2);

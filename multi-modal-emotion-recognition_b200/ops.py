@@ -47,7 +47,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_l
          bias=None, residual=None, gate=None, gate_scale=1.0, relu=False, drop_p=0.0, seed=0, site=0,
          out: Optional[torch.Tensor] = None, out_dtype=None, accumulate=False,
          a_rowsum: Optional[torch.Tensor] = None, relu_mask_out: Optional[torch.Tensor] = None,
-         gate_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+         gate_bits: Optional[torch.Tensor] = None, d_colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M,N] = epilogue(A[M,K] . B[N,K]^T); see mmer_gemm in include/mmer.h."""
     for t in (A, B, bias, residual, gate, out):
         if t is not None and not t.is_cuda:
@@ -75,6 +75,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major=_l
             if t.dtype != torch.uint8 or not t.is_cuda or t.numel() != M * N // 8:
                 raise TypeError(f"{name} must be a CUDA uint8 tensor of M*N/8 bytes")
             setattr(a, name, t.data_ptr())
+    if d_colsum is not None:
+        if d_colsum.dtype != torch.float32 or not d_colsum.is_cuda or d_colsum.numel() != N:
+            raise TypeError("d_colsum must be a CUDA float32 tensor of N elements")
+        a.d_colsum = d_colsum.data_ptr()
     a.drop_p, a.gate_scale, a.seed, a.drop_site = float(drop_p), float(gate_scale), int(seed), int(site)
     call("mmer_gemm", C.byref(a), _stream())
     return out
