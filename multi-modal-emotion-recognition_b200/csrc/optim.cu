@@ -106,13 +106,19 @@ __global__ void publish_slot_mc_kernel(const float* __restrict__ local, float* _
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(slots_mc + rank), "f"(*local) : "memory");
 }
 
+// Four independent 16-byte chunks per thread: the switch-reduced gradient load (multimem.ld_reduce) is a ~2-4 us round
+// trip through NVSwitch, and with one chunk per thread the kernel was bound by that latency (0.12 ms for a 1/8 shard of
+// 7.77 M parameters, profiles/r02_bench_n8.json dp_wait) -- all four reductions and the twelve local loads are issued
+// before the first result is used.
+constexpr int ADAM_MC_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 adam_shard_mc_kernel(const float* __restrict__ p, float* __restrict__ p_mc, const float* __restrict__ g_mc,
                      float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow_mc, long long lo, long long hi,
                      float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps, float wd,
                      float inv_sqrt_bc2, float grad_scale, const float* __restrict__ sumsq_slots, int n_slots, float max_norm) {
-  const long long i = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= hi) return;   // lo, hi and the buffer length are multiples of 4
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long i0 = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;   // lo, hi, buffer length: multiples of 4
+  if (i0 >= hi) return;
   if (sumsq_slots != nullptr) {
     // torch.nn.utils.clip_grad_norm_ on the averaged gradient: coef = max_norm / (total_norm + 1e-6), clamped to 1
     float ss = 0.f;
@@ -120,24 +126,40 @@ adam_shard_mc_kernel(const float* __restrict__ p, float* __restrict__ p_mc, cons
     const float total = sqrtf(ss) * fabsf(grad_scale);
     grad_scale *= fminf(max_norm / (total + 1e-6f), 1.f);
   }
-  float4 pv = *reinterpret_cast<const float4*>(p + i);
-  const float4 gv = mc_ld_reduce_add(g_mc + i);
-  float4 mv = *reinterpret_cast<float4*>(m + (i - lo));   // the moments exist for this rank's shard only (ZeRO-1)
-  float4 vv = *reinterpret_cast<float4*>(v + (i - lo));
-  float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
+  float4 gv[ADAM_MC_UNROLL], pv[ADAM_MC_UNROLL], mv[ADAM_MC_UNROLL], vv[ADAM_MC_UNROLL];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {   // same arithmetic, in the same order, as adam_kernel
-    const float gr = fmaf(wd, pp[k], gg[k] * grad_scale);
-    mm[k] = fmaf(beta1, mm[k], omb1 * gr);
-    vq[k] = fmaf(beta2, vq[k], omb2 * gr * gr);
-    pp[k] -= lr_over_bc1 * mm[k] / (sqrtf(vq[k]) * inv_sqrt_bc2 + eps);
+  for (int u = 0; u < ADAM_MC_UNROLL; ++u) {
+    const long long i = i0 + (long long)u * nthreads * 4;
+    if (i < hi) gv[u] = mc_ld_reduce_add(g_mc + i);
   }
-  *reinterpret_cast<float4*>(m + (i - lo)) = mv;
-  *reinterpret_cast<float4*>(v + (i - lo)) = vv;
-  mc_st_f32x4(p_mc + i, pv);
-  if (shadow_mc != nullptr) {
-    __nv_bfloat162 l2 = __floats2bfloat162_rn(pv.x, pv.y), h2 = __floats2bfloat162_rn(pv.z, pv.w);
-    mc_st_b32x2(shadow_mc + i, *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&h2));
+#pragma unroll
+  for (int u = 0; u < ADAM_MC_UNROLL; ++u) {
+    const long long i = i0 + (long long)u * nthreads * 4;
+    if (i < hi) {
+      pv[u] = *reinterpret_cast<const float4*>(p + i);
+      mv[u] = *reinterpret_cast<float4*>(m + (i - lo));   // the moments exist for this rank's shard only (ZeRO-1)
+      vv[u] = *reinterpret_cast<float4*>(v + (i - lo));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < ADAM_MC_UNROLL; ++u) {
+    const long long i = i0 + (long long)u * nthreads * 4;
+    if (i >= hi) continue;
+    float* pp = &pv[u].x; const float* gg = &gv[u].x; float* mm = &mv[u].x; float* vq = &vv[u].x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // same arithmetic, in the same order, as adam_kernel
+      const float gr = fmaf(wd, pp[k], gg[k] * grad_scale);
+      mm[k] = fmaf(beta1, mm[k], omb1 * gr);
+      vq[k] = fmaf(beta2, vq[k], omb2 * gr * gr);
+      pp[k] -= lr_over_bc1 * mm[k] / (sqrtf(vq[k]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(m + (i - lo)) = mv[u];
+    *reinterpret_cast<float4*>(v + (i - lo)) = vv[u];
+    mc_st_f32x4(p_mc + i, pv[u]);
+    if (shadow_mc != nullptr) {
+      __nv_bfloat162 l2 = __floats2bfloat162_rn(pv[u].x, pv[u].y), h2 = __floats2bfloat162_rn(pv[u].z, pv[u].w);
+      mc_st_b32x2(shadow_mc + i, *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&h2));
+    }
   }
 }
 
@@ -236,7 +258,7 @@ int mmer_adam_step_multicast(const float* p_local, float* p_mc, const float* g_m
   const double b2 = strtod(buf, nullptr);
   const double bc1 = 1.0 - pow(b1, (double)step);
   const double bc2 = 1.0 - pow(b2, (double)step);
-  const long long nt = (hi - lo) / 4;
+  const long long nt = ((hi - lo) / 4 + ADAM_MC_UNROLL - 1) / ADAM_MC_UNROLL;   // threads: four 16-byte chunks each
   adam_shard_mc_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       p_local, p_mc, g_mc, m, v, (bf16*)shadow_mc, lo, hi, (float)(lr / bc1), beta1, beta2, (float)(1.0 - b1),
       (float)(1.0 - b2), eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale, sumsq_slots, n_slots, max_norm);

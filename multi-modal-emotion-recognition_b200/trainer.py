@@ -401,13 +401,20 @@ class FusedTrainStep:
         names = ["pre_barrier_ms", "clip_ms", "adam_ms", "post_barrier_ms"]
         acc = [0.0] * 4
         step_ms = 0.0
+        # No host synchronisation inside the loop: the host must stay AHEAD of the device as it does in a real run,
+        # otherwise the gaps between the events measure Python launch latency instead of device-side waiting.
+        for _ in range(3):
+            self.step(video, audio, mask, labels)
+        traces = []
         for _ in range(steps):
             self._trace = []
             e0 = self._mark()
             self.step(video, audio, mask, labels)
             e1 = self._mark()
-            torch.cuda.synchronize()
-            tr, self._trace = self._trace, None
+            traces.append((e0, e1, self._trace))
+            self._trace = None
+        torch.cuda.synchronize()
+        for e0, e1, tr in traces:
             step_ms += e0.elapsed_time(e1)
             if len(tr) == 5:
                 for i in range(4):
