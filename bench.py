@@ -315,7 +315,7 @@ def time_dominant_kernel(dev, pk):
     tflops = tot_flop / (tot_ms * 1e-3) / 1e12
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")) as f:
             traffic = json.load(f)["traffic_bytes"]
     except Exception:
         pass
@@ -324,7 +324,7 @@ def time_dominant_kernel(dev, pk):
             "peak_source": pk["src"] + " bf16_tflops (burst: kernels timed alone)", "ms_per_launch": tot_ms / launches,
             "launches_per_step": launches, "algorithmic_flop_per_step": tot_flop, "shapes": per_shape, "traffic": traffic,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the linear1 launch (dW[2048,512], 69,632 "
-                              "tokens), profiles/r01_roofline_traffic.json"}
+                              "tokens), profiles/r02_roofline_traffic.json"}
 
 
 def time_other_gemms(dev, pk):
