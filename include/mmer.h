@@ -60,6 +60,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_FORCE_SPLITS 10 /* tcgen05 GEMM, accumulate mode: force the split-K factor; A/B timing */
 #define MMER_DEBUG_LN_VARIANT 12 /* fused GEMM+LayerNorm kernel: switch parts of the epilogue off (bit mask); A/B timing only, results are wrong */
 #define MMER_DEBUG_NO_LN_FUSE 11 /* engine, post-norm sub-layer tails: 0 default (GEMM with residual epilogue -> z, then LayerNorm(z)); 1 GEMM -> a, add_ln(x, a); 2 the fully fused GEMM+LayerNorm kernel; A/B timing */
+#define MMER_DEBUG_SERVE_GLOBAL 13 /* batch-1 serving kernel: exchange activations through the global scratch buffer even when S <= 8 (A/B timing) */
 #define MMER_DEBUG_ATT_SIMT 4    /* bf16 short-sequence attention: use the FMA kernels instead of the MMA ones (A/B timing) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);

@@ -521,6 +521,9 @@ static int serve_launch(const ServeParams& p, cudaStream_t st) {
 
 }  // namespace
 
+extern int g_debug[16];
+int serve_forward_dsmem(const mmer_model* m, long long* stamps, cudaStream_t st);
+
 }  // namespace mmer
 
 using namespace mmer;
@@ -548,6 +551,11 @@ int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream) {
   for (int i = 0; i < MMER_G_COUNT; ++i) p.off_g[i] = m->off_g[i];
   for (int l = 0; l < MMER_MAX_LAYERS; ++l)
     for (int i = 0; i < MMER_L_COUNT; ++i) p.off_l[l][i] = m->off_l[l][i];
+  // S <= 8: the distributed-shared-memory kernel (serve_dsmem.cu); the stamps keep their place in the scratch buffer
+  if (!g_debug[MMER_DEBUG_SERVE_GLOBAL]) {
+    const int r = serve_forward_dsmem(m, reinterpret_cast<long long*>(reinterpret_cast<float*>(scratch) + SC_STAMPS), (cudaStream_t)stream);
+    if (r <= 0) return r;
+  }
   p.video = reinterpret_cast<const bf16*>(m->video);
   p.audio = reinterpret_cast<const bf16*>(m->audio);
   p.mask = m->has_mask ? m->mask : nullptr;

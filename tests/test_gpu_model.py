@@ -607,7 +607,7 @@ def test_layernorm_tail_modes_agree_bf16():
 
 
 # ---------------------------------------------------------------- batch-1 serving forward (one cluster kernel)
-@pytest.mark.parametrize("T,masked", [(5, False), (5, True), (1, False), (8, True), (15, True)])
+@pytest.mark.parametrize("T,masked", [(5, False), (5, True), (1, False), (7, True), (8, True), (15, True)])
 def test_serving_forward_single_launch_matches_module_and_stock_reference(T, masked):
     """mmer_serve_forward (csrc/serve.cu) on the served shape (back-end/app/libs/inference.py:494-495): same logits as
     the layer-by-layer bf16 engine and as the stock fp32 modules on bf16-rounded weights, to bf16 tolerance; argmax equal;
@@ -651,3 +651,28 @@ def test_serving_forward_single_launch_matches_module_and_stock_reference(T, mas
     assert float((logits3 - logits).abs().max()) > 1e-4
     with pytest.raises(mm.MmerError):
         run(video[:, :-1] if T > 1 else torch.zeros(1, 2, 768, device="cuda"), audio, None)
+
+
+@pytest.mark.parametrize("T", [1, 5, 7])
+def test_serving_forward_shared_memory_exchange_equals_global_scratch_exchange(T):
+    """S <= 8 runs csrc/serve_dsmem.cu (activations stored into every CTA's shared memory); MMER_DEBUG_SERVE_GLOBAL
+    forces csrc/serve.cu (global scratch).  Same roundings at the same places (summation order differs): the logits agree to a few bf16 flips."""
+    from mmer_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(40 + T)
+    model = mm.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512).cuda().eval()
+    g = torch.Generator().manual_seed(7 + T)
+    video = torch.randn(1, T, 768, generator=g).bfloat16().cuda()
+    audio = torch.randn(1, 1024, generator=g).bfloat16().cuda()
+    mask = torch.zeros(1, T, dtype=torch.bool, device="cuda")
+    if T > 2:
+        mask[0, T - 2:] = True
+    run = mm.ServingForward(model, frames=T, use_graph=False)
+    try:
+        _, l_shared = run(video, audio, mask)
+        l_shared = l_shared.clone()
+        lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 1)
+        _, l_global = run(video, audio, mask)
+    finally:
+        lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 0)
+    assert float((l_shared - l_global).abs().max()) < 5e-3 * float(l_global.abs().max())
