@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmmer_sm100.so")
 SOURCES = ["api", "gemm_tc", "gemm_ln", "gemm_simt", "rowops", "attention", "attention_fwd_bf16", "attention_fwd_f32", "attention_bwd_bf16",
-           "attention_bwd_f32", "attention_generic", "attention_mma", "attention_long", "ln_pipe", "loss_head", "optim", "bn", "attribution", "batch", "evalops", "serve", "serve_dsmem",
+           "attention_bwd_f32", "attention_generic", "attention_mma", "attention_long", "ln_pipe", "loss_head", "optim", "bn", "attribution", "batch", "evalops", "serve", "serve_dsmem", "serve_small",
            "engine"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

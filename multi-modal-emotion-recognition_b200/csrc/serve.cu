@@ -523,6 +523,7 @@ static int serve_launch(const ServeParams& p, cudaStream_t st) {
 
 extern int g_debug[16];
 int serve_forward_dsmem(const mmer_model* m, long long* stamps, cudaStream_t st);
+int serve_forward_small(const mmer_model* m, float* scratch, long long* stamps, int64_t scratch_floats_before_stamps, cudaStream_t st);
 
 }  // namespace mmer
 
@@ -551,9 +552,15 @@ int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream) {
   for (int i = 0; i < MMER_G_COUNT; ++i) p.off_g[i] = m->off_g[i];
   for (int l = 0; l < MMER_MAX_LAYERS; ++l)
     for (int i = 0; i < MMER_L_COUNT; ++i) p.off_l[l][i] = m->off_l[l][i];
-  // S <= 8: the distributed-shared-memory kernel (serve_dsmem.cu); the stamps keep their place in the scratch buffer
-  if (!g_debug[MMER_DEBUG_SERVE_GLOBAL]) {
-    const int r = serve_forward_dsmem(m, reinterpret_cast<long long*>(reinterpret_cast<float*>(scratch) + SC_STAMPS), (cudaStream_t)stream);
+  // S <= 8 at the default widths: the head-local / split-K kernel (serve_small.cu); knob 2: the variant that broadcasts
+  // activations into every CTA's shared memory (serve_dsmem.cu, measured slower).  The stamps keep their place.
+  {
+    long long* stamps = reinterpret_cast<long long*>(reinterpret_cast<float*>(scratch) + SC_STAMPS);
+    int r = 1;
+    if (g_debug[MMER_DEBUG_SERVE_GLOBAL] == 0)
+      r = serve_forward_small(m, reinterpret_cast<float*>(scratch), stamps, SC_STAMPS, (cudaStream_t)stream);
+    else if (g_debug[MMER_DEBUG_SERVE_GLOBAL] == 2)
+      r = serve_forward_dsmem(m, stamps, (cudaStream_t)stream);
     if (r <= 0) return r;
   }
   p.video = reinterpret_cast<const bf16*>(m->video);

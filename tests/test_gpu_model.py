@@ -640,8 +640,12 @@ def test_serving_forward_single_launch_matches_module_and_stock_reference(T, mas
     if float(top2[0] - top2[1]) > 3e-2 * scale:
         assert int(logits.argmax()) == int(l_ref.argmax())
     # same call again: identical bits; after an in-place parameter change: follows the module
+    # (S <= 8 sums split-K partial products with fp32 reductions in L2: the order varies, the last bits may)
     probs2, logits2 = run(video, audio, mask)
-    assert torch.equal(logits2, logits)
+    if T + 1 > 8:
+        assert torch.equal(logits2, logits)
+    else:
+        assert float((logits2 - logits).abs().max()) < 5e-3 * scale
     with torch.no_grad():
         for p_ in model.parameters():
             p_.mul_(1.05)
@@ -654,9 +658,10 @@ def test_serving_forward_single_launch_matches_module_and_stock_reference(T, mas
 
 
 @pytest.mark.parametrize("T", [1, 5, 7])
-def test_serving_forward_shared_memory_exchange_equals_global_scratch_exchange(T):
-    """S <= 8 runs csrc/serve_dsmem.cu (activations stored into every CTA's shared memory); MMER_DEBUG_SERVE_GLOBAL
-    forces csrc/serve.cu (global scratch).  Same roundings at the same places (summation order differs): the logits agree to a few bf16 flips."""
+def test_serving_forward_variants_agree(T):
+    """S <= 8 runs csrc/serve_small.cu (head-local attention, split-K sums in L2); MMER_DEBUG_SERVE_GLOBAL = 1 forces
+    csrc/serve.cu (output-feature split, L2 exchange; bit-reproducible run to run), 2 csrc/serve_dsmem.cu (shared-memory
+    broadcast).  Same roundings at the same places, different summation orders: the logits agree to a few bf16 flips."""
     from mmer_b200 import _lib
     lib = _lib.load()
     torch.manual_seed(40 + T)
@@ -668,11 +673,17 @@ def test_serving_forward_shared_memory_exchange_equals_global_scratch_exchange(T
     if T > 2:
         mask[0, T - 2:] = True
     run = mm.ServingForward(model, frames=T, use_graph=False)
+    out = {}
     try:
-        _, l_shared = run(video, audio, mask)
-        l_shared = l_shared.clone()
-        lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 1)
-        _, l_global = run(video, audio, mask)
+        for knob in (0, 1, 2):
+            lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, knob)
+            _, l = run(video, audio, mask)
+            out[knob] = l.clone()
+            if knob == 1:
+                _, l2 = run(video, audio, mask)
+                assert torch.equal(l2, out[1])
     finally:
         lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 0)
-    assert float((l_shared - l_global).abs().max()) < 5e-3 * float(l_global.abs().max())
+    scale = float(out[1].abs().max())
+    assert float((out[0] - out[1]).abs().max()) < 5e-3 * scale, (out[0], out[1])
+    assert float((out[2] - out[1]).abs().max()) < 5e-3 * scale

@@ -13,7 +13,7 @@ m.compute_dtype = torch.bfloat16
 v, a = torch.randn(1, 5, 768, device=dev).bfloat16(), torch.randn(1, 1024, device=dev).bfloat16()
 mk = torch.zeros(1, 5, dtype=torch.bool, device=dev)
 out = {}
-for name, knob in (("shared", 0), ("global", 1)):
+for name, knob in (("small", 0), ("global", 1), ("shared", 2)):
     lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, knob)
     srv = mm.ServingForward(m, frames=5)
     srv(v, a, mk)
@@ -24,3 +24,9 @@ for name, knob in (("shared", 0), ("global", 1)):
         out[name]["kernel_ns"] = sum(out[name]["phase_ns"])
 lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 0)
 print(json.dumps(out))
+lib.mmer_debug_set(_lib.DEBUG_SERVE_STAMPS, 1)
+srv = mm.ServingForward(m, frames=5)
+for _ in range(5):
+    srv(v, a, mk)
+print(json.dumps({"small_fine_stamps_ns": srv.phase_times()}))
+lib.mmer_debug_set(_lib.DEBUG_SERVE_STAMPS, 0)
