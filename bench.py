@@ -517,8 +517,18 @@ def bench_cfg5(dev, pk):
     out["b1_t5_graph_us"] = _event_ms(lambda: run(v, a, mk), 200, warm=10) * 1e3
     srv = mm.ServingForward(m, frames=5)            # the whole forward as ONE cluster kernel (csrc/serve.cu)
     out["b1_t5_single_kernel_call_us"] = _event_ms(lambda: srv(v, a, mk), 200, warm=10) * 1e3
-    out["b1_t5_single_kernel_graph_only_us"] = _event_ms(srv.graph.replay, 200, warm=10) * 1e3
-    out["b1_t5_single_kernel_phase_ns"] = srv.phase_times()
+    out["b1_t5_single_kernel_graph_only_us"] = _event_ms(srv.replay, 200, warm=10) * 1e3   # request already in the server's buffers
+    ph = srv.phase_times()
+    out["b1_t5_single_kernel_phase_ns"] = ph
+    out["b1_t5_single_kernel_first_to_last_stamp_us"] = (ph[-1] - ph[0]) * 1e-3 if ph else None
+    from mmer_b200 import _lib
+    lib = _lib.load()
+    lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 1)     # the output-feature-split kernel (bit-reproducible), for comparison
+    try:
+        srv1 = mm.ServingForward(m, frames=5)
+        out["b1_t5_single_kernel_reproducible_variant_us"] = _event_ms(srv1.replay, 200, warm=10) * 1e3
+    finally:
+        lib.mmer_debug_set(_lib.DEBUG_SERVE_GLOBAL, 0)
     torch.manual_seed(0)
     m = mm.MultimodalEmotionModel(max_seq_len=T + 1, fusion_num_layers=2, classifier_hidden_dim=512).to(dev).eval()
     m.compute_dtype = torch.bfloat16

@@ -378,9 +378,16 @@ int mmer_stream_wait_event(void* stream, void* event);
  * by output feature over the cluster's CTAs; activations are exchanged through `scratch` (mmer_serve_scratch_bytes(),
  * fp32, stays L2-resident) between cluster barriers.  m: variant 2, dtype MMER_BF16, B == 1, T + 1 <= 16, fused 512,
  * 8 heads; uses params, shadow, off_g / off_l, video [T, video_dim] and audio [audio_dim] (bf16), mask, logits, probs.
- * Anything else (batches, longer clips, attention weights) goes through mmer_model_forward. */
+ * Anything else (batches, longer clips, attention weights) goes through mmer_model_forward.
+ * Up to 8 tokens at the train2.py default widths a second kernel (csrc/serve_small.cu) needs two cluster barriers per
+ * layer instead of four: attention is computed where the head's q / k / v are produced, out_proj and linear2 are
+ * split-K partial products summed by fp32 reductions in L2 (so the last bits may differ between identical calls;
+ * MMER_DEBUG_SERVE_GLOBAL = 1 selects the bit-reproducible kernel).  It reads the weights from `packed`, a copy of the
+ * bf16 shadow in MMA-fragment order at the same offsets: mmer_serve_pack(m, packed, stream) fills it (same size as the
+ * shadow; call again whenever the shadow is re-cast).  packed may be NULL: the first kernel is used. */
 int64_t mmer_serve_scratch_bytes(void);
-int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream);
+int mmer_serve_pack(const mmer_model* m, void* packed, void* stream);
+int mmer_serve_forward(const mmer_model* m, void* scratch, const void* packed, void* stream);
 
 int64_t mmer_workspace_bytes(const mmer_model* m);
 int mmer_model_forward(const mmer_model* m, void* stream);

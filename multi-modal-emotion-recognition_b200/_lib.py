@@ -109,7 +109,8 @@ SIGNATURES = {
     "mmer_bn_fwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _F, _F, _U64, _U32, _P],
     "mmer_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _F, _U64, _U32, _P],
     "mmer_serve_scratch_bytes": [],
-    "mmer_serve_forward": [C.POINTER(Model), _P, _P],
+    "mmer_serve_forward": [C.POINTER(Model), _P, _P, _P],
+    "mmer_serve_pack": [C.POINTER(Model), _P, _P],
     "mmer_workspace_bytes": [C.POINTER(Model)],
     "mmer_model_forward": [C.POINTER(Model), _P],
     "mmer_model_backward": [C.POINTER(Model), _P],

@@ -523,7 +523,9 @@ static int serve_launch(const ServeParams& p, cudaStream_t st) {
 
 extern int g_debug[16];
 int serve_forward_dsmem(const mmer_model* m, long long* stamps, cudaStream_t st);
-int serve_forward_small(const mmer_model* m, float* scratch, long long* stamps, int64_t scratch_floats_before_stamps, cudaStream_t st);
+int serve_forward_small(const mmer_model* m, const void* packed, float* scratch, long long* stamps, int64_t scratch_floats_before_stamps,
+                        cudaStream_t st);
+int serve_pack_weights(const mmer_model* m, void* packed, cudaStream_t st);
 
 }  // namespace mmer
 
@@ -533,7 +535,13 @@ extern "C" {
 
 int64_t mmer_serve_scratch_bytes(void) { return (int64_t)SC_TOTAL * 4; }
 
-int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream) {
+int mmer_serve_pack(const mmer_model* m, void* packed, void* stream) {
+  MMER_CHECK_ARG(m != nullptr && packed != nullptr && m->shadow != nullptr, "serve_pack: null pointer");
+  MMER_CHECK_ARG(m->variant == 2 && m->dtype == MMER_BF16, "serve_pack: the LayerNorm (train2.py) model in bf16 only");
+  return serve_pack_weights(m, packed, (cudaStream_t)stream);
+}
+
+int mmer_serve_forward(const mmer_model* m, void* scratch, const void* packed, void* stream) {
   MMER_CHECK_ARG(m != nullptr && scratch != nullptr, "serve_forward: null pointer");
   MMER_CHECK_ARG(m->variant == 2 && m->dtype == MMER_BF16, "serve_forward: the LayerNorm (train2.py) model in bf16 only");
   MMER_CHECK_ARG(m->B == 1 && m->T >= 1 && m->T + 1 <= SV_MAXS, "serve_forward: one sample of at most %d frames (B=%d T=%d)",
@@ -558,7 +566,7 @@ int mmer_serve_forward(const mmer_model* m, void* scratch, void* stream) {
     long long* stamps = reinterpret_cast<long long*>(reinterpret_cast<float*>(scratch) + SC_STAMPS);
     int r = 1;
     if (g_debug[MMER_DEBUG_SERVE_GLOBAL] == 0)
-      r = serve_forward_small(m, reinterpret_cast<float*>(scratch), stamps, SC_STAMPS, (cudaStream_t)stream);
+      r = serve_forward_small(m, packed, reinterpret_cast<float*>(scratch), stamps, SC_STAMPS, (cudaStream_t)stream);
     else if (g_debug[MMER_DEBUG_SERVE_GLOBAL] == 2)
       r = serve_forward_dsmem(m, stamps, (cudaStream_t)stream);
     if (r <= 0) return r;

@@ -10,12 +10,20 @@
 //   * the 16 partial products of a sub-layer meet in a [512 features][8 tokens] fp32 accumulator in L2 through
 //     red.global.add.v2.f32 issued straight from the MMA accumulator fragments (a warp instruction covers two full
 //     128-byte lines), then one cluster barrier, then every CTA reads the 16 KB sum and does residual + LayerNorm itself.
-//   * the weight fragments of the GEMV that follows a barrier are loaded BEFORE it (they do not depend on activations).
+//   * the weight fragments of the GEMV that follows a barrier are requested between its arrive and its wait (they do
+//     not depend on activations): the loads fly while the slowest CTA arrives;
+//   * every bias / LayerNorm vector is staged in shared memory at start, so no phase begins with an L2 round trip for
+//     parameters;
+//   * the weights are read from a copy packed in MMA-fragment order (mmer_serve_pack): the 16 rows x 32 columns a warp
+//     needs for one k-step are 1 KB contiguous, so each 16-byte-per-lane load covers four whole 128-byte lines instead of
+//     eight half lines (the loads, not the MMAs, pace every phase: ~1 us per 128 KB per SM in the row-major layout).
 //
 // The fp32 adds arrive in arbitrary order, so two identical calls may differ in the last bits (bf16 flips downstream);
 // serve.cu (MMER_DEBUG_SERVE_GLOBAL) is the run-to-run bit-reproducible version.
 // Input projections and the classifier head keep the output-feature split with an L2 exchange (their LayerNorms need
 // whole rows).  Barriers: 1 + 2 per layer + 2.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -44,6 +52,18 @@ constexpr int SS_MAXH = 2048;            // classifier hidden width
 constexpr int SS_MAXL = 4;              // layers (the kernel parameter block stays small: it is read cold at every launch)
 constexpr int SS_LN_STAGED = 2;         // layers whose LayerNorm / bias vectors are staged in shared memory at kernel start
 constexpr float SS_EPS = 1e-5f;
+constexpr int SS_HN = 512;               // head LayerNorm vectors are staged up to this hidden width
+
+// sm.sv (floats): every small vector a phase would otherwise fetch from L2 on its critical path
+constexpr int SV_BV = 0;                          // [32] video projection bias slice
+constexpr int SV_BA = SV_BV + 32;                 // [32] audio projection bias slice
+constexpr int SV_C0B = SV_BA + 32;                // [<= 128] head linear 0 bias slice
+constexpr int SV_C4B = SV_C0B + 128;              // [<= 128] head linear 1 bias slice
+constexpr int SV_FF1B = SV_C4B + 128;             // [SS_MAXL][128] linear1 bias slice
+constexpr int SV_INB = SV_FF1B + SS_MAXL * 128;   // [SS_MAXL][3][64] in_proj bias of this CTA's head
+constexpr int SV_ON = SV_INB + SS_MAXL * 192;     // [2][512] out_norm weight, bias
+constexpr int SV_HN = SV_ON + 2 * SS_F;           // [4][SS_HN] head norm 0 weight, bias, head norm 1 weight, bias
+constexpr int SV_TOTAL = SV_HN + 4 * SS_HN;
 
 // scratch (floats), inside the buffer of mmer_serve_scratch_bytes()
 constexpr int SF_PRE = 0;                // [8][512] projections before LayerNorm
@@ -55,7 +75,7 @@ constexpr int SF_ACC_SZ = SS_F * 8;
 struct ServeParamsS {
   int T, S;
   int video_dim, audio_dim, hidden, classes, layers;
-  const bf16* shadow;
+  const bf16* shadow;                  // the PACKED copy (mmer_serve_pack), same offsets as the row-major shadow
   const float* params;
   int64_t off_g[MMER_G_COUNT];
   int64_t off_l[SS_MAXL][MMER_L_COUNT];
@@ -82,6 +102,7 @@ struct SmemS {
   float part[SS_WARPS][8 * SS_PART_LD];
   uint4 wpark[12 * 16 * 32];           // in_proj weight fragments of k-steps 8..15, parked by cp.async ahead of the barrier
   float lnp[SS_LN_STAGED][6][SS_F];     // out_proj bias, norm1 w / b, linear2 bias, norm2 w / b of the first layers
+  float sv[SV_TOTAL];                  // this CTA's slices of every other bias / norm vector (offsets SV_*), staged at start
   float nrm[SS_MAXH];                  // pooled embedding; head hidden vector after its LayerNorm
   float red[64];
 };
@@ -91,23 +112,12 @@ __device__ __forceinline__ uint32_t ss_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-// all threads of all CTAs; global writes and reductions before it are visible to every CTA after it.  (Splitting the
-// release into an early fence plus arrive.relaxed, so that the weight prefetch issued in between is not waited for, was
-// measured: no gain -- the barrier instruction queues behind the outstanding loads either way.)
-__device__ __forceinline__ void ss_cluster_sync() {
-  __syncthreads();
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-template <typename Stamp>
-__device__ __forceinline__ void ss_cluster_sync_stamped(Stamp& stp) {
-  stp.mark_fine();
-  __syncthreads();
-  stp.mark_fine();
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  stp.mark_fine();
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// The cluster barrier in its two halves.  arrive: this thread's global writes and reductions are released to the
+// cluster.  The caller then issues the NEXT phase's weight loads (they depend on no activation), then waits: the loads
+// fly while the slowest CTA arrives.  (Issued before the arrive they were waited for by its release fence: 1.1 us per
+// barrier.)  Every thread arrives itself, so the barrier also orders this CTA's shared memory: no __syncthreads.
+__device__ __forceinline__ void ss_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ss_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // a weight load that stays where it is written (ahead of the barrier), not where its value is first used
 __device__ __forceinline__ uint4 ss_ldw(const bf16* p) {
   uint4 v;
@@ -161,6 +171,12 @@ struct WPre8 {
   uint4 a0[8], a1[8];
 };
 
+// Packed weights: block (tile, k-step) = rows [16 tile, 16 tile + 16) x columns [32 ks, 32 ks + 32) of W[N][K], 512
+// elements: lane L = 4 g + t holds row g, columns t*8..t*8+7 at L*8 (fragment a0) and row g + 8 at 256 + L*8 (a1).
+__device__ __forceinline__ const bf16* ss_wp(const bf16* Wp, int K, int tile, int ks) {
+  return Wp + ((long long)(tile * (K >> 5) + ks) << 9) + (threadIdx.x & 31) * 8;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // (1) output-feature split with a k-split across warps: a warp owns (tile, k-range); partial tiles meet in shared memory.
 struct PlanS {
@@ -176,17 +192,16 @@ __device__ __forceinline__ PlanS ss_plan(int K, int n0, int n1) {
   return pl;
 }
 __device__ __forceinline__ void ss_nsplit_prefetch(WPre8& w, const bf16* __restrict__ W, int K, int n0, int n1) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5;
   const PlanS pl = ss_plan(K, n0, n1);
   if (warp < pl.units) {
     const int tile = warp / pl.ksplit, ks = warp - tile * pl.ksplit;
-    const bf16* w0 = W + (long long)(n0 + tile * 16 + g) * K + ks * pl.klen + t * 8;
-    const bf16* w1 = w0 + (long long)8 * K;
+    const bf16* w0 = ss_wp(W, K, (n0 >> 4) + tile, (ks * pl.klen) >> 5);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (i * 32 < pl.klen) {
-        w.a0[i] = ss_ldw(w0 + i * 32);
-        w.a1[i] = ss_ldw(w1 + i * 32);
+        w.a0[i] = ss_ldw(w0 + i * 512);
+        w.a1[i] = ss_ldw(w0 + i * 512 + 256);
       }
   }
 }
@@ -198,8 +213,7 @@ __device__ __forceinline__ void ss_nsplit_mma(SmemS& sm, const WPre8& pre, const
   const PlanS pl = ss_plan(K, n0, n1);
   if (warp < pl.units) {
     const int tile = warp / pl.ksplit, ks = warp - tile * pl.ksplit;
-    const bf16* w0 = W + (long long)(n0 + tile * 16 + g) * K + ks * pl.klen + t * 8;
-    const bf16* w1 = w0 + (long long)8 * K;
+    const bf16* w0 = ss_wp(W, K, (n0 >> 4) + tile, (ks * pl.klen) >> 5);
     const bf16* x0 = xs + g * ldx + ks * pl.klen + t * 8;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -211,8 +225,8 @@ __device__ __forceinline__ void ss_nsplit_mma(SmemS& sm, const WPre8& pre, const
       }
 #pragma unroll 4
     for (int kb = 8 * 32; kb < pl.klen; kb += 32) {       // wider-than-default layers only
-      const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(w0 + kb));
-      const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(w1 + kb));
+      const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(w0 + (kb >> 5) * 512));
+      const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(w0 + (kb >> 5) * 512 + 256));
       const uint4 b = *reinterpret_cast<const uint4*>(x0 + kb);
       mma_bf16_16816(c, a0.x, a1.x, a0.y, a1.y, b.x, b.y);
       mma_bf16_16816(c, a0.z, a1.z, a0.w, a1.w, b.z, b.w);
@@ -225,8 +239,9 @@ __device__ __forceinline__ void ss_nsplit_mma(SmemS& sm, const WPre8& pre, const
   }
 }
 // Part 2: emit8(s, n, v[8]) for token s < S and each 8-feature group n of [n0, n1): v = act(x[s] . W[n..n+7] + bias)
+// bias: this CTA's slice (element 0 = feature n0), shared memory.
 template <typename Emit>
-__device__ __forceinline__ void ss_nsplit_reduce(SmemS& sm, int K, const float* __restrict__ bias, int n0, int n1, int S, bool relu,
+__device__ __forceinline__ void ss_nsplit_reduce(SmemS& sm, int K, const float* bias, int n0, int n1, int S, bool relu,
                                                  Emit emit8) {
   const PlanS pl = ss_plan(K, n0, n1);
   __syncthreads();
@@ -236,7 +251,7 @@ __device__ __forceinline__ void ss_nsplit_reduce(SmemS& sm, int K, const float* 
     const int tl = grp >> 1, half = grp & 1;
     const int n = n0 + tl * 16 + half * 8;
     float v[8];
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + (n - n0)), b1 = *reinterpret_cast<const float4*>(bias + (n - n0) + 4);
     v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
     for (int ks = 0; ks < pl.ksplit; ++ks) {
       const float* pp = sm.part[tl * pl.ksplit + ks] + s * SS_PART_LD + half * 8;
@@ -259,14 +274,14 @@ __device__ __forceinline__ void ss_nsplit_reduce(SmemS& sm, int K, const float* 
 template <int ITERS>
 __device__ __forceinline__ void ss_ksplit_prefetch(WPre8& w, const bf16* __restrict__ W, int K, int k0) {
   static_assert(2 * ITERS <= 8, "prefetch slots");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
   for (int tl = 0; tl < 2; ++tl) {
-    const bf16* w0 = W + (long long)((warp * 2 + tl) * 16 + g) * K + k0 + t * 8;
+    const bf16* w0 = ss_wp(W, K, warp * 2 + tl, k0 >> 5);
 #pragma unroll
     for (int i = 0; i < ITERS; ++i) {
-      w.a0[tl * ITERS + i] = ss_ldw(w0 + i * 32);
-      w.a1[tl * ITERS + i] = ss_ldw(w0 + (long long)8 * K + i * 32);
+      w.a0[tl * ITERS + i] = ss_ldw(w0 + i * 512);
+      w.a1[tl * ITERS + i] = ss_ldw(w0 + i * 512 + 256);
     }
   }
 }
@@ -292,30 +307,30 @@ __device__ __forceinline__ void ss_ksplit(const WPre8& w, const bf16* xs, int ld
 // ---------------------------------------------------------------------------------------------------------------------
 // (3) in_proj rows of one head: 12 tiles (q, k, v x 64 features), warp i < 12 owns tile i over the whole K = 512;
 // the first 8 k-steps come from the prefetch.
-__device__ __forceinline__ const bf16* ss_head_row(const bf16* W, int h, int tile, int g) {
+__device__ __forceinline__ const bf16* ss_head_tile(const bf16* Wp, int h, int tile) {
   const int which = tile >> 2, sub = tile & 3;
-  return W + (long long)(which * SS_F + h * SS_D + sub * 16 + g) * SS_F;
+  return ss_wp(Wp, SS_F, (which * SS_F + h * SS_D + sub * 16) >> 4, 0);
 }
 __device__ __forceinline__ void ss_head_prefetch(SmemS& sm, WPre8& w, const bf16* __restrict__ W, int h) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < 12) {
-    const bf16* w0 = ss_head_row(W, h, warp, g) + t * 8;
+    const bf16* w0 = ss_head_tile(W, h, warp);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      w.a0[i] = ss_ldw(w0 + i * 32);
-      w.a1[i] = ss_ldw(w0 + 8 * SS_F + i * 32);
+      w.a0[i] = ss_ldw(w0 + i * 512);
+      w.a1[i] = ss_ldw(w0 + i * 512 + 256);
     }
     // k-steps 8..15: each lane parks its own future fragments in shared memory (no register room for them)
     uint4* park = sm.wpark + (warp * 16) * 32 + lane;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      cp_async_16(smem_u32(park + (2 * i) * 32), w0 + (8 + i) * 32);
-      cp_async_16(smem_u32(park + (2 * i + 1) * 32), w0 + 8 * SS_F + (8 + i) * 32);
+      cp_async_16(smem_u32(park + (2 * i) * 32), w0 + (8 + i) * 512);
+      cp_async_16(smem_u32(park + (2 * i + 1) * 32), w0 + (8 + i) * 512 + 256);
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");   // every thread: group counts stay uniform across the CTA
 }
-__device__ __forceinline__ void ss_head_qkv(SmemS& sm, const WPre8& w, const float* __restrict__ bias, int h) {
+__device__ __forceinline__ void ss_head_qkv(SmemS& sm, const WPre8& w, const float* bias /* staged [3][64] */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   if (warp >= 12) return;
   const bf16* x0 = sm.xs + g * SS_LDX + t * 8;
@@ -336,7 +351,7 @@ __device__ __forceinline__ void ss_head_qkv(SmemS& sm, const WPre8& w, const flo
     mma_bf16_16816(c, a0.z, a1.z, a0.w, a1.w, b.z, b.w);
   }
   const int which = warp >> 2, f = (warp & 3) * 16 + g;            // feature of the head (and f + 8)
-  const float b_lo = __ldg(bias + which * SS_F + h * SS_D + f), b_hi = __ldg(bias + which * SS_F + h * SS_D + f + 8);
+  const float b_lo = bias[which * SS_D + f], b_hi = bias[which * SS_D + f + 8];
   c[0] += b_lo; c[1] += b_lo; c[2] += b_hi; c[3] += b_hi;          // (f, token 2t), (f, 2t+1), (f+8, 2t), (f+8, 2t+1)
   if (which == 2) {
     *reinterpret_cast<uint32_t*>(sm.vt + f * 8 + 2 * t) = pack_bf16x2(c[0], c[1]);
@@ -352,7 +367,7 @@ __device__ __forceinline__ void ss_head_qkv(SmemS& sm, const WPre8& w, const flo
 
 // (4) softmax(q k^T / 8 + key mask) v for one head on tensor cores, one warp.  Token slots >= S hold finite values
 // (rows of xs beyond S are zero) and are switched off by select, never by arithmetic.
-__device__ __forceinline__ void ss_attention(SmemS& sm, int S, int T, const uint8_t* __restrict__ mask) {
+__device__ __forceinline__ void ss_attention(SmemS& sm, unsigned valid) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -365,8 +380,7 @@ __device__ __forceinline__ void ss_attention(SmemS& sm, int S, int T, const uint
   }
   // c[0], c[1]: query g, keys 2t, 2t+1
   const int j0 = 2 * t, j1 = 2 * t + 1;
-  const bool off0 = j0 >= S || (j0 < T && mask != nullptr && mask[j0] != 0);
-  const bool off1 = j1 >= S || (j1 < T && mask != nullptr && mask[j1] != 0);
+  const bool off0 = !((valid >> j0) & 1u), off1 = !((valid >> j1) & 1u);
   const float s0 = off0 ? -INFINITY : c[0] * 0.125f, s1 = off1 ? -INFINITY : c[1] * 0.125f;
   float mx = fmaxf(s0, s1);
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -484,15 +498,16 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
   const bf16* Wa = p.shadow + g[MMER_G_WA];
   ss_nsplit_prefetch(w, Wv, p.video_dim, nF0, nF1);
   {
-    // bias / LayerNorm vectors of the first layers -> shared memory (12 KB per layer, needed from the second barrier on)
-    static constexpr int which[6] = {MMER_L_OUT_B, MMER_L_N1_W, MMER_L_N1_B, MMER_L_FF2_B, MMER_L_N2_W, MMER_L_N2_B};
-    const int nl = min(p.layers, SS_LN_STAGED);
-    for (int i = threadIdx.x; i < nl * 6 * (SS_F / 4); i += SS_THREADS) {
-      const int l = i / (6 * (SS_F / 4)), r = i - l * 6 * (SS_F / 4), v = r / (SS_F / 4), c = (r - v * (SS_F / 4)) * 4;
-      cp_async_16(smem_u32(&sm.lnp[l][v][c]), p.params + p.off_l[l][which[v]] + c);
+    // the projection biases (needed in this phase) as their own cp.async group
+    for (int i = threadIdx.x * 4; i < nF1 - nF0; i += SS_THREADS * 4) {
+      cp_async_16(smem_u32(sm.sv + SV_BV + i), p.params + g[MMER_G_BV] + nF0 + i);
+      cp_async_16(smem_u32(sm.sv + SV_BA + i), p.params + g[MMER_G_BA] + nF0 + i);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  // key padding mask as bits (bit s set = token s takes part); the audio token always does
+  unsigned valid = 0u;
+  for (int s = 0; s < S; ++s) valid |= ((s < T && p.mask != nullptr && p.mask[s] != 0) ? 0u : 1u) << s;
   for (int i = threadIdx.x; i < 8 * (p.video_dim / 8); i += SS_THREADS) {
     const int s = i / (p.video_dim / 8), c = (i % (p.video_dim / 8)) * 8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -506,6 +521,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     float4* z = reinterpret_cast<float4*>(sc + SF_ACC) + (long long)rank * share;
     for (int i = threadIdx.x; i < share; i += SS_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // the projection biases
   __syncthreads();
   stp.mark_fine();
   auto put_rows = [sc](int row0) {
@@ -517,16 +533,49 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
   };
   ss_nsplit_mma(sm, w, sm.xs, SS_LDX, p.video_dim, Wv, nF0, nF1);
   ss_nsplit_prefetch(w, Wa, p.audio_dim, nF0, nF1);
+  {
+    // every bias / LayerNorm vector this CTA will need -> shared memory (one L2 round trip, off the start-up path),
+    // instead of a round trip on the critical path of each phase
+    static constexpr int which[6] = {MMER_L_OUT_B, MMER_L_N1_W, MMER_L_N1_B, MMER_L_FF2_B, MMER_L_N2_W, MMER_L_N2_B};
+    const int nl = min(p.layers, SS_LN_STAGED);
+    for (int i = threadIdx.x; i < nl * 6 * (SS_F / 4); i += SS_THREADS) {
+      const int l = i / (6 * (SS_F / 4)), r = i - l * 6 * (SS_F / 4), v = r / (SS_F / 4), c = (r - v * (SS_F / 4)) * 4;
+      cp_async_16(smem_u32(&sm.lnp[l][v][c]), p.params + p.off_l[l][which[v]] + c);
+    }
+    auto stage = [&](int dst, const float* src, int count) {       // count % 4 == 0, src 16-byte aligned
+      for (int i = threadIdx.x * 4; i < count; i += SS_THREADS * 4) cp_async_16(smem_u32(sm.sv + dst + i), src + i);
+    };
+    stage(SV_C0B, p.params + g[MMER_G_C0_B] + nC0, nC1 - nC0);
+    stage(SV_C4B, p.params + g[MMER_G_C4_B] + nC0, nC1 - nC0);
+    for (int l = 0; l < p.layers; ++l) {
+      stage(SV_FF1B + l * 128, p.params + p.off_l[l][MMER_L_FF1_B] + nH0, SS_HS);
+      for (int q = 0; q < 3; ++q)
+        stage(SV_INB + l * 192 + q * SS_D, p.params + p.off_l[l][MMER_L_IN_B] + q * SS_F + head * SS_D, SS_D);
+    }
+    stage(SV_ON, p.params + g[MMER_G_ON_W], SS_F);
+    stage(SV_ON + SS_F, p.params + g[MMER_G_ON_B], SS_F);
+    if (p.hidden <= SS_HN) {
+      stage(SV_HN, p.params + g[MMER_G_C1_W], p.hidden);
+      stage(SV_HN + SS_HN, p.params + g[MMER_G_C1_B], p.hidden);
+      stage(SV_HN + 2 * SS_HN, p.params + g[MMER_G_C5_W], p.hidden);
+      stage(SV_HN + 3 * SS_HN, p.params + g[MMER_G_C5_B], p.hidden);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   stp.mark_fine();
-  ss_nsplit_reduce(sm, p.video_dim, p.params + g[MMER_G_BV], nF0, nF1, T, false, put_rows(0));
+  ss_nsplit_reduce(sm, p.video_dim, sm.sv + SV_BV, nF0, nF1, T, false, put_rows(0));
   stp.mark_fine();
   ss_nsplit_mma(sm, w, sm.arow, 0, p.audio_dim, Wa, nF0, nF1);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");   // the staged vectors (visible to the CTA after the next barrier)
-  ss_head_prefetch(sm, w, p.shadow + p.off_l[0][MMER_L_IN_W], head);
-  ss_nsplit_reduce(sm, p.audio_dim, p.params + g[MMER_G_BA], nF0, nF1, 1, false, put_rows(T));
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // all staged vectors
+  ss_nsplit_reduce(sm, p.audio_dim, sm.sv + SV_BA, nF0, nF1, 1, false, put_rows(T));
   // rows >= T of xs held zeros through the video GEMV; from here on rows >= S stay zero (finite q / k / v in the
   // unused token slots): the LayerNorms write rows < S only
-  ss_cluster_sync_stamped(stp);                                            // B1
+  stp.mark_fine();
+  ss_cluster_arrive();                                                     // B1
+  stp.mark_fine();
+  ss_head_prefetch(sm, w, p.shadow + p.off_l[0][MMER_L_IN_W], head);
+  stp.mark_fine();
+  ss_cluster_wait();
   stp.mark();
 
   // ---- token assembly (train2.py:151-160)
@@ -548,17 +597,20 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     const float* n2w = staged ? sm.lnp[l][4] : p.params + o[MMER_L_N2_W];
     const float* n2b = staged ? sm.lnp[l][5] : p.params + o[MMER_L_N2_B];
     // ---- q, k, v of this CTA's head; attention; its half of the head's columns times out_proj -> L2 sum
-    ss_head_qkv(sm, w, p.params + o[MMER_L_IN_B], head);
+    ss_head_qkv(sm, w, sm.sv + SV_INB + l * 192);
     ss_ksplit_prefetch<1>(w, p.shadow + o[MMER_L_OUT_W], SS_F, head * SS_D + khalf);
     stp.mark_fine();
     __syncthreads();
-    if (warp == 0) ss_attention(sm, S, T, p.mask);
+    if (warp == 0) ss_attention(sm, valid);
     __syncthreads();
     stp.mark_fine();
     ss_ksplit<1>(w, sm.ao + khalf, SS_LDO, acc_a, S);
     stp.mark_fine();
+    ss_cluster_arrive();                                                   // B2
+    stp.mark_fine();
     ss_nsplit_prefetch(w, p.shadow + o[MMER_L_FF1_W], SS_F, nH0, nH1);
-    ss_cluster_sync_stamped(stp);                                          // B2
+    stp.mark_fine();
+    ss_cluster_wait();
     stp.mark();
     // ---- x = norm1(x + out_proj(attention)); relu(linear1) slice stays here; times its linear2 columns -> L2 sum
     ss_fetch_sum(sm, acc_a);
@@ -569,16 +621,19 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     ss_nsplit_mma(sm, w, sm.xs, SS_LDX, SS_F, p.shadow + o[MMER_L_FF1_W], nH0, nH1);
     ss_ksplit_prefetch<4>(w, p.shadow + o[MMER_L_FF2_W], SS_FFN, nH0);
     stp.mark_fine();
-    ss_nsplit_reduce(sm, SS_F, p.params + o[MMER_L_FF1_B], nH0, nH1, 8, true, [&](int s, int n, const float (&v)[8]) {
+    ss_nsplit_reduce(sm, SS_F, sm.sv + SV_FF1B + l * 128, nH0, nH1, 8, true, [&](int s, int n, const float (&v)[8]) {
       *reinterpret_cast<uint4*>(sm.hs + s * SS_LDH + (n - nH0)) =
           make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     });
     stp.mark_fine();
     ss_ksplit<4>(w, sm.hs, SS_LDH, acc_f, S);
     stp.mark_fine();
+    ss_cluster_arrive();                                                   // B3
+    stp.mark_fine();
     if (l + 1 < p.layers) ss_head_prefetch(sm, w, p.shadow + p.off_l[l + 1][MMER_L_IN_W], head);
     else ss_nsplit_prefetch(w, p.shadow + g[MMER_G_C0_W], SS_F, nC0, nC1);
-    ss_cluster_sync_stamped(stp);                                          // B3
+    stp.mark_fine();
+    ss_cluster_wait();
     stp.mark();
     ss_fetch_sum(sm, acc_f);
     __syncthreads();
@@ -590,19 +645,16 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
 
   // ---- masked mean pooling + out_norm (train2.py:184-191) -> row 0 of xf / xs
   {
-    float cnt = 0.f;
-    for (int s = 0; s < S; ++s) cnt += ((s < T) && p.mask != nullptr && p.mask[s] != 0) ? 0.f : 1.f;
-    const float inv = 1.f / fmaxf(cnt, 1e-6f);
+    const float inv = 1.f / fmaxf((float)__popc(valid), 1e-6f);
     float* pooled = sm.nrm;
     for (int c = threadIdx.x; c < SS_F; c += SS_THREADS) {
       float a = 0.f;
       for (int s = 0; s < S; ++s)
-        if (!((s < T) && p.mask != nullptr && p.mask[s] != 0)) a += sm.xf[s * SS_F + c];
+        if ((valid >> s) & 1u) a += sm.xf[s * SS_F + c];
       pooled[c] = a * inv;
     }
     __syncthreads();
-    ss_ln_rows<true>(sm, pooled, SS_F, false, nullptr, nullptr, 1, p.params + g[MMER_G_ON_W], p.params + g[MMER_G_ON_B], nullptr, nullptr,
-               1, nullptr);
+    ss_ln_rows<false>(sm, pooled, SS_F, false, nullptr, nullptr, 1, sm.sv + SV_ON, sm.sv + SV_ON + SS_F, nullptr, nullptr, 1, nullptr);
     __syncthreads();
   }
   stp.mark();
@@ -618,8 +670,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
       v[j] = 0.f;
       if (c < Hd) {
         v[j] = __ldcg(src + c);
-        gv[j] = __ldg(gm + c);
-        bv[j] = __ldg(bt + c);
+        gv[j] = gm[c];
+        bv[j] = bt[c];
       }
       sum += v[j];
     }
@@ -660,14 +712,18 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     };
   };
   ss_nsplit_mma(sm, w, sm.xs, 0, SS_F, p.shadow + g[MMER_G_C0_W], nC0, nC1);
+  ss_nsplit_reduce(sm, SS_F, sm.sv + SV_C0B, nC0, nC1, 1, false, put_vec(sc + SF_H1));
+  ss_cluster_arrive();
   ss_nsplit_prefetch(w, p.shadow + g[MMER_G_C4_W], Hd, nC0, nC1);
-  ss_nsplit_reduce(sm, SS_F, p.params + g[MMER_G_C0_B], nC0, nC1, 1, false, put_vec(sc + SF_H1));
-  ss_cluster_sync();
+  ss_cluster_wait();
   stp.mark();
-  head_norm(sc + SF_H1, p.params + g[MMER_G_C1_W], p.params + g[MMER_G_C1_B]);
+  const bool hn_staged = Hd <= SS_HN;
+  head_norm(sc + SF_H1, hn_staged ? sm.sv + SV_HN : p.params + g[MMER_G_C1_W],
+            hn_staged ? sm.sv + SV_HN + SS_HN : p.params + g[MMER_G_C1_B]);
   ss_nsplit_mma(sm, w, sm.arow, 0, Hd, p.shadow + g[MMER_G_C4_W], nC0, nC1);
-  ss_nsplit_reduce(sm, Hd, p.params + g[MMER_G_C4_B], nC0, nC1, 1, false, put_vec(sc + SF_H2));
-  // the output layer (fp32 masters, one class per warp): its first 512 columns are in registers before the last barrier
+  ss_nsplit_reduce(sm, Hd, sm.sv + SV_C4B, nC0, nC1, 1, false, put_vec(sc + SF_H2));
+  ss_cluster_arrive();
+  // the output layer (fp32 masters, one class per warp): its first 512 columns fly during the last barrier
   const float* W8 = p.params + g[MMER_G_C8_W];
   float w8[16];
   float b8 = 0.f;
@@ -676,10 +732,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     for (int i = 0; i < 16; ++i) w8[i] = (i * 32 + lane < Hd) ? __ldg(W8 + (long long)warp * Hd + i * 32 + lane) : 0.f;
     b8 = __ldg(p.params + g[MMER_G_C8_B] + warp);
   }
-  ss_cluster_sync();
+  ss_cluster_wait();
   stp.mark();
   if (rank == 0) {
-    head_norm(sc + SF_H2, p.params + g[MMER_G_C5_W], p.params + g[MMER_G_C5_B]);
+    head_norm(sc + SF_H2, hn_staged ? sm.sv + SV_HN + 2 * SS_HN : p.params + g[MMER_G_C5_W],
+              hn_staged ? sm.sv + SV_HN + 3 * SS_HN : p.params + g[MMER_G_C5_B]);
     const float* h2 = sm.nrm;
     if (warp < p.classes) {
       float a = 0.f;
@@ -706,11 +763,25 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
   stp.mark();
 }
 
+// row-major W[N][K] -> fragment order (ss_wp): one 16-byte chunk per thread
+__global__ void serve_pack_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int K) {
+  const long long chunks = (long long)N * K / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long block = i >> 6;                       // 64 chunks per (tile, k-step) block
+    const int in = (int)(i & 63), half = in >> 5, L = in & 31, g = L >> 2, t = L & 3;
+    const int kst = K >> 5;
+    const int tile = (int)(block / kst), ks = (int)(block - (long long)tile * kst);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (long long)(tile * 16 + half * 8 + g) * K + ks * 32 + t * 8);
+    *reinterpret_cast<uint4*>(dst + i * 8) = v;
+  }
+}
+
 }  // namespace
 
 // returns 1 when this kernel does not apply (the caller falls back to serve.cu), 0 on success, < 0 on error
-int serve_forward_small(const mmer_model* m, float* scratch, long long* stamps, int64_t scratch_floats_before_stamps, cudaStream_t st) {
-  if (m->T + 1 > 8 || m->layers > SS_MAXL || m->fused != SS_F || m->heads != SS_HEADS || m->ffn != SS_FFN || m->video_dim > SS_KX || m->audio_dim > SS_KX ||
+int serve_forward_small(const mmer_model* m, const void* packed, float* scratch, long long* stamps, int64_t scratch_floats_before_stamps,
+                        cudaStream_t st) {
+  if (packed == nullptr || m->T + 1 > 8 || m->layers > SS_MAXL || m->fused != SS_F || m->heads != SS_HEADS || m->ffn != SS_FFN || m->video_dim > SS_KX || m->audio_dim > SS_KX ||
       m->hidden > SS_MAXH || m->hidden % 256 != 0 || m->video_dim % 256 != 0 || m->audio_dim % 256 != 0 ||
       SF_ACC + 2LL * m->layers * SF_ACC_SZ > scratch_floats_before_stamps)
     return 1;
@@ -742,7 +813,7 @@ int serve_forward_small(const mmer_model* m, float* scratch, long long* stamps, 
   ServeParamsS p;
   p.T = m->T; p.S = m->T + 1;
   p.video_dim = m->video_dim; p.audio_dim = m->audio_dim; p.hidden = m->hidden; p.classes = m->classes; p.layers = m->layers;
-  p.shadow = reinterpret_cast<const bf16*>(m->shadow);
+  p.shadow = reinterpret_cast<const bf16*>(packed);
   p.params = m->params;
   for (int i = 0; i < MMER_G_COUNT; ++i) p.off_g[i] = m->off_g[i];
   for (int l = 0; l < SS_MAXL; ++l)
@@ -767,6 +838,31 @@ int serve_forward_small(const mmer_model* m, float* scratch, long long* stamps, 
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(serve_small)");
   MMER_LAUNCH_CHECK("serve_small_kernel");
+  return 0;
+}
+
+// every matrix serve_small_kernel multiplies, from the row-major bf16 shadow into `packed` at the same offsets
+int serve_pack_weights(const mmer_model* m, void* packed, cudaStream_t st) {
+  const bf16* src = reinterpret_cast<const bf16*>(m->shadow);
+  bf16* dst = reinterpret_cast<bf16*>(packed);
+  auto one = [&](int64_t off, int N, int K) -> int {
+    if (off < 0 || N % 16 != 0 || K % 32 != 0) return 0;     // not packable: serve_forward_small rejects such models
+    const long long chunks = (long long)N * K / 8;
+    const int blocks = (int)std::min<long long>((chunks + 255) / 256, 1184);
+    serve_pack_kernel<<<blocks, 256, 0, st>>>(src + off, dst + off, N, K);
+    MMER_LAUNCH_CHECK("serve_pack_kernel");
+    return 0;
+  };
+  MMER_TRY(one(m->off_g[MMER_G_WV], m->fused, m->video_dim));
+  MMER_TRY(one(m->off_g[MMER_G_WA], m->fused, m->audio_dim));
+  for (int l = 0; l < m->layers; ++l) {
+    MMER_TRY(one(m->off_l[l][MMER_L_IN_W], 3 * m->fused, m->fused));
+    MMER_TRY(one(m->off_l[l][MMER_L_OUT_W], m->fused, m->fused));
+    MMER_TRY(one(m->off_l[l][MMER_L_FF1_W], m->ffn, m->fused));
+    MMER_TRY(one(m->off_l[l][MMER_L_FF2_W], m->fused, m->ffn));
+  }
+  MMER_TRY(one(m->off_g[MMER_G_C0_W], m->hidden, m->fused));
+  MMER_TRY(one(m->off_g[MMER_G_C4_W], m->hidden, m->hidden));
   return 0;
 }
 

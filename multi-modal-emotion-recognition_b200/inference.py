@@ -65,7 +65,8 @@ class GraphedInference:
 class ServingForward:
     """The served call -- one clip window, ``probs, logits, _ = fusion_model(video[1, T, 768], audio[1, 1024], mask)``
     (back-end/app/libs/inference.py:494-495, T <= window_size = 5) -- as ONE kernel launch: a thread-block cluster walks
-    the whole model (``mmer_serve_forward``, csrc/serve.cu) instead of ~30 launch-bound kernels.
+    the whole model (``mmer_serve_forward``: csrc/serve_small.cu for up to 8 tokens, csrc/serve.cu beyond) instead of ~30
+    launch-bound kernels.
 
     ``run = ServingForward(model, frames=5); probs, logits = run(video, audio, mask)``.  bf16 weights (the shadow is
     re-cast from the live fp32 parameters inside the captured graph, so ``load_state_dict`` between calls is picked up),
@@ -91,6 +92,7 @@ class ServingForward:
         self.probs = torch.zeros_like(self.logits)
         lib = _lib.load()
         self.scratch = torch.zeros(int(lib.mmer_serve_scratch_bytes()), device=dev, dtype=torch.uint8)
+        self.packed = None                            # the bf16 weights in MMA-fragment order (mmer_serve_pack)
         self._lib, self._C = lib, C
 
         def launch(cast: bool = True):
@@ -101,8 +103,14 @@ class ServingForward:
             m.video, m.audio = self.video.data_ptr(), self.audio.data_ptr()
             m.mask, m.has_mask = self.mask.view(torch.uint8).data_ptr(), 1
             m.logits, m.probs = self.logits.data_ptr(), self.probs.data_ptr()
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if self.packed is None or self.packed.numel() != eng.ctx.shadow.numel():
+                self.packed = torch.zeros_like(eng.ctx.shadow)
+                cast = True
+            if cast:                                  # ... and from the shadow into the fragment-order copy
+                _lib.check(lib.mmer_serve_pack(C.byref(m), C.c_void_p(self.packed.data_ptr()), stream), "mmer_serve_pack")
             _lib.check(lib.mmer_serve_forward(C.byref(m), C.c_void_p(self.scratch.data_ptr()),
-                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mmer_serve_forward")
+                                              C.c_void_p(self.packed.data_ptr()), stream), "mmer_serve_forward")
 
         self._launch = launch
         self.graph = self.graph_cast = None
@@ -143,6 +151,20 @@ class ServingForward:
         return [t - st[1] for t in st[1:1 + n]]
 
     @torch.no_grad()
+    def replay(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The zero-copy form for a server that owns the buffers: write the request into ``self.video`` [1, T, 768],
+        ``self.audio`` [1, 1024] (bf16) and ``self.mask`` [1, T] (bool, True = padded chunk) -- e.g. as the output buffers
+        of the feature extractors -- then ``probs, logits = run.replay()``.  ONE launch on the stream, no staging copies;
+        the returned tensors are the static output buffers (valid until the next call)."""
+        fresh = self._weights_state() == self._cast_state
+        if self.graph is not None:
+            (self.graph if fresh else self.graph_cast).replay()
+        else:
+            self._launch(not fresh)
+        self._cast_state = self._weights_state()
+        return self.probs, self.logits
+
+    @torch.no_grad()
     def __call__(self, video: torch.Tensor, audio: torch.Tensor, mask: Optional[torch.Tensor] = None
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
         if tuple(video.shape) != tuple(self.video.shape) or tuple(audio.shape) != tuple(self.audio.shape):
@@ -153,11 +175,5 @@ class ServingForward:
             self.mask.zero_()
         else:
             self.mask.copy_(mask, non_blocking=True)
-        state = self._weights_state()
-        fresh = state == self._cast_state
-        if self.graph is not None:
-            (self.graph if fresh else self.graph_cast).replay()
-        else:
-            self._launch(not fresh)
-        self._cast_state = self._weights_state()
-        return self.probs.clone(), self.logits.clone()
+        probs, logits = self.replay()
+        return probs.clone(), logits.clone()

@@ -655,6 +655,13 @@ def test_serving_forward_single_launch_matches_module_and_stock_reference(T, mas
     assert float((logits3 - logits).abs().max()) > 1e-4
     with pytest.raises(mm.MmerError):
         run(video[:, :-1] if T > 1 else torch.zeros(1, 2, 768, device="cuda"), audio, None)
+    # zero-copy form: the request written into the server's own buffers, outputs read in place
+    run.video.copy_(video)
+    run.audio.copy_(audio)
+    run.mask.copy_(mask) if mask is not None else run.mask.zero_()
+    p4, l4 = run.replay()
+    assert l4.data_ptr() == run.logits.data_ptr()
+    assert float((l4 - logits3).abs().max()) < 5e-3 * float(logits3.abs().max())
 
 
 @pytest.mark.parametrize("T", [1, 5, 7])
