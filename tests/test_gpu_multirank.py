@@ -37,20 +37,41 @@ def _free_port():
     return p
 
 
-def _spawn(worker, world, *args, timeout=600):
+def _entry(name, rank, world, port, q, *args):
+    """Child process: run the named worker; a failure travels to the parent as text instead of a silent exit."""
+    import traceback
+    try:
+        globals()[name](rank, world, port, q, *args)
+    except BaseException:
+        q.put(("error", rank, traceback.format_exc()))
+        raise
+
+
+def _spawn(worker, world, *args, timeout=240):
+    import queue as _queue
+    import time
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=worker, args=(r, world, port, q) + args) for r in range(world)]
+    procs = [ctx.Process(target=_entry, args=(worker.__name__, r, world, port, q) + args) for r in range(world)]
     for p in procs:
         p.start()
     res = []
+    deadline = time.time() + timeout
     try:
-        for _ in range(world):
-            res.append(q.get(timeout=timeout))
+        while len(res) < world:
+            try:
+                item = q.get(timeout=2)
+            except _queue.Empty:
+                dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+                assert not dead, f"a worker died without reporting (exit codes {dead})"
+                assert time.time() < deadline, "workers timed out"
+                continue
+            assert item[0] != "error", f"rank {item[1]} failed:\n{item[2]}"
+            res.append(item)
     finally:
         for p in procs:
-            p.join(60)
+            p.join(60 if len(res) == world else 5)
             if p.is_alive():
                 p.kill()
     for p in procs:
