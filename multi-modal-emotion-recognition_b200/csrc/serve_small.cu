@@ -191,22 +191,27 @@ __device__ __forceinline__ PlanS ss_plan(int K, int n0, int n1) {
   pl.klen = K / pl.ksplit;
   return pl;
 }
+// The first NSLOTS k-steps of this warp's unit go into prefetch slots [SLOT0, SLOT0 + NSLOTS): two GEMVs with short
+// k-ranges (the input projections) can share one register set.
+template <int SLOT0 = 0, int NSLOTS = 8>
 __device__ __forceinline__ void ss_nsplit_prefetch(WPre8& w, const bf16* __restrict__ W, int K, int n0, int n1) {
+  static_assert(SLOT0 + NSLOTS <= 8, "prefetch slots");
   const int warp = threadIdx.x >> 5;
   const PlanS pl = ss_plan(K, n0, n1);
   if (warp < pl.units) {
     const int tile = warp / pl.ksplit, ks = warp - tile * pl.ksplit;
     const bf16* w0 = ss_wp(W, K, (n0 >> 4) + tile, (ks * pl.klen) >> 5);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < NSLOTS; ++i)
       if (i * 32 < pl.klen) {
-        w.a0[i] = ss_ldw(w0 + i * 512);
-        w.a1[i] = ss_ldw(w0 + i * 512 + 256);
+        w.a0[SLOT0 + i] = ss_ldw(w0 + i * 512);
+        w.a1[SLOT0 + i] = ss_ldw(w0 + i * 512 + 256);
       }
   }
 }
 // Part 1: this warp's (tile, k-range) partial tile -> sm.part.  x rows of ldx elements in shared memory (ldx = 0: one
 // row for every token slot).  One round: tiles * ksplit <= 16 (output slices of at most 256 features).
+template <int SLOT0 = 0, int NSLOTS = 8>
 __device__ __forceinline__ void ss_nsplit_mma(SmemS& sm, const WPre8& pre, const bf16* xs, int ldx, int K, const bf16* __restrict__ W,
                                               int n0, int n1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -217,14 +222,15 @@ __device__ __forceinline__ void ss_nsplit_mma(SmemS& sm, const WPre8& pre, const
     const bf16* x0 = xs + g * ldx + ks * pl.klen + t * 8;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < NSLOTS; ++i)
       if (i * 32 < pl.klen) {
         const uint4 b = *reinterpret_cast<const uint4*>(x0 + i * 32);
-        mma_bf16_16816(c, pre.a0[i].x, pre.a1[i].x, pre.a0[i].y, pre.a1[i].y, b.x, b.y);
-        mma_bf16_16816(c, pre.a0[i].z, pre.a1[i].z, pre.a0[i].w, pre.a1[i].w, b.z, b.w);
+        const uint4 a0 = pre.a0[SLOT0 + i], a1 = pre.a1[SLOT0 + i];
+        mma_bf16_16816(c, a0.x, a1.x, a0.y, a1.y, b.x, b.y);
+        mma_bf16_16816(c, a0.z, a1.z, a0.w, a1.w, b.z, b.w);
       }
 #pragma unroll 4
-    for (int kb = 8 * 32; kb < pl.klen; kb += 32) {       // wider-than-default layers only
+    for (int kb = NSLOTS * 32; kb < pl.klen; kb += 32) {  // k-steps beyond the prefetched ones
       const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(w0 + (kb >> 5) * 512));
       const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(w0 + (kb >> 5) * 512 + 256));
       const uint4 b = *reinterpret_cast<const uint4*>(x0 + kb);
@@ -496,7 +502,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
   WPre8 w;
   const bf16* Wv = p.shadow + g[MMER_G_WV];
   const bf16* Wa = p.shadow + g[MMER_G_WA];
-  ss_nsplit_prefetch(w, Wv, p.video_dim, nF0, nF1);
+  ss_nsplit_prefetch<0, 4>(w, Wv, p.video_dim, nF0, nF1);     // both input projections' weights now: k-ranges of <= 128 each
+  ss_nsplit_prefetch<4, 4>(w, Wa, p.audio_dim, nF0, nF1);
   {
     // the projection biases (needed in this phase) as their own cp.async group
     for (int i = threadIdx.x * 4; i < nF1 - nF0; i += SS_THREADS * 4) {
@@ -521,7 +528,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     float4* z = reinterpret_cast<float4*>(sc + SF_ACC) + (long long)rank * share;
     for (int i = threadIdx.x; i < share; i += SS_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  asm volatile("cp.async.wait_group 1;" ::: "memory");   // the projection biases
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // the projection biases
   __syncthreads();
   stp.mark_fine();
   auto put_rows = [sc](int row0) {
@@ -531,11 +538,21 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
       d[1] = make_float4(v[4], v[5], v[6], v[7]);
     };
   };
-  ss_nsplit_mma(sm, w, sm.xs, SS_LDX, p.video_dim, Wv, nF0, nF1);
-  ss_nsplit_prefetch(w, Wa, p.audio_dim, nF0, nF1);
+  ss_nsplit_mma<0, 4>(sm, w, sm.xs, SS_LDX, p.video_dim, Wv, nF0, nF1);
+  stp.mark_fine();
+  ss_nsplit_reduce(sm, p.video_dim, sm.sv + SV_BV, nF0, nF1, T, false, put_rows(0));
+  stp.mark_fine();
+  ss_nsplit_mma<4, 4>(sm, w, sm.arow, 0, p.audio_dim, Wa, nF0, nF1);
+  ss_nsplit_reduce(sm, p.audio_dim, sm.sv + SV_BA, nF0, nF1, 1, false, put_rows(T));
+  // rows >= T of xs held zeros through the video GEMV; from here on rows >= S stay zero (finite q / k / v in the
+  // unused token slots): the LayerNorms write rows < S only
+  stp.mark_fine();
+  ss_cluster_arrive();                                                     // B1
+  stp.mark_fine();
+  ss_head_prefetch(sm, w, p.shadow + p.off_l[0][MMER_L_IN_W], head);
   {
-    // every bias / LayerNorm vector this CTA will need -> shared memory (one L2 round trip, off the start-up path),
-    // instead of a round trip on the critical path of each phase
+    // every bias / LayerNorm vector this CTA will need -> shared memory, requested while this CTA waits at the
+    // first barrier (instead of an L2 round trip at the head of each later phase)
     static constexpr int which[6] = {MMER_L_OUT_B, MMER_L_N1_W, MMER_L_N1_B, MMER_L_FF2_B, MMER_L_N2_W, MMER_L_N2_B};
     const int nl = min(p.layers, SS_LN_STAGED);
     for (int i = threadIdx.x; i < nl * 6 * (SS_F / 4); i += SS_THREADS) {
@@ -563,24 +580,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1) serve_small_kernel(const ServeP
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   stp.mark_fine();
-  ss_nsplit_reduce(sm, p.video_dim, sm.sv + SV_BV, nF0, nF1, T, false, put_rows(0));
-  stp.mark_fine();
-  ss_nsplit_mma(sm, w, sm.arow, 0, p.audio_dim, Wa, nF0, nF1);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");   // all staged vectors
-  ss_nsplit_reduce(sm, p.audio_dim, sm.sv + SV_BA, nF0, nF1, 1, false, put_rows(T));
-  // rows >= T of xs held zeros through the video GEMV; from here on rows >= S stay zero (finite q / k / v in the
-  // unused token slots): the LayerNorms write rows < S only
-  stp.mark_fine();
-  ss_cluster_arrive();                                                     // B1
-  stp.mark_fine();
-  ss_head_prefetch(sm, w, p.shadow + p.off_l[0][MMER_L_IN_W], head);
-  stp.mark_fine();
   ss_cluster_wait();
   stp.mark();
 
   // ---- token assembly (train2.py:151-160)
   ss_ln_rows<true>(sm, sc + SF_PRE, SS_F, true, nullptr, nullptr, S, p.params + g[MMER_G_NV_W], p.params + g[MMER_G_NV_B],
              p.params + g[MMER_G_NA_W], p.params + g[MMER_G_NA_B], T, p.params + g[MMER_G_POS]);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // staged vectors and parked in_proj fragments
   __syncthreads();
   stp.mark();
 
