@@ -115,13 +115,18 @@ __device__ __forceinline__ void zero_pad_rows(uint8_t* tiles, int ntiles, const 
     *reinterpret_cast<uint4*>(tiles + (size_t)tl * g.tile_bytes + g.load_bytes + o) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
-__device__ __forceinline__ void fill_valid(uint8_t* valid, const uint8_t* __restrict__ mask, int b, const LongGeom& g) {
-  for (int j = threadIdx.x; j < g.SR + 32; j += blockDim.x) {
+// valid[j] (bytes) and vbits[j / 32] (bit j % 32): key j takes part (j < S and not padded).  blockDim.x % 32 == 0.
+__device__ __forceinline__ void fill_valid(uint8_t* valid, uint32_t* vbits, const uint8_t* __restrict__ mask, int b, const LongGeom& g) {
+  const int n = (g.SR + 32 + 31) & ~31;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
     bool ok = j < g.S;
     if (ok && j < g.Tn && mask != nullptr) ok = mask[(long long)b * g.Tn + j] == 0;
-    valid[j] = ok ? 1 : 0;
+    if (j < g.SR + 32) valid[j] = ok ? 1 : 0;
+    const uint32_t w = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) vbits[j >> 5] = w;
   }
 }
+constexpr int AL_VWORDS = 16;   // (384 + 32 + 31) / 32 bit words, rounded up
 
 // online row statistics of one 16 x 32 score block (rows g and g+8 of the tile; quad-uniform maxima)
 __device__ __forceinline__ void stats_update(const float (&sc)[4][4], const uint8_t* valid, int key0, int t, float sl2,
@@ -149,6 +154,13 @@ __device__ __forceinline__ void stats_update(const float (&sc)[4][4], const uint
   }
 }
 
+// bytes of the validity region: valid[SR + 32] bytes, then AL_VWORDS bit words
+__device__ __host__ __forceinline__ int valid_region_bytes(int SR) { return ((SR + 32 + 15) & ~15) + AL_VWORDS * 4; }
+
+// PROBS (return_attn): two passes over the key blocks (statistics, then normalised probabilities written out and P V).
+// Otherwise ONE pass with running maxima: O and the row sums are rescaled when a block raises the maximum, the division
+// by the row sum happens once at the end (a third fewer MMAs, every exponential computed once).
+template <bool DROP, bool PROBS>
 __global__ void __launch_bounds__(AL_WARPS * 32, 2)
 mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
                     const uint8_t* __restrict__ mask, bf16* __restrict__ out, float* __restrict__ probs,
@@ -162,13 +174,14 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   uint8_t* k_s = q_s + g.tile_bytes;
   uint8_t* v_s = k_s + g.tile_bytes;
   uint8_t* valid = v_s + g.tile_bytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + ((g.SR + 32 + 15) & ~15));
+  uint32_t* vbits = reinterpret_cast<uint32_t*>(valid + ((g.SR + 32 + 15) & ~15));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + valid_region_bytes(g.SR));
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
   }
-  fill_valid(valid, mask, b, g);
+  fill_valid(valid, vbits, mask, b, g);
   zero_pad_rows(q_s, 3, g);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -186,57 +199,125 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     uint32_t qa[4][4];
     load_a16(q_a, q0, lane, qa);
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-    for (int kb = 0; kb < nkb; ++kb) {
-      float sc[4][4];
-      block_nt(qa, k_a, kb * 32, lane, sc);
-      stats_update(sc, valid, kb * 32, t, sl2, m, l);
-    }
     float inv[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float s = l[r];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      inv[r] = 1.f / s;
-      // softmax statistics of the row for the backward kernel (saves it two of its four score recomputations)
-      if (lse != nullptr && t == 0 && q0 + gq + 8 * r < S) lse[bh * S + q0 + gq + 8 * r] = make_float2(m[r], inv[r]);
-    }
     float o[8][4];
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd)
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
-      float sc[4][4];
-      block_nt(qa, k_a, kb * 32, lane, sc);
+    if (PROBS) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        float sc[4][4];
+        block_nt(qa, k_a, kb * 32, lane, sc);
+        stats_update(sc, valid, kb * 32, t, sl2, m, l);
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int i = q0 + gq + 8 * r;
+        float s = l[r];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        inv[r] = 1.f / s;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        float sc[4][4];
+        block_nt(qa, k_a, kb * 32, lane, sc);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int j = kb * 32 + nt * 8 + t * 2;
-          float p0 = valid[j] ? ex2_approx((sc[nt][r * 2] - m[r]) * sl2) * inv[r] : 0.f;
-          float p1 = valid[j + 1] ? ex2_approx((sc[nt][r * 2 + 1] - m[r]) * sl2) * inv[r] : 0.f;
-          if (i < S) {
-            if (probs != nullptr) {
-              if (j < S) probs[(bh * S + i) * S + j] = p0;
-              if (j + 1 < S) probs[(bh * S + i) * S + j + 1] = p1;
+        for (int r = 0; r < 2; ++r) {
+          const int i = q0 + gq + 8 * r;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int j = kb * 32 + nt * 8 + t * 2;
+            float p0 = valid[j] ? ex2_approx((sc[nt][r * 2] - m[r]) * sl2) * inv[r] : 0.f;
+            float p1 = valid[j + 1] ? ex2_approx((sc[nt][r * 2 + 1] - m[r]) * sl2) * inv[r] : 0.f;
+            if (i < S) {
+              if (probs != nullptr) {
+                if (j < S) probs[(bh * S + i) * S + j] = p0;
+                if (j + 1 < S) probs[(bh * S + i) * S + j + 1] = p1;
+              }
+              if (DROP) {
+                float f0, f1;
+                drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
+                p0 *= f0;
+                p1 *= f1;
+              }
             }
-            if (dc.thr) {
+            sc[nt][r * 2] = p0;
+            sc[nt][r * 2 + 1] = p1;
+          }
+        }
+        uint32_t pa[2][4];
+        pack_block(sc, pa);
+        acc_rows(o, pa, v_a, kb * 32, lane);
+      }
+    } else {
+      // dropout index of (row, key 0) per fragment row; rows >= S (last tile only) produce unused output rows
+      const long long drow[2] = {(bh * S + q0 + gq) * dstride, (bh * S + q0 + gq + 8) * dstride};
+      for (int kb = 0; kb < nkb; ++kb) {
+        float sc[4][4];
+        block_nt(qa, k_a, kb * 32, lane, sc);
+        const uint32_t vm = vbits[kb] >> (t * 2);      // bit (nt * 8 + e): key kb*32 + nt*8 + t*2 + e takes part
+        const bool all = vbits[kb] == 0xffffffffu;     // uniform: every block but the last unless a mask is given
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float bm = -INFINITY;
+          if (all) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][r * 2], sc[nt][r * 2 + 1]));
+          } else {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if ((vm >> (nt * 8 + e)) & 1u) bm = fmaxf(bm, sc[nt][r * 2 + e]);
+          }
+          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+          const float mn = fmaxf(m[r], bm);
+          const float ms = (mn == -INFINITY) ? 0.f : mn * sl2;       // nothing valid yet: every p below is 0
+          const float corr = ex2_approx(fmaf(m[r], sl2, -ms));        // m = -inf -> 0
+          m[r] = mn;
+          l[r] *= corr;
+#pragma unroll
+          for (int nd = 0; nd < 8; ++nd) { o[nd][2 * r] *= corr; o[nd][2 * r + 1] *= corr; }
+          float add = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms));
+            float p1 = ex2_approx(fmaf(sc[nt][r * 2 + 1], sl2, -ms));
+            if (!all) {
+              p0 = ((vm >> (nt * 8)) & 1u) ? p0 : 0.f;
+              p1 = ((vm >> (nt * 8 + 1)) & 1u) ? p1 : 0.f;
+            }
+            add += p0 + p1;
+            if (DROP) {
               float f0, f1;
-              drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
+              drop2(dc, (uint64_t)(drow[r] + kb * 32 + nt * 8 + t * 2), f0, f1);
               p0 *= f0;
               p1 *= f1;
             }
+            sc[nt][r * 2] = p0;
+            sc[nt][r * 2 + 1] = p1;
           }
-          sc[nt][r * 2] = p0;
-          sc[nt][r * 2 + 1] = p1;
+          l[r] += add;
         }
+        uint32_t pa[2][4];
+        pack_block(sc, pa);
+        acc_rows(o, pa, v_a, kb * 32, lane);
       }
-      uint32_t pa[2][4];
-      pack_block(sc, pa);
-      acc_rows(o, pa, v_a, kb * 32, lane);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float sum = l[r];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        inv[r] = 1.f / sum;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) { o[nd][2 * r] *= inv[r]; o[nd][2 * r + 1] *= inv[r]; }
+      }
     }
+    // softmax statistics of the rows for the backward kernel (saves it two of its four score recomputations)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      if (lse != nullptr && t == 0 && q0 + gq + 8 * r < S) lse[bh * S + q0 + gq + 8 * r] = make_float2(m[r], inv[r]);
     // O overwrites this warp's own (now dead) Q rows, then leaves as 16-byte coalesced row stores
     const SwzRow off;
     __syncwarp();
@@ -258,6 +339,7 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------
 // The backward kernel's warp count is a launch parameter: a warp owns 16-row query / key tiles, and S = 257 has 17 of
 // them -- 9 warps need two rounds per pass where 8 need three (17 / 8 = 2.1).
+template <bool DROP>
 __global__ void __launch_bounds__(AL_BWD_MAX_WARPS * 32, 1)
 mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
                     const __grid_constant__ CUtensorMap d64, const __grid_constant__ CUtensorMap dtail,
@@ -272,21 +354,20 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   uint8_t* k_s = q_s + g.tile_bytes;
   uint8_t* v_s = k_s + g.tile_bytes;
   uint8_t* do_s = v_s + g.tile_bytes;
-  float* st_m = reinterpret_cast<float*>(do_s + g.tile_bytes);     // row maxima            [SR + 32]
-  float* st_i = st_m + g.SR + 32;                                   // 1 / row sums          [SR + 32]
-  float* st_d = st_i + g.SR + 32;                                   // D_i = dO_i . O_i      [SR + 32]
-  uint8_t* valid = reinterpret_cast<uint8_t*>(st_d + g.SR + 32);
-  uint8_t* stage = valid + ((g.SR + 32 + 15) & ~15) + warp * (16 * 144);
+  float4* st_q = reinterpret_cast<float4*>(do_s + g.tile_bytes);   // per query: (m * sl2, 1 / l, D = dO . O, scale / l)  [SR + 32]
+  uint8_t* valid = reinterpret_cast<uint8_t*>(st_q + g.SR + 32);
+  uint32_t* vbits = reinterpret_cast<uint32_t*>(valid + ((g.SR + 32 + 15) & ~15));
+  uint8_t* stage = valid + valid_region_bytes(g.SR) + warp * (16 * 144);
   const int nwarps = (int)(blockDim.x >> 5);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + ((g.SR + 32 + 15) & ~15) + AL_BWD_MAX_WARPS * 16 * 144);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(valid + valid_region_bytes(g.SR) + AL_BWD_MAX_WARPS * 16 * 144);
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), do_a = smem_u32(do_s);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     mbar_init_fence();
   }
-  fill_valid(valid, mask, b, g);
+  fill_valid(valid, vbits, mask, b, g);
   zero_pad_rows(q_s, 4, g);
-  for (int j = threadIdx.x; j < g.SR + 32; j += blockDim.x) { st_m[j] = 0.f; st_i[j] = 0.f; st_d[j] = 0.f; }
+  for (int j = threadIdx.x; j < g.SR + 32; j += blockDim.x) st_q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_a, 4u * g.load_bytes);
@@ -373,7 +454,8 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
       dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
       const int i = q0 + gq + 8 * r;
-      if (t == 0) { st_m[i] = m[r]; st_i[i] = (i < S) ? inv[r] : 0.f; st_d[i] = dsum[r]; }
+      if (i >= S) { m[r] = 0.f; inv[r] = 0.f; }        // rows beyond the sequence: every probability below is exactly 0
+      if (t == 0) st_q[i] = make_float4(m[r] * sl2, inv[r], dsum[r], inv[r] * scale);
     }
     // dQ = dS K
     float dq[8][4];
@@ -381,27 +463,40 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     for (int nd = 0; nd < 8; ++nd)
 #pragma unroll
       for (int i = 0; i < 4; ++i) dq[nd][i] = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
-      float sc[4][4], dp[4][4];
-      block_nt(qa, k_a, kb * 32, lane, sc);
-      block_nt(doa, v_a, kb * 32, lane, dp);
+    {
+      // dS = P o (dP o f - D) / sqrt(d) = [ex2(s * sl2 - m * sl2) * (scale / l)] * (dP * f - D); rows >= S have 1 / l = 0
+      const float ms[2] = {m[0] * sl2, m[1] * sl2}, is[2] = {inv[0] * scale, inv[1] * scale};
+      const long long drow[2] = {(bh * S + q0 + gq) * dstride, (bh * S + q0 + gq + 8) * dstride};
+      for (int kb = 0; kb < nkb; ++kb) {
+        float sc[4][4], dp[4][4];
+        block_nt(qa, k_a, kb * 32, lane, sc);
+        block_nt(doa, v_a, kb * 32, lane, dp);
+        const uint32_t vm = vbits[kb] >> (t * 2);
+        const bool all = vbits[kb] == 0xffffffffu;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int i = q0 + gq + 8 * r;
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int j = kb * 32 + nt * 8 + t * 2;
-          const float p0 = valid[j] ? ex2_approx((sc[nt][r * 2] - m[r]) * sl2) * inv[r] : 0.f;
-          const float p1 = valid[j + 1] ? ex2_approx((sc[nt][r * 2 + 1] - m[r]) * sl2) * inv[r] : 0.f;
-          float f0 = 1.f, f1 = 1.f;
-          if (dc.thr && i < S) drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
-          sc[nt][r * 2] = (i < S) ? p0 * (dp[nt][r * 2] * f0 - dsum[r]) * scale : 0.f;
-          sc[nt][r * 2 + 1] = (i < S) ? p1 * (dp[nt][r * 2 + 1] * f1 - dsum[r]) * scale : 0.f;
-        }
+          for (int nt = 0; nt < 4; ++nt) {
+            float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms[r])) * is[r];
+            float p1 = ex2_approx(fmaf(sc[nt][r * 2 + 1], sl2, -ms[r])) * is[r];
+            if (!all) {
+              p0 = ((vm >> (nt * 8)) & 1u) ? p0 : 0.f;
+              p1 = ((vm >> (nt * 8 + 1)) & 1u) ? p1 : 0.f;
+            }
+            float g0 = dp[nt][r * 2] - dsum[r], g1 = dp[nt][r * 2 + 1] - dsum[r];
+            if (DROP) {
+              float f0, f1;
+              drop2(dc, (uint64_t)(drow[r] + kb * 32 + nt * 8 + t * 2), f0, f1);
+              g0 = fmaf(dp[nt][r * 2], f0, -dsum[r]);
+              g1 = fmaf(dp[nt][r * 2 + 1], f1, -dsum[r]);
+            }
+            sc[nt][r * 2] = p0 * g0;
+            sc[nt][r * 2 + 1] = p1 * g1;
+          }
+        uint32_t dsa[2][4];
+        pack_block(sc, dsa);
+        acc_rows(dq, dsa, k_a, kb * 32, lane);
       }
-      uint32_t dsa[2][4];
-      pack_block(sc, dsa);
-      acc_rows(dq, dsa, k_a, kb * 32, lane);
     }
     store_tile_global(dq, stage, dqkv + ((long long)b * S + q0) * 3 * F + h * AL_D, 3 * F, S - q0, lane);
   }
@@ -418,25 +513,49 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     for (int nd = 0; nd < 8; ++nd)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { dk[nd][i] = 0.f; dv[nd][i] = 0.f; }
+    // keys of this tile: validity per fragment row (uniform fast path when all 16 take part); dropout: the key part of
+    // the element index and which 16-bit half of which word of the octet it selects are fixed per row
+    const bool jv[2] = {valid[k0 + gq] != 0, valid[k0 + gq + 8] != 0};
+    const bool tile_all = __all_sync(0xffffffffu, jv[0] && jv[1]);
+    const int jj[2] = {k0 + gq, k0 + gq + 8};
+    const uint32_t dmul[2] = {drop_mult((jj[0] >> 1) & 3), drop_mult((jj[1] >> 1) & 3)};
+    const int dsh[2] = {(jj[0] & 1) ? 0 : 16, (jj[1] & 1) ? 0 : 16};
+    const long long doct = (long long)dstride >> 3;                 // octets per (head, query) row
     for (int qb = 0; qb < nqb; ++qb) {
       float st[4][4], dpt[4][4], pd[4][4];
       block_nt(ka, q_a, qb * 32, lane, st);     // S^T block: rows = keys k0.., columns = queries qb*32..
       block_nt(va, do_a, qb * 32, lane, dpt);   // dP^T block
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int j = k0 + gq + 8 * r;
-        const bool jv = valid[j] != 0;
+      for (int nt = 0; nt < 4; ++nt) {
+        const int i0 = qb * 32 + nt * 8 + t * 2;                    // this lane's two query columns: i0, i0 + 1
+        const float4 qs0 = st_q[i0], qs1 = st_q[i0 + 1];            // (m * sl2, 1 / l, D, scale / l); 1 / l = 0 beyond S
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = qb * 32 + nt * 8 + t * 2 + e;
-            const float p = (jv && i < S) ? ex2_approx((st[nt][r * 2 + e] - st_m[i]) * sl2) * st_i[i] : 0.f;
-            float f = 1.f;
-            if (dc.thr && i < S && j < S) f = drop1(dc, att_drop_index(bh * S + i, j, dstride));
-            pd[nt][r * 2 + e] = p * f;
-            st[nt][r * 2 + e] = p * (dpt[nt][r * 2 + e] * f - st_d[i]) * scale;
+        for (int r = 0; r < 2; ++r) {
+          const float e0 = ex2_approx(fmaf(st[nt][r * 2], sl2, -qs0.x)), e1 = ex2_approx(fmaf(st[nt][r * 2 + 1], sl2, -qs1.x));
+          float p0 = e0 * qs0.y, p1 = e1 * qs1.y;                  // P (for dV)
+          float s0 = e0 * qs0.w, s1 = e1 * qs1.w;                  // P * scale (for dS)
+          if (!tile_all) {
+            p0 = jv[r] ? p0 : 0.f; p1 = jv[r] ? p1 : 0.f;
+            s0 = jv[r] ? s0 : 0.f; s1 = jv[r] ? s1 : 0.f;
           }
+          float g0 = dpt[nt][r * 2] - qs0.z, g1 = dpt[nt][r * 2 + 1] - qs1.z;
+          if (DROP) {
+            // factor of element (query i, key j): word (j >> 1) & 3 of octet (bh * S + i) * stride / 8 + j / 8
+            const long long o0 = (bh * S + i0) * doct + (jj[r] >> 3);
+            const uint32_t w0 = drop_word(drop_base(dc, (uint32_t)o0), dmul[r]);
+            const uint32_t w1 = drop_word(drop_base(dc, (uint32_t)(o0 + doct)), dmul[r]);
+            const float f0 = (w0 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+            const float f1 = (w1 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+            p0 *= f0;
+            p1 *= f1;
+            g0 = fmaf(dpt[nt][r * 2], f0, -qs0.z);
+            g1 = fmaf(dpt[nt][r * 2 + 1], f1, -qs1.z);
+          }
+          pd[nt][r * 2] = p0;
+          pd[nt][r * 2 + 1] = p1;
+          st[nt][r * 2] = s0 * g0;
+          st[nt][r * 2 + 1] = s1 * g1;
+        }
       }
       uint32_t a2[2][4];
       pack_block(pd, a2);
@@ -462,8 +581,8 @@ static int long_geom(int B, int Tn, int H, LongGeom* g) {
   return 0;
 }
 static size_t long_smem(const LongGeom& g, int tiles, bool backward) {
-  size_t n = (size_t)tiles * g.tile_bytes + ((g.SR + 32 + 15) & ~15) + 16;
-  if (backward) n += (size_t)3 * (g.SR + 32) * sizeof(float) + (size_t)AL_BWD_MAX_WARPS * 16 * 144;
+  size_t n = (size_t)tiles * g.tile_bytes + valid_region_bytes(g.SR) + 16;
+  if (backward) n += (size_t)4 * (g.SR + 32) * sizeof(float) + (size_t)AL_BWD_MAX_WARPS * 16 * 144;
   return n;
 }
 static int long_maps(const void* ptr, int cols_total, const LongGeom& g, CUtensorMap* m64, CUtensorMap* mtail) {
@@ -483,13 +602,21 @@ int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, 
   MMER_TRY(long_maps(qkv, 3 * g.F, g, &m64, &mtail));
   const size_t smem = long_smem(g, 3, false);
   MMER_CHECK_ARG(smem <= 232448, "mha_fwd(long): %lld bytes of shared memory needed", (long long)smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mha_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_fwd_long)");
-    configured = smem;
-  }
-  mha_fwd_long_kernel<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, reinterpret_cast<float2*>(lse), g, dc);
+  auto launch = [&](auto kern, size_t* configured) -> int {
+    if (smem > *configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_fwd_long)");
+      *configured = smem;
+    }
+    kern<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, reinterpret_cast<float2*>(lse), g, dc);
+    return 0;
+  };
+  static size_t conf[4] = {0, 0, 0, 0};
+  const bool drop = dc.thr != 0, pr = probs != nullptr;
+  if (drop && pr) MMER_TRY(launch(mha_fwd_long_kernel<true, true>, &conf[0]));
+  else if (drop) MMER_TRY(launch(mha_fwd_long_kernel<true, false>, &conf[1]));
+  else if (pr) MMER_TRY(launch(mha_fwd_long_kernel<false, true>, &conf[2]));
+  else MMER_TRY(launch(mha_fwd_long_kernel<false, false>, &conf[3]));
   MMER_LAUNCH_CHECK("mha_fwd_long_kernel");
   return 0;
 }
@@ -504,17 +631,22 @@ int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* d
   MMER_TRY(long_maps(dout, g.F, g, &d64, &dtail));
   const size_t smem = long_smem(g, 4, true);
   MMER_CHECK_ARG(smem <= 232448, "mha_bwd(long): %lld bytes of shared memory needed", (long long)smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mha_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_bwd_long)");
-    configured = smem;
-  }
   // fewest rounds over the 16-row tiles with 8 or 9 warps
   const int ntile = (g.S + 15) / 16;
   const int nw = ((ntile + 8) / 9 < (ntile + 7) / 8) ? 9 : 8;
-  mha_bwd_long_kernel<<<(unsigned)((long long)B * H), nw * 32, smem, st>>>(m64, mtail, d64, dtail, mask, (bf16*)dqkv, reinterpret_cast<const float2*>(lse),
-                                                                           (const bf16*)fwd_out, g, dc);
+  auto launch = [&](auto kern, size_t* configured) -> int {
+    if (smem > *configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_bwd_long)");
+      *configured = smem;
+    }
+    kern<<<(unsigned)((long long)B * H), nw * 32, smem, st>>>(m64, mtail, d64, dtail, mask, (bf16*)dqkv, reinterpret_cast<const float2*>(lse),
+                                                            (const bf16*)fwd_out, g, dc);
+    return 0;
+  };
+  static size_t conf[2] = {0, 0};
+  if (dc.thr != 0) MMER_TRY(launch(mha_bwd_long_kernel<true>, &conf[0]));
+  else MMER_TRY(launch(mha_bwd_long_kernel<false>, &conf[1]));
   MMER_LAUNCH_CHECK("mha_bwd_long_kernel");
   return 0;
 }
