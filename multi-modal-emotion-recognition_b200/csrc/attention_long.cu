@@ -28,39 +28,52 @@ struct SwzRow {   // byte offset of (row, col) in a tile of 128-byte rows, 128B-
   }
 };
 
-// A fragments (16 rows x 64 columns = 4 k-steps) of rows [r0, r0+16) of a tile
-__device__ __forceinline__ void load_a16(uint32_t tile_a, int r0, int lane, uint32_t (&a)[4][4]) {
-  const SwzRow off;
+// Per-lane byte offsets of the ldmatrix row addresses inside a swizzled tile.  Tile rows handled together start at
+// multiples of 8, so the swizzle term (chunk ^ row) & 7 depends on the lane only: computed once per kernel, the address
+// of every ldmatrix is base + immediate.
+struct LaneOff {
+  uint32_t nt[2];   // B fragments of 8 tile rows (non-transposed), k2 = 0, 1: row (lane & 7), 16-byte chunk k2*4 + (lane >> 3)
+  uint32_t tr[4];   // 16 tile rows, chunk pair n2 = 0..3: row (lane & 7) + 8 * ((lane >> 3) & 1), chunk n2*2 + (lane >> 4)
+};
+__device__ __forceinline__ LaneOff lane_offsets(int lane) {
+  LaneOff o;
+  const uint32_t r7 = lane & 7;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(tile_a + off(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 16 + (lane >> 4) * 8), a[ks][0], a[ks][1], a[ks][2],
-            a[ks][3]);
+  for (int k2 = 0; k2 < 2; ++k2) o.nt[k2] = r7 * 128u + ((((uint32_t)(k2 * 4 + (lane >> 3)) ^ r7) & 7u) << 4);
+  const uint32_t lrow = r7 + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) o.tr[n2] = lrow * 128u + ((((uint32_t)(n2 * 2 + (lane >> 4)) ^ r7) & 7u) << 4);
+  return o;
 }
-// c[nt][..] = A(16 x 64) . X[rows c0 .. c0+32)^T : 16 x 32 block of products against 32 rows of tile X
-__device__ __forceinline__ void block_nt(const uint32_t (&a)[4][4], uint32_t x_a, int c0, int lane, float (&c)[4][4]) {
-  const SwzRow off;
+// A fragments (16 rows x 64 columns = 4 k-steps) of rows [r0, r0+16) of a tile (r0 % 8 == 0)
+__device__ __forceinline__ void load_a16(uint32_t tile_a, int r0, const LaneOff& lo, uint32_t (&a)[4][4]) {
+  const uint32_t base = tile_a + (uint32_t)r0 * 128u;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(base + lo.tr[ks], a[ks][0], a[ks][1], a[ks][2], a[ks][3]);
+}
+// c[nt][..] = A(16 x 64) . X[rows c0 .. c0+32)^T : 16 x 32 block of products against 32 rows of tile X (c0 % 8 == 0)
+__device__ __forceinline__ void block_nt(const uint32_t (&a)[4][4], uint32_t x_a, int c0, const LaneOff& lo, float (&c)[4][4]) {
+  const uint32_t b0 = x_a + (uint32_t)c0 * 128u + lo.nt[0], b1 = x_a + (uint32_t)c0 * 128u + lo.nt[1];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     uint32_t xf[4][2];
-#pragma unroll
-    for (int k2 = 0; k2 < 2; ++k2)
-      ldsm_x4(x_a + off(c0 + nt * 8 + (lane & 7), k2 * 32 + (lane >> 3) * 8), xf[2 * k2][0], xf[2 * k2][1], xf[2 * k2 + 1][0],
-              xf[2 * k2 + 1][1]);
+    ldsm_x4(b0 + nt * 1024, xf[0][0], xf[0][1], xf[1][0], xf[1][1]);
+    ldsm_x4(b1 + nt * 1024, xf[2][0], xf[2][1], xf[3][0], xf[3][1]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) mma_bf16_16816(c[nt], a[ks][0], a[ks][1], a[ks][2], a[ks][3], xf[ks][0], xf[ks][1]);
   }
 }
-// acc(16 x 64) += P(16 x 32, as two A fragments) . X[rows r0 .. r0+32) (X row-major: ldmatrix.trans)
-__device__ __forceinline__ void acc_rows(float (&acc)[8][4], const uint32_t (&pa)[2][4], uint32_t x_a, int r0, int lane) {
-  const SwzRow off;
+// acc(16 x 64) += P(16 x 32, as two A fragments) . X[rows r0 .. r0+32) (X row-major: ldmatrix.trans; r0 % 8 == 0)
+__device__ __forceinline__ void acc_rows(float (&acc)[8][4], const uint32_t (&pa)[2][4], uint32_t x_a, int r0, const LaneOff& lo) {
+  const uint32_t base = x_a + (uint32_t)r0 * 128u;
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
       uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(x_a + off(r0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, n2 * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      ldsm_x4_t(base + ks * 2048 + lo.tr[n2], b0, b1, b2, b3);
       mma_bf16_16816(acc[2 * n2], pa[ks][0], pa[ks][1], pa[ks][2], pa[ks][3], b0, b1);
       mma_bf16_16816(acc[2 * n2 + 1], pa[ks][0], pa[ks][1], pa[ks][2], pa[ks][3], b2, b3);
     }
@@ -157,6 +170,66 @@ __device__ __forceinline__ void stats_update(const float (&sc)[4][4], const uint
 // bytes of the validity region: valid[SR + 32] bytes, then AL_VWORDS bit words
 __device__ __host__ __forceinline__ int valid_region_bytes(int SR) { return ((SR + 32 + 15) & ~15) + AL_VWORDS * 4; }
 
+// One 16 x 32 score block of the one-pass forward: running maxima (O and the row sums are rescaled only when some row
+// of the warp's tile raises its maximum), unnormalised probabilities back into sc (dropout applied), row sums into l.
+// vm: this lane's validity bits (bit nt * 8 + e); ALL: every key of the block takes part.  key0: key of sc[0][0].
+template <bool DROP, bool ALL>
+__device__ __forceinline__ void fwd_block_softmax(float (&sc)[4][4], uint32_t vm, float sl2, float (&m)[2], float (&l)[2],
+                                                  float (&o)[8][4], const DropCfg& dc, const long long (&drow)[2], int key0) {
+  float mn[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float bm = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (ALL) {
+        bm = fmaxf(bm, fmaxf(sc[nt][r * 2], sc[nt][r * 2 + 1]));
+      } else {
+        bm = fmaxf(bm, ((vm >> (nt * 8)) & 1u) ? sc[nt][r * 2] : -INFINITY);
+        bm = fmaxf(bm, ((vm >> (nt * 8 + 1)) & 1u) ? sc[nt][r * 2 + 1] : -INFINITY);
+      }
+    }
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+    mn[r] = fmaxf(m[r], bm);
+  }
+  if (__any_sync(0xffffffffu, mn[0] != m[0] || mn[1] != m[1])) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float ms = (mn[r] == -INFINITY) ? 0.f : mn[r] * sl2;
+      const float corr = ex2_approx(fmaf(m[r], sl2, -ms));       // m = -inf -> 0; unchanged maximum -> 1
+      l[r] *= corr;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) { o[nd][2 * r] *= corr; o[nd][2 * r + 1] *= corr; }
+      m[r] = mn[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float ms = (m[r] == -INFINITY) ? 0.f : m[r] * sl2;     // nothing valid yet: every p below is selected to 0
+    float add = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms));
+      float p1 = ex2_approx(fmaf(sc[nt][r * 2 + 1], sl2, -ms));
+      if (!ALL) {
+        p0 = ((vm >> (nt * 8)) & 1u) ? p0 : 0.f;
+        p1 = ((vm >> (nt * 8 + 1)) & 1u) ? p1 : 0.f;
+      }
+      add += p0 + p1;
+      if (DROP) {
+        float f0, f1;
+        drop2(dc, (uint64_t)(drow[r] + key0 + nt * 8), f0, f1);
+        p0 *= f0;
+        p1 *= f1;
+      }
+      sc[nt][r * 2] = p0;
+      sc[nt][r * 2 + 1] = p1;
+    }
+    l[r] += add;
+  }
+}
+
 // PROBS (return_attn): two passes over the key blocks (statistics, then normalised probabilities written out and P V).
 // Otherwise ONE pass with running maxima: O and the row sums are rescaled when a block raises the maximum, the division
 // by the row sum happens once at the end (a third fewer MMAs, every exponential computed once).
@@ -195,9 +268,10 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   const float sl2 = rsqrtf((float)AL_D) * 1.4426950408889634f;
   const int dstride = att_drop_stride(S);
   const int nkb = (S + 31) / 32;
+  const LaneOff lo = lane_offsets(lane);
   for (int q0 = warp * 16; q0 < S; q0 += AL_WARPS * 16) {
     uint32_t qa[4][4];
-    load_a16(q_a, q0, lane, qa);
+    load_a16(q_a, q0, lo, qa);
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
     float inv[2];
     float o[8][4];
@@ -208,7 +282,7 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     if (PROBS) {
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4];
-        block_nt(qa, k_a, kb * 32, lane, sc);
+        block_nt(qa, k_a, kb * 32, lo, sc);
         stats_update(sc, valid, kb * 32, t, sl2, m, l);
       }
 #pragma unroll
@@ -220,7 +294,7 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       }
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4];
-        block_nt(qa, k_a, kb * 32, lane, sc);
+        block_nt(qa, k_a, kb * 32, lo, sc);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int i = q0 + gq + 8 * r;
@@ -247,62 +321,22 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
         }
         uint32_t pa[2][4];
         pack_block(sc, pa);
-        acc_rows(o, pa, v_a, kb * 32, lane);
+        acc_rows(o, pa, v_a, kb * 32, lo);
       }
     } else {
       // dropout index of (row, key 0) per fragment row; rows >= S (last tile only) produce unused output rows
       const long long drow[2] = {(bh * S + q0 + gq) * dstride, (bh * S + q0 + gq + 8) * dstride};
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4];
-        block_nt(qa, k_a, kb * 32, lane, sc);
-        const uint32_t vm = vbits[kb] >> (t * 2);      // bit (nt * 8 + e): key kb*32 + nt*8 + t*2 + e takes part
-        const bool all = vbits[kb] == 0xffffffffu;     // uniform: every block but the last unless a mask is given
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          float bm = -INFINITY;
-          if (all) {
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bm = fmaxf(bm, fmaxf(sc[nt][r * 2], sc[nt][r * 2 + 1]));
-          } else {
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-              for (int e = 0; e < 2; ++e)
-                if ((vm >> (nt * 8 + e)) & 1u) bm = fmaxf(bm, sc[nt][r * 2 + e]);
-          }
-          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-          const float mn = fmaxf(m[r], bm);
-          const float ms = (mn == -INFINITY) ? 0.f : mn * sl2;       // nothing valid yet: every p below is 0
-          const float corr = ex2_approx(fmaf(m[r], sl2, -ms));        // m = -inf -> 0
-          m[r] = mn;
-          l[r] *= corr;
-#pragma unroll
-          for (int nd = 0; nd < 8; ++nd) { o[nd][2 * r] *= corr; o[nd][2 * r + 1] *= corr; }
-          float add = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms));
-            float p1 = ex2_approx(fmaf(sc[nt][r * 2 + 1], sl2, -ms));
-            if (!all) {
-              p0 = ((vm >> (nt * 8)) & 1u) ? p0 : 0.f;
-              p1 = ((vm >> (nt * 8 + 1)) & 1u) ? p1 : 0.f;
-            }
-            add += p0 + p1;
-            if (DROP) {
-              float f0, f1;
-              drop2(dc, (uint64_t)(drow[r] + kb * 32 + nt * 8 + t * 2), f0, f1);
-              p0 *= f0;
-              p1 *= f1;
-            }
-            sc[nt][r * 2] = p0;
-            sc[nt][r * 2 + 1] = p1;
-          }
-          l[r] += add;
-        }
+        block_nt(qa, k_a, kb * 32, lo, sc);
+        const uint32_t vw = vbits[kb];
+        if (vw == 0xffffffffu)   // warp-uniform: every block but the last, unless a padding mask is given
+          fwd_block_softmax<DROP, true>(sc, 0u, sl2, m, l, o, dc, drow, kb * 32 + t * 2);
+        else
+          fwd_block_softmax<DROP, false>(sc, vw >> (t * 2), sl2, m, l, o, dc, drow, kb * 32 + t * 2);
         uint32_t pa[2][4];
         pack_block(sc, pa);
-        acc_rows(o, pa, v_a, kb * 32, lane);
+        acc_rows(o, pa, v_a, kb * 32, lo);
       }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -332,6 +366,73 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       if (q0 + r < S)
         *reinterpret_cast<uint4*>(out + ((long long)b * S + q0 + r) * F + h * AL_D + c8 * 8) =
             *reinterpret_cast<const uint4*>(q_s + off(q0 + r, c8 * 8));
+    }
+  }
+}
+
+// Backward, query-major block: sc <- dS = [ex2(s * sl2 - m * sl2) * (scale / l)] * (dP * f - D) for a 16 x 32 block
+// (rows beyond the sequence carry scale / l = 0).  vm: this lane's validity bits; key0: key of sc[0][0].
+template <bool DROP, bool ALL>
+__device__ __forceinline__ void bwd_block_ds(float (&sc)[4][4], const float (&dp)[4][4], uint32_t vm, float sl2, const float (&ms)[2],
+                                             const float (&is)[2], const float (&dsum)[2], const DropCfg& dc,
+                                             const long long (&drow)[2], int key0) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms[r])) * is[r];
+      float p1 = ex2_approx(fmaf(sc[nt][r * 2 + 1], sl2, -ms[r])) * is[r];
+      if (!ALL) {
+        p0 = ((vm >> (nt * 8)) & 1u) ? p0 : 0.f;
+        p1 = ((vm >> (nt * 8 + 1)) & 1u) ? p1 : 0.f;
+      }
+      float g0 = dp[nt][r * 2] - dsum[r], g1 = dp[nt][r * 2 + 1] - dsum[r];
+      if (DROP) {
+        float f0, f1;
+        drop2(dc, (uint64_t)(drow[r] + key0 + nt * 8), f0, f1);
+        g0 = fmaf(dp[nt][r * 2], f0, -dsum[r]);
+        g1 = fmaf(dp[nt][r * 2 + 1], f1, -dsum[r]);
+      }
+      sc[nt][r * 2] = p0 * g0;
+      sc[nt][r * 2 + 1] = p1 * g1;
+    }
+}
+// Backward, key-major (transposed) block: rows = two keys of this lane (jj), columns = queries.  pd <- P o f (for dV),
+// st <- dS^T (for dK).  qs: per-query statistics of this lane's first column (m * sl2, 1 / l, D, scale / l).
+// Dropout factor of element (query i, key j): word (j >> 1) & 3 of octet (bh * S + i) * stride / 8 + j / 8, low or high
+// half by j & 1 -- the key part is fixed per row (dmul, dsh), the query part advances by doct per column.
+template <bool DROP, bool ALL>
+__device__ __forceinline__ void bwd_block_dst(float (&st)[4][4], const float (&dpt)[4][4], float (&pd)[4][4], const float4* qs,
+                                              const bool (&jv)[2], float sl2, const DropCfg& dc, long long oct0, long long doct,
+                                              const int (&jj)[2], const uint32_t (&dmul)[2], const int (&dsh)[2]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float4 qs0 = qs[nt * 8], qs1 = qs[nt * 8 + 1];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float e0 = ex2_approx(fmaf(st[nt][r * 2], sl2, -qs0.x)), e1 = ex2_approx(fmaf(st[nt][r * 2 + 1], sl2, -qs1.x));
+      float p0 = e0 * qs0.y, p1 = e1 * qs1.y;                  // P (for dV)
+      float s0 = e0 * qs0.w, s1 = e1 * qs1.w;                  // P * scale (for dS)
+      if (!ALL) {
+        p0 = jv[r] ? p0 : 0.f; p1 = jv[r] ? p1 : 0.f;
+        s0 = jv[r] ? s0 : 0.f; s1 = jv[r] ? s1 : 0.f;
+      }
+      float g0 = dpt[nt][r * 2] - qs0.z, g1 = dpt[nt][r * 2 + 1] - qs1.z;
+      if (DROP) {
+        const long long o0 = oct0 + nt * 8 * doct + (jj[r] >> 3);
+        const uint32_t w0 = drop_word(drop_base(dc, (uint32_t)o0), dmul[r]);
+        const uint32_t w1 = drop_word(drop_base(dc, (uint32_t)(o0 + doct)), dmul[r]);
+        const float f0 = (w0 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+        const float f1 = (w1 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+        p0 *= f0;
+        p1 *= f1;
+        g0 = fmaf(dpt[nt][r * 2], f0, -qs0.z);
+        g1 = fmaf(dpt[nt][r * 2 + 1], f1, -qs1.z);
+      }
+      pd[nt][r * 2] = p0;
+      pd[nt][r * 2 + 1] = p1;
+      st[nt][r * 2] = s0 * g0;
+      st[nt][r * 2 + 1] = s1 * g1;
     }
   }
 }
@@ -383,15 +484,16 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   const int dstride = att_drop_stride(S);
   const int nkb = (S + 31) / 32;
   const SwzRow off;
+  const LaneOff lo = lane_offsets(lane);
 
   // ---------------- pass A + B per query tile: statistics, then dQ
   for (int q0 = warp * 16; q0 < S; q0 += nwarps * 16) {
     uint32_t qa[4][4], doa[4][4];
-    load_a16(q_a, q0, lane, qa);
+    load_a16(q_a, q0, lo, qa);
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
     float inv[2];
     float dsum[2] = {0.f, 0.f};
-    load_a16(do_a, q0, lane, doa);
+    load_a16(do_a, q0, lo, doa);
     if (lse != nullptr) {
       // The forward kernel stored (max, 1 / sum) of every row, and D_i = sum_j P_ij f_ij dP_ij equals dO_i . O_i with
       // the forward output O (dropout included): two of the four score recomputations disappear.
@@ -418,7 +520,7 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     } else {
     for (int kb = 0; kb < nkb; ++kb) {
       float sc[4][4];
-      block_nt(qa, k_a, kb * 32, lane, sc);
+      block_nt(qa, k_a, kb * 32, lo, sc);
       stats_update(sc, valid, kb * 32, t, sl2, m, l);
     }
 #pragma unroll
@@ -431,8 +533,8 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     // D_i = sum_j P_ij f_ij dP_ij  with dP_ij = dO_i . V_j   (equals dO_i . O_i; accumulated block by block)
     for (int kb = 0; kb < nkb; ++kb) {
       float sc[4][4], dp[4][4];
-      block_nt(qa, k_a, kb * 32, lane, sc);
-      block_nt(doa, v_a, kb * 32, lane, dp);
+      block_nt(qa, k_a, kb * 32, lo, sc);
+      block_nt(doa, v_a, kb * 32, lo, dp);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int i = q0 + gq + 8 * r;
@@ -469,33 +571,14 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       const long long drow[2] = {(bh * S + q0 + gq) * dstride, (bh * S + q0 + gq + 8) * dstride};
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4], dp[4][4];
-        block_nt(qa, k_a, kb * 32, lane, sc);
-        block_nt(doa, v_a, kb * 32, lane, dp);
-        const uint32_t vm = vbits[kb] >> (t * 2);
-        const bool all = vbits[kb] == 0xffffffffu;
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms[r])) * is[r];
-            float p1 = ex2_approx(fmaf(sc[nt][r * 2 + 1], sl2, -ms[r])) * is[r];
-            if (!all) {
-              p0 = ((vm >> (nt * 8)) & 1u) ? p0 : 0.f;
-              p1 = ((vm >> (nt * 8 + 1)) & 1u) ? p1 : 0.f;
-            }
-            float g0 = dp[nt][r * 2] - dsum[r], g1 = dp[nt][r * 2 + 1] - dsum[r];
-            if (DROP) {
-              float f0, f1;
-              drop2(dc, (uint64_t)(drow[r] + kb * 32 + nt * 8 + t * 2), f0, f1);
-              g0 = fmaf(dp[nt][r * 2], f0, -dsum[r]);
-              g1 = fmaf(dp[nt][r * 2 + 1], f1, -dsum[r]);
-            }
-            sc[nt][r * 2] = p0 * g0;
-            sc[nt][r * 2 + 1] = p1 * g1;
-          }
+        block_nt(qa, k_a, kb * 32, lo, sc);
+        block_nt(doa, v_a, kb * 32, lo, dp);
+        const uint32_t vw = vbits[kb];
+        if (vw == 0xffffffffu) bwd_block_ds<DROP, true>(sc, dp, 0u, sl2, ms, is, dsum, dc, drow, kb * 32 + t * 2);
+        else bwd_block_ds<DROP, false>(sc, dp, vw >> (t * 2), sl2, ms, is, dsum, dc, drow, kb * 32 + t * 2);
         uint32_t dsa[2][4];
         pack_block(sc, dsa);
-        acc_rows(dq, dsa, k_a, kb * 32, lane);
+        acc_rows(dq, dsa, k_a, kb * 32, lo);
       }
     }
     store_tile_global(dq, stage, dqkv + ((long long)b * S + q0) * 3 * F + h * AL_D, 3 * F, S - q0, lane);
@@ -506,8 +589,8 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   const int nqb = (S + 31) / 32;
   for (int k0 = warp * 16; k0 < S; k0 += nwarps * 16) {
     uint32_t ka[4][4], va[4][4];
-    load_a16(k_a, k0, lane, ka);
-    load_a16(v_a, k0, lane, va);
+    load_a16(k_a, k0, lo, ka);
+    load_a16(v_a, k0, lo, va);
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd)
@@ -523,45 +606,15 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     const long long doct = (long long)dstride >> 3;                 // octets per (head, query) row
     for (int qb = 0; qb < nqb; ++qb) {
       float st[4][4], dpt[4][4], pd[4][4];
-      block_nt(ka, q_a, qb * 32, lane, st);     // S^T block: rows = keys k0.., columns = queries qb*32..
-      block_nt(va, do_a, qb * 32, lane, dpt);   // dP^T block
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int i0 = qb * 32 + nt * 8 + t * 2;                    // this lane's two query columns: i0, i0 + 1
-        const float4 qs0 = st_q[i0], qs1 = st_q[i0 + 1];            // (m * sl2, 1 / l, D, scale / l); 1 / l = 0 beyond S
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const float e0 = ex2_approx(fmaf(st[nt][r * 2], sl2, -qs0.x)), e1 = ex2_approx(fmaf(st[nt][r * 2 + 1], sl2, -qs1.x));
-          float p0 = e0 * qs0.y, p1 = e1 * qs1.y;                  // P (for dV)
-          float s0 = e0 * qs0.w, s1 = e1 * qs1.w;                  // P * scale (for dS)
-          if (!tile_all) {
-            p0 = jv[r] ? p0 : 0.f; p1 = jv[r] ? p1 : 0.f;
-            s0 = jv[r] ? s0 : 0.f; s1 = jv[r] ? s1 : 0.f;
-          }
-          float g0 = dpt[nt][r * 2] - qs0.z, g1 = dpt[nt][r * 2 + 1] - qs1.z;
-          if (DROP) {
-            // factor of element (query i, key j): word (j >> 1) & 3 of octet (bh * S + i) * stride / 8 + j / 8
-            const long long o0 = (bh * S + i0) * doct + (jj[r] >> 3);
-            const uint32_t w0 = drop_word(drop_base(dc, (uint32_t)o0), dmul[r]);
-            const uint32_t w1 = drop_word(drop_base(dc, (uint32_t)(o0 + doct)), dmul[r]);
-            const float f0 = (w0 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
-            const float f1 = (w1 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
-            p0 *= f0;
-            p1 *= f1;
-            g0 = fmaf(dpt[nt][r * 2], f0, -qs0.z);
-            g1 = fmaf(dpt[nt][r * 2 + 1], f1, -qs1.z);
-          }
-          pd[nt][r * 2] = p0;
-          pd[nt][r * 2 + 1] = p1;
-          st[nt][r * 2] = s0 * g0;
-          st[nt][r * 2 + 1] = s1 * g1;
-        }
-      }
+      block_nt(ka, q_a, qb * 32, lo, st);     // S^T block: rows = keys k0.., columns = queries qb*32..
+      block_nt(va, do_a, qb * 32, lo, dpt);   // dP^T block
+      if (tile_all) bwd_block_dst<DROP, true>(st, dpt, pd, st_q + qb * 32 + t * 2, jv, sl2, dc, (bh * S + qb * 32 + t * 2) * doct, doct, jj, dmul, dsh);
+      else bwd_block_dst<DROP, false>(st, dpt, pd, st_q + qb * 32 + t * 2, jv, sl2, dc, (bh * S + qb * 32 + t * 2) * doct, doct, jj, dmul, dsh);
       uint32_t a2[2][4];
       pack_block(pd, a2);
-      acc_rows(dv, a2, do_a, qb * 32, lane);
+      acc_rows(dv, a2, do_a, qb * 32, lo);
       pack_block(st, a2);
-      acc_rows(dk, a2, q_a, qb * 32, lane);
+      acc_rows(dk, a2, q_a, qb * 32, lo);
     }
     bf16* base = dqkv + ((long long)b * S + k0) * 3 * F + h * AL_D;
     store_tile_global(dk, stage, base + F, 3 * F, S - k0, lane);
