@@ -371,13 +371,16 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
 }
 
 // Backward, query-major block: sc <- dS = [ex2(s * sl2 - m * sl2) * (scale / l)] * (dP * f - D) for a 16 x 32 block
-// (rows beyond the sequence carry scale / l = 0).  vm: this lane's validity bits; key0: key of sc[0][0].
+// (rows beyond the sequence carry scale / l = 0).  vm: this lane's validity bits.  Dropout: oct[r] = octet index of
+// (row, key 0 of the block) -- the lane's pair nt sits in octet oct[r] + nt, word t (mult hoisted).  keep[r] collects
+// this lane's keep bits of the block (bit nt * 8 + t * 2 + e) for the transposed pass.
 template <bool DROP, bool ALL>
 __device__ __forceinline__ void bwd_block_ds(float (&sc)[4][4], const float (&dp)[4][4], uint32_t vm, float sl2, const float (&ms)[2],
                                              const float (&is)[2], const float (&dsum)[2], const DropCfg& dc,
-                                             const long long (&drow)[2], int key0) {
+                                             const uint32_t (&oct)[2], uint32_t mult, int t, uint32_t (&keep)[2]) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 2; ++r) {
+    uint32_t kb = 0u;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms[r])) * is[r];
@@ -388,26 +391,37 @@ __device__ __forceinline__ void bwd_block_ds(float (&sc)[4][4], const float (&dp
       }
       float g0 = dp[nt][r * 2] - dsum[r], g1 = dp[nt][r * 2 + 1] - dsum[r];
       if (DROP) {
-        float f0, f1;
-        drop2(dc, (uint64_t)(drow[r] + key0 + nt * 8), f0, f1);
-        g0 = fmaf(dp[nt][r * 2], f0, -dsum[r]);
-        g1 = fmaf(dp[nt][r * 2 + 1], f1, -dsum[r]);
+        const uint32_t w = drop_word(drop_base(dc, oct[r] + nt), mult);
+        const bool k0 = (w << 16) >= dc.thr_hi, k1 = w >= dc.thr_hi;
+        kb |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (nt * 8);
+        g0 = fmaf(dp[nt][r * 2], k0 ? dc.scale : 0.f, -dsum[r]);
+        g1 = fmaf(dp[nt][r * 2 + 1], k1 ? dc.scale : 0.f, -dsum[r]);
       }
       sc[nt][r * 2] = p0 * g0;
       sc[nt][r * 2 + 1] = p1 * g1;
     }
+    keep[r] = kb << (t * 2);
+  }
 }
 // Backward, key-major (transposed) block: rows = two keys of this lane (jj), columns = queries.  pd <- P o f (for dV),
 // st <- dS^T (for dK).  qs: per-query statistics of this lane's first column (m * sl2, 1 / l, D, scale / l).
 // Dropout factor of element (query i, key j): word (j >> 1) & 3 of octet (bh * S + i) * stride / 8 + j / 8, low or high
 // half by j & 1 -- the key part is fixed per row (dmul, dsh), the query part advances by doct per column.
-template <bool DROP, bool ALL>
+// BITS: the keep decisions come from the bit map the query-major pass wrote (kbits: row of this lane's first column, nw
+// words per query row, word = key block of this tile, kpos[r] = bit of key jj[r]) instead of a hash per element.
+template <bool DROP, bool ALL, bool BITS>
 __device__ __forceinline__ void bwd_block_dst(float (&st)[4][4], const float (&dpt)[4][4], float (&pd)[4][4], const float4* qs,
                                               const bool (&jv)[2], float sl2, const DropCfg& dc, long long oct0, long long doct,
-                                              const int (&jj)[2], const uint32_t (&dmul)[2], const int (&dsh)[2]) {
+                                              const int (&jj)[2], const uint32_t (&dmul)[2], const int (&dsh)[2],
+                                              const uint32_t* kbits, int nw, const int (&kpos)[2]) {
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     const float4 qs0 = qs[nt * 8], qs1 = qs[nt * 8 + 1];
+    uint32_t kw0 = 0u, kw1 = 0u;
+    if (DROP && BITS) {
+      kw0 = kbits[(nt * 8) * nw];
+      kw1 = kbits[(nt * 8 + 1) * nw];
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float e0 = ex2_approx(fmaf(st[nt][r * 2], sl2, -qs0.x)), e1 = ex2_approx(fmaf(st[nt][r * 2 + 1], sl2, -qs1.x));
@@ -419,11 +433,17 @@ __device__ __forceinline__ void bwd_block_dst(float (&st)[4][4], const float (&d
       }
       float g0 = dpt[nt][r * 2] - qs0.z, g1 = dpt[nt][r * 2 + 1] - qs1.z;
       if (DROP) {
-        const long long o0 = oct0 + nt * 8 * doct + (jj[r] >> 3);
-        const uint32_t w0 = drop_word(drop_base(dc, (uint32_t)o0), dmul[r]);
-        const uint32_t w1 = drop_word(drop_base(dc, (uint32_t)(o0 + doct)), dmul[r]);
-        const float f0 = (w0 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
-        const float f1 = (w1 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+        float f0, f1;
+        if (BITS) {
+          f0 = ((kw0 >> kpos[r]) & 1u) ? dc.scale : 0.f;
+          f1 = ((kw1 >> kpos[r]) & 1u) ? dc.scale : 0.f;
+        } else {
+          const long long o0 = oct0 + nt * 8 * doct + (jj[r] >> 3);
+          const uint32_t w0 = drop_word(drop_base(dc, (uint32_t)o0), dmul[r]);
+          const uint32_t w1 = drop_word(drop_base(dc, (uint32_t)(o0 + doct)), dmul[r]);
+          f0 = (w0 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+          f1 = (w1 << dsh[r]) >= dc.thr_hi ? dc.scale : 0.f;
+        }
         p0 *= f0;
         p1 *= f1;
         g0 = fmaf(dpt[nt][r * 2], f0, -qs0.z);
@@ -440,7 +460,8 @@ __device__ __forceinline__ void bwd_block_dst(float (&st)[4][4], const float (&d
 // ---------------------------------------------------------------------------------------------------------
 // The backward kernel's warp count is a launch parameter: a warp owns 16-row query / key tiles, and S = 257 has 17 of
 // them -- 9 warps need two rounds per pass where 8 need three (17 / 8 = 2.1).
-template <bool DROP>
+// BITS: room for the dropout keep-bit map [query][key block] in shared memory (always at S = 257; not at S = 384)
+template <bool DROP, bool BITS>
 __global__ void __launch_bounds__(AL_BWD_MAX_WARPS * 32, 1)
 mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
                     const __grid_constant__ CUtensorMap d64, const __grid_constant__ CUtensorMap dtail,
@@ -461,6 +482,7 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   uint8_t* stage = valid + valid_region_bytes(g.SR) + warp * (16 * 144);
   const int nwarps = (int)(blockDim.x >> 5);
   uint64_t* bar = reinterpret_cast<uint64_t*>(valid + valid_region_bytes(g.SR) + AL_BWD_MAX_WARPS * 16 * 144);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(bar + 2);             // [SR + 32][nkb] keep bits (DROP && BITS)
   const uint32_t bar_a = smem_u32(bar), q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), do_a = smem_u32(do_s);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
@@ -568,14 +590,26 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     {
       // dS = P o (dP o f - D) / sqrt(d) = [ex2(s * sl2 - m * sl2) * (scale / l)] * (dP * f - D); rows >= S have 1 / l = 0
       const float ms[2] = {m[0] * sl2, m[1] * sl2}, is[2] = {inv[0] * scale, inv[1] * scale};
-      const long long drow[2] = {(bh * S + q0 + gq) * dstride, (bh * S + q0 + gq + 8) * dstride};
+      const uint32_t orow[2] = {(uint32_t)((bh * S + q0 + gq) * (dstride >> 3)), (uint32_t)((bh * S + q0 + gq + 8) * (dstride >> 3))};
+      const uint32_t mult_t = drop_mult(t);
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4], dp[4][4];
         block_nt(qa, k_a, kb * 32, lo, sc);
         block_nt(doa, v_a, kb * 32, lo, dp);
         const uint32_t vw = vbits[kb];
-        if (vw == 0xffffffffu) bwd_block_ds<DROP, true>(sc, dp, 0u, sl2, ms, is, dsum, dc, drow, kb * 32 + t * 2);
-        else bwd_block_ds<DROP, false>(sc, dp, vw >> (t * 2), sl2, ms, is, dsum, dc, drow, kb * 32 + t * 2);
+        const uint32_t oct[2] = {orow[0] + kb * 4, orow[1] + kb * 4};
+        uint32_t keep[2];
+        if (vw == 0xffffffffu) bwd_block_ds<DROP, true>(sc, dp, 0u, sl2, ms, is, dsum, dc, oct, mult_t, t, keep);
+        else bwd_block_ds<DROP, false>(sc, dp, vw >> (t * 2), sl2, ms, is, dsum, dc, oct, mult_t, t, keep);
+        if (DROP && BITS) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            uint32_t w = keep[r];
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            if (t == 0) kbits[(q0 + gq + 8 * r) * nkb + kb] = w;
+          }
+        }
         uint32_t dsa[2][4];
         pack_block(sc, dsa);
         acc_rows(dq, dsa, k_a, kb * 32, lo);
@@ -604,12 +638,18 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
     const uint32_t dmul[2] = {drop_mult((jj[0] >> 1) & 3), drop_mult((jj[1] >> 1) & 3)};
     const int dsh[2] = {(jj[0] & 1) ? 0 : 16, (jj[1] & 1) ? 0 : 16};
     const long long doct = (long long)dstride >> 3;                 // octets per (head, query) row
+    const int kpos[2] = {(k0 & 31) + gq, (k0 & 31) + gq + 8};
     for (int qb = 0; qb < nqb; ++qb) {
       float st[4][4], dpt[4][4], pd[4][4];
       block_nt(ka, q_a, qb * 32, lo, st);     // S^T block: rows = keys k0.., columns = queries qb*32..
       block_nt(va, do_a, qb * 32, lo, dpt);   // dP^T block
-      if (tile_all) bwd_block_dst<DROP, true>(st, dpt, pd, st_q + qb * 32 + t * 2, jv, sl2, dc, (bh * S + qb * 32 + t * 2) * doct, doct, jj, dmul, dsh);
-      else bwd_block_dst<DROP, false>(st, dpt, pd, st_q + qb * 32 + t * 2, jv, sl2, dc, (bh * S + qb * 32 + t * 2) * doct, doct, jj, dmul, dsh);
+      const uint32_t* kb0 = kbits + (qb * 32 + t * 2) * nkb + (k0 >> 5);
+      if (tile_all)
+        bwd_block_dst<DROP, true, BITS>(st, dpt, pd, st_q + qb * 32 + t * 2, jv, sl2, dc, (bh * S + qb * 32 + t * 2) * doct, doct, jj, dmul, dsh,
+                                        kb0, nkb, kpos);
+      else
+        bwd_block_dst<DROP, false, BITS>(st, dpt, pd, st_q + qb * 32 + t * 2, jv, sl2, dc, (bh * S + qb * 32 + t * 2) * doct, doct, jj, dmul,
+                                         dsh, kb0, nkb, kpos);
       uint32_t a2[2][4];
       pack_block(pd, a2);
       acc_rows(dv, a2, do_a, qb * 32, lo);
@@ -682,8 +722,11 @@ int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* d
   CUtensorMap m64, mtail, d64, dtail;
   MMER_TRY(long_maps(qkv, 3 * g.F, g, &m64, &mtail));
   MMER_TRY(long_maps(dout, g.F, g, &d64, &dtail));
-  const size_t smem = long_smem(g, 4, true);
+  size_t smem = long_smem(g, 4, true);
   MMER_CHECK_ARG(smem <= 232448, "mha_bwd(long): %lld bytes of shared memory needed", (long long)smem);
+  const size_t bits_bytes = (size_t)(g.SR + 32) * ((g.S + 31) / 32) * 4;      // dropout keep-bit map, when it fits
+  const bool bits = dc.thr != 0 && smem + bits_bytes <= 232448;
+  if (bits) smem += bits_bytes;
   // fewest rounds over the 16-row tiles with 8 or 9 warps
   const int ntile = (g.S + 15) / 16;
   const int nw = ((ntile + 8) / 9 < (ntile + 7) / 8) ? 9 : 8;
@@ -697,9 +740,10 @@ int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* d
                                                             (const bf16*)fwd_out, g, dc);
     return 0;
   };
-  static size_t conf[2] = {0, 0};
-  if (dc.thr != 0) MMER_TRY(launch(mha_bwd_long_kernel<true>, &conf[0]));
-  else MMER_TRY(launch(mha_bwd_long_kernel<false>, &conf[1]));
+  static size_t conf[3] = {0, 0, 0};
+  if (bits) MMER_TRY(launch(mha_bwd_long_kernel<true, true>, &conf[0]));
+  else if (dc.thr != 0) MMER_TRY(launch(mha_bwd_long_kernel<true, false>, &conf[1]));
+  else MMER_TRY(launch(mha_bwd_long_kernel<false, false>, &conf[2]));
   MMER_LAUNCH_CHECK("mha_bwd_long_kernel");
   return 0;
 }

@@ -391,7 +391,7 @@ def test_mha_dropout_fwd_bwd_consistent(B, T):
 
 
 @pytest.mark.parametrize("T,H,d", [(16, 8, 64), (5, 8, 64), (31, 4, 32), (9, 16, 64), (23, 2, 64), (70, 2, 64),
-                                   (256, 2, 64)])
+                                   (256, 2, 64), (340, 1, 64)])   # 340: no room for the long backward's keep-bit map
 @pytest.mark.parametrize("p", [0.0, 0.1])
 def test_mha_mma_kernels_match_fma_kernels_bf16(T, H, d, p):
     """bf16: the tensor-core (mma.sync) kernels and the FMA kernels regenerate the same dropout decisions from the
