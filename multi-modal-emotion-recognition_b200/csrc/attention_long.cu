@@ -172,10 +172,12 @@ __device__ __host__ __forceinline__ int valid_region_bytes(int SR) { return ((SR
 
 // One 16 x 32 score block of the one-pass forward: running maxima (O and the row sums are rescaled only when some row
 // of the warp's tile raises its maximum), unnormalised probabilities back into sc (dropout applied), row sums into l.
-// vm: this lane's validity bits (bit nt * 8 + e); ALL: every key of the block takes part.  key0: key of sc[0][0].
+// vm: this lane's validity bits (bit nt * 8 + e); ALL: every key of the block takes part.  keep: this lane's dropout
+// keep bits of the block (bit nt * 8 + t * 2 + e), handed to the backward kernel through global memory.
 template <bool DROP, bool ALL>
 __device__ __forceinline__ void fwd_block_softmax(float (&sc)[4][4], uint32_t vm, float sl2, float (&m)[2], float (&l)[2],
-                                                  float (&o)[8][4], const DropCfg& dc, const long long (&drow)[2], int key0) {
+                                                  float (&o)[8][4], const DropCfg& dc, const uint32_t (&oct)[2], uint32_t mult, int t,
+                                                  uint32_t (&keep)[2]) {
   float mn[2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -208,6 +210,7 @@ __device__ __forceinline__ void fwd_block_softmax(float (&sc)[4][4], uint32_t vm
   for (int r = 0; r < 2; ++r) {
     const float ms = (m[r] == -INFINITY) ? 0.f : m[r] * sl2;     // nothing valid yet: every p below is selected to 0
     float add = 0.f;
+    uint32_t kb = 0u;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms));
@@ -218,16 +221,25 @@ __device__ __forceinline__ void fwd_block_softmax(float (&sc)[4][4], uint32_t vm
       }
       add += p0 + p1;
       if (DROP) {
-        float f0, f1;
-        drop2(dc, (uint64_t)(drow[r] + key0 + nt * 8), f0, f1);
-        p0 *= f0;
-        p1 *= f1;
+        // the lane's pair nt sits in octet oct[r] + nt of the row, word t (mult = drop_mult(t))
+        const uint32_t w = drop_word(drop_base(dc, oct[r] + nt), mult);
+        const bool k0 = (w << 16) >= dc.thr_hi, k1 = w >= dc.thr_hi;
+        kb |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (nt * 8);
+        p0 = k0 ? p0 * dc.scale : 0.f;
+        p1 = k1 ? p1 * dc.scale : 0.f;
       }
       sc[nt][r * 2] = p0;
       sc[nt][r * 2 + 1] = p1;
     }
     l[r] += add;
+    keep[r] = kb << (t * 2);
   }
+}
+// the four lanes of a quad hold the keep bits of one (row, 32-key block): OR them, lane t == 0 stores the word
+__device__ __forceinline__ void store_keep_word(uint32_t w, int t, bool row_ok, uint32_t* dst) {
+  w |= __shfl_xor_sync(0xffffffffu, w, 1);
+  w |= __shfl_xor_sync(0xffffffffu, w, 2);
+  if (t == 0 && row_ok) *dst = w;
 }
 
 // PROBS (return_attn): two passes over the key blocks (statistics, then normalised probabilities written out and P V).
@@ -237,7 +249,7 @@ template <bool DROP, bool PROBS>
 __global__ void __launch_bounds__(AL_WARPS * 32, 2)
 mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
                     const uint8_t* __restrict__ mask, bf16* __restrict__ out, float* __restrict__ probs,
-                    float2* __restrict__ lse, LongGeom g, DropCfg dc) {
+                    float2* __restrict__ lse, uint32_t* __restrict__ keep_g, LongGeom g, DropCfg dc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = g.S, H = g.H, F = g.F;
@@ -295,6 +307,7 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4];
         block_nt(qa, k_a, kb * 32, lo, sc);
+        uint32_t kw[2] = {0u, 0u};
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int i = q0 + gq + 8 * r;
@@ -313,11 +326,17 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
                 drop2(dc, att_drop_index(bh * S + i, j, dstride), f0, f1);
                 p0 *= f0;
                 p1 *= f1;
+                kw[r] |= ((f0 != 0.f ? 1u : 0u) | (f1 != 0.f ? 2u : 0u)) << (nt * 8 + t * 2);
               }
             }
             sc[nt][r * 2] = p0;
             sc[nt][r * 2 + 1] = p1;
           }
+        }
+        if (DROP && keep_g != nullptr) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            store_keep_word(kw[r], t, q0 + gq + 8 * r < S, keep_g + (bh * S + q0 + gq + 8 * r) * nkb + kb);
         }
         uint32_t pa[2][4];
         pack_block(sc, pa);
@@ -325,15 +344,23 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
       }
     } else {
       // dropout index of (row, key 0) per fragment row; rows >= S (last tile only) produce unused output rows
-      const long long drow[2] = {(bh * S + q0 + gq) * dstride, (bh * S + q0 + gq + 8) * dstride};
+      const uint32_t orow[2] = {(uint32_t)((bh * S + q0 + gq) * (dstride >> 3)), (uint32_t)((bh * S + q0 + gq + 8) * (dstride >> 3))};
+      const uint32_t mult_t = drop_mult(t);
       for (int kb = 0; kb < nkb; ++kb) {
         float sc[4][4];
         block_nt(qa, k_a, kb * 32, lo, sc);
         const uint32_t vw = vbits[kb];
+        const uint32_t oct[2] = {orow[0] + kb * 4, orow[1] + kb * 4};
+        uint32_t keep[2];
         if (vw == 0xffffffffu)   // warp-uniform: every block but the last, unless a padding mask is given
-          fwd_block_softmax<DROP, true>(sc, 0u, sl2, m, l, o, dc, drow, kb * 32 + t * 2);
+          fwd_block_softmax<DROP, true>(sc, 0u, sl2, m, l, o, dc, oct, mult_t, t, keep);
         else
-          fwd_block_softmax<DROP, false>(sc, vw >> (t * 2), sl2, m, l, o, dc, drow, kb * 32 + t * 2);
+          fwd_block_softmax<DROP, false>(sc, vw >> (t * 2), sl2, m, l, o, dc, oct, mult_t, t, keep);
+        if (DROP && keep_g != nullptr) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            store_keep_word(keep[r], t, q0 + gq + 8 * r < S, keep_g + (bh * S + q0 + gq + 8 * r) * nkb + kb);
+        }
         uint32_t pa[2][4];
         pack_block(sc, pa);
         acc_rows(o, pa, v_a, kb * 32, lo);
@@ -374,13 +401,15 @@ mha_fwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
 // (rows beyond the sequence carry scale / l = 0).  vm: this lane's validity bits.  Dropout: oct[r] = octet index of
 // (row, key 0 of the block) -- the lane's pair nt sits in octet oct[r] + nt, word t (mult hoisted).  keep[r] collects
 // this lane's keep bits of the block (bit nt * 8 + t * 2 + e) for the transposed pass.
-template <bool DROP, bool ALL>
+// GB: the keep bits of the block come from the forward pass (keep[r] holds the row's word on entry) -- no hash.
+template <bool DROP, bool ALL, bool GB>
 __device__ __forceinline__ void bwd_block_ds(float (&sc)[4][4], const float (&dp)[4][4], uint32_t vm, float sl2, const float (&ms)[2],
                                              const float (&is)[2], const float (&dsum)[2], const DropCfg& dc,
                                              const uint32_t (&oct)[2], uint32_t mult, int t, uint32_t (&keep)[2]) {
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     uint32_t kb = 0u;
+    const uint32_t given = keep[r] >> (t * 2);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       float p0 = ex2_approx(fmaf(sc[nt][r * 2], sl2, -ms[r])) * is[r];
@@ -391,16 +420,23 @@ __device__ __forceinline__ void bwd_block_ds(float (&sc)[4][4], const float (&dp
       }
       float g0 = dp[nt][r * 2] - dsum[r], g1 = dp[nt][r * 2 + 1] - dsum[r];
       if (DROP) {
-        const uint32_t w = drop_word(drop_base(dc, oct[r] + nt), mult);
-        const bool k0 = (w << 16) >= dc.thr_hi, k1 = w >= dc.thr_hi;
-        kb |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (nt * 8);
+        bool k0, k1;
+        if (GB) {
+          k0 = (given >> (nt * 8)) & 1u;
+          k1 = (given >> (nt * 8 + 1)) & 1u;
+        } else {
+          const uint32_t w = drop_word(drop_base(dc, oct[r] + nt), mult);
+          k0 = (w << 16) >= dc.thr_hi;
+          k1 = w >= dc.thr_hi;
+          kb |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (nt * 8);
+        }
         g0 = fmaf(dp[nt][r * 2], k0 ? dc.scale : 0.f, -dsum[r]);
         g1 = fmaf(dp[nt][r * 2 + 1], k1 ? dc.scale : 0.f, -dsum[r]);
       }
       sc[nt][r * 2] = p0 * g0;
       sc[nt][r * 2 + 1] = p1 * g1;
     }
-    keep[r] = kb << (t * 2);
+    if (!GB) keep[r] = kb << (t * 2);
   }
 }
 // Backward, key-major (transposed) block: rows = two keys of this lane (jj), columns = queries.  pd <- P o f (for dV),
@@ -461,12 +497,14 @@ __device__ __forceinline__ void bwd_block_dst(float (&st)[4][4], const float (&d
 // The backward kernel's warp count is a launch parameter: a warp owns 16-row query / key tiles, and S = 257 has 17 of
 // them -- 9 warps need two rounds per pass where 8 need three (17 / 8 = 2.1).
 // BITS: room for the dropout keep-bit map [query][key block] in shared memory (always at S = 257; not at S = 384)
-template <bool DROP, bool BITS>
+// GB (implies BITS): the forward pass wrote the map to global memory (keep_g); it is copied in at the start and no
+// element of this kernel is hashed.
+template <bool DROP, bool BITS, bool GB>
 __global__ void __launch_bounds__(AL_BWD_MAX_WARPS * 32, 1)
 mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_constant__ CUtensorMap mtail,
                     const __grid_constant__ CUtensorMap d64, const __grid_constant__ CUtensorMap dtail,
                     const uint8_t* __restrict__ mask, bf16* __restrict__ dqkv, const float2* __restrict__ lse,
-                    const bf16* __restrict__ fwd_out, LongGeom g, DropCfg dc) {
+                    const bf16* __restrict__ fwd_out, const uint32_t* __restrict__ keep_g, LongGeom g, DropCfg dc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = g.S, H = g.H, F = g.F;
@@ -491,6 +529,11 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
   fill_valid(valid, vbits, mask, b, g);
   zero_pad_rows(q_s, 4, g);
   for (int j = threadIdx.x; j < g.SR + 32; j += blockDim.x) st_q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (DROP && GB) {
+    const int nw = (S + 31) / 32;
+    const uint32_t* src = keep_g + bh * S * nw;
+    for (int j = threadIdx.x; j < (g.SR + 32) * nw; j += blockDim.x) kbits[j] = j < S * nw ? src[j] : 0u;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_a, 4u * g.load_bytes);
@@ -598,10 +641,14 @@ mha_bwd_long_kernel(const __grid_constant__ CUtensorMap m64, const __grid_consta
         block_nt(doa, v_a, kb * 32, lo, dp);
         const uint32_t vw = vbits[kb];
         const uint32_t oct[2] = {orow[0] + kb * 4, orow[1] + kb * 4};
-        uint32_t keep[2];
-        if (vw == 0xffffffffu) bwd_block_ds<DROP, true>(sc, dp, 0u, sl2, ms, is, dsum, dc, oct, mult_t, t, keep);
-        else bwd_block_ds<DROP, false>(sc, dp, vw >> (t * 2), sl2, ms, is, dsum, dc, oct, mult_t, t, keep);
-        if (DROP && BITS) {
+        uint32_t keep[2] = {0u, 0u};
+        if (DROP && GB) {
+          keep[0] = kbits[(q0 + gq) * nkb + kb];
+          keep[1] = kbits[(q0 + gq + 8) * nkb + kb];
+        }
+        if (vw == 0xffffffffu) bwd_block_ds<DROP, true, GB>(sc, dp, 0u, sl2, ms, is, dsum, dc, oct, mult_t, t, keep);
+        else bwd_block_ds<DROP, false, GB>(sc, dp, vw >> (t * 2), sl2, ms, is, dsum, dc, oct, mult_t, t, keep);
+        if (DROP && BITS && !GB) {
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             uint32_t w = keep[r];
@@ -701,7 +748,9 @@ int mha_fwd_long(const void* qkv, const uint8_t* mask, void* out, float* probs, 
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mha_fwd_long)");
       *configured = smem;
     }
-    kern<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, reinterpret_cast<float2*>(lse), g, dc);
+    // the statistics buffer: (max, 1 / sum) per row, then one keep word per (row, 32-key block) when dropout is on
+    uint32_t* keep_g = lse != nullptr ? reinterpret_cast<uint32_t*>(lse + (size_t)B * H * g.S * 2) : nullptr;
+    kern<<<(unsigned)((long long)B * H), AL_WARPS * 32, smem, st>>>(m64, mtail, mask, (bf16*)out, probs, reinterpret_cast<float2*>(lse), keep_g, g, dc);
     return 0;
   };
   static size_t conf[4] = {0, 0, 0, 0};
@@ -727,6 +776,8 @@ int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* d
   const size_t bits_bytes = (size_t)(g.SR + 32) * ((g.S + 31) / 32) * 4;      // dropout keep-bit map, when it fits
   const bool bits = dc.thr != 0 && smem + bits_bytes <= 232448;
   if (bits) smem += bits_bytes;
+  // with the forward's statistics comes its keep-bit map (same buffer, behind the (max, 1 / sum) pairs)
+  const uint32_t* keep_g = (lse != nullptr && bits) ? reinterpret_cast<const uint32_t*>(lse + (size_t)B * H * g.S * 2) : nullptr;
   // fewest rounds over the 16-row tiles with 8 or 9 warps
   const int ntile = (g.S + 15) / 16;
   const int nw = ((ntile + 8) / 9 < (ntile + 7) / 8) ? 9 : 8;
@@ -737,13 +788,14 @@ int mha_bwd_long(const void* qkv, const uint8_t* mask, const void* dout, void* d
       *configured = smem;
     }
     kern<<<(unsigned)((long long)B * H), nw * 32, smem, st>>>(m64, mtail, d64, dtail, mask, (bf16*)dqkv, reinterpret_cast<const float2*>(lse),
-                                                            (const bf16*)fwd_out, g, dc);
+                                                            (const bf16*)fwd_out, keep_g, g, dc);
     return 0;
   };
-  static size_t conf[3] = {0, 0, 0};
-  if (bits) MMER_TRY(launch(mha_bwd_long_kernel<true, true>, &conf[0]));
-  else if (dc.thr != 0) MMER_TRY(launch(mha_bwd_long_kernel<true, false>, &conf[1]));
-  else MMER_TRY(launch(mha_bwd_long_kernel<false, false>, &conf[2]));
+  static size_t conf[4] = {0, 0, 0, 0};
+  if (keep_g != nullptr) MMER_TRY(launch(mha_bwd_long_kernel<true, true, true>, &conf[0]));
+  else if (bits) MMER_TRY(launch(mha_bwd_long_kernel<true, true, false>, &conf[1]));
+  else if (dc.thr != 0) MMER_TRY(launch(mha_bwd_long_kernel<true, false, false>, &conf[2]));
+  else MMER_TRY(launch(mha_bwd_long_kernel<false, false, false>, &conf[3]));
   MMER_LAUNCH_CHECK("mha_bwd_long_kernel");
   return 0;
 }

@@ -125,7 +125,8 @@ static void carve(const mmer_model* m, void* base, Ws* w) {
     L.x2 = c.take(M * F * e);
     L.st1 = (float*)c.take(M * 2 * 4);
     L.st2 = (float*)c.take(M * 2 * 4);
-    L.lse = S > 32 ? (float*)c.take(B * (size_t)m->heads * S * 2 * 4) : nullptr;
+    // (max, 1 / sum) per softmax row, then the dropout keep bits of the row (one word per 32 keys): mha_long_stats_floats
+    L.lse = S > 32 ? (float*)c.take(B * (size_t)m->heads * S * (2 + (S + 31) / 32) * 4) : nullptr;
   }
   w->pooled = (float*)c.take(B * F * 4);
   w->fused = c.take(B * F * e);
