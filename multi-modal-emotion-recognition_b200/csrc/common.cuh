@@ -240,6 +240,13 @@ __device__ __forceinline__ void drop2(const DropCfg& d, uint64_t idx, float& f0,
   f0 = drop_lo(d, w);
   f1 = drop_hi(d, w);
 }
+// the same factors as drop2(d, octet * 8 + 2 * k) for a caller that knows its octet and hoists mult = drop_mult(k)
+// (a lane of an MMA accumulator fragment always owns pair k = lane & 3 of its octets)
+__device__ __forceinline__ void drop2_at(const DropCfg& d, uint32_t octet, uint32_t mult, float& f0, float& f1) {
+  const uint32_t w = drop_word(drop_base(d, octet), mult);
+  f0 = drop_lo(d, w);
+  f1 = drop_hi(d, w);
+}
 __device__ __forceinline__ float drop1(const DropCfg& d, uint64_t idx) {
   const uint32_t w = drop_word(drop_base(d, (uint32_t)(idx >> 3)), drop_mult((int)((idx >> 1) & 3)));
   return (idx & 1) ? drop_hi(d, w) : drop_lo(d, w);
