@@ -401,10 +401,10 @@ def time_memory_bound_kernels(dev, pk):
     dpos = torch.zeros(S, F, device=dev)
     sets = [(rnd(B * T, F), rnd(B, F), rnd(M, F)) for _ in range(3)]
     e_stats = ops.embed_fwd(sets[0][0], sets[0][1], gam, bet, gam, bet, pos, B, T)[1]
-    add("embed_fwd_pipe_kernel (p=0.1)", [lambda pv=pv, pa=pa: ops.embed_fwd(pv, pa, gam, bet, gam, bet, pos, B, T, drop_p=0.1,
+    add("embed_fwd_pos_kernel (p=0.1)", [lambda pv=pv, pa=pa: ops.embed_fwd(pv, pa, gam, bet, gam, bet, pos, B, T, drop_p=0.1,
                                                                            seed=1, site=1) for pv, pa, _ in sets],
         2 * M * F * 2 + S * F * 4)
-    add("embed_bwd_pipe_kernel + embed_dpos_kernel (p=0.1)",
+    add("embed_bwd_pos_kernel incl. dpos / dbeta sums (p=0.1)",
         [lambda pv=pv, pa=pa, dx=dx: ops.embed_bwd(dx, pv, pa, e_stats, gam, gam, B, T, dgv, dbv, dga, dba, dpos, drop_p=0.1,
                                                    seed=1, site=1, dbias_v=dbias_v, dbias_a=dbias_a) for pv, pa, dx in sets],
         3 * M * F * 2)

@@ -62,6 +62,7 @@ const char* mmer_last_error(void);
 #define MMER_DEBUG_NO_LN_FUSE 11 /* engine, post-norm sub-layer tails: 0 default (GEMM with residual epilogue -> z, then LayerNorm(z)); 1 GEMM -> a, add_ln(x, a); 2 the fully fused GEMM+LayerNorm kernel; A/B timing */
 #define MMER_DEBUG_SERVE_GLOBAL 13 /* batch-1 serving forward, S <= 8: 0 head-local / split-K kernel (serve_small.cu); 1 output-feature split with the L2 exchange (serve.cu; run-to-run bit-reproducible); 2 shared-memory broadcast (serve_dsmem.cu); A/B timing */
 #define MMER_DEBUG_SERVE_STAMPS 14 /* serve_small.cu: extra globaltimer marks inside phase 0 and layer 0 (they cost time) */
+#define MMER_DEBUG_EMBED_GENERIC 15 /* token assembly (LayerNorm variant): always the general tile kernels + embed_dpos, never the position-stable ones; A/B timing */
 #define MMER_DEBUG_ATT_SIMT 4    /* bf16 short-sequence attention: use the FMA kernels instead of the MMA ones (A/B timing) */
 int mmer_debug_set(int key, int value);
 int mmer_debug_get(int key);

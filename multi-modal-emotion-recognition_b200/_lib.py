@@ -18,7 +18,7 @@ LOSS_FOCAL, LOSS_WCE = 0, 1
 REDUCE_MEAN, REDUCE_SUM, REDUCE_NONE = 0, 1, 2
 DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT, DEBUG_DIRECT_STORE, DEBUG_ATT_SIMT, DEBUG_NO_PAIR, DEBUG_GENERIC_EPI, DEBUG_ATT_ROWS, DEBUG_NO_PDL, DEBUG_RESERVE_SMS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 DEBUG_FORCE_SPLITS, DEBUG_NO_LN_FUSE = 10, 11
-DEBUG_SERVE_GLOBAL, DEBUG_SERVE_STAMPS = 13, 14
+DEBUG_SERVE_GLOBAL, DEBUG_SERVE_STAMPS, DEBUG_EMBED_GENERIC = 13, 14, 15
 MAX_LAYERS = 16
 G_NAMES = ["POS", "WV", "BV", "WA", "BA", "NV_W", "NV_B", "NA_W", "NA_B", "ON_W", "ON_B", "C0_W", "C0_B", "C1_W",
            "C1_B", "C4_W", "C4_B", "C5_W", "C5_B", "C8_W", "C8_B"]

@@ -551,6 +551,10 @@ struct EmbedGeom {
   long long Mtot;    // B * S output rows
   int F, W, stages, S, Tn, with_grad;
   uint32_t row_bytes, stage_bytes;   // stage = [W rows of sources][W rows of gradients (backward)]
+  // position-stable kernels (below): tile stride of a CTA (a multiple of S / gcd(S, W), so that G * W rows are whole
+  // samples), first slot of the audio rows and of the gradient rows inside a stage.  G == 0: the general kernels
+  // (tile stride = gridDim.x, audio rows packed right behind the video rows).
+  int G, aslot, gslot;
 };
 
 template <typename T>
@@ -559,15 +563,16 @@ __device__ __forceinline__ void embed_produce(const EmbedGeom& g, const T* pv, c
   int stage = 0;
   uint32_t phase = 0;
   EmbedWalk wk;
-  for (wk.init(blockIdx.x, gridDim.x, g.W, g.Mtot, g.S, g.Tn); wk.valid(); wk.next()) {
+  for (wk.init(blockIdx.x, g.G ? g.G : gridDim.x, g.W, g.Mtot, g.S, g.Tn); wk.valid(); wk.next()) {
     const EmbedTile e = wk.tile();
     mbar_wait(empty_a + 8 * stage, phase ^ 1);
     const uint32_t full = full_a + 8 * stage;
     mbar_expect_tx(full, (uint32_t)(e.nv + e.na + (g.with_grad ? e.rows : 0)) * g.row_bytes);
     const uint32_t base = smem_a + stage * g.stage_bytes;
+    const uint32_t aslot = g.G ? (uint32_t)g.aslot : (uint32_t)e.nv, gslot = g.G ? (uint32_t)g.gslot : (uint32_t)g.W;
     if (e.nv > 0) bulk_g2s(base, pv + e.v0 * g.F, (uint32_t)e.nv * g.row_bytes, full);
-    if (e.na > 0) bulk_g2s(base + (uint32_t)e.nv * g.row_bytes, pa + (long long)e.a0 * g.F, (uint32_t)e.na * g.row_bytes, full);
-    if (g.with_grad) bulk_g2s(base + (uint32_t)g.W * g.row_bytes, dx0 + e.r0 * g.F, (uint32_t)e.rows * g.row_bytes, full);
+    if (e.na > 0) bulk_g2s(base + aslot * g.row_bytes, pa + (long long)e.a0 * g.F, (uint32_t)e.na * g.row_bytes, full);
+    if (g.with_grad) bulk_g2s(base + gslot * g.row_bytes, dx0 + e.r0 * g.F, (uint32_t)e.rows * g.row_bytes, full);
     if (++stage == g.stages) { stage = 0; phase ^= 1; }
   }
 }
@@ -860,9 +865,284 @@ embed_dpos_kernel(const T* __restrict__ dx0, float* __restrict__ dpos, float* __
   }
 }
 
+// =========================================================================================================
+// Position-stable token assembly.  When the tile stride of a CTA, G tiles of W rows, is a whole number of samples
+// (G * W = k * S), row w of EVERY tile a CTA sees sits at the same position s of its sample, k samples further on.
+// A warp is then bound to one position for the whole kernel: pos_embed[s] and the LayerNorm parameters of its
+// modality (video / audio) live in registers, the slot of its source row inside a stage is a constant, nothing is
+// divided or fetched from global memory inside the loop, and in backward the column sums per position (dpos, both
+// dbeta) are register partials flushed once -- the separate embed_dpos pass over the gradient (a third of the
+// backward traffic) disappears.  The price is a grid of G <= SMs CTAs (136 of 148 at S = 17, W = 15).
+// Stage layout: [W video slots][NA audio slots][W gradient rows (backward)], NA = W / S + 2.
+// =========================================================================================================
+struct EmbedPosWarp {
+  long long row0;   // first output row of this warp
+  long long step;   // rows between two tiles of the CTA
+  int b0, kb;       // its sample in the first tile, samples per step
+  int s, slot;      // position, source slot inside a stage
+  bool audio;
+  __device__ __forceinline__ void init(const EmbedGeom& g, int warp) {
+    const long long r00 = (long long)blockIdx.x * g.W;
+    const int b00 = (int)(r00 / g.S), s00 = (int)(r00 % g.S);
+    const int q = (s00 + warp) / g.S;
+    s = s00 + warp - q * g.S;
+    audio = s == g.Tn;
+    slot = audio ? g.aslot + q : q * g.Tn + s - (s00 < g.Tn ? s00 : g.Tn);
+    row0 = r00 + warp;
+    step = (long long)g.G * g.W;
+    b0 = b00 + q;
+    kb = (int)(step / g.S);
+  }
+};
+
+// FULL: F == NCH * 256 (no column guards); DROP: dropout enabled (dc.thr != 0).  The dropout scale is folded into the
+// warp's constants: out = keep ? xhat * (gamma * scale) + (beta + pos) * scale : 0, one select per element.
+template <typename T, int NCH, bool FULL, bool DROP>
+__global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
+embed_fwd_pos_kernel(const T* __restrict__ pv, const T* __restrict__ pa, const float* __restrict__ gv,
+                     const float* __restrict__ bv, const float* __restrict__ ga, const float* __restrict__ ba,
+                     const float* __restrict__ pos, T* __restrict__ x0, float* __restrict__ stats, EmbedGeom g, DropCfg dc) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LnSmem sm = embed_setup(g, smem);
+  const int F = FULL ? NCH * 256 : g.F;
+  if (warp == g.W) {
+    if (lane == 0) embed_produce<T>(g, pv, pa, nullptr, sm.data_a, sm.full_a, sm.empty_a);
+    return;
+  }
+  EmbedPosWarp me;
+  me.init(g, warp);
+  float gm[NCH][8], bp[NCH][8];   // this warp's gamma * scale and (beta + pos_embed[s]) * scale
+  {
+    const float* gsrc = me.audio ? ga : gv;
+    const float* bsrc = me.audio ? ba : bv;
+    const float sc = DROP ? dc.scale : 1.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (FULL || c < F) {
+        float pe[8];
+        load8(gsrc + c, gm[i]);
+        load8(bsrc + c, bp[i]);
+        load8(pos + (long long)me.s * F + c, pe);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gm[i][j] *= sc; bp[i][j] = (bp[i][j] + pe[j]) * sc; }
+      }
+    }
+  }
+  const float invF = 1.f / (float)F;
+  int stage = 0;
+  uint32_t phase = 0;
+  long long row = me.row0;
+  for (long long r0 = (long long)blockIdx.x * g.W; r0 < g.Mtot; r0 += me.step, row += me.step) {
+    const bool have = row < g.Mtot;
+    mbar_wait(sm.full_a + 8 * stage, phase);
+    float z[NCH][8];
+    float sum = 0.f;
+    if (have) {
+      const T* src = reinterpret_cast<const T*>(sm.data + (size_t)stage * g.stage_bytes) + (size_t)me.slot * F;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (FULL || c < F) { load8(src + c, z[i]); sum += sum8f(z[i]); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[i][j] = 0.f;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm.empty_a + 8 * stage);
+    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+    if (!have) continue;
+    const float mean = warp_sum(sum) * invF;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (FULL || c < F) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = z[i][j] - mean; q = fmaf(d, d, q); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invF + LNP_EPS);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+    const float nmr = -mean * rstd;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (FULL || c < F) {
+        const long long off = row * F + c;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(z[i][j], rstd, nmr), gm[i][j], bp[i][j]);
+        if (DROP) {
+          const uint32_t a = drop_base(dc, (uint32_t)((uint64_t)off >> 3));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t w = drop_word(a, drop_mult(k));
+            if (!((w << 16) >= dc.thr_hi)) o[2 * k] = 0.f;
+            if (!(w >= dc.thr_hi)) o[2 * k + 1] = 0.f;
+          }
+        }
+        store8(x0 + off, o);
+      }
+    }
+  }
+}
+
+// Column partials of the compute warps -> global vectors, video and audio warps apart; optionally every warp's own
+// partial into row `wpos[w]` of a [S][F] matrix (dpos).  `sred` is [W][F] fp32 scratch, `waud` / `wpos` per-warp flags.
+template <int NCH>
+__device__ __forceinline__ void embed_pos_flush(float (&part)[NCH][8], float* __restrict__ gvid, float* __restrict__ gaud,
+                                                float* __restrict__ gpos, int F, int W, float* sred, const int* waud,
+                                                const int* wpos, bool compute_warp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (compute_warp) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+        *reinterpret_cast<float4*>(sred + warp * F + c) = make_float4(part[i][0], part[i][1], part[i][2], part[i][3]);
+        *reinterpret_cast<float4*>(sred + warp * F + c + 4) = make_float4(part[i][4], part[i][5], part[i][6], part[i][7]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float sv = 0.f, sa = 0.f;
+    bool any_a = false;
+    for (int w = 0; w < W; ++w) {
+      const float v = sred[w * F + c];
+      if (waud[w]) { sa += v; any_a = true; } else sv += v;
+    }
+    if (gvid != nullptr) atomicAdd(gvid + c, sv);
+    if (gaud != nullptr && any_a) atomicAdd(gaud + c, sa);
+  }
+  if (gpos != nullptr) {
+    const int F4 = F >> 2;
+    for (int idx = threadIdx.x; idx < W * F4; idx += blockDim.x) {
+      const int w = idx / F4, c = (idx - w * F4) * 4;
+      if (wpos[w] >= 0)
+        atomicAdd(reinterpret_cast<float4*>(gpos + (long long)wpos[w] * F + c), *reinterpret_cast<const float4*>(sred + w * F + c));
+    }
+  }
+}
+
+template <typename T, int NCH, bool FULL, bool DROP>
+__global__ void __launch_bounds__((LNP_MAX_WARPS + 1) * 32, 1)
+embed_bwd_pos_kernel(const T* __restrict__ dx0, const T* __restrict__ pv, const T* __restrict__ pa,
+                     const float* __restrict__ stats, const float* __restrict__ gv, const float* __restrict__ ga,
+                     T* __restrict__ dpv, T* __restrict__ dpa, float* __restrict__ dgv, float* __restrict__ dbv,
+                     float* __restrict__ dga, float* __restrict__ dba, float* __restrict__ dpos,
+                     float* __restrict__ dbias_v, float* __restrict__ dbias_a, EmbedGeom g, DropCfg dc) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LnSmem sm = embed_setup(g, smem);
+  const int F = FULL ? NCH * 256 : g.F, Tn = g.Tn;
+  const bool compute_warp = warp < g.W;
+  // both gamma vectors in shared memory (a per-lane register copy would cost 16 registers), per-warp flags behind them
+  float* sgam = reinterpret_cast<float*>(smem + (size_t)g.stages * g.stage_bytes + 2 * LNP_MAX_STAGES * 8);
+  int* waud = reinterpret_cast<int*>(sgam + 2 * F);
+  int* wpos = waud + LNP_MAX_WARPS + 1;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) { sgam[c] = gv[c]; sgam[F + c] = ga[c]; }
+  EmbedPosWarp me;
+  me.init(g, compute_warp ? warp : 0);
+  if (compute_warp && lane == 0) {
+    waud[warp] = me.audio ? 1 : 0;
+    wpos[warp] = me.row0 < g.Mtot ? me.s : -1;   // a warp without a single row has nothing to add to dpos
+  }
+  __syncthreads();
+  float pg[NCH][8], pb[NCH][8], pbias[NCH][8];   // dgamma, dbeta (= dpos of this position), projection bias gradient
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; pbias[i][j] = 0.f; }
+  if (!compute_warp) {
+    if (lane == 0) embed_produce<T>(g, pv, pa, dx0, sm.data_a, sm.full_a, sm.empty_a);
+  } else {
+    const float* gam = sgam + (me.audio ? F : 0);
+    const bool want_bias = (me.audio ? dbias_a : dbias_v) != nullptr;
+    const float invF = 1.f / (float)F;
+    int stage = 0;
+    uint32_t phase = 0;
+    long long row = me.row0;
+    int b = me.b0;
+    float2 st_next = make_float2(0.f, 0.f);
+    if (row < g.Mtot) st_next = *reinterpret_cast<const float2*>(stats + row * 2);
+    for (long long r0 = (long long)blockIdx.x * g.W; r0 < g.Mtot; r0 += me.step, row += me.step, b += me.kb) {
+      const bool have = row < g.Mtot;
+      const float mean = st_next.x, rstd = st_next.y;
+      if (row + me.step < g.Mtot) st_next = *reinterpret_cast<const float2*>(stats + (row + me.step) * 2);
+      mbar_wait(sm.full_a + 8 * stage, phase);
+      float xh[NCH][8], gd[NCH][8];
+      float s1 = 0.f, s2 = 0.f;
+      if (have) {
+        const uint8_t* sb = sm.data + (size_t)stage * g.stage_bytes;
+        const T* sz = reinterpret_cast<const T*>(sb) + (size_t)me.slot * F;
+        const T* sd = reinterpret_cast<const T*>(sb) + (size_t)(g.gslot + warp) * F;
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c = lane * 8 + i * 256;
+          if (FULL || c < F) {
+            float d[8], z[8], gg[8];
+            load8(sd + c, d);
+            if (DROP) {
+              float f[8];
+              drop8(dc, (uint64_t)(row * F + c), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] *= f[j];
+            }
+            load8(sz + c, z);
+            load8(gam + c, gg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              xh[i][j] = fmaf(z[j], rstd, nmr);
+              pg[i][j] = fmaf(d[j], xh[i][j], pg[i][j]);
+              pb[i][j] += d[j];
+              gd[i][j] = d[j] * gg[j];
+              s1 += gd[i][j];
+              s2 = fmaf(gd[i][j], xh[i][j], s2);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.empty_a + 8 * stage);
+      if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      if (!have) continue;
+      const float c1r = warp_sum(s1) * invF * rstd;
+      const float c2r = warp_sum(s2) * invF * rstd;
+      T* dst = me.audio ? dpa + (long long)b * F : dpv + ((long long)b * Tn + me.s) * F;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (FULL || c < F) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[i][j], -c2r, fmaf(gd[i][j], rstd, -c1r));
+          store8(dst + c, o);
+          if (want_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pbias[i][j] += round_as<T>(o[j]);
+          }
+        }
+      }
+    }
+  }
+  float* sred = reinterpret_cast<float*>(smem);   // every stage has been consumed: the ring is the reduction scratch
+  embed_pos_flush<NCH>(pg, dgv, dga, nullptr, F, g.W, sred, waud, wpos, compute_warp);
+  embed_pos_flush<NCH>(pb, dbv, dba, dpos, F, g.W, sred, waud, wpos, compute_warp);
+  if (dbias_v != nullptr || dbias_a != nullptr)
+    embed_pos_flush<NCH>(pbias, dbias_v, dbias_a, nullptr, F, g.W, sred, waud, wpos, compute_warp);
+}
+
 static int embed_geometry(long long B, long long T, long long F, int elt, int with_grad, EmbedGeom* g, size_t* smem_bytes) {
   g->Mtot = B * (T + 1);
   g->F = (int)F; g->S = (int)T + 1; g->Tn = (int)T; g->with_grad = with_grad;
+  g->G = 0; g->aslot = 0; g->gslot = 0;
   g->row_bytes = (uint32_t)(F * elt);
   const size_t budget = 200 * 1024;
   const int arrays = with_grad ? 2 : 1;
@@ -882,12 +1162,70 @@ static int embed_geometry(long long B, long long T, long long F, int elt, int wi
   return 0;
 }
 
+static int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// Plan of the position-stable kernels: the warp count W (<= 15) and tile stride G (<= SMs, a multiple of
+// S / gcd(S, W)) with the most rows in flight.  Returns false when no plan keeps at least 85 % of the rows the
+// general kernel has in flight (long sequences: S / gcd(S, W) exceeds the SM count), for rows wider than 512 columns,
+// or when the debug knob asks for the general kernels.
+static bool embed_pos_plan(long long B, long long T, long long F, int elt, int with_grad, EmbedGeom* g, size_t* smem_bytes) {
+  if (g_debug[MMER_DEBUG_EMBED_GENERIC]) return false;
+  if (F > 512) return false;   // wider rows: the per-warp parameter registers of these kernels would spill
+  const int S = (int)T + 1;
+  const long long Mtot = B * S;
+  const uint32_t row_bytes = (uint32_t)(F * elt);
+  const size_t budget = 200 * 1024;
+  const int cap = sm_count();
+  int bestW = 0, bestG = 0, maxW = 0;
+  for (int W = LNP_MAX_WARPS; W >= 1; --W) {
+    const size_t stage = (size_t)(W + W / S + 2 + (with_grad ? W : 0)) * row_bytes;
+    if (2 * stage > budget) continue;
+    if (maxW == 0) maxW = W;
+    const int g0 = S / gcd_int(S, W);
+    if (g0 > cap) continue;
+    const int G = (cap / g0) * g0;
+    if ((long long)G * W > (long long)bestG * bestW) { bestG = G; bestW = W; }
+  }
+  if (bestW == 0 || (long long)bestG * bestW * 100 < (long long)cap * maxW * 85) return false;
+  g->Mtot = Mtot;
+  g->F = (int)F; g->S = S; g->Tn = (int)T; g->with_grad = with_grad;
+  g->row_bytes = row_bytes;
+  g->W = bestW;
+  g->G = bestG;
+  g->aslot = bestW;
+  g->gslot = bestW + bestW / S + 2;
+  g->stage_bytes = (uint32_t)(g->gslot + (with_grad ? bestW : 0)) * row_bytes;
+  int stages = (int)(budget / g->stage_bytes);
+  if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
+  g->stages = stages;
+  size_t data = (size_t)stages * g->stage_bytes;
+  const size_t red = (size_t)bestW * F * sizeof(float);
+  if (data < red) data = red;
+  *smem_bytes = data + 2 * LNP_MAX_STAGES * 8 + (size_t)2 * F * sizeof(float) + 2 * (LNP_MAX_WARPS + 1) * sizeof(int) + 16;
+  return true;
+}
+
 template <typename T, int NCH>
 static int embed_fwd_launch(const void* pv, const void* pa, const float* gv, const float* bv, const float* ga,
                             const float* ba, const float* pos, void* x0, float* stats, long long B, long long T_, long long F,
                             DropCfg dc, cudaStream_t st) {
   EmbedGeom g;
   size_t smem;
+  if constexpr (NCH <= 2) {
+    if (embed_pos_plan(B, T_, F, sizeof(T), 0, &g, &smem)) {
+      const bool full = F == NCH * 256, drop = dc.thr != 0;
+      auto kpos = full ? (drop ? embed_fwd_pos_kernel<T, NCH, true, true> : embed_fwd_pos_kernel<T, NCH, true, false>)
+                       : (drop ? embed_fwd_pos_kernel<T, NCH, false, true> : embed_fwd_pos_kernel<T, NCH, false, false>);
+      static size_t configured_pos[4] = {0, 0, 0, 0};
+      MMER_TRY(lnp_set_smem(kpos, smem, &configured_pos[(full ? 2 : 0) + (drop ? 1 : 0)]));
+      const long long tiles = (g.Mtot + g.W - 1) / g.W;
+      cudaError_t e = launch_dep(kpos, dim3((unsigned)(tiles < g.G ? tiles : g.G)), dim3((g.W + 1) * 32), smem, st, 1,
+                                 (const T*)pv, (const T*)pa, gv, bv, ga, ba, pos, (T*)x0, stats, g, dc);
+      if (e != cudaSuccess) return cuda_fail(e, "launch(embed_fwd_pos)");
+      MMER_LAUNCH_CHECK("embed_fwd_pos_kernel");
+      return 0;
+    }
+  }
   MMER_TRY(embed_geometry(B, T_, F, sizeof(T), 0, &g, &smem));
   static size_t configured = 0;
   auto kern = embed_fwd_pipe_kernel<T, NCH>;
@@ -907,6 +1245,22 @@ static int embed_bwd_launch(const void* dx0, const void* pv, const void* pa, con
                             cudaStream_t st) {
   EmbedGeom g;
   size_t smem;
+  if constexpr (NCH <= 2) {
+    if (embed_pos_plan(B, T_, F, sizeof(T), 1, &g, &smem)) {
+      const bool full = F == NCH * 256, drop = dc.thr != 0;
+      auto kpos = full ? (drop ? embed_bwd_pos_kernel<T, NCH, true, true> : embed_bwd_pos_kernel<T, NCH, true, false>)
+                       : (drop ? embed_bwd_pos_kernel<T, NCH, false, true> : embed_bwd_pos_kernel<T, NCH, false, false>);
+      static size_t configured_pos[4] = {0, 0, 0, 0};
+      MMER_TRY(lnp_set_smem(kpos, smem, &configured_pos[(full ? 2 : 0) + (drop ? 1 : 0)]));
+      const long long tiles = (g.Mtot + g.W - 1) / g.W;
+      cudaError_t e = launch_dep(kpos, dim3((unsigned)(tiles < g.G ? tiles : g.G)), dim3((g.W + 1) * 32), smem, st, 1,
+                                 (const T*)dx0, (const T*)pv, (const T*)pa, stats, gv, ga, (T*)dpv, (T*)dpa, dgv, dbv, dga, dba,
+                                 dpos, dbias_v, dbias_a, g, dc);
+      if (e != cudaSuccess) return cuda_fail(e, "launch(embed_bwd_pos)");
+      MMER_LAUNCH_CHECK("embed_bwd_pos_kernel");
+      return 0;
+    }
+  }
   MMER_TRY(embed_geometry(B, T_, F, sizeof(T), 1, &g, &smem));
   static size_t configured = 0;
   auto kern = embed_bwd_pipe_kernel<T, NCH>;

@@ -291,6 +291,66 @@ def test_embed_fwd_bwd(dt, B, T, F):
 
 
 @pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,T,F,p", [(2500, 16, 512, 0.0), (2500, 16, 512, 0.2), (3001, 5, 512, 0.1), (4099, 1, 256, 0.0),
+                                     (1200, 31, 264, 0.1), (300, 162, 512, 0.1)])
+def test_embed_position_stable_kernels_match_the_general_ones(dt, B, T, F, p):
+    """Token assembly with more tiles than CTAs (several tiles per CTA, ragged last tile): the position-stable kernels
+    (a warp bound to one position, dpos / dbeta from register partials) against the general tile kernels + embed_dpos
+    (debug knob) -- statistics, dropout mask and input gradients bit for bit, outputs and column sums to rounding -- and
+    against float64 math.  T = 162 has no position-stable plan (163 is prime and above the SM count): both runs take the
+    general path."""
+    lib = _lib.load()
+    pv, pa = rnd(B * T, F, dt=dt, seed=1), rnd(B, F, dt=dt, seed=2)
+    gv, bv, ga, ba = rnd(F, seed=3) * .2 + 1, rnd(F, seed=4) * .2, rnd(F, seed=5) * .2 + 1, rnd(F, seed=6) * .2
+    pos = rnd(T + 1, F, seed=7)
+    dx0 = rnd(B * (T + 1), F, dt=dt, seed=8)
+    runs = []
+    try:
+        for knob in (0, 1):
+            lib.mmer_debug_set(_lib.DEBUG_EMBED_GENERIC, knob)
+            x0, stats = ops.embed_fwd(pv, pa, gv, bv, ga, ba, pos, B, T, drop_p=p, seed=11, site=3)
+            acc = [torch.zeros(F, device=DEV) for _ in range(4)] + [torch.zeros(T + 1, F, device=DEV)] + \
+                  [torch.zeros(F, device=DEV) for _ in range(2)]
+            dgv, dbv, dga, dba, dpos, dbias_v, dbias_a = acc
+            dpv, dpa = ops.embed_bwd(dx0, pv, pa, stats, gv, ga, B, T, dgv, dbv, dga, dba, dpos, drop_p=p, seed=11, site=3,
+                                     dbias_v=dbias_v, dbias_a=dbias_a)
+            # the dropout mask of this kernel, from a run whose kept outputs cannot be zero (pos_embed shifted by 100;
+            # the mask depends on seed, site and element index only)
+            kept = (ops.embed_fwd(pv, pa, gv, bv, ga, ba, pos + 100, B, T, drop_p=p, seed=11, site=3)[0] != 0) if p > 0 else None
+            torch.cuda.synchronize()
+            runs.append((x0, stats, dpv, dpa, acc, kept))
+    finally:
+        lib.mmer_debug_set(_lib.DEBUG_EMBED_GENERIC, 0)
+    (x0, stats, dpv, dpa, acc, kept), (x0g, statsg, dpvg, dpag, accg, keptg) = runs
+    # forward: the position-stable kernel folds the dropout scale and pos_embed into its per-warp constants (last-bit
+    # differences); the statistics and the dropout mask are identical
+    assert torch.equal(stats, statsg) and (p == 0 or torch.equal(kept, keptg))
+    assert rel(x0, x0g) < (1e-6 if dt == torch.float32 else 8e-3)
+    assert torch.equal(dpv, dpvg) and torch.equal(dpa, dpag)
+    for a, b in zip(acc, accg):
+        assert rel(a, b) < 2e-5
+    # float64 reference with the mask the kernel drew
+    leaves = [t.double().requires_grad_(True) for t in (pv, pa, gv, bv, ga, ba, pos)]
+    pvr, par, gvr, bvr, gar, bar, posr = leaves
+    ref = torch.cat([O.layer_norm(pvr.view(B, T, F), gvr, bvr), O.layer_norm(par, gar, bar).unsqueeze(1)], 1) + posr
+    scale = 1.0 if p == 0 else 1 / (1 - round(p * 65536) / 65536)
+    keep = torch.ones_like(ref)
+    if p > 0:
+        keep = kept.double().view(B, T + 1, F)
+    if p > 0:
+        assert abs(float(keep.mean()) - (1 - p)) < 0.01
+    out = ref * keep * scale
+    assert rel(x0.view(B, T + 1, F), out) < tol(dt)
+    out.backward(dx0.double().view(B, T + 1, F))
+    dgv, dbv, dga, dba, dpos, dbias_v, dbias_a = acc
+    for got, want in ((dpv, pvr.grad), (dpa, par.grad), (dgv, gvr.grad), (dbv, bvr.grad), (dga, gar.grad),
+                      (dba, bar.grad), (dpos, posr.grad)):
+        assert rel(got, want) < tol(dt)
+    assert rel(dbias_v, dpv.double().sum(0)) < (1e-5 if dt == torch.float32 else 2e-3)
+    assert rel(dbias_a, dpa.double().sum(0)) < (1e-5 if dt == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("use_mask,use_ln", [(True, True), (False, True), (True, False)])
 def test_pool_ln_fwd_bwd(dt, use_mask, use_ln):
     B, T, F = 11, 6, 512
