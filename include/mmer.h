@@ -328,7 +328,15 @@ typedef struct mmer_model {
   int32_t bn_world;
   int (*bn_sync)(void* user, float* buf, int64_t n, void* stream);
   void* bn_sync_user;
+  /* variant 2 with `use_layernorm=False` (train2.py:96,104-105,121 and :208,215; back-end/app/libs/model.py:16,23-24,39,
+   * 88,95): bit MMER_NORM_FUSION_IDENTITY -- norm_video, norm_audio and out_norm are nn.Identity (stage 0 / 1);
+   * bit MMER_NORM_HEAD_BATCHNORM -- the classifier normalises with nn.BatchNorm1d instead of nn.LayerNorm (stage 0 / 2):
+   * C1 / C5 are the BatchNorm weights and biases and bn_state = [running_mean, running_var] of net[1], then of net[5]
+   * (4 * hidden floats).  0 = the model as every caller in the reference builds it. */
+  int32_t norms;
 } mmer_model;
+#define MMER_NORM_FUSION_IDENTITY 1
+#define MMER_NORM_HEAD_BATCHNORM 2
 
 /* Integrated Gradients around the model (captum.attr.IntegratedGradients.attribute as called at train2.py:826-834 and
  * back-end/app/libs/inference.py:313-321; Captum's default method "gausslegendre", multiply_by_inputs = True).

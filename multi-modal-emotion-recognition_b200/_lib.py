@@ -20,6 +20,7 @@ DEBUG_MN_SWAP, DEBUG_FORCE_BN, DEBUG_FORCE_SIMT, DEBUG_DIRECT_STORE, DEBUG_ATT_S
 DEBUG_FORCE_SPLITS, DEBUG_NO_LN_FUSE = 10, 11
 DEBUG_SERVE_GLOBAL, DEBUG_SERVE_STAMPS, DEBUG_EMBED_GENERIC = 13, 14, 15
 MAX_LAYERS = 16
+NORM_FUSION_IDENTITY, NORM_HEAD_BATCHNORM = 1, 2   # mmer_model.norms (use_layernorm=False variants of train2.py)
 G_NAMES = ["POS", "WV", "BV", "WA", "BA", "NV_W", "NV_B", "NA_W", "NA_B", "ON_W", "ON_B", "C0_W", "C0_B", "C1_W",
            "C1_B", "C4_W", "C4_B", "C5_W", "C5_B", "C8_W", "C8_B"]
 L_NAMES = ["IN_W", "IN_B", "OUT_W", "OUT_B", "FF1_W", "FF1_B", "FF2_W", "FF2_B", "N1_W", "N1_B", "N2_W", "N2_B"]
@@ -59,7 +60,7 @@ class Model(C.Structure):
                 ("stage", C.c_int32), ("input_grads_only", C.c_int32),
                 ("fused_in", C.c_void_p), ("dfused_in", C.c_void_p), ("dfused_out", C.c_void_p),
                 ("grad_events", C.POINTER(C.c_void_p)), ("n_grad_events", C.c_int32), ("bn_world", C.c_int32),
-                ("bn_sync", C.c_void_p), ("bn_sync_user", C.c_void_p)]
+                ("bn_sync", C.c_void_p), ("bn_sync_user", C.c_void_p), ("norms", C.c_int32)]
 
 
 # int (*bn_sync)(void* user, float* buf, int64_t n, void* stream): SyncBatchNorm hook of mmer_model

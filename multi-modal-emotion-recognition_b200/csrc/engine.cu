@@ -85,7 +85,7 @@ struct LayerWs {
 };
 struct Ws {
   void *pv, *pa, *pvn, *pan, *x0;
-  float *st_e, *st_bnv, *st_bna, *st_fc;
+  float *st_e, *st_bnv, *st_bna, *st_fc, *st_fc2;
   LayerWs L[MMER_MAX_LAYERS];
   float* pooled;
   void* fused;
@@ -113,6 +113,7 @@ static void carve(const mmer_model* m, void* base, Ws* w) {
   w->st_bnv = (float*)c.take(2 * F * 4);
   w->st_bna = (float*)c.take(2 * F * 4);
   w->st_fc = (float*)c.take(2 * Hd * 4);
+  w->st_fc2 = (float*)c.take(2 * Hd * 4);
   for (int l = 0; l < m->layers; ++l) {
     LayerWs& L = w->L[l];
     L.qkv = c.take(M * 3 * F * e);
@@ -162,6 +163,7 @@ static void carve(const mmer_model* m, void* base, Ws* w) {
 static int validate(const mmer_model* m, bool need_ws) {
   MMER_CHECK_ARG(m != nullptr, "model: null");
   MMER_CHECK_ARG(m->variant == 1 || m->variant == 2, "model: variant must be 1 (train.py) or 2 (train2.py)");
+  MMER_CHECK_ARG((m->norms & ~3) == 0 && (m->variant == 2 || m->norms == 0), "model: norms flags are for variant 2 only");
   MMER_CHECK_ARG(m->dtype == MMER_F32 || m->dtype == MMER_BF16, "model: bad dtype");
   MMER_CHECK_ARG(m->B > 0 && m->T > 0, "model: empty batch (B=%d T=%d)", m->B, m->T);
   MMER_CHECK_ARG(m->layers >= 1 && m->layers <= MMER_MAX_LAYERS, "model: layers out of range");
@@ -177,6 +179,8 @@ static int validate(const mmer_model* m, bool need_ws) {
     MMER_CHECK_ARG(m->params != nullptr, "model: params is null");
     MMER_CHECK_ARG(m->dtype != MMER_BF16 || m->shadow != nullptr, "model: bf16 mode needs the bf16 shadow weights");
     MMER_CHECK_ARG(m->variant != 1 || m->bn_state != nullptr, "model: variant 1 needs bn_state");
+    MMER_CHECK_ARG(!(m->variant == 2 && (m->norms & MMER_NORM_HEAD_BATCHNORM)) || m->bn_state != nullptr,
+                   "model: a BatchNorm classifier head needs bn_state");
     Ws w;
     carve(m, nullptr, &w);
     MMER_CHECK_ARG(m->workspace != nullptr && (size_t)m->workspace_bytes >= w.total,
@@ -250,11 +254,15 @@ struct Dims {
   const uint8_t* mask;
   const int64_t* g;
   BnSync sy;
+  bool ln_fusion, ln_head, bn_head;   // which normalisation the fusion module / the classifier head use
   explicit Dims(const mmer_model* m)
       : B(m->B), T(m->T), S(m->T + 1), F(m->fused), Hd(m->hidden), FF(m->ffn), M((int64_t)m->B * (m->T + 1)),
         Mv((int64_t)m->B * m->T), dt(m->dtype), tr(m->training != 0), pf(tr ? m->p_fusion : 0.f),
         pc(tr ? m->p_classifier : 0.f), seed(m->seed), mask(m->has_mask ? m->mask : nullptr), g(m->off_g),
-        sy{m->bn_sync, m->bn_sync_user, m->bn_world} {}
+        sy{m->bn_sync, m->bn_sync_user, m->bn_world},
+        ln_fusion(m->variant == 2 && !(m->norms & MMER_NORM_FUSION_IDENTITY)),
+        ln_head(m->variant == 2 && !(m->norms & MMER_NORM_HEAD_BATCHNORM)),
+        bn_head(m->variant == 2 && (m->norms & MMER_NORM_HEAD_BATCHNORM)) {}
 };
 
 // CrossModalFusion.forward: projections -> token assembly -> encoder layers -> pooling (+ out_norm)
@@ -264,9 +272,12 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
   const int64_t* g = d.g;
   MMER_TRY(lin_fwd(m, m->video, Mv, m->video_dim, g[MMER_G_WV], g[MMER_G_BV], w.pv, F, 0, 0.f, 0, st));
   MMER_TRY(lin_fwd(m, m->audio, B, m->audio_dim, g[MMER_G_WA], g[MMER_G_BA], w.pa, F, 0, 0.f, 0, st));
-  if (m->variant == 2) {
+  if (d.ln_fusion) {
     MMER_TRY(mmer_embed_fwd(w.pv, w.pa, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), P(m, g[MMER_G_NA_W]),
                             P(m, g[MMER_G_NA_B]), P(m, g[MMER_G_POS]), w.x0, w.st_e, B, T, F, d.dt, d.pf, d.seed, 0, st));
+  } else if (m->variant == 2) {   // use_layernorm=False: norm_video / norm_audio are nn.Identity (train2.py:104-105)
+    MMER_TRY(mmer_embed_fwd(w.pv, w.pa, nullptr, nullptr, nullptr, nullptr, P(m, g[MMER_G_POS]), w.x0, w.st_e, B, T, F,
+                            d.dt, d.pf, d.seed, 0, st));
   } else {
     float* bs = m->bn_state;
     MMER_TRY(bn_fwd_sync(w.pv, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NV_B]), bs, bs + F, w.pvn, w.st_bnv, Mv, F, d.dt, d.tr,
@@ -314,8 +325,8 @@ static int fusion_forward(const mmer_model* m, Ws& w, cudaStream_t st) {
     }
     x = L.x2;
   }
-  MMER_TRY(mmer_pool_ln_fwd(x, d.mask, m->variant == 2 ? P(m, g[MMER_G_ON_W]) : nullptr,
-                            m->variant == 2 ? P(m, g[MMER_G_ON_B]) : nullptr, w.pooled, w.fused, w.st_o, B, T, F, d.dt, st));
+  MMER_TRY(mmer_pool_ln_fwd(x, d.mask, d.ln_fusion ? P(m, g[MMER_G_ON_W]) : nullptr,
+                            d.ln_fusion ? P(m, g[MMER_G_ON_B]) : nullptr, w.pooled, w.fused, w.st_o, B, T, F, d.dt, st));
   if (m->fused_out) {
     cudaError_t e = cudaMemcpyAsync(m->fused_out, w.fused, (size_t)B * F * (d.dt == MMER_BF16 ? 2 : 4),
                                     cudaMemcpyDeviceToDevice, st);
@@ -330,7 +341,16 @@ static int head_forward(const mmer_model* m, Ws& w, const void* fused, cudaStrea
   const int64_t B = d.B, F = d.F, Hd = d.Hd;
   const int64_t* g = d.g;
   MMER_TRY(lin_fwd(m, fused, B, F, g[MMER_G_C0_W], g[MMER_G_C0_B], w.h1p, Hd, 0, 0.f, 0, st));
-  if (m->variant == 2) {
+  if (d.bn_head) {   // use_layernorm=False: Linear -> BatchNorm1d -> ReLU -> Dropout, twice (train2.py:215-228)
+    float* bs = m->bn_state;
+    MMER_TRY(bn_fwd_sync(w.h1p, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), bs, bs + Hd, w.h1, w.st_fc, B, Hd, d.dt, d.tr,
+                         1, 0.1f, d.pc, d.seed, 200, st, &d.sy));
+    MMER_TRY(lin_fwd(m, w.h1, B, Hd, g[MMER_G_C4_W], g[MMER_G_C4_B], w.h2p, Hd, 0, 0.f, 0, st));
+    MMER_TRY(bn_fwd_sync(w.h2p, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), bs + 2 * Hd, bs + 3 * Hd, w.h2, w.st_fc2, B, Hd,
+                         d.dt, d.tr, 1, 0.1f, d.pc, d.seed, 201, st, &d.sy));
+    MMER_TRY(mmer_head_out_fwd(w.h2, P(m, g[MMER_G_C8_W]), P(m, g[MMER_G_C8_B]), m->logits, m->probs, B, Hd, m->classes,
+                               d.dt, st));
+  } else if (m->variant == 2) {
     MMER_TRY(mmer_add_ln_fwd(nullptr, w.h1p, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.h1, w.st_h1, B, Hd, d.dt, 1,
                              0.f, 0, d.pc, 200, d.seed, st));
     MMER_TRY(lin_fwd(m, w.h1, B, Hd, g[MMER_G_C4_W], g[MMER_G_C4_B], w.h2p, Hd, 0, 0.f, 0, st));
@@ -367,7 +387,16 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
   const Dims d(m);
   const int64_t B = d.B, F = d.F, Hd = d.Hd;
   const int64_t* g = d.g;
-  if (m->variant == 2) {
+  if (d.bn_head) {
+    MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h2, P(m, g[MMER_G_C8_W]), w.g_h2, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
+                               B, Hd, m->classes, d.dt, st));
+    MMER_TRY(bn_bwd_sync(w.g_h2, w.h2p, w.st_fc2, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), w.g_h2p, G(m, g[MMER_G_C5_W]),
+                         G(m, g[MMER_G_C5_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 201, st, &d.sy));
+    MMER_TRY(lin_wgrad(m, w.g_h2p, w.h1, B, Hd, Hd, g[MMER_G_C4_W], g[MMER_G_C4_B], st));
+    MMER_TRY(lin_dgrad(m, w.g_h2p, B, Hd, g[MMER_G_C4_W], Hd, w.g_h1, nullptr, nullptr, 0.f, st));
+    MMER_TRY(bn_bwd_sync(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
+                         G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st, &d.sy));
+  } else if (m->variant == 2) {
     MMER_TRY(mmer_head_out_bwd(m->dlogits, w.h2, P(m, g[MMER_G_C8_W]), w.g_h2, G(m, g[MMER_G_C8_W]), G(m, g[MMER_G_C8_B]),
                                B, Hd, m->classes, d.dt, st));
     MMER_TRY(mmer_add_ln_bwd(w.g_h2, nullptr, w.h2p, w.st_h2, P(m, g[MMER_G_C5_W]), P(m, g[MMER_G_C5_B]), w.g_h2p, nullptr,
@@ -384,7 +413,7 @@ static int head_backward(const mmer_model* m, Ws& w, const void* fused, cudaStre
     MMER_TRY(bn_bwd_sync(w.g_h1, w.h1p, w.st_fc, P(m, g[MMER_G_C1_W]), P(m, g[MMER_G_C1_B]), w.g_h1p, G(m, g[MMER_G_C1_W]),
                          G(m, g[MMER_G_C1_B]), w.bn_scratch, B, Hd, d.dt, d.tr, 1, d.pc, d.seed, 200, st, &d.sy));
   }
-  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], m->variant == 2 ? -1 : g[MMER_G_C0_B], st));
+  MMER_TRY(lin_wgrad(m, w.g_h1p, fused, B, Hd, F, g[MMER_G_C0_W], d.ln_head ? -1 : g[MMER_G_C0_B], st));
   MMER_TRY(lin_dgrad(m, w.g_h1p, B, Hd, g[MMER_G_C0_W], F, w.g_fused, nullptr, nullptr, 0.f, st));
   return 0;
 }
@@ -401,9 +430,9 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
   const int64_t B = d.B, T = d.T, F = d.F, M = d.M, Mv = d.Mv, FF = d.FF;
   const int64_t* g = d.g;
   const float pf = d.pf;
-  MMER_TRY(mmer_pool_ln_bwd(dfused, w.pooled, w.st_o, m->variant == 2 ? P(m, g[MMER_G_ON_W]) : nullptr, d.mask, w.g_x,
-                            m->variant == 2 ? G(m, g[MMER_G_ON_W]) : nullptr,
-                            m->variant == 2 ? G(m, g[MMER_G_ON_B]) : nullptr, B, T, F, d.dt, st));
+  MMER_TRY(mmer_pool_ln_bwd(dfused, w.pooled, w.st_o, d.ln_fusion ? P(m, g[MMER_G_ON_W]) : nullptr, d.mask, w.g_x,
+                            d.ln_fusion ? G(m, g[MMER_G_ON_W]) : nullptr,
+                            d.ln_fusion ? G(m, g[MMER_G_ON_B]) : nullptr, B, T, F, d.dt, st));
   MMER_TRY(bucket_done(m, 0, st));   // classifier + out_norm
   const float relu_gate_scale = pf > 0.f ? make_drop(pf, d.seed, 0).scale : 1.f;
   for (int l = m->layers - 1; l >= 0; --l) {
@@ -455,7 +484,10 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
   }
   const void* dpv = w.g_pv;
   const void* dpa = w.g_pa;
-  if (m->variant == 2) {
+  if (m->variant == 2 && !d.ln_fusion) {   // Identity norms: the gradient rows pass through the dropout mask
+    MMER_TRY(mmer_embed_bwd(w.g_x, w.pv, w.pa, w.st_e, nullptr, nullptr, w.g_pv, w.g_pa, nullptr, nullptr, nullptr, nullptr,
+                            G(m, g[MMER_G_POS]), nullptr, nullptr, B, T, F, d.dt, pf, d.seed, 0, st));
+  } else if (m->variant == 2) {
     MMER_TRY(mmer_embed_bwd(w.g_x, w.pv, w.pa, w.st_e, P(m, g[MMER_G_NV_W]), P(m, g[MMER_G_NA_W]), w.g_pv, w.g_pa,
                             G(m, g[MMER_G_NV_W]), G(m, g[MMER_G_NV_B]), G(m, g[MMER_G_NA_W]), G(m, g[MMER_G_NA_B]),
                             G(m, g[MMER_G_POS]), G(m, g[MMER_G_BV]), G(m, g[MMER_G_BA]), B, T, F, d.dt, pf, d.seed, 0, st));
@@ -467,8 +499,8 @@ static int fusion_backward(const mmer_model* m, Ws& w, const void* dfused, cudaS
     MMER_TRY(bn_bwd_sync(w.g_pan, w.pa, w.st_bna, P(m, g[MMER_G_NA_W]), P(m, g[MMER_G_NA_B]), w.g_pa, G(m, g[MMER_G_NA_W]),
                          G(m, g[MMER_G_NA_B]), w.bn_scratch, B, F, d.dt, d.tr, 0, 0.f, d.seed, 0, st, &d.sy));
   }
-  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], m->variant == 2 ? -1 : g[MMER_G_BV], st));
-  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], m->variant == 2 ? -1 : g[MMER_G_BA], st));
+  MMER_TRY(lin_wgrad(m, dpv, m->video, Mv, F, m->video_dim, g[MMER_G_WV], d.ln_fusion ? -1 : g[MMER_G_BV], st));
+  MMER_TRY(lin_wgrad(m, dpa, m->audio, B, F, m->audio_dim, g[MMER_G_WA], d.ln_fusion ? -1 : g[MMER_G_BA], st));
   MMER_TRY(bucket_done(m, m->layers + 1, st));   // projections, input norms, pos_embed
   if (m->dvideo) MMER_TRY(lin_dgrad(m, dpv, Mv, F, g[MMER_G_WV], m->video_dim, m->dvideo, nullptr, nullptr, 0.f, st));
   if (m->daudio) MMER_TRY(lin_dgrad(m, dpa, B, F, g[MMER_G_WA], m->audio_dim, m->daudio, nullptr, nullptr, 0.f, st));

@@ -122,7 +122,8 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
   const bool drop_y = MODE < 0 ? dy.thr != 0 : (MODE & LNM_DROP_Y) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LnSmem sm = lnp_setup(g, smem);
-  const int F = g.F;
+  constexpr bool FULLW = MODE >= 0;   // the specialised instances are launched with F == NCH * 256 only: no column guards
+  const int F = FULLW ? NCH * 256 : g.F;
   if (warp == g.W) {
     if (lane == 0) {
       const T* const src[3] = {a, x, nullptr};
@@ -134,7 +135,7 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = lane * 8 + i * 256;
-    if (c < F) { load8(gamma + c, gm[i]); load8(beta + c, bt[i]); }
+    if (FULLW || c < F) { load8(gamma + c, gm[i]); load8(beta + c, bt[i]); }
   }
   const float invF = 1.f / (float)F;
   const long long tiles = (g.M + g.W - 1) / g.W;
@@ -151,7 +152,7 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         const int c = lane * 8 + i * 256;
-        if (c < F) {
+        if (FULLW || c < F) {
           load8(sa + c, z[i]);
           if (drop_a) {
             float f[8];
@@ -181,7 +182,7 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = lane * 8 + i * 256;
-      if (c < F) {
+      if (FULLW || c < F) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = z[i][j] - mean; q = fmaf(d, d, q); }
       }
@@ -192,7 +193,7 @@ add_ln_fwd_pipe_kernel(const T* __restrict__ a, const T* __restrict__ x, const f
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = lane * 8 + i * 256;
-      if (c < F) {
+      if (FULLW || c < F) {
         const long long off = row * F + c;
         float o[8];
 #pragma unroll
@@ -235,7 +236,8 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
   const bool want_dbias = MODE < 0 ? dbias != nullptr : (MODE & LNM_DBIAS) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LnSmem sm = lnp_setup(g, smem);
-  const int F = g.F;
+  constexpr bool FULLW = MODE >= 0;   // the specialised instances are launched with F == NCH * 256 only: no column guards
+  const int F = FULLW ? NCH * 256 : g.F;
   const bool compute_warp = warp < g.W;
   float* sgamma = reinterpret_cast<float*>(smem + (size_t)g.stages * g.stage_bytes + 2 * LNP_MAX_STAGES * 8);
   for (int c = threadIdx.x; c < F; c += blockDim.x) sgamma[c] = gamma[c];
@@ -277,7 +279,7 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
           const int c = lane * 8 + i * 256;
-          if (c < F) {
+          if (FULLW || c < F) {
             const long long off = row * F + c;
             float z[8], d[8], gm8[8];
             load8(sgamma + c, gm8);     // gamma lives in shared memory: 16 registers fewer than a per-lane copy
@@ -330,7 +332,7 @@ add_ln_bwd_pipe_kernel(const T* __restrict__ dyp, const T* __restrict__ a, const
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         const int c = lane * 8 + i * 256;
-        if (c < F) {
+        if (FULLW || c < F) {
           const long long off = row * F + c;
           float o[8];
 #pragma unroll
@@ -415,7 +417,7 @@ static int fwd_launch(const void* x, const void* a, const float* gamma, const fl
   LnPipeGeom g;
   size_t smem;
   MMER_TRY(lnp_geometry(M, F, sizeof(T), x ? 2 : 1, &g, &smem));
-  if (NCH == 2 && sizeof(T) == 2) {   // the encoder sub-layer instances of the bf16 step
+  if (NCH == 2 && sizeof(T) == 2 && F == NCH * 256) {   // the encoder sub-layer instances of the bf16 step
     const int mode = (x ? LNM_X : 0) | (relu ? LNM_RELU : 0) | (da.thr ? LNM_DROP_A : 0) | (dy.thr ? LNM_DROP_Y : 0);
     if (mode == (LNM_X | LNM_DROP_A))
       return fwd_launch_mode<T, NCH, LNM_X | LNM_DROP_A>(x, a, gamma, beta, y, stats, g, smem, relu, da, dy, st);
@@ -445,7 +447,7 @@ static int bwd_launch(const void* dy, const void* x, const void* a, const float*
   LnPipeGeom g;
   size_t smem;
   MMER_TRY(lnp_geometry(M, F, sizeof(T), x ? 3 : 2, &g, &smem));
-  if (NCH == 2 && sizeof(T) == 2) {
+  if (NCH == 2 && sizeof(T) == 2 && F == NCH * 256) {
     const int mode = (x ? LNM_X : 0) | (relu ? LNM_RELU : 0) | (da.thr ? LNM_DROP_A : 0) | (ddy.thr ? LNM_DROP_Y : 0) |
                      (dbias ? LNM_DBIAS : 0) | (zin ? LNM_ZIN : 0);
     if (mode == (LNM_X | LNM_DROP_A | LNM_DBIAS))

@@ -537,13 +537,13 @@ int64_t mmer_serve_scratch_bytes(void) { return (int64_t)SC_TOTAL * 4; }
 
 int mmer_serve_pack(const mmer_model* m, void* packed, void* stream) {
   MMER_CHECK_ARG(m != nullptr && packed != nullptr && m->shadow != nullptr, "serve_pack: null pointer");
-  MMER_CHECK_ARG(m->variant == 2 && m->dtype == MMER_BF16, "serve_pack: the LayerNorm (train2.py) model in bf16 only");
+  MMER_CHECK_ARG(m->variant == 2 && m->norms == 0 && m->dtype == MMER_BF16, "serve_pack: the LayerNorm (train2.py) model in bf16 only");
   return serve_pack_weights(m, packed, (cudaStream_t)stream);
 }
 
 int mmer_serve_forward(const mmer_model* m, void* scratch, const void* packed, void* stream) {
   MMER_CHECK_ARG(m != nullptr && scratch != nullptr, "serve_forward: null pointer");
-  MMER_CHECK_ARG(m->variant == 2 && m->dtype == MMER_BF16, "serve_forward: the LayerNorm (train2.py) model in bf16 only");
+  MMER_CHECK_ARG(m->variant == 2 && m->norms == 0 && m->dtype == MMER_BF16, "serve_forward: the LayerNorm (train2.py) model in bf16 only");
   MMER_CHECK_ARG(m->B == 1 && m->T >= 1 && m->T + 1 <= SV_MAXS, "serve_forward: one sample of at most %d frames (B=%d T=%d)",
                  SV_MAXS - 1, m->B, m->T);
   MMER_CHECK_ARG(m->fused == SV_F && m->heads == 8 && m->ffn % 256 == 0 && m->ffn <= SV_KMAX && m->video_dim % 256 == 0 &&

@@ -238,10 +238,10 @@ class Engine:
     """Builds the ``mmer_model`` struct for one call and runs the C forward / backward."""
 
     def __init__(self, ctx: ParamContext, *, variant: int, video_dim: int, audio_dim: int, fused: int, heads: int,
-                 layers: int, ffn: int, hidden: int, classes: int):
+                 layers: int, ffn: int, hidden: int, classes: int, norms: int = 0):
         self.ctx = ctx
         self.cfg = dict(variant=variant, video_dim=video_dim, audio_dim=audio_dim, fused=fused, heads=heads,
-                        layers=layers, ffn=ffn, hidden=hidden, classes=classes)
+                        layers=layers, ffn=ffn, hidden=hidden, classes=classes, norms=norms)
         if layers > _lib.MAX_LAYERS:
             raise MmerError(f"at most {_lib.MAX_LAYERS} encoder layers are supported")
 

@@ -111,19 +111,19 @@ class CrossModalFusion(nn.Module, _EngineOwner):
     def __init__(self, video_dim: int = 768, audio_dim: int = 1024, fused_dim: int = 512, num_layers: int = 4,
                  num_heads: int = 8, dropout: float = 0.1, max_seq_len: int = 101, use_layernorm: bool = True):
         super().__init__()
-        if not use_layernorm:
-            raise NotImplementedError("use_layernorm=False (Identity norms) has no CUDA path; the reference never uses it")
         self.video_proj = nn.Linear(video_dim, fused_dim)
         self.audio_proj = nn.Linear(audio_dim, fused_dim)
-        self.norm_video = nn.LayerNorm(fused_dim)
-        self.norm_audio = nn.LayerNorm(fused_dim)
+        # use_layernorm=False: the three norms are nn.Identity (train2.py:104-105,121) -- engine flag NORM_FUSION_IDENTITY
+        self.norm_video = nn.LayerNorm(fused_dim) if use_layernorm else nn.Identity()
+        self.norm_audio = nn.LayerNorm(fused_dim) if use_layernorm else nn.Identity()
         self.pos_embed = nn.Parameter(torch.zeros(1, max_seq_len, fused_dim))
         nn.init.normal_(self.pos_embed, mean=0.0, std=0.02)
         encoder_layer = nn.TransformerEncoderLayer(d_model=fused_dim, nhead=num_heads, dim_feedforward=4 * fused_dim,
                                                    dropout=dropout, batch_first=False)
         self.transformer = nn.TransformerEncoder(encoder_layer, num_layers=num_layers, enable_nested_tensor=False)
         self.dropout_layer = nn.Dropout(dropout)
-        self.out_norm = nn.LayerNorm(fused_dim)
+        self.out_norm = nn.LayerNorm(fused_dim) if use_layernorm else nn.Identity()
+        self.use_layernorm = bool(use_layernorm)
         self.num_layers = num_layers
         self.num_heads = num_heads
         self.dropout = dropout  # float, read by the reference's logging (train2.py:541)
@@ -131,11 +131,16 @@ class CrossModalFusion(nn.Module, _EngineOwner):
 
     # engine wiring -----------------------------------------------------------
     def _g_slots(self):
-        return {"POS": self.pos_embed, "WV": self.video_proj.weight, "BV": self.video_proj.bias,
-                "WA": self.audio_proj.weight, "BA": self.audio_proj.bias,
-                "NV_W": self.norm_video.weight, "NV_B": self.norm_video.bias,
-                "NA_W": self.norm_audio.weight, "NA_B": self.norm_audio.bias,
-                "ON_W": self.out_norm.weight, "ON_B": self.out_norm.bias}
+        g = {"POS": self.pos_embed, "WV": self.video_proj.weight, "BV": self.video_proj.bias,
+             "WA": self.audio_proj.weight, "BA": self.audio_proj.bias}
+        if self.use_layernorm:
+            g.update({"NV_W": self.norm_video.weight, "NV_B": self.norm_video.bias,
+                      "NA_W": self.norm_audio.weight, "NA_B": self.norm_audio.bias,
+                      "ON_W": self.out_norm.weight, "ON_B": self.out_norm.bias})
+        return g
+
+    def _norms(self) -> int:
+        return 0 if self.use_layernorm else _lib.NORM_FUSION_IDENTITY
 
     def _l_slots(self):
         return [_layer_slots(l) for l in self.transformer.layers]
@@ -147,7 +152,7 @@ class CrossModalFusion(nn.Module, _EngineOwner):
 
     def _make_engine(self) -> Engine:
         ctx = ParamContext(2, self._g_slots(), self._l_slots())
-        return Engine(ctx, variant=2, hidden=8, classes=1, **self._dims())
+        return Engine(ctx, variant=2, hidden=8, classes=1, norms=self._norms(), **self._dims())
 
     @property
     def _p_fusion(self):
@@ -171,18 +176,33 @@ class EmotionClassifier(nn.Module, _EngineOwner):
     def __init__(self, input_dim: int = 512, num_classes: int = 6, hidden_dim: Optional[int] = None,
                  dropout: float = 0.2, use_layernorm: bool = True):
         super().__init__()
-        if not use_layernorm:
-            raise NotImplementedError("use_layernorm=False has no CUDA path; the reference never uses it")
         if hidden_dim is None:
             hidden_dim = input_dim // 2
+        # use_layernorm=False: nn.BatchNorm1d in both blocks (train2.py:215) -- engine flag NORM_HEAD_BATCHNORM
+        Norm = nn.LayerNorm if use_layernorm else nn.BatchNorm1d
         self.net = nn.Sequential(
-            nn.Linear(input_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
-            nn.Linear(hidden_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
+            nn.Linear(input_dim, hidden_dim), Norm(hidden_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
+            nn.Linear(hidden_dim, hidden_dim), Norm(hidden_dim), nn.ReLU(inplace=True), nn.Dropout(dropout),
             nn.Linear(hidden_dim, num_classes),
         )
+        self.use_layernorm = bool(use_layernorm)
         self.dropout = dropout
         self.hidden_dim = hidden_dim
         self._init_owner()
+
+    def _norms(self) -> int:
+        return 0 if self.use_layernorm else _lib.NORM_HEAD_BATCHNORM
+
+    def _bn_buffers(self):
+        if self.use_layernorm:
+            return []
+        n = self.net
+        return [(n[1], "running_mean"), (n[1], "running_var"), (n[5], "running_mean"), (n[5], "running_var")]
+
+    def _count_batches(self):
+        if self.training and not self.use_layernorm:   # nn.BatchNorm1d bookkeeping (momentum is fixed: not used otherwise)
+            self.net[1].num_batches_tracked += 1
+            self.net[5].num_batches_tracked += 1
 
     def _g_slots(self):
         n = self.net
@@ -191,11 +211,11 @@ class EmotionClassifier(nn.Module, _EngineOwner):
                 "C8_W": n[8].weight, "C8_B": n[8].bias}
 
     def _make_engine(self) -> Engine:
-        ctx = ParamContext(2, self._g_slots(), [])
+        ctx = ParamContext(2, self._g_slots(), [], self._bn_buffers())
         fused = self.net[0].in_features
         heads = fused // 64 if fused % 64 == 0 else max(fused // 32, 1)   # unused by the head, must be valid
         return Engine(ctx, variant=2, video_dim=8, audio_dim=8, fused=fused, heads=heads, layers=1,
-                      ffn=8, hidden=self.hidden_dim, classes=self.net[8].out_features)
+                      ffn=8, hidden=self.hidden_dim, classes=self.net[8].out_features, norms=self._norms())
 
     _p_fusion = 0.0
 
@@ -208,6 +228,7 @@ class EmotionClassifier(nn.Module, _EngineOwner):
             raise RuntimeError(f"expected fused embedding of shape (B, {self.net[0].in_features}), got "
                                f"{tuple(fused_embedding.shape)}")
         logits, _, _ = ModelFn.apply(self._anchor, None, None, fused_embedding, self, None, 2, False)
+        self._count_batches()
         return logits
 
 
@@ -236,9 +257,10 @@ class MultimodalEmotionModel(nn.Module, _EngineOwner):
     def _make_engine(self) -> Engine:
         g = dict(self.fusion._g_slots())
         g.update(self.classifier._g_slots())
-        ctx = ParamContext(2, g, self.fusion._l_slots())
-        return Engine(ctx, variant=2, hidden=self.classifier.hidden_dim,
-                      classes=self.classifier.net[8].out_features, **self.fusion._dims())
+        # sub-modules swapped for their use_layernorm=False variants keep working: the flags travel with them
+        ctx = ParamContext(2, g, self.fusion._l_slots(), self.classifier._bn_buffers())
+        return Engine(ctx, variant=2, hidden=self.classifier.hidden_dim, classes=self.classifier.net[8].out_features,
+                      norms=self.fusion._norms() | self.classifier._norms(), **self.fusion._dims())
 
     @property
     def _p_fusion(self):
@@ -253,6 +275,7 @@ class MultimodalEmotionModel(nn.Module, _EngineOwner):
         _check_inputs(self.fusion, video_feats, audio_feats, mask)
         logits, probs, attn = ModelFn.apply(self._anchor, video_feats, audio_feats, None, self, mask, 0,
                                             bool(return_attn))
+        self.classifier._count_batches()
         return probs, logits, (attention_outputs(attn) if return_attn else None)
 
 

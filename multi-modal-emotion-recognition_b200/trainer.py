@@ -303,8 +303,9 @@ class FusedTrainStep:
             elif dp_mode == "nvls":
                 raise MmerError("dp_mode='nvls': symmetric memory / NVSwitch multicast is not available here")
         if self.world > 1:
-            if self.engine.cfg["variant"] == 1 and not getattr(model, "sync_batchnorm", False):
-                raise MmerError("the BatchNorm variant (train.py) is not invariant under data parallelism: per-rank batch "
+            has_bn = self.engine.cfg["variant"] == 1 or (self.engine.cfg.get("norms", 0) & _lib.NORM_HEAD_BATCHNORM)
+            if has_bn and not (self.engine.cfg["variant"] == 1 and getattr(model, "sync_batchnorm", False)):
+                raise MmerError("a model with BatchNorm layers (train.py) is not invariant under data parallelism: per-rank batch "
                                 "statistics differ from the global-batch reference (SURVEY 8e).  Construct the model with "
                                 "sync_batchnorm=True or train it on one GPU")
             # DistributedDataParallel semantics: every replica starts from rank 0's weights (and BatchNorm buffers)
@@ -499,6 +500,8 @@ class FusedTrainStep:
             # BatchNorm bookkeeping of a training-mode forward (train.py:66-74,125): the module path does this in forward()
             self.model.fusion._count_batches()
             self.model.classifier.bn_fc1.num_batches_tracked += 1
+        elif self.engine.cfg.get("norms", 0) & _lib.NORM_HEAD_BATCHNORM:   # train2's head with use_layernorm=False
+            self.model.classifier._count_batches()
         if nvls:
             self._nvls_adam(stream)
             return self._loss, self._probs

@@ -694,3 +694,116 @@ def test_serving_forward_variants_agree(T):
     scale = float(out[1].abs().max())
     assert float((out[0] - out[1]).abs().max()) < 5e-3 * scale, (out[0], out[1])
     assert float((out[2] - out[1]).abs().max()) < 5e-3 * scale
+
+
+# ----------------------------------------------------------------------------- use_layernorm=False (train2.py:96,208)
+def _nolayernorm_modules():
+    """The two train2.py sub-modules built with use_layernorm=False, loaded like tests/golden/make_golden_nolayernorm.py."""
+    g = np.load(os.path.join(GOLD, "v2_nolayernorm_b8_t5_mask.npz"))
+    B, T, HID = int(g["B"]), int(g["T"]), int(g["hidden"])
+    params = detgen.make_params("v2", max_seq_len=T + 1, hidden=HID)
+    fusion = mm.CrossModalFusion(num_layers=2, dropout=0.0, max_seq_len=T + 1, use_layernorm=False)
+    head = mm.EmotionClassifier(input_dim=512, hidden_dim=HID, dropout=0.0, use_layernorm=False)
+    assert isinstance(fusion.norm_video, torch.nn.Identity) and isinstance(fusion.out_norm, torch.nn.Identity)
+    assert isinstance(head.net[1], torch.nn.BatchNorm1d) and isinstance(head.net[5], torch.nn.BatchNorm1d)
+    fsd = {k[len("fusion."):]: torch.from_numpy(v) for k, v in params.items()
+           if k.startswith("fusion.") and "norm_video" not in k and "norm_audio" not in k and "out_norm" not in k}
+    fusion.load_state_dict(fsd, strict=True)
+    hsd = {k[len("classifier."):]: torch.from_numpy(v) for k, v in params.items() if k.startswith("classifier.")}
+    for i in (1, 5):
+        hsd[f"net.{i}.running_mean"] = torch.from_numpy(g[f"bn_init/net.{i}.running_mean"])
+        hsd[f"net.{i}.running_var"] = torch.from_numpy(g[f"bn_init/net.{i}.running_var"])
+        hsd[f"net.{i}.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    head.load_state_dict(hsd, strict=True)
+    v, a, m, y = detgen.make_batch(B, T, tag="nolayernorm")
+    fused_in = torch.from_numpy(detgen.det_array((B, 512), "nolayernorm/fused_in", 1.0)).cuda()
+    wr = torch.from_numpy(detgen.det_array((B, 512), "nolayernorm/wr", 1.0)).cuda()
+    return (g, fusion.cuda(), head.cuda(), hsd, torch.from_numpy(v).cuda(), torch.from_numpy(a).cuda(),
+            torch.from_numpy(m).cuda(), torch.from_numpy(y).cuda(), fused_in, wr)
+
+
+def _check_golden_grads(g, prefix, named, rtol=2e-4):
+    n = 0
+    for k, p in named:
+        got = p.grad.detach().cpu().numpy()
+        if f"{prefix}/gradfull/{k}" in g:
+            want = g[f"{prefix}/gradfull/{k}"]
+        else:
+            want, got = g[f"{prefix}/gradproj/{k}"], detgen.project(got, k)
+        # absolute floor: the bias of a Linear that feeds BatchNorm has a mathematically zero gradient (1e-9 of noise)
+        assert float(np.abs(got - want).max()) < rtol * float(np.abs(want).max()) + 2e-7, (prefix, k)
+        n += 1
+    return n
+
+
+def test_use_layernorm_false_variants_match_reference_golden_fp32():
+    """CrossModalFusion with nn.Identity norms and EmotionClassifier with nn.BatchNorm1d (train2.py:104-105,121,215),
+    each on its own and chained, against outputs, gradients and BatchNorm statistics of the unmodified reference."""
+    g, fusion, head, hsd, video, audio, mask, labels, fused_in, wr = _nolayernorm_modules()
+    # ---- fusion alone
+    fusion.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(fusion(video, audio, mask=mask)[0].cpu().numpy(), g["fusion/eval_fused"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(fusion(video, audio)[0].cpu().numpy(), g["fusion/eval_fused_nomask"], rtol=1e-4, atol=1e-5)
+    fusion.train()
+    vg, ag = video.clone().requires_grad_(True), audio.clone().requires_grad_(True)
+    fused = fusion(vg, ag, mask=mask)[0]
+    np.testing.assert_allclose(fused.detach().cpu().numpy(), g["fusion/train_fused"], rtol=1e-4, atol=1e-5)
+    fusion.zero_grad()
+    (fused * wr).sum().backward()
+    assert _check_golden_grads(g, "fusion", fusion.named_parameters()) == len(list(fusion.parameters()))
+    np.testing.assert_allclose(vg.grad.cpu().numpy(), g["fusion/grad_video"], rtol=1e-3, atol=2e-6)
+    np.testing.assert_allclose(ag.grad.cpu().numpy(), g["fusion/grad_audio"], rtol=1e-3, atol=2e-6)
+    # ---- classifier alone
+    head.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(head(fused_in).cpu().numpy(), g["head/eval_logits"], rtol=1e-4, atol=1e-5)
+    head.train()
+    fg = fused_in.clone().requires_grad_(True)
+    logits = head(fg)
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), g["head/train_logits"], rtol=1e-4, atol=1e-5)
+    head.zero_grad()
+    loss = mm.WeightedCrossEntropyLoss(ALPHA.cuda())(logits, labels)
+    assert abs(float(loss) - float(g["head/loss"])) < 1e-5
+    loss.backward()
+    assert _check_golden_grads(g, "head", head.named_parameters()) == len(list(head.parameters()))
+    np.testing.assert_allclose(fg.grad.cpu().numpy(), g["head/grad_fused"], rtol=1e-3, atol=1e-7)
+    sd = head.state_dict()
+    for i in (1, 5):
+        np.testing.assert_allclose(sd[f"net.{i}.running_mean"].cpu().numpy(), g[f"head/bn_after_fwd/net.{i}.running_mean"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(sd[f"net.{i}.running_var"].cpu().numpy(), g[f"head/bn_after_fwd/net.{i}.running_var"], rtol=1e-5, atol=1e-6)
+        assert int(sd[f"net.{i}.num_batches_tracked"]) == int(g[f"head/bn_after_fwd/net.{i}.num_batches_tracked"]) == 1
+    # ---- chained inside MultimodalEmotionModel (one engine, both flags): sub-modules swapped in like a user would
+    model = mm.MultimodalEmotionModel(max_seq_len=int(g["T"]) + 1, fusion_num_layers=2, classifier_hidden_dim=int(g["hidden"]),
+                                      fusion_dropout=0.0, classifier_dropout=0.0)
+    head.load_state_dict(hsd, strict=True)
+    model.fusion, model.classifier = fusion, head
+    model.cuda().train()
+    vg, ag = video.clone().requires_grad_(True), audio.clone().requires_grad_(True)
+    probs, logits, _ = model(vg, ag, mask=mask)
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), g["chain/train_logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(probs.detach().cpu().numpy(), g["chain/train_probs"], rtol=1e-4, atol=1e-6)
+    model.zero_grad()
+    loss = mm.WeightedCrossEntropyLoss(ALPHA.cuda())(logits, labels)
+    assert abs(float(loss) - float(g["chain/loss"])) < 1e-5
+    loss.backward()
+    assert _check_golden_grads(g, "chain", model.named_parameters()) == len(list(model.parameters()))
+    np.testing.assert_allclose(vg.grad.cpu().numpy(), g["chain/grad_video"], rtol=1e-3, atol=2e-7)
+    model.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(model(video, audio, mask=mask)[1].cpu().numpy(), g["chain/eval_logits_after"], rtol=1e-4, atol=1e-5)
+
+
+def test_use_layernorm_false_variants_bf16_close_to_fp32():
+    g, fusion, head, hsd, video, audio, mask, labels, fused_in, wr = _nolayernorm_modules()
+    fusion.eval()
+    head.eval()
+    with torch.no_grad():
+        f32 = fusion(video, audio, mask=mask)[0]
+        l32 = head(fused_in)
+        fusion.compute_dtype = torch.bfloat16
+        head.compute_dtype = torch.bfloat16
+        f16 = fusion(video, audio, mask=mask)[0]
+        l16 = head(fused_in)
+    assert float((f16.float() - f32).abs().max() / f32.abs().max()) < 2e-2
+    assert float((l16.float() - l32).abs().max() / l32.abs().max()) < 2e-2

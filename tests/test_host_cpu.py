@@ -97,6 +97,19 @@ def test_state_dict_equals_reference_classes():
             assert rs[k].shape == os_[k].shape and torch.equal(rs[k], os_[k]), k   # same default init too
         o.load_state_dict(rs, strict=True)
         r.load_state_dict(o.state_dict(), strict=True)
+    # use_layernorm=False variants of the two sub-modules (train2.py:96,104-105,121 / :208,215): Identity norms in the
+    # fusion module, BatchNorm1d in the head -- same keys, shapes, buffers and default initialisation
+    for ref_cls, our_cls, kw in ((ref_v2.CrossModalFusion, mm.CrossModalFusion, dict(num_layers=2, max_seq_len=17)),
+                                 (ref_v2.EmotionClassifier, mm.EmotionClassifier, dict(hidden_dim=512))):
+        torch.manual_seed(0)
+        r = ref_cls(use_layernorm=False, **kw)
+        torch.manual_seed(0)
+        o = our_cls(use_layernorm=False, **kw)
+        rs, os_ = r.state_dict(), o.state_dict()
+        assert list(rs.keys()) == list(os_.keys())
+        for k in rs:
+            assert rs[k].shape == os_[k].shape and torch.equal(rs[k], os_[k]), k
+        o.load_state_dict(rs, strict=True)
     # attribute reads the reference's logging performs (train2.py:536-544, train.py:262-272)
     assert o2.fusion.video_proj.in_features == 768 and o2.fusion.audio_proj.in_features == 1024
     assert o2.fusion.video_proj.out_features == 512 and o2.classifier.net[-1].out_features == 6
