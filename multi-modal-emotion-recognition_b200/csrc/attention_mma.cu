@@ -30,16 +30,62 @@ struct MmaGeom {
   uint32_t do_row, do_stride;   // bytes of one dO / out row, padded smem stride
 };
 
-// Byte offset of element (row, col) of a [rows][D] bf16 head tile in shared memory.
+// Byte offsets inside a [rows][D] bf16 head tile in shared memory, as the fragment loads and stores of this file need
+// them.  Every access pattern is "a row that depends on the lane (clamped to S - 1 for loads: rows beyond S hold no
+// data) and a 16-byte chunk = a compile-time step + a lane term":
+//   a_off(i, ks)   ldmatrix.x4 of row tile i (16 rows), 16-column step ks: A operands, and the transposed B operands
+//   b_off(nt, k2)  ldmatrix.x4 of key tile nt (8 rows), 32-column step k2: B operands (K, V)
+//   st_base(tile, rowbase) / st_addr(base, nd)   the lane's bf16 pair of row rowbase + g, 8-column block nd (swizzled tiles)
 struct PadAddr {      // row-padded packed rows (bulk-copied whole token rows): offset = row * stride + col * 2
+  static constexpr bool kStaticRows = false;   // a tile has exactly S rows: stores are guarded per row
   uint32_t stride;
+  int lane, S;
+  __device__ __forceinline__ PadAddr(uint32_t stride_, int lane_, int S_) : stride(stride_), lane(lane_), S(S_) {}
   __device__ __forceinline__ uint32_t off(int row, int col) const { return (uint32_t)row * stride + (uint32_t)col * 2u; }
+  __device__ __forceinline__ uint32_t a_off(int i, int ks) const {
+    return off(min(i * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1), ks * 16 + (lane >> 4) * 8);
+  }
+  __device__ __forceinline__ uint32_t b_off(int nt, int k2) const {
+    return off(min(nt * 8 + (lane & 7), S - 1), k2 * 32 + (lane >> 3) * 8);
+  }
 };
-struct SwzAddr {      // one 128-byte row per token, 128B-swizzled as TMA writes it (D = 64): conflict-free ldmatrix
+// One 128-byte row per token, 128B-swizzled as TMA writes it (D = 64, tiles 1024-byte aligned and padded to whole
+// 8-row groups): conflict-free ldmatrix.  offset = row * 128 + ((chunk ^ (row & 7)) << 4) + byte in chunk.  The lane
+// terms are computed ONCE per kernel (they depend on the lane and S only, not on the head): a chunk is a compile-time
+// step XOR a lane term, so every address in the per-head code is `precomputed ^ immediate` (+ the tile base).
+struct SwzAddr {
+  static constexpr bool kStaticRows = true;    // rows up to the next multiple of 8 exist in the tile (never stored to HBM)
+  uint32_t pa[2], pb[4], pst;
+  __device__ __forceinline__ SwzAddr(int lane, int S) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t row = (uint32_t)min(i * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
+      pa[i] = row * 128u + ((((uint32_t)lane >> 4) ^ (row & 7u)) << 4);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint32_t row = (uint32_t)min(nt * 8 + (lane & 7), S - 1);
+      pb[nt] = row * 128u + ((((uint32_t)lane >> 3) ^ (row & 7u)) << 4);
+    }
+    const uint32_t g = (uint32_t)lane >> 2, t = (uint32_t)lane & 3u;
+    pst = g * 128u + (g << 4) + t * 4u;
+  }
   __device__ __forceinline__ uint32_t off(int row, int col) const {
     return (uint32_t)row * 128u + (((((uint32_t)col >> 3) ^ (uint32_t)row) & 7u) << 4) + ((uint32_t)col & 7u) * 2u;
   }
+  __device__ __forceinline__ uint32_t a_off(int i, int ks) const { return pa[i] ^ ((uint32_t)ks << 5); }
+  __device__ __forceinline__ uint32_t b_off(int nt, int k2) const { return pb[nt] ^ ((uint32_t)k2 << 6); }
+  __device__ __forceinline__ uint32_t st_base(uint32_t tile, int rowbase) const { return tile + (uint32_t)rowbase * 128u + pst; }
+  __device__ __forceinline__ uint32_t st_addr(uint32_t base, int nd) const { return base ^ ((uint32_t)nd << 4); }
 };
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 template <int NT>
 __device__ __forceinline__ uint32_t key_valid_bits(const uint8_t* __restrict__ mask, int b, int Tn, int S, int t) {
@@ -66,12 +112,8 @@ __device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, A
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int k2 = 0; k2 < KS / 2; ++k2) {
-      const int row = min(nt * 8 + (lane & 7), S - 1);
-      const int col = k2 * 32 + (lane >> 3) * 8;
-      ldsm_x4(kbase + ad.off(row, col), kf[nt][2 * k2][0], kf[nt][2 * k2][1], kf[nt][2 * k2 + 1][0],
-              kf[nt][2 * k2 + 1][1]);
-    }
+    for (int k2 = 0; k2 < KS / 2; ++k2)
+      ldsm_x4(kbase + ad.b_off(nt, k2), kf[nt][2 * k2][0], kf[nt][2 * k2][1], kf[nt][2 * k2 + 1][0], kf[nt][2 * k2 + 1][1]);
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -81,9 +123,7 @@ __device__ __forceinline__ void scores_softmax(uint32_t qbase, uint32_t kbase, A
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t a0, a1, a2, a3;
-      const int row = min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
-      const int col = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(qbase + ad.off(row, col), a0, a1, a2, a3);
+      ldsm_x4(qbase + ad.a_off(mt, ks), a0, a1, a2, a3);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(p[mt][nt], a0, a1, a2, a3, kf[nt][ks][0], kf[nt][ks][1]);
     }
@@ -156,26 +196,38 @@ __device__ __forceinline__ void mma_rows_x(float (&acc)[D / 8][4], const uint32_
 #pragma unroll
     for (int n2 = 0; n2 < D / 16; ++n2) {
       uint32_t b0, b1, b2, b3;
-      const int row = min(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
-      const int col = n2 * 16 + (lane >> 4) * 8;
-      ldsm_x4_t(xbase + ad.off(row, col), b0, b1, b2, b3);
+      ldsm_x4_t(xbase + ad.a_off(ks, n2), b0, b1, b2, b3);
       mma_bf16_16816(acc[2 * n2], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b0, b1);
       mma_bf16_16816(acc[2 * n2 + 1], a[ks][0], a[ks][1], a[ks][2], a[ks][3], b2, b3);
     }
 }
 
-// store a 16 x D accumulator tile as bf16 rows (row0 + g, row0 + g + 8) of a smem matrix, rows >= S skipped
-template <int D, class AD>
-__device__ __forceinline__ void store_tile(uint8_t* base, AD ad, int row0, int S, int lane,
-                                           const float (&acc)[D / 8][4]) {
-  const int g = lane >> 2, t = lane & 3;
+// store a 16 x D accumulator tile as bf16 rows (row0 + g, row0 + g + 8) of the shared-memory tile at address `tile`.
+// Rows that do not exist are skipped: beyond S in the padded-row layout (per lane), beyond the tile's NT * 8 rows in the
+// swizzled one (decided at compile time; rows S .. NT * 8 - 1 are padding that no TMA store reads).
+template <int D, int NT, class AD>
+__device__ __forceinline__ void store_tile(uint32_t tile, const AD& ad, int row0, int lane, const float (&acc)[D / 8][4]) {
+  if constexpr (AD::kStaticRows) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int row = row0 + g + 8 * r;
-    if (row < S) {
+    for (int r = 0; r < 2; ++r) {
+      const int rowbase = row0 + 8 * r;
+      if (rowbase < NT * 8) {
+        const uint32_t base = ad.st_base(tile, rowbase);
 #pragma unroll
-      for (int nd = 0; nd < D / 8; ++nd)
-        *reinterpret_cast<uint32_t*>(base + ad.off(row, nd * 8 + t * 2)) = pack_bf16x2(acc[nd][2 * r], acc[nd][2 * r + 1]);
+        for (int nd = 0; nd < D / 8; ++nd) sts_b32(ad.st_addr(base, nd), pack_bf16x2(acc[nd][2 * r], acc[nd][2 * r + 1]));
+      }
+    }
+  } else {
+    uint8_t* base = reinterpret_cast<uint8_t*>(__cvta_shared_to_generic(tile));
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + g + 8 * r;
+      if (row < ad.S) {
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd)
+          *reinterpret_cast<uint32_t*>(base + ad.off(row, nd * 8 + t * 2)) = pack_bf16x2(acc[nd][2 * r], acc[nd][2 * r + 1]);
+      }
     }
   }
 }
@@ -183,8 +235,9 @@ __device__ __forceinline__ void store_tile(uint8_t* base, AD ad, int row0, int S
 // One head of the forward pass on fragments: S = Q K^T, masked softmax, dropout, O = P V.  q/k/v are shared-memory
 // addresses of [S][D] tiles laid out per the address policy `ad`; O (bf16) is written to o_ptr with the same policy.
 template <int D, int MT, int NT, class AD>
-__device__ __forceinline__ void mha_fwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint8_t* o_ptr, AD ad, int S,
-                                             int lane, uint32_t kvalid, long long bh, float* __restrict__ probs, DropCfg dc) {
+__device__ __forceinline__ void mha_fwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint32_t o_a, const AD& ad,
+                                             int S, int lane, uint32_t kvalid, long long bh, float* __restrict__ probs,
+                                             DropCfg dc) {
   const int g = lane >> 2, t = lane & 3;
   float p[MT][NT][4];
   scores_softmax<D, MT, NT>(qbase, kbase, ad, S, lane, kvalid, p);
@@ -226,7 +279,7 @@ __device__ __forceinline__ void mha_fwd_head(uint32_t qbase, uint32_t kbase, uin
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
     mma_rows_x<D, (NT + 1) / 2>(o, pa[mt], vbase, ad, S, lane);
-    store_tile<D>(o_ptr, ad, mt * 16, S, lane, o);   // O_h overwrites the dead Q_h slot
+    store_tile<D, NT>(o_a, ad, mt * 16, lane, o);   // O_h overwrites the dead Q_h slot
   }
 }
 
@@ -258,7 +311,7 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 
   for (int h = warp; h < H; h += MMA_WARPS) {
     const uint32_t qbase = in_a + h * D * 2, kbase = qbase + F * 2, vbase = kbase + F * 2;
-    mha_fwd_head<D, MT, NT>(qbase, kbase, vbase, smem + h * D * 2, PadAddr{gm.in_stride}, S, lane, kvalid,
+    mha_fwd_head<D, MT, NT>(qbase, kbase, vbase, in_a + h * D * 2, PadAddr(gm.in_stride, lane, S), S, lane, kvalid,
                             (long long)b * H + h, probs, dc);
   }
   fence_async_smem();
@@ -274,8 +327,8 @@ mha_fwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 // Outputs overwrite dead operand tiles: dV -> dv_ptr (ain), dK -> dk_ptr (ain), dQ -> dq_ptr (ado).
 template <int D, int MT, int NT, class AIN, class ADO>
 __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uint32_t vbase, uint32_t dobase,
-                                             uint8_t* dq_ptr, uint8_t* dk_ptr, uint8_t* dv_ptr, AIN ain, ADO ado,
-                                             int S, int lane, uint32_t kvalid, long long bh, DropCfg dc) {
+                                             uint32_t dq_a, uint32_t dk_a, uint32_t dv_a, const AIN& ain,
+                                             const ADO& ado, int S, int lane, uint32_t kvalid, long long bh, DropCfg dc) {
   constexpr int KS = D / 16;
   constexpr int MTK = (NT + 1) / 2;   // 16-row tiles over keys
   const int g = lane >> 2, t = lane & 3;
@@ -289,12 +342,8 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int k2 = 0; k2 < KS / 2; ++k2) {
-        const int row = min(nt * 8 + (lane & 7), S - 1);
-        const int col = k2 * 32 + (lane >> 3) * 8;
-        ldsm_x4(vbase + ain.off(row, col), vf[nt][2 * k2][0], vf[nt][2 * k2][1], vf[nt][2 * k2 + 1][0],
-                vf[nt][2 * k2 + 1][1]);
-      }
+      for (int k2 = 0; k2 < KS / 2; ++k2)
+        ldsm_x4(vbase + ain.b_off(nt, k2), vf[nt][2 * k2][0], vf[nt][2 * k2][1], vf[nt][2 * k2 + 1][0], vf[nt][2 * k2 + 1][1]);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -304,9 +353,7 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t a0, a1, a2, a3;
-        const int row = min(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, S - 1);
-        const int col = ks * 16 + (lane >> 4) * 8;
-        ldsm_x4(dobase + ado.off(row, col), a0, a1, a2, a3);
+        ldsm_x4(dobase + ado.a_off(mt, ks), a0, a1, a2, a3);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(dp[mt][nt], a0, a1, a2, a3, vf[nt][ks][0], vf[nt][ks][1]);
       }
@@ -360,7 +407,7 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
     mma_rows_x<D, MT>(acc, a, dobase, ado, S, lane);
-    store_tile<D>(dv_ptr, ain, mk * 16, S, lane, acc);   // dV_h -> dead V_h slot
+    store_tile<D, NT>(dv_a, ain, mk * 16, lane, acc);   // dV_h -> dead V_h slot
   }
   // ---- dS as A fragments (for dQ); its transpose is built the same way (for dK)
   uint32_t dsa[MT][(NT + 1) / 2][4];
@@ -374,7 +421,7 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
     mma_rows_x<D, (NT + 1) / 2>(acc, dsa[mt], kbase, ain, S, lane);
-    store_tile<D>(dq_ptr, ado, mt * 16, S, lane, acc);
+    store_tile<D, NT>(dq_a, ado, mt * 16, lane, acc);
   }
   // ---- dK = dS^T Q -> dead K_h slot
   float acck[MTK][D / 8][4];
@@ -392,7 +439,7 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
   __syncwarp();   // every lane has finished reading K_h (dQ) before it is overwritten
 #pragma unroll
   for (int mk = 0; mk < MTK; ++mk)
-    store_tile<D>(dk_ptr, ain, mk * 16, S, lane, acck[mk]);
+    store_tile<D, NT>(dk_a, ain, mk * 16, lane, acck[mk]);
   __syncwarp();
 }
 
@@ -447,9 +494,8 @@ mha_bwd_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mas
 
   for (int h = warp; h < H; h += MMA_WARPS) {
     const uint32_t qbase = in_a + h * D * 2, kbase = qbase + F * 2, vbase = kbase + F * 2, dobase = do_a + h * D * 2;
-    mha_bwd_head<D, MT, NT>(qbase, kbase, vbase, dobase, do_s + h * D * 2, smem + F * 2 + h * D * 2,
-                            smem + 2 * F * 2 + h * D * 2, PadAddr{gm.in_stride}, PadAddr{gm.do_stride}, S, lane, kvalid,
-                            (long long)b * H + h, dc);
+    mha_bwd_head<D, MT, NT>(qbase, kbase, vbase, dobase, dobase, kbase, vbase, PadAddr(gm.in_stride, lane, S),
+                            PadAddr(gm.do_stride, lane, S), S, lane, kvalid, (long long)b * H + h, dc);
   }
   ATT_TICK(1);
   fence_async_smem();
@@ -528,6 +574,7 @@ mha_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const long long units = (long long)B * H;
   const long long stride = (long long)gridDim.x * TMA_FWD_WARPS;
   uint32_t phase = 0;
+  const SwzAddr ad(lane, S);
   for (long long u = (long long)blockIdx.x * TMA_FWD_WARPS + warp; u < units; u += stride) {
     const int b = (int)(u / H), h = (int)(u % H);
     if (lane == 0) {
@@ -539,7 +586,7 @@ mha_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const uint32_t kvalid = key_valid_bits<NT>(mask, b, Tn, S, t);
     mbar_wait(bar_a, phase);
     phase ^= 1;
-    mha_fwd_head<D, MT, NT>(q_a, k_a, v_a, my, SwzAddr{}, S, lane, kvalid, u, probs, dc);
+    mha_fwd_head<D, MT, NT>(q_a, k_a, v_a, q_a, ad, S, lane, kvalid, u, probs, dc);
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -577,7 +624,10 @@ mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   float cs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};           // column sums of dQ | dK | dV, columns 2*lane, 2*lane+1
   int my_h = -1;
   uint32_t phase = 0;
-  const SwzAddr ad{};
+  const SwzAddr ad(lane, S);
+  // column sums of the stored tiles: the lane's bf16 pair (columns 2 * lane, 2 * lane + 1) of row r sits in chunk
+  // (lane >> 2) ^ (r & 7); rows r, r + 8, r + 16, ... share the swizzle, so the loop is unrolled over r & 7
+  const uint32_t pcs = (((uint32_t)lane >> 2) << 4) + ((uint32_t)lane & 3u) * 4u;
   for (long long u = (long long)blockIdx.x * TMA_BWD_WARPS + warp; u < units; u += stride) {
     const int b = (int)(u / H), h = (int)(u % H);
     my_h = h;
@@ -591,8 +641,7 @@ mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const uint32_t kvalid = key_valid_bits<NT>(mask, b, Tn, S, t);
     mbar_wait(bar_a, phase);
     phase ^= 1;
-    mha_bwd_head<D, MT, NT>(q_a, k_a, v_a, do_a, my + 3 * tile_bytes, my + tile_bytes, my + 2 * tile_bytes, ad, ad,
-                            S, lane, kvalid, u, dc);
+    mha_bwd_head<D, MT, NT>(q_a, k_a, v_a, do_a, do_a, k_a, v_a, ad, ad, S, lane, kvalid, u, dc);
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -605,11 +654,18 @@ mha_bwd_tma_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       // column sums of what was stored, two columns per lane, while the stores drain
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
-        const uint8_t* tile = my + (m == 0 ? 3 : m) * tile_bytes;
-        for (int r = 0; r < S; ++r) {
-          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tile + ad.off(r, 2 * lane)));
-          cs[m][0] += v.x;
-          cs[m][1] += v.y;
+        const uint32_t tile = (m == 0 ? do_a : m == 1 ? k_a : v_a) + pcs;
+#pragma unroll
+        for (int r7 = 0; r7 < 8; ++r7) {
+          const uint32_t a = (tile ^ ((uint32_t)r7 << 4)) + (uint32_t)r7 * 128u;
+#pragma unroll
+          for (int k = 0; k < NT; ++k) {
+            if (k < NT - 1 || r7 + 8 * k < S) {     // only the last 8-row group is partial
+              const uint32_t v = lds_b32(a + (uint32_t)k * 1024u);
+              cs[m][0] += __uint_as_float(v << 16);
+              cs[m][1] += __uint_as_float(v & 0xffff0000u);
+            }
+          }
         }
       }
     }
