@@ -423,23 +423,22 @@ __device__ __forceinline__ void mha_bwd_head(uint32_t qbase, uint32_t kbase, uin
     mma_rows_x<D, (NT + 1) / 2>(acc, dsa[mt], kbase, ain, S, lane);
     store_tile<D, NT>(dq_a, ado, mt * 16, lane, acc);
   }
-  // ---- dK = dS^T Q -> dead K_h slot
-  float acck[MTK][D / 8][4];
+  // ---- dK = dS^T Q -> dead K_h slot, one 16-key tile at a time (the accumulators of one tile are live, not of all).
+  // Every lane has finished reading K_h (dQ above) before the first tile overwrites it; the later tiles read Q only.
+  __syncwarp();
 #pragma unroll
   for (int mk = 0; mk < MTK; ++mk) {
     uint32_t a[MT][4];
 #pragma unroll
     for (int kq = 0; kq < MT; ++kq) trans_frag(dsa[kq][mk], a[kq]);
+    float acc[D / 8][4];
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acck[mk][nd][i] = 0.f;
-    mma_rows_x<D, MT>(acck[mk], a, qbase, ain, S, lane);
+      for (int i = 0; i < 4; ++i) acc[nd][i] = 0.f;
+    mma_rows_x<D, MT>(acc, a, qbase, ain, S, lane);
+    store_tile<D, NT>(dk_a, ain, mk * 16, lane, acc);
   }
-  __syncwarp();   // every lane has finished reading K_h (dQ) before it is overwritten
-#pragma unroll
-  for (int mk = 0; mk < MTK; ++mk)
-    store_tile<D, NT>(dk_a, ain, mk * 16, lane, acck[mk]);
   __syncwarp();
 }
 
