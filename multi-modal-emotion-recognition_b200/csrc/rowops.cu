@@ -515,6 +515,125 @@ pool_ln_fwd_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, co
   }
 }
 
+// Long sequences with few samples (cfg4: B = 512, S = 257): a warp per sample leaves most of the machine idle
+// (139 us for 135 MB, 0.15 of the HBM peak), so ONE CTA takes a sample: warp w sums rows w, w + 8, ... (four rows of
+// loads in flight), the eight partial sums meet in shared memory in warp order (deterministic), warp 0 normalises.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+pool_ln_fwd_cta_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float* __restrict__ pooled, T* __restrict__ fused,
+                       float* __restrict__ stats, int B, int Tn, int F) {
+  extern __shared__ float pool_sred[];   // [ROW_WARPS][F] partial sums, then [ROW_WARPS] valid-row counts
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = Tn + 1;
+  int* scnt = reinterpret_cast<int*>(pool_sred + ROW_WARPS * F);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float acc[NCH][8];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    int cnt = 0;
+    constexpr int U = 4;
+    for (int s0 = warp; s0 < S; s0 += ROW_WARPS * U) {
+      Raw8<T> r[U][NCH];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u * ROW_WARPS;
+        ok[u] = s < S && ((s == Tn) || mask == nullptr || mask[(long long)b * Tn + s] == 0);
+        if (ok[u]) {
+          const T* src = x + ((long long)b * S + s) * F;
+#pragma unroll
+          for (int i = 0; i < NCH; ++i)
+            if (lane * 8 + i * 256 < F) r[u][i].load(src + lane * 8 + i * 256);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        ++cnt;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+          if (lane * 8 + i * 256 < F) {
+            float v[8];
+            r[u][i].get(v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] += v[j];
+          }
+      }
+    }
+    __syncthreads();   // the previous sample's partial sums have been consumed
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+        *reinterpret_cast<float4*>(pool_sred + warp * F + c) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(pool_sred + warp * F + c + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+    if (lane == 0) scnt[warp] = cnt;
+    __syncthreads();
+    if (warp != 0) continue;
+    cnt = 0;
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) cnt += scnt[w];
+    const float inv = 1.f / fmaxf((float)cnt, 1e-6f);
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int w = 0; w < ROW_WARPS; ++w) {
+          float v[8];
+          load8(pool_sred + w * F + c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[i][j] *= inv; sm += acc[i][j]; }
+        store8(pooled + (long long)b * F + c, acc[i]);
+      }
+    }
+    if (gamma == nullptr) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane * 8 + i * 256;
+        if (c < F) store8(fused + (long long)b * F + c, acc[i]);
+      }
+      continue;
+    }
+    const float mean = warp_sum(sm) / (float)F;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = acc[i][j] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)F + LN_EPS);
+    if (lane == 0) { stats[b * 2] = mean; stats[b * 2 + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane * 8 + i * 256;
+      if (c < F) {
+        float g[8], be[8], o[8];
+        load8(gamma + c, g);
+        load8(beta + c, be);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (acc[i][j] - mean) * rstd * g[j] + be[j];
+        store8(fused + (long long)b * F + c, o);
+      }
+    }
+  }
+}
+
 template <typename T, int NCH>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 pool_ln_bwd_kernel(const T* __restrict__ dfused, const float* __restrict__ pooled, const float* __restrict__ stats,
@@ -794,6 +913,22 @@ int mmer_pool_ln_fwd(const void* x, const uint8_t* mask, const float* gamma, con
   if (B <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t le = cudaSuccess;
+  // few samples with long sequences: one CTA per sample instead of one warp (see pool_ln_fwd_cta_kernel)
+  if (T + 1 >= 64 && B < (int64_t)sm_count() * ROW_WARPS * 2 && F <= 1024) {
+    const size_t sm_bytes = (size_t)ROW_WARPS * F * sizeof(float) + ROW_WARPS * sizeof(int);
+    const long long cap = (long long)sm_count() * 4;
+    const dim3 grid((unsigned)(B < cap ? B : cap));
+    if (dtype == MMER_BF16) {
+      DISPATCH_NCH(F, (le = launch_dep(pool_ln_fwd_cta_kernel<bf16, NCH>, grid, dim3(ROW_WARPS * 32), sm_bytes, st, 1,
+                                       (const bf16*)x, mask, gamma, beta, pooled, (bf16*)fused, stats, (int)B, (int)T, (int)F)));
+    } else {
+      DISPATCH_NCH(F, (le = launch_dep(pool_ln_fwd_cta_kernel<float, NCH>, grid, dim3(ROW_WARPS * 32), sm_bytes, st, 1,
+                                       (const float*)x, mask, gamma, beta, pooled, (float*)fused, stats, (int)B, (int)T, (int)F)));
+    }
+    if (le != cudaSuccess) return cuda_fail(le, "launch(pool_ln_fwd_cta)");
+    MMER_LAUNCH_CHECK("pool_ln_fwd_cta_kernel");
+    return 0;
+  }
   if (dtype == MMER_BF16) {
     DISPATCH_NCH(F, (le = launch_dep(pool_ln_fwd_kernel<bf16, NCH>, dim3(row_grid(B)), dim3(ROW_WARPS * 32), 0, st, 1,
                                      (const bf16*)x, mask, gamma, beta, pooled, (bf16*)fused, stats, (int)B, (int)T, (int)F)));

@@ -381,6 +381,33 @@ def test_pool_ln_fwd_bwd(dt, use_mask, use_ln):
 
 
 @pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,T,F,use_mask,use_ln", [(37, 256, 512, True, True), (5, 100, 512, False, True), (300, 63, 264, True, False),
+                                                   (3, 300, 1024, True, True)])
+def test_pool_ln_fwd_long_sequences_one_cta_per_sample(dt, B, T, F, use_mask, use_ln):
+    """Few samples with long sequences run pool_ln_fwd_cta_kernel (one CTA per sample, rows strided over its warps):
+    masked mean + out_norm against float64, incl. a fully padded sample (count clamps to the audio row) and ragged lengths."""
+    S = T + 1
+    x = rnd(B * S, F, dt=dt, seed=1)
+    lens = torch.randint(1, T + 1, (B,), generator=torch.Generator().manual_seed(5))
+    lens[0] = T
+    lens[-1] = 1
+    mask = (torch.arange(T)[None] >= lens[:, None])
+    gamma, beta = rnd(F, seed=2) * .2 + 1, rnd(F, seed=3) * .2
+    mk = mask.to(DEV).view(torch.uint8) if use_mask else None
+    fused, pooled, stats = ops.pool_ln_fwd(x, mk, gamma if use_ln else None, beta if use_ln else None, B, T)
+    keep = torch.ones(B, S, 1, dtype=torch.double, device=DEV)
+    if use_mask:
+        keep = (~torch.cat([mask, torch.zeros(B, 1, dtype=torch.bool)], 1)).double().unsqueeze(-1).to(DEV)
+    pr = (x.double().view(B, S, F) * keep).sum(1) / keep.sum(1).clamp(min=1e-6)
+    assert rel(pooled, pr) < 2e-6
+    ref = O.layer_norm(pr, gamma.double(), beta.double()) if use_ln else pr
+    assert rel(fused, ref) < tol(dt)
+    if use_ln:
+        mu = pr.mean(1)
+        assert rel(stats[:, 0], mu) < 1e-4 + 1e-6 / float(mu.abs().max())
+
+
+@pytest.mark.parametrize("dt", DT)
 def test_colsum(dt):
     x = rnd(1000, 1536, dt=dt, seed=1)
     out = torch.ones(1536, device=DEV)
