@@ -380,10 +380,12 @@ def time_memory_bound_kernels(dev, pk):
                     "frac": gbs / pk["hbm"], "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes})
 
     sets = [(rnd(M, 3 * F), rnd(M, F)) for _ in range(3)]
-    add("mha_fwd_mma_kernel (p=0.1)", [lambda q=q: ops.mha_fwd(q, None, B, T, H, D, drop_p=0.1, seed=1, site=1) for q, _ in sets],
+    add("mha_fwd_tma_kernel (p=0.1)", [lambda q=q: ops.mha_fwd(q, None, B, T, H, D, drop_p=0.1, seed=1, site=1) for q, _ in sets],
         M * 3 * F * 2 + M * F * 2)
-    add("mha_bwd_mma_kernel (p=0.1)", [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=0.1, seed=1, site=1)
-                                       for q, d in sets], 2 * M * 3 * F * 2 + M * F * 2)
+    dbias_qkv = torch.zeros(3 * F, device=dev)   # as the step launches it: with the fused in_proj bias gradient
+    add("mha_bwd_tma_kernel incl. in_proj bias-gradient sums (p=0.1)",
+        [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=0.1, seed=1, site=1, dbias=dbias_qkv) for q, d in sets],
+        2 * M * 3 * F * 2 + M * F * 2)
     del sets
     gam, bet = torch.ones(F, device=dev), torch.zeros(F, device=dev)
     dg, db, dbias = (torch.zeros(F, device=dev) for _ in range(3))
