@@ -68,6 +68,10 @@ def bench_mha():
                                              for q, _ in sets], fb)
             timeit(f"mha_bwd[{tag}] p={p}", [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=p, seed=1, site=1)
                                              for q, d in sets], bb)
+            if p > 0:   # as the training step launches it: with the in_proj bias gradient (column sums of what is stored)
+                dbias = torch.zeros(3 * F, device=dev)
+                timeit(f"mha_bwd[{tag}] p={p} +dbias", [lambda q=q, d=d: ops.mha_bwd(q, None, d, B, T, H, D, drop_p=p, seed=1,
+                                                                                    site=1, dbias=dbias) for q, d in sets], bb)
     lib.mmer_debug_set(_lib.DEBUG_ATT_ROWS, 0)
 
 
